@@ -1,0 +1,150 @@
+"""Pins oracle/ref_numpy.py against the UNMODIFIED reference imported from /root/reference through
+oracle/pyquil_shim.  Skips when the reference tree is absent (GPU box); there tests/golden pins it."""
+import numpy as np
+import pytest
+
+from oracle import ref_numpy as orc
+from oracle import reference_bridge as rb
+
+pytestmark = pytest.mark.skipif(not rb.available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return rb.load()
+
+
+def relerr(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(np.asarray(b)), 1e-300)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_pauli_order_bit_exact(ref, n):
+    qubits = list(range(n))
+    basis = ref.ut.n_qubit_pauli_basis(n)
+    assert basis.labels == orc.pauli_labels(n)
+    terms = ref.ut.all_traceless_pauli_terms(qubits)
+    from pyquil.simulation.tools import lifted_pauli
+    for k in range(4 ** n):
+        assert np.array_equal(basis.ops[k], orc.pauli_matrix(k, n))
+        if k:
+            assert np.array_equal(lifted_pauli(terms[k - 1], qubits[::-1]), orc.pauli_matrix(k, n))
+            assert terms[k - 1] == rb.pauli_term(ref, k, qubits)
+
+
+def test_input_state_order(ref):
+    import itertools
+    from pyquil.simulation.tools import lifted_state_operator
+    qubits = [0, 1]
+    for basis, fn in (("pauli", ref.tomo._pauli_process_tomo_settings), ("sic", ref.tomo._sic_process_tomo_settings)):
+        ours = orc.process_tomography_settings(2, basis)
+        theirs = list(fn(qubits))
+        assert len(ours) == len(theirs)
+        for (codes, k), s in zip(ours, theirs):
+            assert s.observable == rb.pauli_term(ref, k, qubits)
+            assert np.allclose(lifted_state_operator(s.in_state, qubits[::-1]),
+                               orc.product_state_matrix(codes), atol=1e-15)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_conversions(ref, n):
+    rng = np.random.default_rng(10 + n)
+    d = 2 ** n
+    ks = [np.sqrt(.7) * orc.haar_unitary(rng, d), np.sqrt(.3) * orc.haar_unitary(rng, d)]
+    ot = ref.ot
+    assert relerr(orc.kraus2choi(ks), ot.kraus2choi(ks)) < 1e-14
+    assert relerr(orc.kraus2superop(ks), ot.kraus2superop(ks)) < 1e-14
+    c = ot.kraus2choi(ks)
+    s = ot.choi2superop(c)
+    assert np.array_equal(orc.choi2superop(c), s)
+    assert np.array_equal(orc.superop2choi(s), ot.superop2choi(s))
+    assert np.array_equal(orc.pauli2computational_basis_matrix(d), ot.pauli2computational_basis_matrix(d))
+    pl = ot.superop2pauli_liouville(s)
+    assert relerr(orc.superop2pauli_liouville(s), pl) < 1e-14
+    assert relerr(orc.pauli_liouville2superop(pl), ot.pauli_liouville2superop(pl)) < 1e-14
+    assert relerr(orc.choi2pauli_liouville(c), ot.choi2pauli_liouville(c)) < 1e-14
+    assert relerr(orc.pauli_liouville2choi(pl), ot.pauli_liouville2choi(pl)) < 1e-14
+    assert relerr(orc.kraus2pauli_liouville(ks), ot.kraus2pauli_liouville(ks)) < 1e-14
+    k1, k2 = orc.choi2kraus(c), ot.choi2kraus(c)
+    assert len(k1) == len(k2) == 2
+    assert relerr(orc.kraus2choi(k1), ot.kraus2choi(k2)) < 1e-12
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_projections(ref, n):
+    rng = np.random.default_rng(20 + n)
+    d2 = 4 ** n
+    x = rng.standard_normal((d2, d2)) + 1j * rng.standard_normal((d2, d2))
+    x = (x + x.conj().T) / 2 / d2
+    x += orc.kraus2choi([orc.haar_unitary(rng, 2 ** n)])
+    ot = ref.ot
+    assert relerr(orc.proj_choi_to_completely_positive(x), ot.proj_choi_to_completely_positive(x)) < 1e-13
+    assert relerr(orc.proj_choi_to_trace_preserving(x), ot.proj_choi_to_trace_preserving(x)) < 1e-14
+    assert relerr(orc.proj_choi_to_trace_non_increasing(x), ot.proj_choi_to_trace_non_increasing(x)) < 1e-13
+    assert relerr(orc.proj_choi_to_physical(x), ot.proj_choi_to_physical(x)) < 1e-12
+    assert relerr(orc.proj_choi_to_physical(x, False), ot.proj_choi_to_physical(x, False)) < 1e-12
+    assert relerr(orc.partial_trace_out(x), ref.partial_trace(x, [0], [2 ** n, 2 ** n])) < 1e-15
+
+
+@pytest.mark.parametrize("n", [1, 2, 4])
+def test_distances(ref, n):
+    rng = np.random.default_rng(30 + n)
+    d = 2 ** n
+    for _ in range(5):
+        r, s = orc.ginibre_state(rng, d), orc.ginibre_state(rng, d)
+        assert abs(orc.fidelity(r, s) - ref.dm.fidelity(r, s)) < 1e-13
+        assert abs(orc.trace_distance(r, s) - ref.dm.trace_distance(r, s)) < 1e-15
+        assert abs(orc.purity(r) - ref.dm.purity(r, dim_renorm=False)) < 1e-14
+    z0 = np.diag([1.0, 0]); z1 = np.diag([0, 1.0])
+    assert orc.trace_distance(z0, z1) == ref.dm.trace_distance(z0, z1) == 0.5
+
+
+@pytest.mark.parametrize("n,kw", [
+    (1, {}), (2, dict(tol=1e-5)), (2, dict(maxiter=50)),
+    (2, dict(entropy_penalty=.001, tol=1e-4)), (2, dict(epsilon=1e-4, beta=.5, tol=1e-3)),
+])
+def test_mle(ref, n, kw):
+    _, pidx, ex, cnt = orc.synth_state_tomography(77 + n, 2, n)
+    qubits = list(range(n))
+    coeffs = np.ones(len(pidx))
+    for b in range(2):
+        res = rb.state_results(ref, pidx, coeffs, ex[b], cnt[b], qubits)
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = ref.tomo.iterative_mle_state_estimate(res, qubits, **kw)
+        got, _ = orc.mle_state_estimate(pidx, coeffs, ex[b], cnt[b], n, **kw)
+        assert relerr(got, want) < 1e-11
+        if not kw.get("entropy_penalty") and not kw.get("beta"):
+            kb = {k: v for k, v in kw.items() if k in ("epsilon", "tol", "maxiter")}
+            gotb, _ = orc.mle_state_estimate_batch(pidx, coeffs, ex[b:b + 1], n, **kb)
+            assert relerr(gotb[0], want) < 1e-11
+        assert relerr(orc.linear_inv_state_estimate(pidx, coeffs, ex[b], n),
+                      ref.tomo.linear_inv_state_estimate(res, qubits)) < 1e-12
+
+
+def test_r_operator_with_coefficients_and_identity(ref):
+    rng = np.random.default_rng(5)
+    rho = orc.ginibre_state(rng, 4)
+    qubits = [3, 7]
+    pidx, coeffs, ex = [0, 7, 7, 12], [1.0, -1.0, 0.5, 1.0], [1.0, -.2, .1, .4]
+    res = rb.state_results(ref, pidx, coeffs, ex, [10] * 4, qubits)
+    want = ref.tomo._R(rho, res, qubits[::-1])
+    got = orc.r_operator(rho, [c * orc.pauli_matrix(k, 2) for k, c in zip(pidx, coeffs)], ex)
+    assert relerr(got, want) < 1e-14
+
+
+@pytest.mark.parametrize("n,basis,tp", [(1, "pauli", True), (1, "sic", True), (1, "pauli", False), (2, "sic", True)])
+def test_pgdb(ref, n, basis, tp):
+    _, settings, ex, cnt = orc.synth_process_tomography(91 + n, 1, n, in_basis=basis)
+    qubits = list(range(n))
+    coeffs = np.ones(len(settings))
+    res = rb.process_results(ref, settings, coeffs, ex[0], cnt[0], qubits)
+    a_ref, n_ref = ref.tomo._extract_from_results(res, qubits[::-1])
+    a, nn = orc.extract_design(settings, coeffs, ex[0], cnt[0], n)
+    assert relerr(a, a_ref) < 1e-15 and relerr(nn, n_ref) < 1e-15
+    want = ref.tomo.pgdb_process_estimate(res, qubits, trace_preserving=tp)
+    got = orc.pgdb_process_estimate(settings, coeffs, ex[0], cnt[0], n, trace_preserving=tp)
+    assert relerr(got, want) < 1e-10
+    assert relerr(orc.linear_inv_process_estimate(settings, coeffs, ex[0], n),
+                  ref.tomo.linear_inv_process_estimate(res, qubits)) < 1e-11
