@@ -1,0 +1,212 @@
+// Batched state distance measures: one pair (rho_b, sigma_b) per warp.
+//
+//   trace_distance  distance_measures.py:100-114  0.5 * ||rho - sigma||_1 with NumPy's INDUCED 1-norm
+//                   (max column abs-sum) -- the reference's actual behaviour, pinned by its own test
+//                   tests/test_distance_measures.py:73-82.  Pure streaming, HBM-bound.
+//   trace_distance_nuclear   the textbook 0.5 * sum |eig(rho - sigma)| (extra, not a reference function)
+//   fidelity        distance_measures.py:64-84 + calculational.py:77-91
+//                   (tr sqrt( sqrt(rho) sigma sqrt(rho) ))^2 = (sum_i sqrt(max(lambda_i, 0)))^2
+//   purity          distance_measures.py:14-37    tr(rho^2)
+#include "qt_common.cuh"
+#include "qt_eigh.cuh"
+#include "../../include/qtomo.h"
+
+template <int D>
+__global__ void trace_distance_kernel(int64_t B, const cplx* __restrict__ rho, const cplx* __restrict__ sigma,
+                                      double* __restrict__ out) {
+  constexpr int DD = D * D;
+  constexpr int G = (D >= 32) ? 1 : 32 / D;  // row groups held by one warp pass
+  const int lane = threadIdx.x & 31;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  const cplx* r = rho + b * DD;
+  const cplx* s = sigma + b * DD;
+  double colsum = 0.0;  // lane owns column lane % D, rows lane / D + k*G
+  if (D <= 32) {
+    for (int e = lane; e < DD; e += 32) {
+      const cplx a = r[e], c = s[e];
+      colsum += sqrt(cabs2(csub(a, c)));
+    }
+#pragma unroll
+    for (int o = 16; o >= D; o >>= 1) colsum += __shfl_xor_sync(0xffffffffu, colsum, o);
+    double m = colsum;
+#pragma unroll
+    for (int o = (D < 32 ? D : 32) / 2; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) out[b] = 0.5 * m;
+  }
+  (void)G;
+}
+
+template <int D>
+__global__ void purity_kernel(int64_t B, const cplx* __restrict__ rho, double* __restrict__ out) {
+  constexpr int DD = D * D;
+  const int lane = threadIdx.x & 31;
+  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (b >= B) return;
+  const cplx* r = rho + b * DD;
+  // tr(rho rho) = sum_{ij} rho_ij rho_ji ; real part
+  double acc = 0.0;
+  for (int e = lane; e < DD; e += 32) {
+    const int i = e / D, j = e % D;
+    const cplx a = r[e], c = r[j * D + i];
+    acc += a.x * c.x - a.y * c.y;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) out[b] = acc;
+}
+
+// shared memory per warp: 3 matrices + eigenvalues + Jacobi scratch
+template <int D>
+struct FidSmem {
+  static constexpr size_t bytes = sizeof(cplx) * D * D * 3 + sizeof(double) * (D + JacobiScratch<D>::doubles);
+};
+
+// MODE 0: fidelity.  MODE 1: nuclear-norm trace distance.
+template <int D, int MODE>
+__global__ void fidelity_kernel(int64_t B, const cplx* __restrict__ rho, const cplx* __restrict__ sigma,
+                                double* __restrict__ out) {
+  constexpr int DD = D * D;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  cplx* A = reinterpret_cast<cplx*>(smem_raw + FidSmem<D>::bytes * wib);
+  cplx* V = A + DD;
+  cplx* W = V + DD;
+  double* ev = reinterpret_cast<double*>(W + DD);
+  const int64_t b = (int64_t)blockIdx.x * wpb + wib;
+  if (b >= B) return;
+  const cplx* r = rho + b * DD;
+  const cplx* s = sigma + b * DD;
+  if constexpr (MODE == 1) {
+    for (int e = lane; e < DD; e += 32) {
+      // Hermitian part of rho - sigma
+      const int i = e / D, j = e % D;
+      const cplx d1 = csub(r[e], s[e]), d2 = csub(r[j * D + i], s[j * D + i]);
+      A[e] = cmake(0.5 * (d1.x + d2.x), 0.5 * (d1.y - d2.y));
+    }
+    __syncwarp();
+    jacobi_eigh<D, 32, SyncWarp, false>(A, nullptr, ev, ev + D, lane);
+    double acc = 0.0;
+    for (int k = lane; k < D; k += 32) acc += fabs(ev[k]);
+    acc = warp_sum(acc);
+    if (lane == 0) out[b] = 0.5 * acc;
+    return;
+  }
+  // scipy.linalg.eigh reads the lower triangle only: build the Hermitian matrix it sees
+  for (int e = lane; e < DD; e += 32) {
+    const int i = e / D, j = e % D;
+    cplx v = (i >= j) ? r[e] : cconj(r[j * D + i]);
+    if (i == j) v.y = 0.0;
+    A[e] = v;
+  }
+  __syncwarp();
+  jacobi_eigh<D, 32, SyncWarp, true>(A, V, ev, ev + D, lane);
+  // S = V sqrt(max(ev,0)) V^dagger  -> A
+  for (int e = lane; e < DD; e += 32) {
+    const int i = e / D, j = e % D;
+    cplx acc = cmake(0.0, 0.0);
+    for (int k = 0; k < D; ++k) {
+      const double w = sqrt(fmax(ev[k], 0.0));
+      cfma_conj(acc, cscale(V[i * D + k], w), V[j * D + k]);
+    }
+    A[e] = acc;
+  }
+  __syncwarp();
+  // W = S sigma
+  for (int e = lane; e < DD; e += 32) {
+    const int i = e / D, j = e % D;
+    cplx acc = cmake(0.0, 0.0);
+    for (int k = 0; k < D; ++k) cfma(acc, A[i * D + k], s[k * D + j]);
+    W[e] = acc;
+  }
+  __syncwarp();
+  // V = W S, then the Hermitian matrix eigh would see (lower triangle)
+  for (int e = lane; e < DD; e += 32) {
+    const int i = e / D, j = e % D;
+    cplx acc = cmake(0.0, 0.0);
+    for (int k = 0; k < D; ++k) cfma(acc, W[i * D + k], A[k * D + j]);
+    V[e] = acc;
+  }
+  __syncwarp();
+  for (int e = lane; e < DD; e += 32) {
+    const int i = e / D, j = e % D;
+    cplx v = (i >= j) ? V[e] : cconj(V[j * D + i]);
+    if (i == j) v.y = 0.0;
+    W[e] = v;
+  }
+  __syncwarp();
+  jacobi_eigh<D, 32, SyncWarp, false>(W, nullptr, ev, ev + D, lane);
+  double acc = 0.0;
+  for (int k = lane; k < D; k += 32) acc += sqrt(fmax(ev[k], 0.0));
+  acc = warp_sum(acc);
+  if (lane == 0) out[b] = acc * acc;
+}
+
+template <int D>
+static int launch_td(int64_t B, const void* rho, const void* sigma, double* out, cudaStream_t st) {
+  const int wpb = 8;
+  trace_distance_kernel<D><<<(unsigned)((B + wpb - 1) / wpb), 32 * wpb, 0, st>>>(B, (const cplx*)rho,
+                                                                                 (const cplx*)sigma, out);
+  return qt_check_launch("trace_distance_kernel");
+}
+template <int D>
+static int launch_purity(int64_t B, const void* rho, double* out, cudaStream_t st) {
+  const int wpb = 8;
+  purity_kernel<D><<<(unsigned)((B + wpb - 1) / wpb), 32 * wpb, 0, st>>>(B, (const cplx*)rho, out);
+  return qt_check_launch("purity_kernel");
+}
+template <int D, int MODE>
+static int launch_fid(int64_t B, const void* rho, const void* sigma, double* out, cudaStream_t st) {
+  const size_t per_warp = FidSmem<D>::bytes;
+  int wpb = (int)max((size_t)1, min((size_t)8, (size_t)(100 * 1024) / per_warp));
+  const size_t smem = per_warp * wpb;
+  QT_CUDA(cudaFuncSetAttribute(fidelity_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  fidelity_kernel<D, MODE><<<(unsigned)((B + wpb - 1) / wpb), 32 * wpb, smem, st>>>(B, (const cplx*)rho,
+                                                                                    (const cplx*)sigma, out);
+  return qt_check_launch("fidelity_kernel");
+}
+
+#define DISPATCH_D(n, CALL)                      \
+  switch (n) {                                   \
+    case 1: return CALL(2);                      \
+    case 2: return CALL(4);                      \
+    case 3: return CALL(8);                      \
+    case 4: return CALL(16);                     \
+    case 5: return CALL(32);                     \
+    default:                                     \
+      qt_set_error("n=%d out of range 1..5", n); \
+      return QT_ERR_ARG;                         \
+  }
+
+extern "C" int qt_trace_distance_batch(int n, int64_t B, const void* rho, const void* sigma, double* out,
+                                       void* stream) {
+  QT_REQUIRE(rho && sigma && out, "qt_trace_distance_batch: null argument");
+  if (B == 0) return QT_OK;
+#define CALL(D) launch_td<D>(B, rho, sigma, out, (cudaStream_t)stream)
+  DISPATCH_D(n, CALL)
+#undef CALL
+}
+
+extern "C" int qt_trace_distance_nuclear_batch(int n, int64_t B, const void* rho, const void* sigma, double* out,
+                                               void* stream) {
+  QT_REQUIRE(rho && sigma && out, "qt_trace_distance_nuclear_batch: null argument");
+  if (B == 0) return QT_OK;
+#define CALL(D) launch_fid<D, 1>(B, rho, sigma, out, (cudaStream_t)stream)
+  DISPATCH_D(n, CALL)
+#undef CALL
+}
+
+extern "C" int qt_fidelity_batch(int n, int64_t B, const void* rho, const void* sigma, double* out, void* stream) {
+  QT_REQUIRE(rho && sigma && out, "qt_fidelity_batch: null argument");
+  if (B == 0) return QT_OK;
+#define CALL(D) launch_fid<D, 0>(B, rho, sigma, out, (cudaStream_t)stream)
+  DISPATCH_D(n, CALL)
+#undef CALL
+}
+
+extern "C" int qt_purity_batch(int n, int64_t B, const void* rho, double* out, void* stream) {
+  QT_REQUIRE(rho && out, "qt_purity_batch: null argument");
+  if (B == 0) return QT_OK;
+#define CALL(D) launch_purity<D>(B, rho, out, (cudaStream_t)stream)
+  DISPATCH_D(n, CALL)
+#undef CALL
+}

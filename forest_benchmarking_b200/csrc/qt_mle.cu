@@ -1,0 +1,592 @@
+// Batched iterative (diluted) maximum-likelihood state tomography -- the R rho R fixed point.
+//
+// Replaces, per experiment, the loop of forest/benchmarking/tomography.py:168-270 and the operator
+// `_R` of tomography.py:273-338.  One experiment = one thread (n <= 2, state in registers) or one
+// warp (n = 3..5, state in shared memory); the batch of independent experiments is the parallel axis.
+//
+// Algebra used (checked against the imported reference to 1e-16):
+//   t_j  = Tr(P_j rho)                                   (forward Pauli transform of rho, real)
+//   a+-  = ((1 +- m_k)/2) / ((1 +- c_k t_j)/2 + tiny)    for every result k whose observable is c_k P_j
+//   R    = (1/K) sum_k [ (a+ + a-)/2 * I + c_k (a+ - a-)/2 * P_j ]      (K = len(results))
+//   M    = I + eps (R - I) (+ maxent / hedging terms);   rho <- M rho M / tr;  stop on ||drho||_F < tol
+// Loop semantics replicated exactly: at most maxiter-1 updates (tomography.py:244), division by
+// len(results) (:338), `tiny` added to the predicted probability (:321,336).
+#include "qt_common.cuh"
+#include "qt_eigh.cuh"
+#include "../../include/qtomo.h"
+
+#include <algorithm>
+#include <vector>
+
+struct qt_mle_plan {
+  int n, K, S;            // qubits, len(results), 4^n
+  int unit_coeff;         // every coefficient == 1 -> register fast path allowed
+  int* d_slot_ptr;        // [S+1]  CSR over canonical Pauli slots
+  int* d_member_col;      // [K]    column of `expect` for each member
+  double* d_member_coeff; // [K]
+  int* d_mask2idx;        // [S]    (x*D + z) -> canonical Pauli index
+};
+
+// =============================================================================================
+// Register kernel: one experiment per thread, n = 1 or 2, unit coefficients, vanilla MLE.
+// rho is kept Hermitian-packed: h[r][c] (r<c) = Re, h[c][r] = Im of element (r,c); h[r][r] = diagonal.
+// =============================================================================================
+template <int D>
+struct Herm {
+  double h[D][D];
+  __device__ __forceinline__ double re(int r, int c) const { return r <= c ? h[r][c] : h[c][r]; }
+  __device__ __forceinline__ double im(int r, int c) const {
+    return r == c ? 0.0 : (r < c ? h[c][r] : -h[r][c]);
+  }
+};
+
+template <int N>
+__global__ void __launch_bounds__(32) mle_reg_kernel(int64_t B, int K, const int* __restrict__ slot_ptr,
+                                                     const int* __restrict__ member_col,
+                                                     const double* __restrict__ expect, double eps, double tol,
+                                                     int maxiter, cplx* __restrict__ rho_out,
+                                                     int* __restrict__ iters_out) {
+  constexpr int D = 1 << N, S = 1 << (2 * N);
+  constexpr double TINY = 2.2250738585072014e-308;
+  __shared__ double fp[S][32], fm[S][32];
+  const int tid = threadIdx.x;
+  const int64_t b = (int64_t)blockIdx.x * 32 + tid;
+  if (b >= B) return;
+
+  // aggregate (1 +- m_k)/2 per canonical Pauli slot
+  for (int s = 0; s < S; ++s) {
+    double ap = 0.0, am = 0.0;
+    for (int m = slot_ptr[s]; m < slot_ptr[s + 1]; ++m) {
+      double e = expect[b * K + member_col[m]];
+      ap += 0.5 * (1.0 + e);
+      am += 0.5 * (1.0 - e);
+    }
+    fp[s][tid] = ap;
+    fm[s][tid] = am;
+  }
+  const double invK = 1.0 / (double)K;
+
+  Herm<D> rho;
+#pragma unroll
+  for (int r = 0; r < D; ++r)
+#pragma unroll
+    for (int c = 0; c < D; ++c) rho.h[r][c] = (r == c) ? 1.0 / D : 0.0;
+
+  int it = 1;
+  while (true) {
+    if (it >= maxiter) break;
+    // ---- forward Pauli transform + likelihood ratios --------------------------------------
+    double w[S];
+    double w0 = 0.0;
+#pragma unroll
+    for (int j = 0; j < S; ++j) {
+      const int x = pauli_xmask(j, N), z = pauli_zmask(j, N);
+      const int ph = popc_c(x & z) & 3;
+      double t = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const int r = c ^ x;  // element rho[c, r]
+        const double sgn = (popc_c(z & c) & 1) ? -1.0 : 1.0;
+        // Re( i^ph * rho[c, r] )
+        double v;
+        if (ph == 0) v = rho.re(c, r);
+        else if (ph == 1) v = -rho.im(c, r);
+        else if (ph == 2) v = -rho.re(c, r);
+        else v = rho.im(c, r);
+        t += sgn * v;
+      }
+      const double ap = fp[j][tid] / (0.5 * (1.0 + t) + TINY);
+      const double am = fm[j][tid] / (0.5 * (1.0 - t) + TINY);
+      w0 += 0.5 * (ap + am);
+      w[j] = 0.5 * (ap - am);
+    }
+    w[0] += w0;
+    // ---- M = (1 - eps) I + eps R,  R = (1/K) sum_j w_j P_j  (Hermitian packed) --------------
+    Herm<D> M;
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int c = r; c < D; ++c) {
+        const int x = r ^ c;
+        double sre = 0.0, sim = 0.0;
+#pragma unroll
+        for (int z = 0; z < D; ++z) {
+          const int j = pauli_from_masks(x, z, N);
+          const int ph = popc_c(x & z) & 3;
+          const double sgn = (popc_c(z & c) & 1) ? -1.0 : 1.0;
+          // P_j[r, c] = i^ph * sgn
+          if (ph == 0) sre += sgn * w[j];
+          else if (ph == 1) sim += sgn * w[j];
+          else if (ph == 2) sre -= sgn * w[j];
+          else sim -= sgn * w[j];
+        }
+        if (r == c) {
+          M.h[r][r] = (1.0 - eps) + eps * invK * sre;
+        } else {
+          M.h[r][c] = eps * invK * sre;
+          M.h[c][r] = eps * invK * sim;
+        }
+      }
+    // ---- T = M rho (full), rho' = T M (upper triangle) ---------------------------------------
+    double Tr_[D][D], Ti_[D][D];
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        double ar = 0.0, ai = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const double mr = M.re(r, k), mi = M.im(r, k), pr = rho.re(k, c), pi = rho.im(k, c);
+          ar = fma(mr, pr, ar);
+          if (k != c) ai = fma(mr, pi, ai);
+          if (r != k) {
+            if (k != c) ar = fma(-mi, pi, ar);
+            ai = fma(mi, pr, ai);
+          }
+        }
+        Tr_[r][c] = ar;
+        Ti_[r][c] = ai;
+      }
+    Herm<D> nw;
+    double tr = 0.0;
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int c = r; c < D; ++c) {
+        double ar = 0.0, ai = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const double mr = M.re(k, c), mi = M.im(k, c);
+          ar = fma(Tr_[r][k], mr, ar);
+          if (k != c) ar = fma(-Ti_[r][k], mi, ar);
+          if (r != c) {
+            ai = fma(Ti_[r][k], mr, ai);
+            if (k != c) ai = fma(Tr_[r][k], mi, ai);
+          }
+        }
+        if (r == c) {
+          nw.h[r][r] = ar;
+          tr += ar;
+        } else {
+          nw.h[r][c] = ar;
+          nw.h[c][r] = ai;
+        }
+      }
+    const double inv = 1.0 / tr;
+    double diff = 0.0;
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const double v = nw.h[r][c] * inv;
+        const double dlt = v - rho.h[r][c];
+        diff = fma((r == c) ? 1.0 : 2.0, dlt * dlt, diff);
+        rho.h[r][c] = v;
+      }
+    if (sqrt(diff) < tol) break;
+    ++it;
+  }
+  cplx* out = rho_out + b * D * D;
+#pragma unroll
+  for (int r = 0; r < D; ++r)
+#pragma unroll
+    for (int c = 0; c < D; ++c) out[r * D + c] = cmake(rho.re(r, c), rho.im(r, c));
+  iters_out[b] = it;
+}
+
+// =============================================================================================
+// Warp kernel: one experiment per warp, any n <= 5, arbitrary observable lists / coefficients,
+// vanilla + maximum-entropy + hedged variants (tomography.py:252-260).  State in shared memory.
+// =============================================================================================
+template <int N>
+struct MleWarpSmem {
+  static constexpr int D = 1 << N, S = 1 << (2 * N);
+  // rho, M, T (+ V for the eigen-decomposition used by the variants)
+  __host__ __device__ static constexpr size_t bytes(bool variants) {
+    return sizeof(cplx) * D * D * (variants ? 4 : 3) + sizeof(double) * S * 2 +
+           sizeof(double) * (D + JacobiScratch<D>::doubles);
+  }
+};
+
+template <int N>
+__global__ void mle_warp_kernel(int64_t B, int K, const int* __restrict__ slot_ptr,
+                                const int* __restrict__ member_col, const double* __restrict__ member_coeff,
+                                const int* __restrict__ mask2idx, const double* __restrict__ expect,
+                                const double* __restrict__ counts, double eps, double entropy_penalty, double beta,
+                                double tol, int maxiter, cplx* __restrict__ rho_out, int* __restrict__ iters_out) {
+  constexpr int D = 1 << N, S = 1 << (2 * N), DD = D * D;
+  constexpr double TINY = 2.2250738585072014e-308;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const bool variants = (entropy_penalty > 0.0) || (beta > 0.0);
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  const size_t per_warp = MleWarpSmem<N>::bytes(variants);
+  unsigned char* base = smem_raw + per_warp * wib;
+  cplx* rho = reinterpret_cast<cplx*>(base);
+  cplx* M = rho + DD;
+  cplx* T = M + DD;
+  cplx* V = T + DD;                       // only when variants
+  double* tv = reinterpret_cast<double*>(rho + (variants ? 4 : 3) * DD);
+  double* wv = tv + S;
+  double* ev = wv + S;                    // [D] eigenvalues, followed by the Jacobi scratch
+  const int64_t b = (int64_t)blockIdx.x * wpb + wib;
+  if (b >= B) return;
+  const double* ex = expect + b * K;
+
+  double num_meas = 0.0;
+  if (beta > 0.0) {
+    double s = 0.0;
+    for (int k = lane; k < K; k += 32) s += counts[b * K + k];
+    num_meas = warp_sum(s);
+  }
+  for (int e = lane; e < DD; e += 32) rho[e] = cmake((e / D == e % D) ? 1.0 / D : 0.0, 0.0);
+  __syncwarp();
+
+  int it = 1;
+  while (true) {
+    if (it >= maxiter) break;
+    // t_j = Tr(P_j rho) and the ratio sums per slot
+    double w0 = 0.0;
+    for (int j = lane; j < S; j += 32) {
+      const int x = pauli_xmask(j, N), z = pauli_zmask(j, N);
+      const int ph = __popc(x & z) & 3;
+      cplx acc = cmake(0.0, 0.0);
+      for (int c = 0; c < D; ++c) {
+        cplx v = rho[c * D + (c ^ x)];
+        if (__popc(z & c) & 1) acc = csub(acc, v); else acc = cadd(acc, v);
+      }
+      const double t = cmul_ipow(acc, ph).x;
+      double wj = 0.0;
+      for (int m = slot_ptr[j]; m < slot_ptr[j + 1]; ++m) {
+        const double e = ex[member_col[m]], cf = member_coeff[m];
+        const double pred = cf * t;
+        const double ap = (0.5 * (1.0 + e)) / (0.5 * (1.0 + pred) + TINY);
+        const double am = (0.5 * (1.0 - e)) / (0.5 * (1.0 - pred) + TINY);
+        w0 += 0.5 * (ap + am);
+        wj += cf * 0.5 * (ap - am);
+      }
+      wv[j] = wj;
+    }
+    w0 = warp_sum(w0);
+    __syncwarp();
+    if (lane == 0) wv[0] += w0;
+    __syncwarp();
+    // Tk = R - I  (stored in M for now)
+    const double invK = 1.0 / (double)K;
+    for (int e = lane; e < DD; e += 32) {
+      const int r = e / D, c = e % D, x = r ^ c;
+      cplx acc = cmake(0.0, 0.0);
+      for (int z = 0; z < D; ++z) {
+        const double wj = wv[mask2idx[x * D + z]];
+        cplx term = cmul_ipow(cmake(wj, 0.0), __popc(x & z) & 3);
+        if (__popc(z & c) & 1) acc = csub(acc, term); else acc = cadd(acc, term);
+      }
+      acc = cscale(acc, invK);
+      if (r == c) acc.x -= 1.0;
+      M[e] = acc;
+    }
+    __syncwarp();
+    if (variants) {
+      // eigen-decomposition of the (Hermitian) current state: rho = V diag(ev) V^dagger
+      for (int e = lane; e < DD; e += 32) T[e] = rho[e];
+      __syncwarp();
+      jacobi_eigh_warp<D>(T, V, ev, lane);
+      if (entropy_penalty > 0.0) {
+        // logm(rho) - I tr(rho logm rho)   (tomography.py:252-254)
+        double s = 0.0;
+        for (int k = lane; k < D; k += 32) s += ev[k] * log(ev[k]);
+        s = warp_sum(s);
+        for (int e = lane; e < DD; e += 32) {
+          const int r = e / D, c = e % D;
+          cplx acc = cmake(0.0, 0.0);
+          for (int k = 0; k < D; ++k) {
+            cplx vv = cscale(V[r * D + k], log(ev[k]));
+            cfma_conj(acc, vv, V[c * D + k]);
+          }
+          if (r == c) acc.x -= s;
+          M[e] = csub(M[e], cscale(acc, entropy_penalty));
+        }
+      }
+      if (beta > 0.0) {
+        // Tk *= num_meas/2;  Tk += beta (pinv(rho) - d I)/2   (tomography.py:257-260)
+        // scipy.linalg.pinv cut-off: singular values <= max(M,N) * eps * sigma_max are dropped.
+        double smax = 0.0;
+        for (int k = 0; k < D; ++k) smax = fmax(smax, fabs(ev[k]));
+        const double cut = D * 2.220446049250313e-16 * smax;
+        for (int e = lane; e < DD; e += 32) {
+          const int r = e / D, c = e % D;
+          cplx acc = cmake(0.0, 0.0);
+          for (int k = 0; k < D; ++k) {
+            if (fabs(ev[k]) > cut) {
+              cplx vv = cscale(V[r * D + k], 1.0 / ev[k]);
+              cfma_conj(acc, vv, V[c * D + k]);
+            }
+          }
+          if (r == c) acc.x -= (double)D;
+          cplx tk = cscale(M[e], 0.5 * num_meas);
+          M[e] = cadd(tk, cscale(acc, 0.5 * beta));
+        }
+      }
+      __syncwarp();
+    }
+    // M = I + eps Tk
+    for (int e = lane; e < DD; e += 32) {
+      cplx v = cscale(M[e], eps);
+      if (e / D == e % D) v.x += 1.0;
+      M[e] = v;
+    }
+    __syncwarp();
+    // T = M rho
+    for (int e = lane; e < DD; e += 32) {
+      const int r = e / D, c = e % D;
+      cplx acc = cmake(0.0, 0.0);
+      for (int k = 0; k < D; ++k) cfma(acc, M[r * D + k], rho[k * D + c]);
+      T[e] = acc;
+    }
+    __syncwarp();
+    // rho' = T M, trace, normalise, ||rho' - rho||_F
+    double tr = 0.0;
+    cplx nv[(DD + 31) / 32];
+#pragma unroll
+    for (int i = 0; i < (DD + 31) / 32; ++i) {
+      const int e = lane + 32 * i;
+      cplx acc = cmake(0.0, 0.0);
+      if (e < DD) {
+        const int r = e / D, c = e % D;
+        for (int k = 0; k < D; ++k) cfma(acc, T[r * D + k], M[k * D + c]);
+        if (r == c) tr += acc.x;
+      }
+      nv[i] = acc;
+    }
+    // the reference divides by the complex trace; its imaginary part is rounding noise (~1e-17)
+    tr = warp_sum(tr);
+    const double inv = 1.0 / tr;
+    double diff = 0.0;
+#pragma unroll
+    for (int i = 0; i < (DD + 31) / 32; ++i) {
+      const int e = lane + 32 * i;
+      if (e < DD) {
+        cplx v = cscale(nv[i], inv);
+        diff += cabs2(csub(v, rho[e]));
+        nv[i] = v;
+      }
+    }
+    diff = warp_sum(diff);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < (DD + 31) / 32; ++i) {
+      const int e = lane + 32 * i;
+      if (e < DD) rho[e] = nv[i];
+    }
+    __syncwarp();
+    if (sqrt(diff) < tol) break;
+    ++it;
+  }
+  cplx* out = rho_out + b * DD;
+  for (int e = lane; e < DD; e += 32) out[e] = rho[e];
+  if (lane == 0) iters_out[b] = it;
+}
+
+// =============================================================================================
+// single-step streaming kernel: one R rho R update per experiment (n = 1, 2), rho read from and
+// written to HBM.  This is the HBM-roofline view of the update: 632 B / item at n=2.
+// =============================================================================================
+template <int N>
+__global__ void mle_step_kernel(int64_t B, int K, const double* __restrict__ expect_canon,
+                                const cplx* __restrict__ rho_in, double eps, cplx* __restrict__ rho_out) {
+  // expect_canon: [S-1, B] canonical-order expectations, item-minor (coalesced); K = S-1 results.
+  constexpr int D = 1 << N, S = 1 << (2 * N), DD = D * D;
+  constexpr double TINY = 2.2250738585072014e-308;
+  __shared__ cplx tile[128 * DD];
+  const int tid = threadIdx.x;
+  const int64_t b0 = (int64_t)blockIdx.x * 128;
+  const int nb = (int)min((int64_t)128, B - b0);
+  // coalesced load of nb matrices (16 B per element, consecutive threads -> consecutive elements)
+  for (int e = tid; e < nb * DD; e += 128) tile[(e % DD) * 128 + (e / DD)] = rho_in[b0 * DD + e];
+  __syncthreads();
+  if (tid < nb) {
+    cplx r[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int j = 0; j < D; ++j) r[i][j] = tile[(i * D + j) * 128 + tid];
+    double w[S];
+    double w0 = 0.0;
+    w[0] = 0.0;
+#pragma unroll
+    for (int j = 1; j < S; ++j) {
+      const int x = pauli_xmask(j, N), z = pauli_zmask(j, N);
+      cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        if (popc_c(z & c) & 1) acc = csub(acc, r[c][c ^ x]); else acc = cadd(acc, r[c][c ^ x]);
+      }
+      const double t = cmul_ipow(acc, popc_c(x & z) & 3).x;
+      const double e = expect_canon[(int64_t)(j - 1) * B + b0 + tid];
+      const double ap = (0.5 * (1.0 + e)) / (0.5 * (1.0 + t) + TINY);
+      const double am = (0.5 * (1.0 - e)) / (0.5 * (1.0 - t) + TINY);
+      w0 += 0.5 * (ap + am);
+      w[j] = 0.5 * (ap - am);
+    }
+    w[0] = w0;
+    const double invK = 1.0 / (double)K;
+    cplx M[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const int x = i ^ c;
+        cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+        for (int z = 0; z < D; ++z) {
+          cplx term = cmul_ipow(cmake(w[pauli_from_masks(x, z, N)], 0.0), popc_c(x & z) & 3);
+          if (popc_c(z & c) & 1) acc = csub(acc, term); else acc = cadd(acc, term);
+        }
+        acc = cscale(acc, eps * invK);
+        if (i == c) acc.x += 1.0 - eps;
+        M[i][c] = acc;
+      }
+    cplx T[D][D];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < D; ++k) cfma(acc, M[i][k], r[k][c]);
+        T[i][c] = acc;
+      }
+    double tr = 0.0;
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < D; ++k) cfma(acc, T[i][k], M[k][c]);
+        r[i][c] = acc;
+        if (i == c) tr += acc.x;
+      }
+    const double inv = 1.0 / tr;
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+      for (int c = 0; c < D; ++c) tile[(i * D + c) * 128 + tid] = cscale(r[i][c], inv);
+  }
+  __syncthreads();
+  for (int e = tid; e < nb * DD; e += 128) rho_out[b0 * DD + e] = tile[(e % DD) * 128 + (e / DD)];
+}
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+extern "C" int qt_mle_plan_create(int n, int K, const int32_t* pauli_idx, const double* coeff,
+                                  qt_mle_plan** plan_out) {
+  QT_REQUIRE(n >= 1 && n <= 5, "qt_mle_plan_create: n=%d out of range 1..5", n);
+  QT_REQUIRE(K >= 1 && pauli_idx && coeff && plan_out, "qt_mle_plan_create: bad arguments");
+  const int S = 1 << (2 * n), D = 1 << n;
+  std::vector<int> slot_ptr(S + 1, 0), col(K), cursor(S, 0), m2i(S);
+  std::vector<double> cf(K);
+  int unit = 1;
+  for (int k = 0; k < K; ++k) {
+    QT_REQUIRE(pauli_idx[k] >= 0 && pauli_idx[k] < S, "qt_mle_plan_create: pauli_idx[%d]=%d out of range", k,
+               pauli_idx[k]);
+    slot_ptr[pauli_idx[k] + 1]++;
+    if (coeff[k] != 1.0) unit = 0;
+  }
+  for (int s = 0; s < S; ++s) slot_ptr[s + 1] += slot_ptr[s];
+  for (int k = 0; k < K; ++k) {  // stable: members keep the order of `results`
+    int s = pauli_idx[k];
+    int pos = slot_ptr[s] + cursor[s]++;
+    col[pos] = k;
+    cf[pos] = coeff[k];
+  }
+  for (int x = 0; x < D; ++x)
+    for (int z = 0; z < D; ++z) m2i[x * D + z] = pauli_from_masks(x, z, n);
+  qt_mle_plan* p = new qt_mle_plan();
+  p->n = n; p->K = K; p->S = S; p->unit_coeff = unit;
+  p->d_slot_ptr = nullptr; p->d_member_col = nullptr; p->d_member_coeff = nullptr; p->d_mask2idx = nullptr;
+  QT_CUDA(cudaMalloc(&p->d_slot_ptr, sizeof(int) * (S + 1)));
+  QT_CUDA(cudaMalloc(&p->d_member_col, sizeof(int) * K));
+  QT_CUDA(cudaMalloc(&p->d_member_coeff, sizeof(double) * K));
+  QT_CUDA(cudaMalloc(&p->d_mask2idx, sizeof(int) * S));
+  QT_CUDA(cudaMemcpy(p->d_slot_ptr, slot_ptr.data(), sizeof(int) * (S + 1), cudaMemcpyHostToDevice));
+  QT_CUDA(cudaMemcpy(p->d_member_col, col.data(), sizeof(int) * K, cudaMemcpyHostToDevice));
+  QT_CUDA(cudaMemcpy(p->d_member_coeff, cf.data(), sizeof(double) * K, cudaMemcpyHostToDevice));
+  QT_CUDA(cudaMemcpy(p->d_mask2idx, m2i.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+  *plan_out = p;
+  return QT_OK;
+}
+
+extern "C" int qt_mle_plan_destroy(qt_mle_plan* p) {
+  if (!p) return QT_OK;
+  cudaFree(p->d_slot_ptr);
+  cudaFree(p->d_member_col);
+  cudaFree(p->d_member_coeff);
+  cudaFree(p->d_mask2idx);
+  delete p;
+  return QT_OK;
+}
+
+template <int N>
+static int launch_warp(const qt_mle_plan* p, int64_t B, const double* expect, const double* counts, double eps,
+                       double entropy_penalty, double beta, double tol, int maxiter, cplx* rho_out, int* iters_out,
+                       cudaStream_t st) {
+  const bool variants = entropy_penalty > 0.0 || beta > 0.0;
+  const size_t per_warp = MleWarpSmem<N>::bytes(variants);
+  int wpb = (int)std::max<size_t>(1, std::min<size_t>(8, (96 * 1024) / per_warp));
+  const size_t smem = per_warp * wpb;
+  QT_CUDA(cudaFuncSetAttribute(mle_warp_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks = (B + wpb - 1) / wpb;
+  mle_warp_kernel<N><<<(unsigned)blocks, 32 * wpb, smem, st>>>(B, p->K, p->d_slot_ptr, p->d_member_col,
+                                                               p->d_member_coeff, p->d_mask2idx, expect, counts, eps,
+                                                               entropy_penalty, beta, tol, maxiter, rho_out,
+                                                               iters_out);
+  return qt_check_launch("mle_warp_kernel");
+}
+
+extern "C" int qt_mle_state_batch(const qt_mle_plan* p, int64_t B, const double* expect, const double* counts,
+                                  double epsilon, double entropy_penalty, double beta, double tol, int maxiter,
+                                  int kernel_variant, void* rho_out, int32_t* iters_out, void* stream) {
+  QT_REQUIRE(p && expect && rho_out && iters_out, "qt_mle_state_batch: null argument");
+  QT_REQUIRE(!(entropy_penalty != 0.0 && beta != 0.0),
+             "qt_mle_state_batch: entropy_penalty and beta cannot both be non-zero (tomography.py:225)");
+  QT_REQUIRE(beta <= 0.0 || counts, "qt_mle_state_batch: hedged MLE needs counts");
+  if (B == 0) return QT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  cplx* out = (cplx*)rho_out;
+  const bool variants = entropy_penalty > 0.0 || beta > 0.0;
+  const bool reg_ok = p->n <= 2 && p->unit_coeff && !variants;
+  QT_REQUIRE(kernel_variant != QT_MLE_KERNEL_REGISTER || reg_ok,
+             "qt_mle_state_batch: register kernel needs n<=2, unit coefficients, vanilla MLE");
+  if (reg_ok && kernel_variant != QT_MLE_KERNEL_WARP) {
+    const unsigned blocks = (unsigned)((B + 31) / 32);
+    if (p->n == 1)
+      mle_reg_kernel<1><<<blocks, 32, 0, st>>>(B, p->K, p->d_slot_ptr, p->d_member_col, expect, epsilon, tol, maxiter,
+                                               out, iters_out);
+    else
+      mle_reg_kernel<2><<<blocks, 32, 0, st>>>(B, p->K, p->d_slot_ptr, p->d_member_col, expect, epsilon, tol, maxiter,
+                                               out, iters_out);
+    return qt_check_launch("mle_reg_kernel");
+  }
+  switch (p->n) {
+    case 1: return launch_warp<1>(p, B, expect, counts, epsilon, entropy_penalty, beta, tol, maxiter, out, iters_out, st);
+    case 2: return launch_warp<2>(p, B, expect, counts, epsilon, entropy_penalty, beta, tol, maxiter, out, iters_out, st);
+    case 3: return launch_warp<3>(p, B, expect, counts, epsilon, entropy_penalty, beta, tol, maxiter, out, iters_out, st);
+    case 4: return launch_warp<4>(p, B, expect, counts, epsilon, entropy_penalty, beta, tol, maxiter, out, iters_out, st);
+    default: return launch_warp<5>(p, B, expect, counts, epsilon, entropy_penalty, beta, tol, maxiter, out, iters_out, st);
+  }
+}
+
+extern "C" int qt_mle_step_batch(int n, int64_t B, const double* expect_canon, const void* rho_in, double epsilon,
+                                 void* rho_out, void* stream) {
+  QT_REQUIRE(n == 1 || n == 2, "qt_mle_step_batch: n must be 1 or 2");
+  if (B == 0) return QT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)((B + 127) / 128);
+  const int K = (1 << (2 * n)) - 1;
+  if (n == 1)
+    mle_step_kernel<1><<<blocks, 128, 0, st>>>(B, K, expect_canon, (const cplx*)rho_in, epsilon, (cplx*)rho_out);
+  else
+    mle_step_kernel<2><<<blocks, 128, 0, st>>>(B, K, expect_canon, (const cplx*)rho_in, epsilon, (cplx*)rho_out);
+  return qt_check_launch("mle_step_kernel");
+}

@@ -1,0 +1,170 @@
+"""Superoperator representation changes -- signatures of
+forest/benchmarking/operator_tools/superoperator_transformations.py, computed by csrc/qt_convert.cu.
+
+``*_batch`` functions take/return complex128 CUDA tensors [B, rows, cols]; the reference-named
+functions take/return numpy arrays (one matrix = a batch of one).  Column-stacking ``vec`` throughout.
+"""
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from .. import _lib
+
+__all__ = ["vec", "unvec", "kraus2choi", "kraus2superop", "kraus2pauli_liouville", "choi2superop",
+           "superop2choi", "superop2pauli_liouville", "pauli_liouville2superop", "choi2pauli_liouville",
+           "pauli_liouville2choi", "kraus2choi_batch", "kraus2superop_batch", "reshuffle_batch",
+           "superop2pauli_liouville_batch", "pauli_liouville2superop_batch",
+           "choi2pauli_liouville_batch", "pauli_liouville2choi_batch"]
+
+
+def vec(matrix: np.ndarray) -> np.ndarray:
+    """Column-stacking vectorisation (reference :33-51); host-side index bookkeeping."""
+    return np.asarray(matrix).T.reshape((-1, 1))
+
+
+def unvec(vector: np.ndarray, shape: Optional[Tuple[int, int]] = None) -> np.ndarray:
+    """Inverse of vec (reference :54-79)."""
+    vector = np.asarray(vector)
+    if shape is None:
+        dim = int(np.sqrt(vector.size))
+        shape = dim, dim
+    return vector.reshape(*shape).T
+
+
+def _check_c128(t, ndim):
+    torch = _lib.require_cuda()
+    if not t.is_cuda or t.dtype != torch.complex128 or t.dim() != ndim:
+        raise ValueError(f"expected a complex128 CUDA tensor with {ndim} dimensions")
+    return t.contiguous()
+
+
+def _nq(d2):
+    n = int(round(np.log2(d2) / 2))
+    if 4 ** n != d2 or not 1 <= n <= 5:
+        raise ValueError(f"superoperator dimension {d2} is not 4^n with 1 <= n <= 5")
+    return n
+
+
+def _kraus_call(name, kraus):
+    torch = _lib.require_cuda()
+    kraus = _check_c128(kraus, 4)
+    b, nk, d, d_ = kraus.shape
+    if d != d_:
+        raise ValueError("batched Kraus conversion needs square Kraus operators")
+    out = torch.empty((b, d * d, d * d), dtype=torch.complex128, device=kraus.device)
+    _lib.check(getattr(_lib.lib(), name)(ctypes.c_int(d), ctypes.c_int(nk), ctypes.c_int64(b), _lib.ptr(kraus),
+                                         _lib.ptr(out), _lib.current_stream_ptr()), name)
+    return out
+
+
+def kraus2choi_batch(kraus):
+    """kraus [B, K, d, d] -> choi [B, d^2, d^2]."""
+    return _kraus_call("qt_kraus2choi_batch", kraus)
+
+
+def kraus2superop_batch(kraus):
+    """kraus [B, K, d, d] -> superop [B, d^2, d^2]."""
+    return _kraus_call("qt_kraus2superop_batch", kraus)
+
+
+def reshuffle_batch(mat, out=None):
+    """choi2superop == superop2choi on a batch [B, d^2, d^2] (out-of-place)."""
+    torch = _lib.require_cuda()
+    mat = _check_c128(mat, 3)
+    b, d2, _ = mat.shape
+    d = 2 ** _nq(d2)
+    if out is None:
+        out = torch.empty_like(mat)
+    _lib.check(_lib.lib().qt_choi_superop_reshuffle_batch(ctypes.c_int(d), ctypes.c_int64(b), _lib.ptr(mat),
+                                                          _lib.ptr(out), _lib.current_stream_ptr()),
+               "qt_choi_superop_reshuffle_batch")
+    return out
+
+
+def _pl_call(name, mat, out, workspace):
+    torch = _lib.require_cuda()
+    mat = _check_c128(mat, 3)
+    b, d2, _ = mat.shape
+    n = _nq(d2)
+    if out is None:
+        out = torch.empty_like(mat)
+    if n >= 4 and workspace is None:
+        workspace = torch.empty_like(mat)
+    _lib.check(getattr(_lib.lib(), name)(ctypes.c_int(n), ctypes.c_int64(b), _lib.ptr(mat), _lib.ptr(out),
+                                         _lib.ptr(workspace), _lib.current_stream_ptr()), name)
+    return out
+
+
+def superop2pauli_liouville_batch(superop, out=None, workspace=None):
+    return _pl_call("qt_superop2pl_batch", superop, out, workspace)
+
+
+def pauli_liouville2superop_batch(pl, out=None, workspace=None):
+    return _pl_call("qt_pl2superop_batch", pl, out, workspace)
+
+
+def choi2pauli_liouville_batch(choi):
+    return superop2pauli_liouville_batch(reshuffle_batch(choi))
+
+
+def pauli_liouville2choi_batch(pl):
+    return reshuffle_batch(pauli_liouville2superop_batch(pl))
+
+
+# ---- reference-named single-matrix functions -------------------------------------------------
+def _to_dev(x):
+    torch = _lib.require_cuda()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.complex128))).cuda()
+
+
+def _kraus_stack(kraus_ops):
+    if isinstance(kraus_ops, np.ndarray) and kraus_ops.ndim == 2:
+        kraus_ops = [kraus_ops]
+    return np.stack([np.asarray(k, dtype=np.complex128) for k in kraus_ops])
+
+
+def kraus2choi(kraus_ops: Sequence[np.ndarray]) -> np.ndarray:
+    """reference :159-182."""
+    return kraus2choi_batch(_to_dev(_kraus_stack(kraus_ops)[None]))[0].cpu().numpy()
+
+
+def kraus2superop(kraus_ops: Sequence[np.ndarray]) -> np.ndarray:
+    """reference :100-145 (square Kraus operators; the reference also allows non-square ones)."""
+    return kraus2superop_batch(_to_dev(_kraus_stack(kraus_ops)[None]))[0].cpu().numpy()
+
+
+def kraus2pauli_liouville(kraus_ops: Sequence[np.ndarray]) -> np.ndarray:
+    """reference :148-156."""
+    s = kraus2superop_batch(_to_dev(_kraus_stack(kraus_ops)[None]))
+    return superop2pauli_liouville_batch(s)[0].cpu().numpy()
+
+
+def choi2superop(choi: np.ndarray) -> np.ndarray:
+    """reference :351-361."""
+    return reshuffle_batch(_to_dev(choi)[None])[0].cpu().numpy()
+
+
+def superop2choi(superop: np.ndarray) -> np.ndarray:
+    """reference :267-277."""
+    return reshuffle_batch(_to_dev(superop)[None])[0].cpu().numpy()
+
+
+def superop2pauli_liouville(superop: np.ndarray) -> np.ndarray:
+    """reference :253-264."""
+    return superop2pauli_liouville_batch(_to_dev(superop)[None])[0].cpu().numpy()
+
+
+def pauli_liouville2superop(pl_matrix: np.ndarray) -> np.ndarray:
+    """reference :301-312."""
+    return pauli_liouville2superop_batch(_to_dev(pl_matrix)[None])[0].cpu().numpy()
+
+
+def choi2pauli_liouville(choi: np.ndarray) -> np.ndarray:
+    """reference :364-371."""
+    return choi2pauli_liouville_batch(_to_dev(choi)[None])[0].cpu().numpy()
+
+
+def pauli_liouville2choi(pl_matrix: np.ndarray) -> np.ndarray:
+    """reference :315-322."""
+    return pauli_liouville2choi_batch(_to_dev(pl_matrix)[None])[0].cpu().numpy()

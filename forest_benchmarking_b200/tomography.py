@@ -1,0 +1,107 @@
+"""State and process tomography estimators -- same call signatures as
+forest/benchmarking/tomography.py, executed by the sm_100a kernels in csrc/.
+
+``iterative_mle_state_estimate`` (reference :168-270), ``pgdb_process_estimate`` (:542-594) and the
+linear-inversion estimators (:130-165, :459-491) keep their signatures; ``*_batch`` twins take a whole
+batch of independent experiments (the data-parallel axis) as dense arrays / device tensors.
+"""
+import ctypes
+import warnings
+from typing import List, Sequence
+
+import numpy as np
+
+from . import _lib
+from .utils import flatten_state_results
+
+MAXITER = "maxiter"
+OPTIMAL = "optimal"
+FRO = "fro"
+
+KERNEL_AUTO, KERNEL_REGISTER, KERNEL_WARP = 0, 1, 2
+
+
+class MlePlan:
+    """Device-side description of one list of observables (shared by every experiment of a batch)."""
+
+    def __init__(self, n_qubits: int, pauli_idx, coeffs=None):
+        _lib.require_cuda()
+        self.n = int(n_qubits)
+        idx = np.ascontiguousarray(pauli_idx, dtype=np.int32)
+        cf = np.ones(len(idx)) if coeffs is None else np.ascontiguousarray(coeffs, dtype=np.float64)
+        self.K = len(idx)
+        self.pauli_idx, self.coeffs = idx, cf
+        self._h = ctypes.c_void_p()
+        _lib.check(_lib.lib().qt_mle_plan_create(
+            self.n, self.K, idx.ctypes.data_as(ctypes.c_void_p), cf.ctypes.data_as(ctypes.c_void_p),
+            ctypes.byref(self._h)), "qt_mle_plan_create")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.lib().qt_mle_plan_destroy(h)
+            except Exception:
+                pass
+
+
+def iterative_mle_state_estimate_batch(plan: MlePlan, expectations, counts=None, epsilon=.1,
+                                       entropy_penalty=0.0, beta=0.0, tol=1e-9, maxiter=10_000,
+                                       kernel=KERNEL_AUTO, out=None, iters_out=None):
+    """Batched diluted MLE.  ``expectations`` / ``counts``: CUDA float64 tensors [B, K] (K = plan.K).
+    Returns (rho [B, d, d] complex128 CUDA tensor, iterations [B] int32 CUDA tensor); iterations equals
+    ``maxiter`` for experiments that hit the cap (where the reference warns, tomography.py:244-246)."""
+    torch = _lib.require_cuda()
+    if (entropy_penalty != 0.0) and (beta != 0.0):
+        raise ValueError("One can't sensibly do entropy penalty and hedging. Do one or the other"
+                         " but not both.")
+    if expectations.dtype != torch.float64 or not expectations.is_cuda or expectations.dim() != 2:
+        raise ValueError("expectations must be a CUDA float64 tensor of shape [B, K]")
+    if expectations.shape[1] != plan.K:
+        raise ValueError(f"expectations has {expectations.shape[1]} columns, plan has {plan.K}")
+    expectations = expectations.contiguous()
+    if counts is not None:
+        counts = counts.to(torch.float64).contiguous()
+    b = expectations.shape[0]
+    d = 2 ** plan.n
+    if out is None:
+        out = torch.empty((b, d, d), dtype=torch.complex128, device=expectations.device)
+    if iters_out is None:
+        iters_out = torch.empty((b,), dtype=torch.int32, device=expectations.device)
+    _lib.check(_lib.lib().qt_mle_state_batch(
+        plan._h, ctypes.c_int64(b), _lib.ptr(expectations), _lib.ptr(counts), ctypes.c_double(epsilon),
+        ctypes.c_double(entropy_penalty), ctypes.c_double(beta), ctypes.c_double(tol), ctypes.c_int(maxiter),
+        ctypes.c_int(kernel), _lib.ptr(out), _lib.ptr(iters_out), _lib.current_stream_ptr()),
+        "qt_mle_state_batch")
+    return out, iters_out
+
+
+def mle_step_batch(n_qubits: int, expect_canon, rho, epsilon=.1, out=None):
+    """ONE R-rho-R update streamed through HBM (n = 1, 2; complete canonical Pauli set).
+    expect_canon: [4^n - 1, B] float64 CUDA (item-minor); rho: [B, d, d] complex128 CUDA."""
+    torch = _lib.require_cuda()
+    b = rho.shape[0]
+    if out is None:
+        out = torch.empty_like(rho)
+    _lib.check(_lib.lib().qt_mle_step_batch(ctypes.c_int(n_qubits), ctypes.c_int64(b), _lib.ptr(expect_canon),
+                                            _lib.ptr(rho), ctypes.c_double(epsilon), _lib.ptr(out),
+                                            _lib.current_stream_ptr()), "qt_mle_step_batch")
+    return out
+
+
+def iterative_mle_state_estimate(results: List, qubits: List[int], epsilon=.1, entropy_penalty=0.0,
+                                 beta=0.0, tol=1e-9, maxiter=10_000) -> np.ndarray:
+    """Drop-in for reference tomography.py:168-270 (one experiment = a batch of one)."""
+    torch = _lib.require_cuda()
+    if (entropy_penalty != 0.0) and (beta != 0.0):
+        raise ValueError("One can't sensibly do entropy penalty and hedging. Do one or the other"
+                         " but not both.")
+    idx, cf, ex, cnt = flatten_state_results(results, qubits)
+    plan = MlePlan(len(qubits), idx, cf)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rho, iters = iterative_mle_state_estimate_batch(
+        plan, torch.from_numpy(ex[None, :]).to(dev), torch.from_numpy(cnt[None, :]).to(dev),
+        epsilon, entropy_penalty, beta, tol, maxiter)
+    if int(iters.item()) >= maxiter:
+        warnings.warn('Maximum number of iterations reached before convergence.')
+    return rho[0].cpu().numpy()

@@ -1,0 +1,78 @@
+/* libqtomo -- C ABI of the B200 (sm_100a) batched quantum-tomography / superoperator-algebra engine.
+ *
+ * The reference (rigetti/forest-benchmarking) is pure Python and has no FFI: its boundary for this
+ * path is a set of Python call signatures taking numpy arrays / ExperimentResult lists.
+ * Each entry point below is the batched device-side replacement of one of those functions; the Python
+ * package forest_benchmarking_b200 binds them with ctypes and re-exposes the reference's signatures.
+ * File:line citations are relative to /root/reference/forest/benchmarking/.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative QT_ERR_* code otherwise; qt_last_error() gives
+ *     the message of the last failure on the calling thread;
+ *   - all array arguments are DEVICE pointers unless the name ends in _host; the caller owns every
+ *     buffer; nothing is allocated behind the caller's back except inside *_plan_create;
+ *   - complex matrices are interleaved complex128, row-major [B, rows, cols] (numpy C order);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream); calls are asynchronous;
+ *   - Pauli index: base-4 digits I=0 X=1 Y=2 Z=3, first qubit most significant (utils.py:146-156);
+ *   - input-state code per qubit: 0..5 = +X,-X,+Y,-Y,+Z,-Z (tomography.py:89), 6..9 = SIC0..3 (:71).
+ */
+#ifndef QTOMO_H
+#define QTOMO_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QT_OK 0
+#define QT_ERR_ARG (-1)
+#define QT_ERR_CUDA (-2)
+#define QT_ERR_UNSUPPORTED (-3)
+#define QT_ERR_WORKSPACE (-4)
+
+int qt_version(void);
+/* copies the last error message of this thread into buf (NUL-terminated, truncated to len) */
+int qt_last_error(char* buf, int len);
+
+/* ---- state tomography: iterative_mle_state_estimate (tomography.py:168-270) + _R (:273-338) ---- */
+typedef struct qt_mle_plan qt_mle_plan;
+/* pauli_idx_host[K], coeff_host[K]: observable of results[k] = coeff * Pauli(pauli_idx); K = len(results) */
+int qt_mle_plan_create(int n, int K, const int32_t* pauli_idx_host, const double* coeff_host, qt_mle_plan** plan);
+int qt_mle_plan_destroy(qt_mle_plan* plan);
+#define QT_MLE_KERNEL_AUTO 0
+#define QT_MLE_KERNEL_REGISTER 1 /* one experiment per thread, n<=2, unit coefficients, vanilla MLE */
+#define QT_MLE_KERNEL_WARP 2     /* one experiment per warp, any n<=5, all variants */
+/* expect[B,K], counts[B,K] (may be NULL unless beta>0) -> rho_out[B,d,d] complex, iters_out[B]
+ * iters_out = the reference's loop counter at exit (== maxiter when the cap was hit, tomography.py:244) */
+int qt_mle_state_batch(const qt_mle_plan* plan, int64_t B, const double* expect, const double* counts,
+                       double epsilon, double entropy_penalty, double beta, double tol, int maxiter,
+                       int kernel_variant, void* rho_out, int32_t* iters_out, void* stream);
+/* ONE R rho R update, rho streamed HBM -> HBM (n = 1, 2; complete canonical Pauli set, K = 4^n - 1).
+ * expect_canon[K, B] (item-minor).  The HBM-roofline view of the update. */
+int qt_mle_step_batch(int n, int64_t B, const double* expect_canon, const void* rho_in, double epsilon,
+                      void* rho_out, void* stream);
+
+/* ---- superoperator conversions (operator_tools/superoperator_transformations.py) ------------- */
+/* kraus[B, n_kraus, d, d] -> choi[B, d^2, d^2] = sum_k vec(K) vec(K)^dagger            (:159-182) */
+int qt_kraus2choi_batch(int d, int n_kraus, int64_t B, const void* kraus, void* choi_out, void* stream);
+/* kraus[B, n_kraus, d, d] -> superop[B, d^2, d^2] = sum_k conj(K) (x) K                 (:100-145) */
+int qt_kraus2superop_batch(int d, int n_kraus, int64_t B, const void* kraus, void* superop_out, void* stream);
+/* choi2superop == superop2choi: reshape [d]*4, swapaxes(0,3); out-of-place    (:267-277, :351-361) */
+int qt_choi_superop_reshuffle_batch(int d, int64_t B, const void* in, void* out, void* stream);
+/* superop2pauli_liouville (:253-264) / pauli_liouville2superop (:301-312), n qubits, [B,4^n,4^n].
+ * workspace: NULL for n<=3; B*16^n*16 bytes of device memory for n = 4, 5 (two-pass path). */
+int qt_superop2pl_batch(int n, int64_t B, const void* superop, void* pl_out, void* workspace, void* stream);
+int qt_pl2superop_batch(int n, int64_t B, const void* pl, void* superop_out, void* workspace, void* stream);
+
+/* ---- distance measures (distance_measures.py) -------------------------------------------------- */
+/* rho, sigma: [B, 2^n, 2^n]; out[B] doubles */
+int qt_fidelity_batch(int n, int64_t B, const void* rho, const void* sigma, double* out, void* stream);         /* :64-84 */
+/* reference semantics: 0.5 * induced 1-norm (max column abs-sum), :100-114 */
+int qt_trace_distance_batch(int n, int64_t B, const void* rho, const void* sigma, double* out, void* stream);
+/* textbook 0.5 * nuclear norm (extra; not the reference's behaviour) */
+int qt_trace_distance_nuclear_batch(int n, int64_t B, const void* rho, const void* sigma, double* out, void* stream);
+int qt_purity_batch(int n, int64_t B, const void* rho, double* out, void* stream);                             /* :14-37 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QTOMO_H */

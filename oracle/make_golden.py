@@ -1,0 +1,158 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (through oracle/pyquil_shim)
+on seeded synthetic inputs.  Run here (the reference tree does not travel to the GPU box):
+
+    python oracle/make_golden.py [--skip-3q]
+
+TEST INFRASTRUCTURE ONLY.  Counters (iterations, eigh calls, cost evaluations) are obtained by
+wrapping reference functions at run time -- the reference source is not modified.
+"""
+import argparse
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_numpy as orc          # noqa: E402
+from oracle import reference_bridge as rb    # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+
+class CallCounter:
+    def __init__(self, module, name):
+        self.module, self.name, self.n = module, name, 0
+        self.orig = getattr(module, name)
+
+    def __enter__(self):
+        def wrapped(*a, **k):
+            self.n += 1
+            return self.orig(*a, **k)
+        setattr(self.module, self.name, wrapped)
+        return self
+
+    def __exit__(self, *exc):
+        setattr(self.module, self.name, self.orig)
+
+
+def golden_mle(ref, name, seed, batch, n, **kw):
+    truth, pidx, ex, cnt = orc.synth_state_tomography(seed, batch, n)
+    qubits = list(range(n))
+    coeffs = np.ones(len(pidx))
+    rho = np.empty_like(truth)
+    iters = np.empty(batch, dtype=np.int32)
+    maxiter = kw.get("maxiter", 10_000)
+    t0 = time.time()
+    for b in range(batch):
+        res = rb.state_results(ref, pidx, coeffs, ex[b], cnt[b], qubits)
+        with CallCounter(ref.tomo, "_R") as c, warnings.catch_warnings(record=True) as w:
+            warnings.simplefilter("always")
+            rho[b] = ref.tomo.iterative_mle_state_estimate(res, qubits, **kw)
+        iters[b] = maxiter if len(w) else c.n
+    print(f"{name}: {batch} items in {time.time() - t0:.1f}s iters={iters.tolist()}")
+    np.savez_compressed(os.path.join(OUT, name), seed=seed, n=n, pauli_idx=pidx, expectations=ex,
+                        counts=cnt, rho_true=truth, rho_ref=rho, iters_ref=iters,
+                        kwargs=np.array(repr(kw)))
+
+
+def golden_pgdb(ref, name, seed, batch, n, basis, tp=True, unitary=True):
+    import forest.benchmarking.operator_tools.project_superoperators as ps
+    truth, settings, ex, cnt = orc.synth_process_tomography(seed, batch, n, in_basis=basis, unitary=unitary)
+    qubits = list(range(n))
+    coeffs = np.ones(len(settings))
+    est = np.empty_like(truth)
+    counters = np.empty((batch, 2), dtype=np.int32)
+    t0 = time.time()
+    for b in range(batch):
+        res = rb.process_results(ref, settings, coeffs, ex[b], cnt[b], qubits)
+        with CallCounter(ps, "proj_choi_to_completely_positive") as ce, CallCounter(ref.tomo, "_cost") as cc:
+            est[b] = ref.tomo.pgdb_process_estimate(res, qubits, trace_preserving=tp)
+        counters[b] = (ce.n, cc.n)
+    print(f"{name}: {batch} items in {time.time() - t0:.1f}s (eigh, cost evals)={counters.tolist()}")
+    np.savez_compressed(os.path.join(OUT, name), seed=seed, n=n, basis=np.array(basis), trace_preserving=tp,
+                        state_codes=np.array([s for s, _ in settings], dtype=np.int32),
+                        pauli_idx=np.array([k for _, k in settings], dtype=np.int32),
+                        expectations=ex, counts=cnt, choi_true=truth, choi_ref=est, counters_ref=counters)
+
+
+def golden_algebra(ref, name, seed, n, batch):
+    rng = np.random.default_rng(seed)
+    d = 2 ** n
+    ot = ref.ot
+    kraus = np.stack([np.stack([np.sqrt(.7) * orc.haar_unitary(rng, d), np.sqrt(.3) * orc.haar_unitary(rng, d)])
+                      for _ in range(batch)])
+    choi = np.stack([ot.kraus2choi(list(k)) for k in kraus])
+    superop = np.stack([ot.choi2superop(c) for c in choi])
+    ksup = np.stack([ot.kraus2superop(list(k)) for k in kraus])
+    pl = np.stack([ot.superop2pauli_liouville(s) for s in superop])
+    back = np.stack([ot.pauli_liouville2superop(p) for p in pl])
+    # non-physical Hermitian-perturbed Choi matrices for the projections
+    noisy = np.empty_like(choi)
+    for b in range(batch):
+        x = rng.standard_normal((d * d, d * d)) + 1j * rng.standard_normal((d * d, d * d))
+        noisy[b] = choi[b] + (x + x.conj().T) / (4 * d * d)
+    cp = np.stack([ot.proj_choi_to_completely_positive(x) for x in noisy])
+    tp = np.stack([ot.proj_choi_to_trace_preserving(x) for x in noisy])
+    tni = np.stack([ot.proj_choi_to_trace_non_increasing(x) for x in noisy])
+    phys = np.stack([ot.proj_choi_to_physical(x) for x in noisy])
+    phys_tni = np.stack([ot.proj_choi_to_physical(x, False) for x in noisy])
+    np.savez_compressed(os.path.join(OUT, name), seed=seed, n=n, kraus=kraus, choi=choi, superop=superop,
+                        kraus2superop=ksup, pauli_liouville=pl, pl2superop=back, noisy=noisy, proj_cp=cp,
+                        proj_tp=tp, proj_tni=tni, proj_physical=phys, proj_physical_tni=phys_tni)
+    print(f"{name}: done")
+
+
+def golden_distances(ref, name, seed, n, batch):
+    rng = np.random.default_rng(seed)
+    d = 2 ** n
+    rho = np.stack([orc.ginibre_state(rng, d) for _ in range(batch)])
+    sigma = np.stack([orc.ginibre_state(rng, d, rank=(1 if b % 4 == 0 else None)) for b in range(batch)])
+    fid = np.array([ref.dm.fidelity(r, s) for r, s in zip(rho, sigma)])
+    td = np.array([ref.dm.trace_distance(r, s) for r, s in zip(rho, sigma)])
+    pur = np.array([ref.dm.purity(r, dim_renorm=False) for r in rho])
+    wiz = np.stack([ref.project_state_matrix_to_physical(r - 0.3 * s) for r, s in zip(rho, sigma)])
+    np.savez_compressed(os.path.join(OUT, name), seed=seed, n=n, rho=rho, sigma=sigma, fidelity=fid,
+                        trace_distance=td, purity=pur, wizard_in=rho - 0.3 * sigma, wizard_out=wiz)
+    print(f"{name}: done")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--skip-3q", action="store_true")
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    os.makedirs(OUT, exist_ok=True)
+    ref = rb.load()
+    jobs = {
+        "algebra": lambda: [golden_algebra(ref, f"algebra_n{n}", 4004 + n, n, 4 if n < 3 else 2) for n in (1, 2, 3)],
+        "dist": lambda: [golden_distances(ref, f"distances_n{n}", 5005 + n, n, 32) for n in (1, 2, 4)],
+        "mle1": lambda: golden_mle(ref, "mle_1q", 1001, 8, 1),
+        "mle2": lambda: golden_mle(ref, "mle_2q", 2002, 8, 2),
+        "mle2_tol": lambda: golden_mle(ref, "mle_2q_tol1e-4", 2003, 8, 2, tol=1e-4),
+        "mle2_maxiter": lambda: golden_mle(ref, "mle_2q_maxiter200", 2004, 4, 2, maxiter=200),
+        "mle2_ent": lambda: golden_mle(ref, "mle_2q_maxent", 2005, 2, 2, entropy_penalty=.001, tol=1e-5),
+        "mle2_hedge": lambda: golden_mle(ref, "mle_2q_hedged", 2006, 4, 2, epsilon=1e-4, beta=.5, tol=1e-3),
+        "mle3": lambda: golden_mle(ref, "mle_3q_tol1e-5", 2007, 2, 3, tol=1e-5),
+        "pgdb1": lambda: [golden_pgdb(ref, "pgdb_1q_pauli", 3001, 8, 1, "pauli"),
+                          golden_pgdb(ref, "pgdb_1q_sic", 3002, 8, 1, "sic"),
+                          golden_pgdb(ref, "pgdb_1q_pauli_tni", 3004, 4, 1, "pauli", tp=False),
+                          golden_pgdb(ref, "pgdb_1q_pauli_mixed", 3005, 4, 1, "pauli", unitary=False)],
+        "pgdb2": lambda: [golden_pgdb(ref, "pgdb_2q_pauli", 3003, 4, 2, "pauli"),
+                          golden_pgdb(ref, "pgdb_2q_sic", 3006, 4, 2, "sic"),
+                          golden_pgdb(ref, "pgdb_2q_sic_mixed", 3007, 2, 2, "sic", unitary=False)],
+        "pgdb3": lambda: [golden_pgdb(ref, "pgdb_3q_sic", 3008, 1, 3, "sic"),
+                          golden_pgdb(ref, "pgdb_3q_pauli", 3003, 1, 3, "pauli")],
+    }
+    for key, fn in jobs.items():
+        if args.only and key not in args.only.split(","):
+            continue
+        if args.skip_3q and key == "pgdb3":
+            continue
+        fn()
+
+
+if __name__ == "__main__":
+    main()

@@ -424,16 +424,17 @@ def extract_design(settings, coeffs, expectations, counts, n):
 
 
 def pgdb_cost(a, nn, est, eps=1e-6):
-    """tomography.py:597-614 (probabilities are real for Hermitian est; the reference's complex
-    clip/compare acts on the real part -- SURVEY.md 7.2)."""
-    p = np.real(a @ vec(est))
+    """tomography.py:597-614.  Like the reference this keeps the complex dtype: np.clip / np.log act
+    on complex numbers (lexicographic clip == clip of the real part; the imaginary parts are ~1e-17
+    rounding noise) and the returned cost is a complex scalar whose comparisons are lexicographic."""
+    p = a @ vec(est)
     p = np.clip(p, eps, None)
-    return float(-(nn.T @ np.log(p))[0, 0])
+    return (-nn.T @ np.log(p))[0, 0]
 
 
 def pgdb_grad(a, nn, est, eps=1e-6):
     """tomography.py:617-633."""
-    p = np.real(a @ vec(est))
+    p = a @ vec(est)
     p = np.clip(p, eps, None)
     return unvec(-a.conj().T @ (nn / p))
 
@@ -458,7 +459,7 @@ def pgdb_process_estimate(settings, coeffs, expectations, counts, n, trace_prese
         alpha = 1.0
         new_cost = pgdb_cost(a, nn, est + alpha * upd)
         cost_evals += 1
-        change = gamma * alpha * np.real(np.vdot(upd, g))
+        change = gamma * alpha * np.vdot(upd, g)
         while new_cost > old_cost + change:
             alpha *= .5
             change *= .5

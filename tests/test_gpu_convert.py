@@ -1,0 +1,96 @@
+"""GPU parity: superoperator conversions vs the oracle and the reference's golden vectors."""
+import numpy as np
+import pytest
+
+from oracle import ref_numpy as orc
+from util import golden, relerr, max_relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_golden_chain(torch, n):
+    from forest_benchmarking_b200.operator_tools import superoperator_transformations as st
+    g = golden(f"algebra_n{n}")
+    kraus = torch.from_numpy(g["kraus"]).cuda()
+    choi = st.kraus2choi_batch(kraus)
+    assert max_relerr(choi.cpu().numpy(), g["choi"]) < 1e-14
+    assert max_relerr(st.kraus2superop_batch(kraus).cpu().numpy(), g["kraus2superop"]) < 1e-14
+    sup = st.reshuffle_batch(choi)
+    assert np.array_equal(st.reshuffle_batch(torch.from_numpy(g["choi"]).cuda()).cpu().numpy(), g["superop"])  # bit-exact
+    pl = st.superop2pauli_liouville_batch(torch.from_numpy(g["superop"]).cuda())
+    assert max_relerr(pl.cpu().numpy(), g["pauli_liouville"]) < 1e-14
+    back = st.pauli_liouville2superop_batch(torch.from_numpy(g["pauli_liouville"]).cuda())
+    assert max_relerr(back.cpu().numpy(), g["pl2superop"]) < 1e-14
+    assert max_relerr(st.pauli_liouville2choi_batch(pl).cpu().numpy(), g["choi"]) < 1e-13
+    assert max_relerr(st.choi2pauli_liouville_batch(choi).cpu().numpy(), g["pauli_liouville"]) < 1e-13
+    assert sup.shape == choi.shape
+
+
+@pytest.mark.parametrize("n,batch", [(1, 1000), (2, 333), (3, 37), (4, 5), (5, 2)])
+def test_sweep_vs_oracle_and_roundtrip(torch, n, batch):
+    from forest_benchmarking_b200.operator_tools import superoperator_transformations as st
+    rng = np.random.default_rng(4004 + n)
+    d = 2 ** n
+    kraus = np.stack([np.stack([np.sqrt(.7) * orc.haar_unitary(rng, d), np.sqrt(.3) * orc.haar_unitary(rng, d)])
+                      for _ in range(batch)])
+    kd = torch.from_numpy(kraus).cuda()
+    choi = st.kraus2choi_batch(kd)
+    sup = st.reshuffle_batch(choi)
+    pl = st.superop2pauli_liouville_batch(sup)
+    sup2 = st.pauli_liouville2superop_batch(pl)
+    choi2 = st.reshuffle_batch(sup2)
+    torch.cuda.synchronize()
+    # round trip (size-independent property) and reshuffle involution (bit-exact)
+    assert max_relerr(choi2.cpu().numpy(), choi.cpu().numpy()) < 1e-13
+    assert torch.equal(st.reshuffle_batch(sup), choi)
+    # PTM of a CPTP map: real, first row (1,0,...,0)
+    plh = pl.cpu().numpy()
+    assert np.abs(plh.imag).max() < 1e-13 and np.allclose(plh[:, 0, 0], 1) and np.abs(plh[:, 0, 1:]).max() < 1e-13
+    # spot checks against the oracle (dense c2p @ S @ c2p^dagger is slow at n=5: one item)
+    picks = range(batch) if n <= 3 else [0]
+    ch = choi.cpu().numpy(); sh = sup.cpu().numpy(); ks = st.kraus2superop_batch(kd).cpu().numpy()
+    for b in picks:
+        assert relerr(ch[b], orc.kraus2choi(list(kraus[b]))) < 1e-14
+        assert np.array_equal(sh[b], orc.choi2superop(ch[b]))
+        assert relerr(ks[b], orc.kraus2superop(list(kraus[b]))) < 1e-14
+        if n <= 4:
+            assert relerr(plh[b], orc.superop2pauli_liouville(sh[b])) < 1e-13
+
+
+def test_pauli_basis_index_pin(torch):
+    """reference tests/test_superoperator_transformations.py:192-201: index 7 of the 2-qubit basis is X(x)Z."""
+    from forest_benchmarking_b200.operator_tools import superoperator_transformations as st
+    xz = np.kron(np.array([[0, 1], [1, 0]]), np.diag([1.0, -1.0]))
+    sup = orc.kraus2superop([xz])  # conjugation by XZ: diagonal +-1 PTM
+    pl = st.superop2pauli_liouville(sup)
+    want = np.array([1 if np.allclose(xz @ orc.pauli_matrix(k, 2) @ xz.conj().T, orc.pauli_matrix(k, 2)) else -1
+                     for k in range(16)], dtype=float)
+    assert np.allclose(pl, np.diag(want), atol=1e-15)
+    e7 = np.zeros((16, 16), dtype=complex); e7[7, 0] = 1.0
+    s = st.pauli_liouville2superop(e7)  # column 0 of p2c-basis: vec(P_7)/d x vec(I)^dagger
+    assert relerr(s, orc.pauli_liouville2superop(e7)) < 1e-15
+
+
+def test_dropin_functions(torch):
+    from forest_benchmarking_b200 import operator_tools as ot
+    had = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+    assert np.allclose(ot.kraus2pauli_liouville(had), np.array([[1, 0, 0, 0], [0, 0, 0, 1], [0, 0, -1, 0], [0, 1, 0, 0]]),
+                       atol=1e-15)  # Hadamard PTM, tests/test_superoperator_transformations.py:43-73 re-derived
+    p = .1
+    ad = [np.array([[1, 0], [0, np.sqrt(1 - p)]]), np.array([[0, np.sqrt(p)], [0, 0]])]
+    c = ot.kraus2choi(ad)
+    assert np.allclose(c, orc.kraus2choi(ad), atol=1e-16)
+    assert np.allclose(ot.choi2superop(c), orc.choi2superop(c)) and np.allclose(ot.superop2choi(ot.choi2superop(c)), c)
+    assert np.allclose(ot.choi2pauli_liouville(c), orc.choi2pauli_liouville(c), atol=1e-15)
+    assert np.allclose(ot.pauli_liouville2choi(ot.choi2pauli_liouville(c)), c, atol=1e-15)
+    assert np.allclose(ot.kraus2superop(ad), orc.kraus2superop(ad), atol=1e-16)
+    assert np.array_equal(ot.vec(np.arange(4).reshape(2, 2)), np.array([[0], [2], [1], [3]]))
+    assert np.array_equal(ot.unvec(ot.vec(np.arange(4).reshape(2, 2))), np.arange(4).reshape(2, 2))

@@ -1,0 +1,161 @@
+"""GPU parity: batched MLE state tomography and distance measures vs the oracle / reference goldens.
+Tolerance (BASELINE.json north_star): <= 1e-6 relative Frobenius error; integer bookkeeping bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import ref_numpy as orc
+from util import golden, relerr, max_relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _run_mle(torch, n, pidx, ex, cnt=None, coeffs=None, kernel=0, **kw):
+    from forest_benchmarking_b200 import tomography as tm
+    plan = tm.MlePlan(n, pidx, coeffs)
+    e = torch.from_numpy(np.ascontiguousarray(ex)).cuda()
+    c = None if cnt is None else torch.from_numpy(np.ascontiguousarray(cnt)).cuda()
+    rho, iters = tm.iterative_mle_state_estimate_batch(plan, e, c, kernel=kernel, **kw)
+    torch.cuda.synchronize()
+    return rho.cpu().numpy(), iters.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", ["mle_1q", "mle_2q", "mle_2q_tol1e-4", "mle_2q_maxiter200", "mle_3q_tol1e-5",
+                                  "mle_2q_maxent", "mle_2q_hedged"])
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_mle_golden(torch, name, kernel):
+    g = golden(name)
+    kw = eval(str(g["kwargs"]))
+    n = int(g["n"])
+    variants = bool(kw.get("entropy_penalty")) or bool(kw.get("beta"))
+    if kernel == 1 and (n > 2 or variants):
+        pytest.skip("register kernel: n<=2 vanilla only")
+    rho, iters = _run_mle(torch, n, g["pauli_idx"], g["expectations"], g["counts"], kernel=kernel, **kw)
+    assert max_relerr(rho, g["rho_ref"]) < TOL
+    # iteration counters: identical stopping rule; allow +-1 only where ||drho|| sits within rounding of tol
+    mism = np.nonzero(iters != g["iters_ref"])[0]
+    assert len(mism) <= max(1, len(iters) // 8), (iters, g["iters_ref"])
+    assert np.all(np.abs(iters - g["iters_ref"]) <= 2)
+
+
+@pytest.mark.parametrize("n,kernel", [(1, 1), (1, 2), (2, 1), (2, 2), (3, 2)])
+def test_mle_vs_oracle_batch(torch, n, kernel):
+    _, pidx, ex, cnt = orc.synth_state_tomography(500 + n, 40, n)
+    kw = dict(tol=1e-6, maxiter=3000)
+    rho, iters = _run_mle(torch, n, pidx, ex, cnt, kernel=kernel, **kw)
+    want, witers = orc.mle_state_estimate_batch(pidx, np.ones(len(pidx)), ex, n, **kw)
+    assert max_relerr(rho, want) < TOL
+    assert np.all(np.abs(iters - witers) <= 2) and np.mean(iters != witers) < 0.1
+    # size-independent properties: Hermitian, unit trace, positive
+    assert np.allclose(rho, rho.conj().transpose(0, 2, 1), atol=1e-13)
+    assert np.allclose(np.trace(rho, axis1=1, axis2=2), 1, atol=1e-12)
+    assert np.linalg.eigvalsh(rho).min() > -1e-12
+
+
+def test_mle_4q_and_5q_warp_kernel(torch):
+    for n, maxiter in ((4, 60), (5, 12)):
+        _, pidx, ex, cnt = orc.synth_state_tomography(600 + n, 3, n)
+        rho, iters = _run_mle(torch, n, pidx, ex, cnt, kernel=2, maxiter=maxiter)
+        want, witers = orc.mle_state_estimate_batch(pidx, np.ones(len(pidx)), ex, n, maxiter=maxiter)
+        assert max_relerr(rho, want) < TOL
+        assert np.array_equal(iters, witers)
+
+
+def test_mle_general_observable_lists(torch):
+    """identity observable, duplicates, non-unit coefficients, incomplete sets (test_state_tomography.py:60-115)."""
+    rng = np.random.default_rng(3)
+    pidx = np.array([0, 7, 7, 12, 3, 1, 9], dtype=np.int32)
+    coeffs = np.array([1.0, -1.0, 0.5, 1.0, 1.0, 2.0, 1.0])
+    ex = rng.uniform(-.6, .6, size=(5, len(pidx)))
+    ex[:, 0] = 1.0
+    kw = dict(tol=1e-7, maxiter=500)
+    rho, iters = _run_mle(torch, 2, pidx, ex, np.full_like(ex, 50.), coeffs=coeffs, **kw)
+    for b in range(5):
+        want, it = orc.mle_state_estimate(pidx, coeffs, ex[b], np.full(len(pidx), 50.), 2, **kw)
+        assert relerr(rho[b], want) < TOL and abs(int(iters[b]) - it) <= 1
+    # unit coefficients with duplicates + identity -> register kernel path
+    coeffs1 = np.ones(len(pidx))
+    rho1, _ = _run_mle(torch, 2, pidx, ex, None, coeffs=coeffs1, kernel=1, **kw)
+    rho2, _ = _run_mle(torch, 2, pidx, ex, None, coeffs=coeffs1, kernel=2, **kw)
+    for b in range(5):
+        want, _ = orc.mle_state_estimate(pidx, coeffs1, ex[b], np.full(len(pidx), 50.), 2, **kw)
+        assert relerr(rho1[b], want) < TOL and relerr(rho2[b], want) < TOL
+
+
+def test_mle_dropin_signature_and_errors(torch):
+    from forest_benchmarking_b200 import tomography as tm
+    from forest_benchmarking_b200.observable_estimation import ExperimentResult, ExperimentSetting, zeros_state
+    from forest_benchmarking_b200.utils import all_traceless_pauli_terms
+    qubits = [4, 2]
+    _, pidx, ex, cnt = orc.synth_state_tomography(9, 1, 2)
+    res = [ExperimentResult(ExperimentSetting(zeros_state(qubits), t), e, int(c))
+           for t, e, c in zip(all_traceless_pauli_terms(qubits), ex[0], cnt[0])]
+    rho = tm.iterative_mle_state_estimate(res, qubits, tol=1e-6)
+    want, _ = orc.mle_state_estimate(pidx, np.ones(15), ex[0], cnt[0], 2, tol=1e-6)
+    assert relerr(rho, want) < TOL
+    with pytest.raises(ValueError):
+        tm.iterative_mle_state_estimate(res, qubits, entropy_penalty=.1, beta=.1)
+    with pytest.warns(UserWarning):
+        tm.iterative_mle_state_estimate(res, qubits, maxiter=5)
+    assert tm.iterative_mle_state_estimate_batch(tm.MlePlan(2, pidx), torch.empty((0, 15), dtype=torch.float64,
+                                                                                 device="cuda"))[0].shape[0] == 0
+
+
+def test_mle_single_step_kernel(torch):
+    from forest_benchmarking_b200 import tomography as tm
+    for n in (1, 2):
+        truth, pidx, ex, _ = orc.synth_state_tomography(40 + n, 300, n)
+        rho0 = np.stack([orc.ginibre_state(np.random.default_rng(b), 2 ** n) for b in range(300)])
+        out = tm.mle_step_batch(n, torch.from_numpy(np.ascontiguousarray(ex.T)).cuda(),
+                                torch.from_numpy(rho0).cuda(), epsilon=.1).cpu().numpy()
+        ops = [orc.pauli_matrix(int(k), n) for k in pidx]
+        for b in range(0, 300, 37):
+            m = np.eye(2 ** n) + .1 * (orc.r_operator(rho0[b], ops, ex[b]) - np.eye(2 ** n))
+            want = m @ rho0[b] @ m
+            assert relerr(out[b], want / np.trace(want)) < 1e-12
+
+
+@pytest.mark.parametrize("n", [1, 2, 4])
+def test_distances_golden(torch, n):
+    from forest_benchmarking_b200 import distance_measures as dm
+    g = golden(f"distances_n{n}")
+    rho, sigma = torch.from_numpy(g["rho"]).cuda(), torch.from_numpy(g["sigma"]).cuda()
+    fid = dm.fidelity_batch(rho, sigma).cpu().numpy()
+    td = dm.trace_distance_batch(rho, sigma).cpu().numpy()
+    pur = dm.purity_batch(rho).cpu().numpy()
+    assert np.max(np.abs(fid - g["fidelity"]) / np.maximum(np.abs(g["fidelity"]), 1e-12)) < TOL
+    assert np.max(np.abs(td - g["trace_distance"])) < 1e-14
+    assert np.max(np.abs(pur - g["purity"])) < 1e-13
+    nuc = dm.trace_distance_nuclear_batch(rho, sigma).cpu().numpy()
+    want = [0.5 * np.abs(np.linalg.eigvalsh(r - s)).sum() for r, s in zip(g["rho"], g["sigma"])]
+    assert np.max(np.abs(nuc - want)) < 1e-12
+
+
+@pytest.mark.parametrize("n", [3, 5])
+def test_distances_vs_oracle(torch, n):
+    from forest_benchmarking_b200 import distance_measures as dm
+    rng = np.random.default_rng(n)
+    d = 2 ** n
+    rho = np.stack([orc.ginibre_state(rng, d) for _ in range(50)])
+    sigma = np.stack([orc.ginibre_state(rng, d, rank=(1 if b % 5 == 0 else None)) for b in range(50)])
+    fid = dm.fidelity_batch(torch.from_numpy(rho).cuda(), torch.from_numpy(sigma).cuda()).cpu().numpy()
+    td = dm.trace_distance_batch(torch.from_numpy(rho).cuda(), torch.from_numpy(sigma).cuda()).cpu().numpy()
+    for b in range(50):
+        assert abs(fid[b] - orc.fidelity(rho[b], sigma[b])) < 1e-10
+        assert abs(td[b] - orc.trace_distance(rho[b], sigma[b])) < 1e-14
+
+
+def test_distance_known_answers_and_dropin(torch):
+    from forest_benchmarking_b200 import distance_measures as dm
+    z0, z1 = np.diag([1.0, 0]), np.diag([0, 1.0])
+    assert dm.trace_distance(z0, z1) == 0.5          # reference tests/test_distance_measures.py:73-82 (sic)
+    assert abs(dm.fidelity(z0, z1)) < 1e-15 and abs(dm.fidelity(z0, z0) - 1) < 1e-14
+    assert abs(dm.purity(np.eye(2) / 2, dim_renorm=False) - 0.5) < 1e-15
+    assert abs(dm.infidelity(z0, z0)) < 1e-14

@@ -1,0 +1,91 @@
+"""CPU: the oracle (oracle/ref_numpy.py) against the golden vectors produced by the reference itself
+(oracle/make_golden.py).  This is what pins the oracle on machines without /root/reference."""
+import numpy as np
+import pytest
+
+from oracle import ref_numpy as orc
+from util import golden, relerr, max_relerr
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_algebra(n):
+    g = golden(f"algebra_n{n}")
+    for b in range(g["kraus"].shape[0]):
+        ks = list(g["kraus"][b])
+        assert relerr(orc.kraus2choi(ks), g["choi"][b]) < 1e-14
+        assert relerr(orc.kraus2superop(ks), g["kraus2superop"][b]) < 1e-14
+        assert np.array_equal(orc.choi2superop(g["choi"][b]), g["superop"][b])
+        assert relerr(orc.superop2pauli_liouville(g["superop"][b]), g["pauli_liouville"][b]) < 1e-14
+        assert relerr(orc.pauli_liouville2superop(g["pauli_liouville"][b]), g["pl2superop"][b]) < 1e-14
+        x = g["noisy"][b]
+        assert relerr(orc.proj_choi_to_completely_positive(x), g["proj_cp"][b]) < 1e-13
+        assert relerr(orc.proj_choi_to_trace_preserving(x), g["proj_tp"][b]) < 1e-14
+        assert relerr(orc.proj_choi_to_trace_non_increasing(x), g["proj_tni"][b]) < 1e-13
+        assert relerr(orc.proj_choi_to_physical(x), g["proj_physical"][b]) < 1e-12
+        assert relerr(orc.proj_choi_to_physical(x, False), g["proj_physical_tni"][b]) < 1e-12
+
+
+@pytest.mark.parametrize("n", [1, 2, 4])
+def test_distances(n):
+    g = golden(f"distances_n{n}")
+    for b in range(g["rho"].shape[0]):
+        assert abs(orc.fidelity(g["rho"][b], g["sigma"][b]) - g["fidelity"][b]) < 1e-13
+        assert abs(orc.trace_distance(g["rho"][b], g["sigma"][b]) - g["trace_distance"][b]) < 1e-15
+        assert abs(orc.purity(g["rho"][b]) - g["purity"][b]) < 1e-14
+
+
+def test_known_answers():
+    # reference tests/test_distance_measures.py:49-82 (values re-derived): |0> vs |1>
+    z0, z1 = np.diag([1.0, 0]).astype(complex), np.diag([0, 1.0]).astype(complex)
+    assert orc.fidelity(z0, z1) == 0.0 and orc.fidelity(z0, z0) == pytest.approx(1.0)
+    assert orc.trace_distance(z0, z1) == 0.5      # sic: induced 1-norm
+    # amplitude damping (tests/test_superoperator_transformations.py:12-40, re-derived), p = 0.1
+    p = 0.1
+    k0 = np.array([[1, 0], [0, np.sqrt(1 - p)]]); k1 = np.array([[0, np.sqrt(p)], [0, 0]])
+    pl = np.array([[1, 0, 0, 0], [0, np.sqrt(1 - p), 0, 0], [0, 0, np.sqrt(1 - p), 0], [p, 0, 0, 1 - p]])
+    assert np.allclose(orc.kraus2pauli_liouville([k0, k1]), pl, atol=1e-15)
+    choi = np.array([[1, 0, 0, np.sqrt(1 - p)], [0, 0, 0, 0], [0, 0, p, 0], [np.sqrt(1 - p), 0, 0, 1 - p]])
+    assert np.allclose(orc.kraus2choi([k0, k1]), choi, atol=1e-15)
+    # CP projection of -Z, X (tests/test_project_superoperators.py:15-31 re-derived)
+    had = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+    neg = orc.kraus2choi([had]) * -1
+    assert np.allclose(orc.proj_choi_to_completely_positive(neg), 0, atol=1e-14)
+
+
+@pytest.mark.parametrize("name,tol", [("mle_1q", 1e-11), ("mle_2q_tol1e-4", 1e-11), ("mle_2q_maxiter200", 1e-12),
+                                      ("mle_2q_hedged", 1e-10), ("mle_3q_tol1e-5", 1e-10)])
+def test_mle(name, tol):
+    g = golden(name)
+    kw = eval(str(g["kwargs"]))
+    n = int(g["n"])
+    coeffs = np.ones(len(g["pauli_idx"]))
+    if not kw.get("entropy_penalty") and not kw.get("beta"):
+        rho, iters = orc.mle_state_estimate_batch(g["pauli_idx"], coeffs, g["expectations"], n, **kw)
+        assert max_relerr(rho, g["rho_ref"]) < tol
+        assert np.array_equal(iters, g["iters_ref"])
+    b = 0
+    rho, it = orc.mle_state_estimate(g["pauli_idx"], coeffs, g["expectations"][b], g["counts"][b], n, **kw)
+    assert relerr(rho, g["rho_ref"][b]) < tol
+    assert it == g["iters_ref"][b]
+
+
+@pytest.mark.slow
+def test_mle_2q_default_and_maxent():
+    g = golden("mle_2q")
+    rho, iters = orc.mle_state_estimate_batch(g["pauli_idx"], np.ones(15), g["expectations"], 2)
+    assert max_relerr(rho, g["rho_ref"]) < 1e-9
+    assert np.array_equal(iters, g["iters_ref"])
+
+
+@pytest.mark.parametrize("name", ["pgdb_1q_pauli", "pgdb_1q_sic", "pgdb_1q_pauli_tni", "pgdb_1q_pauli_mixed",
+                                  "pgdb_2q_sic"])
+def test_pgdb(name):
+    g = golden(name)
+    n = int(g["n"])
+    settings = [(tuple(int(c) for c in s), int(k)) for s, k in zip(g["state_codes"], g["pauli_idx"])]
+    nb = 2 if n == 2 else g["expectations"].shape[0]
+    for b in range(nb):
+        est, cnt = orc.pgdb_process_estimate(settings, np.ones(len(settings)), g["expectations"][b], g["counts"][b],
+                                             n, trace_preserving=bool(g["trace_preserving"]), return_counters=True)
+        assert relerr(est, g["choi_ref"][b]) < 1e-9
+        assert (cnt["eighs"], cnt["cost_evals"]) == tuple(g["counters_ref"][b])
