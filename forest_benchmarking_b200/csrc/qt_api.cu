@@ -31,3 +31,23 @@ extern "C" int qt_last_error(char* buf, int len) {
   buf[len - 1] = '\0';
   return QT_OK;
 }
+
+// FP64 FMA throughput probe: the measured denominator for the FP64-bound kernels' roofline
+// (MEASURED_PEAKS.json only carries HBM and bf16 numbers).  Each thread runs 8 independent DFMA chains.
+__global__ void fp64_probe_kernel(int iters, double seed, double* out) {
+  double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+         a7 = a0 + 7;
+  const double m = 0.999999, c = 1e-9;
+  for (int i = 0; i < iters; ++i) {
+    a0 = fma(a0, m, c); a1 = fma(a1, m, c); a2 = fma(a2, m, c); a3 = fma(a3, m, c);
+    a4 = fma(a4, m, c); a5 = fma(a5, m, c); a6 = fma(a6, m, c); a7 = fma(a7, m, c);
+  }
+  if (a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 == 42.0) out[0] = a0;
+}
+
+// Launches the probe; total FLOPs = blocks * threads * 8 chains * iters * 2.
+extern "C" int qt_fp64_probe(int blocks, int threads, int iters, double* scratch, void* stream) {
+  QT_REQUIRE(blocks > 0 && threads > 0 && threads <= 1024 && iters > 0 && scratch, "qt_fp64_probe: bad arguments");
+  fp64_probe_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(iters, 1.0, scratch);
+  return qt_check_launch("fp64_probe_kernel");
+}

@@ -58,7 +58,8 @@ __global__ void purity_kernel(int64_t B, const cplx* __restrict__ rho, double* _
 // shared memory per warp: 3 matrices + eigenvalues + Jacobi scratch
 template <int D>
 struct FidSmem {
-  static constexpr size_t bytes = sizeof(cplx) * D * D * 3 + sizeof(double) * (D + JacobiScratch<D>::doubles);
+  static constexpr size_t bytes =
+      (sizeof(cplx) * D * D * 3 + sizeof(double) * (D + JacobiScratch<D>::doubles) + 15) / 16 * 16;
 };
 
 // MODE 0: fidelity.  MODE 1: nuclear-norm trace distance.

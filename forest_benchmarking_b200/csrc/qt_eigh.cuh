@@ -69,7 +69,7 @@ __device__ __forceinline__ double group_sum(double v, double* red, int tid) {
   return tot;
 }
 
-// Scratch layout (doubles): rc[M/2] | rs[M/2] (complex) | red[32]
+// Scratch layout (doubles, 16-byte aligned base): rs[M/2] (complex) | rc[M/2] | red[32]
 template <int M>
 struct JacobiScratch {
   static constexpr int doubles = M / 2 + M + 32;
@@ -84,9 +84,9 @@ template <int M, int NT, class Sync, bool WANT_V>
 __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v = true,
                            int max_sweeps = 30) {
   constexpr int HP = M / 2;
-  double* rc = scratch;
-  cplx* rs = reinterpret_cast<cplx*>(scratch + HP);
-  double* red = scratch + HP + M;
+  cplx* rs = reinterpret_cast<cplx*>(scratch);  // scratch must be 16-byte aligned
+  double* rc = scratch + M;
+  double* red = scratch + M + HP;
 
   if (WANT_V && init_v) {
     for (int e = tid; e < M * M; e += NT) V[e] = cmake((e / M == e % M) ? 1.0 : 0.0, 0.0);

@@ -203,8 +203,8 @@ struct MleWarpSmem {
   static constexpr int D = 1 << N, S = 1 << (2 * N);
   // rho, M, T (+ V for the eigen-decomposition used by the variants)
   __host__ __device__ static constexpr size_t bytes(bool variants) {
-    return sizeof(cplx) * D * D * (variants ? 4 : 3) + sizeof(double) * S * 2 +
-           sizeof(double) * (D + JacobiScratch<D>::doubles);
+    return (sizeof(cplx) * D * D * (variants ? 4 : 3) + sizeof(double) * S * 2 +
+            sizeof(double) * (D + JacobiScratch<D>::doubles) + 15) / 16 * 16;
   }
 };
 
@@ -547,7 +547,9 @@ static int launch_warp(const qt_mle_plan* p, int64_t B, const double* expect, co
 extern "C" int qt_mle_state_batch(const qt_mle_plan* p, int64_t B, const double* expect, const double* counts,
                                   double epsilon, double entropy_penalty, double beta, double tol, int maxiter,
                                   int kernel_variant, void* rho_out, int32_t* iters_out, void* stream) {
-  QT_REQUIRE(p && expect && rho_out && iters_out, "qt_mle_state_batch: null argument");
+  QT_REQUIRE(p, "qt_mle_state_batch: null plan");
+  if (B == 0) return QT_OK;
+  QT_REQUIRE(expect && rho_out && iters_out, "qt_mle_state_batch: null argument");
   QT_REQUIRE(!(entropy_penalty != 0.0 && beta != 0.0),
              "qt_mle_state_batch: entropy_penalty and beta cannot both be non-zero (tomography.py:225)");
   QT_REQUIRE(beta <= 0.0 || counts, "qt_mle_state_batch: hedged MLE needs counts");

@@ -33,6 +33,9 @@ int qt_version(void);
 /* copies the last error message of this thread into buf (NUL-terminated, truncated to len) */
 int qt_last_error(char* buf, int len);
 
+/* FP64 FMA throughput probe (bench utility): blocks*threads*8*iters FMAs; scratch = 1 double on device */
+int qt_fp64_probe(int blocks, int threads, int iters, double* scratch, void* stream);
+
 /* ---- state tomography: iterative_mle_state_estimate (tomography.py:168-270) + _R (:273-338) ---- */
 typedef struct qt_mle_plan qt_mle_plan;
 /* pauli_idx_host[K], coeff_host[K]: observable of results[k] = coeff * Pauli(pauli_idx); K = len(results) */

