@@ -67,7 +67,7 @@ def declared_symbols():
     with open(_HEADER) as f:
         text = f.read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
-    return sorted(set(re.findall(r"\bint\s+(qt_\w+)\s*\(", text)))
+    return sorted(set(re.findall(r"\b(?:int|int64_t)\s+(qt_\w+)\s*\(", text)))
 
 
 def lib():
@@ -82,7 +82,7 @@ def lib():
     except OSError as e:  # fail loudly: there is no fallback
         raise QtomoError(f"cannot load {_SO}: {e}") from e
     for name in declared_symbols():
-        getattr(_lib, name).restype = ctypes.c_int
+        getattr(_lib, name).restype = ctypes.c_int64 if name.endswith("_bytes") else ctypes.c_int
     return _lib
 
 

@@ -1,0 +1,194 @@
+// Device-side Choi-matrix projections shared by the standalone projection kernels (qt_project.cu) and
+// the process-tomography kernel (qt_pgdb.cu).
+//
+//   proj CP   operator_tools/project_superoperators.py:19-34   (C+C^dagger)/2 -> eigh -> clamp -> V L V^dagger
+//   proj TP   :62-84 (+ calculational.py:5-35)                 C - kron((Tr_out C - I)/d, I)
+//   proj TNI  :37-59                                           C - kron((Tr_out C - clamp_le1(Tr_out C))/d, I)
+//   physical  :87-144   Dykstra alternating projections with the Birgin-Raydan stopping rule
+//
+// One Choi matrix (m = 4^n) is one GROUP's work: a warp for n <= 2, a 256-thread block for n = 3.
+// The eigensolver operands X, V live in shared memory; the Dykstra state (S = last_state, Q =
+// old_CP_change, CPREV = last_CP_projection) lives behind plain pointers (global/L2 or shared).
+// Structure used: both the TP and TNI corrections are -kron(E, I_d) with a d x d matrix E, so
+// old_TP_change is carried as E (d^2 numbers) and
+//   ||dTP||^2 = d ||E_new - E||_F^2,   <old_TP, S_new - S> = -sum conj(E) (Tr_out S_new - Tr_out S),
+//   new_CP_change - old_CP_change = CP - S   (so ||dCP||^2 = ||CP - S||_F^2).
+#pragma once
+#include "qt_common.cuh"
+#include "qt_eigh.cuh"
+
+template <int N, int NT, class Sync>
+struct ChoiGroup {
+  static constexpr int D = 1 << N;
+  static constexpr int M = D * D;
+  static constexpr int MM = M * M;
+  static constexpr int TS = (M >= 64) ? 4 : (M >= 16 ? 2 : 1);  // register tile of the recomposition
+  // small shared scratch (doubles): ev[M] | jacobi scratch | E[2*D*D] | En[2*D*D] | ptS[2*D*D] | ptC[2*D*D] |
+  //                                 small eigh: P[2*D*D] W[2*D*D] pev[D] + jacobi scratch<D> | red2[64]
+  static constexpr int SMALL_DOUBLES = M + JacobiScratch<M>::doubles + 12 * D * D + D + JacobiScratch<D>::doubles + 64;
+
+  // OUT (shared, M x M) = V max(ev,0) V^dagger, or PRE + V max(-ev,0) V^dagger when fewer negatives.
+  // PRE(e) is a callable returning the Hermitian matrix that was decomposed.
+  template <class PreFn>
+  static __device__ void recompose_psd(cplx* OUT, const cplx* V, const double* ev, PreFn pre, int tid) {
+    int npos = 0;
+    for (int k = 0; k < M; ++k) npos += (ev[k] > 0.0) ? 1 : 0;
+    const bool use_pos = npos <= M / 2;
+    constexpr int T = M / TS;
+    for (int t = tid; t < T * T; t += NT) {
+      const int r0 = (t / T) * TS, c0 = (t % T) * TS;
+      cplx acc[TS][TS];
+#pragma unroll
+      for (int i = 0; i < TS; ++i)
+#pragma unroll
+        for (int j = 0; j < TS; ++j) acc[i][j] = cmake(0.0, 0.0);
+      for (int k = 0; k < M; ++k) {
+        const double lam = ev[k];
+        const double w = use_pos ? fmax(lam, 0.0) : fmax(-lam, 0.0);
+        if (w == 0.0) continue;
+        cplx vr[TS], vc[TS];
+#pragma unroll
+        for (int i = 0; i < TS; ++i) {
+          vr[i] = cscale(V[(r0 + i) * M + k], w);
+          vc[i] = V[(c0 + i) * M + k];
+        }
+#pragma unroll
+        for (int i = 0; i < TS; ++i)
+#pragma unroll
+          for (int j = 0; j < TS; ++j) cfma_conj(acc[i][j], vr[i], vc[j]);
+      }
+#pragma unroll
+      for (int i = 0; i < TS; ++i)
+#pragma unroll
+        for (int j = 0; j < TS; ++j) {
+          const int e = (r0 + i) * M + c0 + j;
+          OUT[e] = use_pos ? acc[i][j] : cadd(pre(e), acc[i][j]);
+        }
+    }
+    Sync::sync();
+  }
+
+  // partial trace over the output factor: pt[a*D + c] = sum_b C[(a*D+b), (c*D+b)]
+  static __device__ void partial_trace_out(const cplx* C, cplx* pt, int tid) {
+    for (int e = tid; e < D * D; e += NT) {
+      const int a = e / D, c = e % D;
+      cplx s = cmake(0.0, 0.0);
+      for (int b = 0; b < D; ++b) s = cadd(s, C[(a * D + b) * M + c * D + b]);
+      pt[e] = s;
+    }
+    Sync::sync();
+  }
+
+  // E = correction matrix of the TP / TNI projection of a matrix whose partial trace is `pt`:
+  //   TP : (pt - I)/d             TNI: (pt - V min(l,1) V^dagger)/d, V l V^dagger = eigh((pt+pt^dagger)/2)
+  // P, W, pev, pscr: d x d scratch for the TNI eigen-decomposition (first warp of the group only).
+  static __device__ void tp_correction(const cplx* pt, cplx* E, bool make_tp, cplx* P, cplx* W, double* pev,
+                                       double* pscr, int tid) {
+    if (make_tp) {
+      for (int e = tid; e < D * D; e += NT) {
+        cplx v = pt[e];
+        if (e / D == e % D) v.x -= 1.0;
+        E[e] = cscale(v, 1.0 / D);
+      }
+      Sync::sync();
+      return;
+    }
+    if (tid < 32) {
+      for (int e = tid; e < D * D; e += 32) {
+        const int a = e / D, c = e % D;
+        const cplx x = pt[e], y = pt[c * D + a];
+        P[e] = cmake(0.5 * (x.x + y.x), 0.5 * (x.y - y.y));
+      }
+      __syncwarp();
+      jacobi_eigh<D, 32, SyncWarp, true>(P, W, pev, pscr, tid);
+      for (int e = tid; e < D * D; e += 32) {
+        const int a = e / D, c = e % D;
+        cplx acc = cmake(0.0, 0.0);
+        for (int k = 0; k < D; ++k) cfma_conj(acc, cscale(W[a * D + k], fmin(pev[k], 1.0)), W[c * D + k]);
+        E[e] = cscale(csub(pt[e], acc), 1.0 / D);
+      }
+    }
+    Sync::sync();
+  }
+
+  // Dykstra.  On entry S holds the (Hermitian) matrix to project; on exit S holds the projection.
+  // X, V: shared M x M work matrices; Q, CPREV: M x M state buffers (any address space); small: shared
+  // scratch of SMALL_DOUBLES doubles (16-byte aligned).  Returns the number of CP projections (eigh calls).
+  static __device__ int project_physical(cplx* S, cplx* Q, cplx* CPREV, cplx* X, cplx* V, double* small,
+                                         bool make_tp, int tid, int max_iter = 10000) {
+    double* ev = small;
+    double* jscr = ev + M;
+    cplx* E = reinterpret_cast<cplx*>(jscr + JacobiScratch<M>::doubles);
+    cplx* En = E + D * D;
+    cplx* ptS = En + D * D;
+    cplx* ptC = ptS + D * D;
+    cplx* P = ptC + D * D;
+    cplx* W = P + D * D;
+    double* pev = reinterpret_cast<double*>(W + D * D);
+    double* pscr = pev + D;
+    double* red = pscr + JacobiScratch<D>::doubles;
+
+    for (int e = tid; e < MM; e += NT) {
+      Q[e] = cmake(0.0, 0.0);
+      CPREV[e] = cmake(0.0, 0.0);
+    }
+    for (int e = tid; e < D * D; e += NT) E[e] = cmake(0.0, 0.0);
+    Sync::sync();
+    int n_eigh = 0;
+    while (true) {
+      // X = pre_CP = S - Q
+      for (int e = tid; e < MM; e += NT) X[e] = csub(S[e], Q[e]);
+      Sync::sync();
+      jacobi_eigh<M, NT, Sync, true>(X, V, ev, jscr, tid);
+      ++n_eigh;
+      recompose_psd(X, V, ev, [&](int e) { return csub(S[e], Q[e]); }, tid);  // X = CP projection
+      // criterion pieces + state update of Q, CPREV
+      double n_dcp = 0.0;
+      cplx ip_q = cmake(0.0, 0.0);
+      for (int e = tid; e < MM; e += NT) {
+        const cplx cp = X[e], s = S[e], q = Q[e], cprev = CPREV[e];
+        const cplx d1 = csub(cp, s);
+        n_dcp += cabs2(d1);
+        cfma_conj(ip_q, csub(cp, cprev), q);  // conj(q) * (cp - cprev)
+        Q[e] = cadd(d1, q);                   // new_CP_change = CP - pre_CP = CP - S + Q
+        CPREV[e] = cp;
+      }
+      partial_trace_out(S, ptS, tid);
+      partial_trace_out(X, ptC, tid);
+      // pre_TP = CP - old_TP_change = CP + kron(E, I):  Tr_out(pre_TP) = ptC + d E
+      for (int e = tid; e < D * D; e += NT) ptC[e] = cadd(ptC[e], cscale(E[e], (double)D));
+      Sync::sync();
+      tp_correction(ptC, En, make_tp, P, W, pev, pscr, tid);
+      // new_state = pre_TP - kron(En, I) = CP + kron(E - En, I)
+      for (int e = tid; e < MM; e += NT) {
+        const int r = e / M, c = e % M;
+        cplx v = X[e];
+        if ((r % D) == (c % D)) {
+          const int a = r / D, cc = c / D;
+          v = cadd(v, csub(E[a * D + cc], En[a * D + cc]));
+        }
+        S[e] = v;
+      }
+      // ||dTP||^2 = d ||En - E||^2 ;  <old_TP, dS> = -sum conj(E) (Tr_out Snew - Tr_out S), Tr_out Snew = ptC - d En
+      double n_dtp = 0.0;
+      cplx ip_t = cmake(0.0, 0.0);
+      for (int e = tid; e < D * D; e += NT) {
+        n_dtp += cabs2(csub(En[e], E[e]));
+        const cplx dpt = csub(csub(ptC[e], cscale(En[e], (double)D)), ptS[e]);
+        cfma_conj(ip_t, dpt, E[e]);
+      }
+      n_dcp = group_sum<NT, Sync>(n_dcp, red, tid);
+      n_dtp = group_sum<NT, Sync>(n_dtp, red, tid);
+      ip_q.x = group_sum<NT, Sync>(ip_q.x, red, tid);
+      ip_q.y = group_sum<NT, Sync>(ip_q.y, red, tid);
+      ip_t.x = group_sum<NT, Sync>(ip_t.x, red, tid);
+      ip_t.y = group_sum<NT, Sync>(ip_t.y, red, tid);
+      const double crit = n_dcp + D * n_dtp + 2.0 * sqrt(cabs2(ip_t)) + 2.0 * sqrt(cabs2(ip_q));
+      Sync::sync();
+      if (crit < 1e-4 || n_eigh >= max_iter) break;
+      for (int e = tid; e < D * D; e += NT) E[e] = En[e];
+      Sync::sync();
+    }
+    return n_eigh;
+  }
+};

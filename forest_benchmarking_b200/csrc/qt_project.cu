@@ -1,0 +1,239 @@
+// Batched Choi-matrix projections: CP, TP, TNI and physical (Dykstra).  See qt_choi.cuh for the math and
+// the reference citations (operator_tools/project_superoperators.py:19-144).
+#include "qt_choi.cuh"
+#include "../../include/qtomo.h"
+
+#include <algorithm>
+#include <type_traits>
+
+template <int N>
+struct ProjCfg {
+  static constexpr int NT = (N >= 3) ? 256 : 32;           // threads per group
+  static constexpr int GPB = (N >= 3) ? 1 : 4;             // groups per block
+  using Sync = typename std::conditional<(N >= 3), SyncBlock, SyncWarp>::type;
+  using G = ChoiGroup<N, NT, Sync>;
+  static constexpr size_t group_smem = (sizeof(cplx) * 2 * G::MM + sizeof(double) * G::SMALL_DOUBLES + 15) / 16 * 16;
+};
+
+// ---- CP ---------------------------------------------------------------------------------------------
+template <int N>
+__global__ void proj_cp_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out) {
+  using C = ProjCfg<N>;
+  using G = typename C::G;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int gib = threadIdx.x / C::NT, tid = threadIdx.x % C::NT;
+  cplx* X = reinterpret_cast<cplx*>(smem_raw + C::group_smem * gib);
+  cplx* V = X + G::MM;
+  double* small = reinterpret_cast<double*>(V + G::MM);
+  const int64_t b = (int64_t)blockIdx.x * C::GPB + gib;
+  if (b >= B) return;
+  const cplx* src = in + b * G::MM;
+  auto herm = [&](int e) {
+    const int r = e / G::M, c = e % G::M;
+    const cplx x = src[e], y = src[c * G::M + r];
+    return cmake(0.5 * (x.x + y.x), 0.5 * (x.y - y.y));
+  };
+  for (int e = tid; e < G::MM; e += C::NT) X[e] = herm(e);
+  C::Sync::sync();
+  jacobi_eigh<G::M, C::NT, typename C::Sync, true>(X, V, small, small + G::M, tid);
+  G::recompose_psd(X, V, small, herm, tid);
+  cplx* dst = out + b * G::MM;
+  for (int e = tid; e < G::MM; e += C::NT) dst[e] = X[e];
+}
+
+// ---- TP / TNI: streaming kernel, several items per block for small n --------------------------------
+template <int N>
+__global__ void proj_tp_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out, int make_tp,
+                               int items_per_block) {
+  constexpr int D = 1 << N, M = D * D, MM = M * M;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  cplx* tile = reinterpret_cast<cplx*>(smem_raw);         // [items][MM]
+  cplx* Eall = tile + (size_t)items_per_block * MM;       // [items][D*D]
+  cplx* scratch = Eall + (size_t)items_per_block * D * D; // TNI only: per item pt, P, W (3 D^2) + pev + jacobi
+  const int64_t b0 = (int64_t)blockIdx.x * items_per_block;
+  const int nb = (int)min((int64_t)items_per_block, B - b0);
+  for (int e = threadIdx.x; e < nb * MM; e += blockDim.x) tile[e] = in[b0 * MM + e];
+  __syncthreads();
+  if (make_tp) {
+    for (int w = threadIdx.x; w < nb * D * D; w += blockDim.x) {
+      const int bi = w / (D * D), a = (w / D) % D, c = w % D;
+      const cplx* Cm = tile + (size_t)bi * MM;
+      cplx s = cmake(0.0, 0.0);
+      for (int bb = 0; bb < D; ++bb) s = cadd(s, Cm[(a * D + bb) * M + c * D + bb]);
+      if (a == c) s.x -= 1.0;
+      Eall[w] = cscale(s, 1.0 / D);
+    }
+  } else {
+    // one warp per item computes pt, its eigen-decomposition and the correction
+    constexpr int PER = 3 * D * D * 2 + D + JacobiScratch<D>::doubles + (D % 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int bi = warp; bi < nb; bi += nw) {
+      double* base = reinterpret_cast<double*>(scratch) + (size_t)bi * ((PER + 1) / 2 * 2);
+      cplx* pt = reinterpret_cast<cplx*>(base);
+      cplx* P = pt + D * D;
+      cplx* W = P + D * D;
+      double* pev = reinterpret_cast<double*>(W + D * D);
+      double* pscr = pev + D;
+      const cplx* Cm = tile + (size_t)bi * MM;
+      for (int e = lane; e < D * D; e += 32) {
+        const int a = e / D, c = e % D;
+        cplx s = cmake(0.0, 0.0);
+        for (int bb = 0; bb < D; ++bb) s = cadd(s, Cm[(a * D + bb) * M + c * D + bb]);
+        pt[e] = s;
+      }
+      __syncwarp();
+      for (int e = lane; e < D * D; e += 32) {
+        const int a = e / D, c = e % D;
+        const cplx x = pt[e], y = pt[c * D + a];
+        P[e] = cmake(0.5 * (x.x + y.x), 0.5 * (x.y - y.y));
+      }
+      __syncwarp();
+      jacobi_eigh<D, 32, SyncWarp, true>(P, W, pev, pscr, lane);
+      for (int e = lane; e < D * D; e += 32) {
+        const int a = e / D, c = e % D;
+        cplx acc = cmake(0.0, 0.0);
+        for (int k = 0; k < D; ++k) cfma_conj(acc, cscale(W[a * D + k], fmin(pev[k], 1.0)), W[c * D + k]);
+        Eall[bi * D * D + e] = cscale(csub(pt[e], acc), 1.0 / D);
+      }
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < nb * MM; e += blockDim.x) {
+    const int bi = e / MM, r = (e / M) % M, c = e % M;
+    cplx v = tile[e];
+    if ((r % D) == (c % D)) v = csub(v, Eall[bi * D * D + (r / D) * D + (c / D)]);
+    out[b0 * MM + e] = v;
+  }
+}
+
+// ---- physical (Dykstra): persistent groups, S = out[b], Q / CPREV in the workspace -------------------
+template <int N>
+__global__ void proj_physical_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out, int make_tp,
+                                     cplx* __restrict__ workspace, int* __restrict__ eigh_calls) {
+  using C = ProjCfg<N>;
+  using G = typename C::G;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int gib = threadIdx.x / C::NT, tid = threadIdx.x % C::NT;
+  cplx* X = reinterpret_cast<cplx*>(smem_raw + C::group_smem * gib);
+  cplx* V = X + G::MM;
+  double* small = reinterpret_cast<double*>(V + G::MM);
+  const int64_t group = (int64_t)blockIdx.x * C::GPB + gib;
+  const int64_t n_groups = (int64_t)gridDim.x * C::GPB;
+  cplx* Q = workspace + group * 2 * G::MM;
+  cplx* CPREV = Q + G::MM;
+  for (int64_t b = group; b < B; b += n_groups) {
+    const cplx* src = in + b * G::MM;
+    cplx* S = out + b * G::MM;
+    for (int e = tid; e < G::MM; e += C::NT) {
+      const int r = e / G::M, c = e % G::M;
+      const cplx x = src[e], y = src[c * G::M + r];
+      S[e] = cmake(0.5 * (x.x + y.x), 0.5 * (x.y - y.y));
+    }
+    C::Sync::sync();
+    const int calls = G::project_physical(S, Q, CPREV, X, V, small, make_tp != 0, tid);
+    if (tid == 0 && eigh_calls) eigh_calls[b] = calls;
+    C::Sync::sync();
+  }
+}
+
+template <int N>
+static int64_t physical_grid(int64_t B) {
+  using C = ProjCfg<N>;
+  const int per_sm = (N >= 3) ? 1 : 8;
+  const int64_t max_blocks = (int64_t)QT_NUM_SMS * per_sm;
+  return std::min<int64_t>((B + C::GPB - 1) / C::GPB, max_blocks);
+}
+
+template <int N>
+static int launch_cp(int64_t B, const void* in, void* out, cudaStream_t st) {
+  using C = ProjCfg<N>;
+  const size_t smem = C::group_smem * C::GPB;
+  QT_CUDA(cudaFuncSetAttribute(proj_cp_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  proj_cp_kernel<N><<<(unsigned)((B + C::GPB - 1) / C::GPB), C::NT * C::GPB, smem, st>>>(B, (const cplx*)in,
+                                                                                         (cplx*)out);
+  return qt_check_launch("proj_cp_kernel");
+}
+
+template <int N>
+static int launch_tp(int64_t B, const void* in, void* out, int make_tp, cudaStream_t st) {
+  constexpr int D = 1 << N, MM = D * D * D * D;
+  const int ipb = make_tp ? std::max(1, 4096 / MM) : std::max(1, std::min(64, 4096 / MM));
+  constexpr int PER = 3 * D * D * 2 + D + JacobiScratch<D>::doubles + (D % 2);
+  const size_t smem = sizeof(cplx) * ((size_t)ipb * MM + (size_t)ipb * D * D) +
+                      (make_tp ? 0 : sizeof(double) * (size_t)ipb * ((PER + 1) / 2 * 2));
+  QT_CUDA(cudaFuncSetAttribute(proj_tp_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  proj_tp_kernel<N><<<(unsigned)((B + ipb - 1) / ipb), 256, smem, st>>>(B, (const cplx*)in, (cplx*)out, make_tp, ipb);
+  return qt_check_launch("proj_tp_kernel");
+}
+
+template <int N>
+static int launch_physical(int64_t B, const void* in, void* out, int make_tp, void* ws, int64_t ws_bytes,
+                           int* eigh_calls, cudaStream_t st) {
+  using C = ProjCfg<N>;
+  const int64_t blocks = physical_grid<N>(B);
+  const int64_t need = blocks * C::GPB * 2 * C::G::MM * (int64_t)sizeof(cplx);
+  if (ws_bytes < need) {
+    qt_set_error("qt_proj_physical_batch: workspace too small (%lld < %lld bytes)", (long long)ws_bytes,
+                 (long long)need);
+    return QT_ERR_WORKSPACE;
+  }
+  const size_t smem = C::group_smem * C::GPB;
+  QT_CUDA(cudaFuncSetAttribute(proj_physical_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  proj_physical_kernel<N><<<(unsigned)blocks, C::NT * C::GPB, smem, st>>>(B, (const cplx*)in, (cplx*)out, make_tp,
+                                                                          (cplx*)ws, eigh_calls);
+  return qt_check_launch("proj_physical_kernel");
+}
+
+#define DISPATCH_N3(n, CALL)                                              \
+  switch (n) {                                                            \
+    case 1: return CALL(1);                                               \
+    case 2: return CALL(2);                                               \
+    case 3: return CALL(3);                                               \
+    default:                                                              \
+      qt_set_error("Choi projections support n = 1..3 qubits (got %d)", n); \
+      return QT_ERR_UNSUPPORTED;                                          \
+  }
+
+extern "C" int qt_proj_cp_batch(int n, int64_t B, const void* choi, void* out, void* stream) {
+  if (B == 0) return QT_OK;
+  QT_REQUIRE(choi && out, "qt_proj_cp_batch: null argument");
+#define CALL(N) launch_cp<N>(B, choi, out, (cudaStream_t)stream)
+  DISPATCH_N3(n, CALL)
+#undef CALL
+}
+
+extern "C" int qt_proj_tp_batch(int n, int64_t B, const void* choi, void* out, void* stream) {
+  if (B == 0) return QT_OK;
+  QT_REQUIRE(choi && out, "qt_proj_tp_batch: null argument");
+#define CALL(N) launch_tp<N>(B, choi, out, 1, (cudaStream_t)stream)
+  DISPATCH_N3(n, CALL)
+#undef CALL
+}
+
+extern "C" int qt_proj_tni_batch(int n, int64_t B, const void* choi, void* out, void* stream) {
+  if (B == 0) return QT_OK;
+  QT_REQUIRE(choi && out, "qt_proj_tni_batch: null argument");
+#define CALL(N) launch_tp<N>(B, choi, out, 0, (cudaStream_t)stream)
+  DISPATCH_N3(n, CALL)
+#undef CALL
+}
+
+extern "C" int64_t qt_proj_physical_workspace_bytes(int n, int64_t B) {
+  switch (n) {
+    case 1: return physical_grid<1>(B) * ProjCfg<1>::GPB * 2 * ProjCfg<1>::G::MM * (int64_t)sizeof(cplx);
+    case 2: return physical_grid<2>(B) * ProjCfg<2>::GPB * 2 * ProjCfg<2>::G::MM * (int64_t)sizeof(cplx);
+    case 3: return physical_grid<3>(B) * ProjCfg<3>::GPB * 2 * ProjCfg<3>::G::MM * (int64_t)sizeof(cplx);
+    default: return -1;
+  }
+}
+
+extern "C" int qt_proj_physical_batch(int n, int64_t B, const void* choi, void* out, int make_trace_preserving,
+                                      void* workspace, int64_t workspace_bytes, int32_t* eigh_calls_out,
+                                      void* stream) {
+  if (B == 0) return QT_OK;
+  QT_REQUIRE(choi && out && workspace, "qt_proj_physical_batch: null argument");
+#define CALL(N) \
+  launch_physical<N>(B, choi, out, make_trace_preserving, workspace, workspace_bytes, eigh_calls_out, (cudaStream_t)stream)
+  DISPATCH_N3(n, CALL)
+#undef CALL
+}

@@ -1,1 +1,2 @@
 from .superoperator_transformations import *  # noqa: F401,F403
+from .project_superoperators import *  # noqa: F401,F403

@@ -1,0 +1,90 @@
+"""Projections of Choi matrices onto CP / TP / TNI / physical maps -- signatures of
+forest/benchmarking/operator_tools/project_superoperators.py, computed by csrc/qt_project.cu
+(batched Jacobi eigensolver + fused Dykstra loop, one matrix per warp or block)."""
+import ctypes
+
+import numpy as np
+
+from .. import _lib
+
+__all__ = ["proj_choi_to_completely_positive", "proj_choi_to_trace_preserving",
+           "proj_choi_to_trace_non_increasing", "proj_choi_to_physical",
+           "proj_choi_to_completely_positive_batch", "proj_choi_to_trace_preserving_batch",
+           "proj_choi_to_trace_non_increasing_batch", "proj_choi_to_physical_batch"]
+
+
+def _prep(choi):
+    torch = _lib.require_cuda()
+    if not choi.is_cuda or choi.dtype != torch.complex128 or choi.dim() != 3 or choi.shape[1] != choi.shape[2]:
+        raise ValueError("expected a complex128 CUDA tensor [B, 4^n, 4^n]")
+    n = int(round(np.log2(choi.shape[1]) / 2))
+    if 4 ** n != choi.shape[1] or not 1 <= n <= 3:
+        raise ValueError("Choi projections support n = 1..3 qubits")
+    return torch, choi.contiguous(), n
+
+
+def _simple(name, choi, out):
+    torch, choi, n = _prep(choi)
+    if out is None:
+        out = torch.empty_like(choi)
+    _lib.check(getattr(_lib.lib(), name)(ctypes.c_int(n), ctypes.c_int64(choi.shape[0]), _lib.ptr(choi),
+                                         _lib.ptr(out), _lib.current_stream_ptr()), name)
+    return out
+
+
+def proj_choi_to_completely_positive_batch(choi, out=None):
+    return _simple("qt_proj_cp_batch", choi, out)
+
+
+def proj_choi_to_trace_preserving_batch(choi, out=None):
+    return _simple("qt_proj_tp_batch", choi, out)
+
+
+def proj_choi_to_trace_non_increasing_batch(choi, out=None):
+    return _simple("qt_proj_tni_batch", choi, out)
+
+
+def proj_choi_to_physical_batch(choi, make_trace_preserving=True, out=None, return_counts=False):
+    """Dykstra CP + TP (or TNI) projection of every matrix of the batch.  The input is Hermitised first
+    (the reference's CP step does the same on every Dykstra iteration, project_superoperators.py:30)."""
+    torch, choi, n = _prep(choi)
+    b = choi.shape[0]
+    if out is None:
+        out = torch.empty_like(choi)
+    lib = _lib.lib()
+    nbytes = int(lib.qt_proj_physical_workspace_bytes(ctypes.c_int(n), ctypes.c_int64(b)))
+    ws = torch.empty((max(nbytes, 16) // 16,), dtype=torch.complex128, device=choi.device)
+    counts = torch.empty((b,), dtype=torch.int32, device=choi.device)
+    _lib.check(lib.qt_proj_physical_batch(ctypes.c_int(n), ctypes.c_int64(b), _lib.ptr(choi), _lib.ptr(out),
+                                          ctypes.c_int(1 if make_trace_preserving else 0), _lib.ptr(ws),
+                                          ctypes.c_int64(nbytes), _lib.ptr(counts), _lib.current_stream_ptr()),
+               "qt_proj_physical_batch")
+    return (out, counts) if return_counts else out
+
+
+def _one(x):
+    torch = _lib.require_cuda()
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.complex128))[None]).cuda()
+
+
+def proj_choi_to_completely_positive(choi: np.ndarray, check_finite: bool = True) -> np.ndarray:
+    """reference project_superoperators.py:19-34."""
+    choi = np.asarray(choi)
+    if check_finite and not np.isfinite(choi).all():
+        raise ValueError("array must not contain infs or NaNs")
+    return proj_choi_to_completely_positive_batch(_one(choi))[0].cpu().numpy()
+
+
+def proj_choi_to_trace_non_increasing(choi: np.ndarray) -> np.ndarray:
+    """reference project_superoperators.py:37-59."""
+    return proj_choi_to_trace_non_increasing_batch(_one(choi))[0].cpu().numpy()
+
+
+def proj_choi_to_trace_preserving(choi: np.ndarray) -> np.ndarray:
+    """reference project_superoperators.py:62-84."""
+    return proj_choi_to_trace_preserving_batch(_one(choi))[0].cpu().numpy()
+
+
+def proj_choi_to_physical(choi: np.ndarray, make_trace_preserving: bool = True) -> np.ndarray:
+    """reference project_superoperators.py:87-144."""
+    return proj_choi_to_physical_batch(_one(choi), make_trace_preserving)[0].cpu().numpy()

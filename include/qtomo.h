@@ -75,6 +75,17 @@ int qt_trace_distance_batch(int n, int64_t B, const void* rho, const void* sigma
 int qt_trace_distance_nuclear_batch(int n, int64_t B, const void* rho, const void* sigma, double* out, void* stream);
 int qt_purity_batch(int n, int64_t B, const void* rho, double* out, void* stream);                             /* :14-37 */
 
+/* ---- Choi-matrix projections (operator_tools/project_superoperators.py), n = 1..3, [B,4^n,4^n] ---- */
+int qt_proj_cp_batch(int n, int64_t B, const void* choi, void* out, void* stream);   /* :19-34 */
+int qt_proj_tp_batch(int n, int64_t B, const void* choi, void* out, void* stream);   /* :62-84 */
+int qt_proj_tni_batch(int n, int64_t B, const void* choi, void* out, void* stream);  /* :37-59 */
+/* Dykstra CP+TP (or CP+TNI) projection, :87-144.  The input is Hermitised first.  workspace: device
+ * buffer of qt_proj_physical_workspace_bytes(n, B) bytes; eigh_calls_out[B] (may be NULL) = number of CP
+ * projections each item needed. */
+int64_t qt_proj_physical_workspace_bytes(int n, int64_t B);
+int qt_proj_physical_batch(int n, int64_t B, const void* choi, void* out, int make_trace_preserving,
+                           void* workspace, int64_t workspace_bytes, int32_t* eigh_calls_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,77 @@
+"""GPU parity: Choi projections (CP / TP / TNI / Dykstra physical) vs reference goldens and the oracle."""
+import numpy as np
+import pytest
+
+from oracle import ref_numpy as orc
+from util import golden, relerr, max_relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_golden(torch, n):
+    from forest_benchmarking_b200.operator_tools import project_superoperators as ps
+    g = golden(f"algebra_n{n}")
+    x = torch.from_numpy(g["noisy"]).cuda()
+    assert max_relerr(ps.proj_choi_to_completely_positive_batch(x).cpu().numpy(), g["proj_cp"]) < 1e-12
+    assert max_relerr(ps.proj_choi_to_trace_preserving_batch(x).cpu().numpy(), g["proj_tp"]) < 1e-14
+    assert max_relerr(ps.proj_choi_to_trace_non_increasing_batch(x).cpu().numpy(), g["proj_tni"]) < 1e-12
+    assert max_relerr(ps.proj_choi_to_physical_batch(x).cpu().numpy(), g["proj_physical"]) < TOL
+    assert max_relerr(ps.proj_choi_to_physical_batch(x, False).cpu().numpy(), g["proj_physical_tni"]) < TOL
+
+
+@pytest.mark.parametrize("n,batch", [(1, 301), (2, 67), (3, 5)])
+def test_vs_oracle_and_properties(torch, n, batch):
+    from forest_benchmarking_b200.operator_tools import project_superoperators as ps
+    rng = np.random.default_rng(70 + n)
+    d, m = 2 ** n, 4 ** n
+    xs = []
+    for b in range(batch):
+        base = orc.kraus2choi([orc.haar_unitary(rng, d)]) if b % 2 else np.eye(m) / d
+        noise = rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m))
+        xs.append(base + (noise + noise.conj().T) * (0.3 / m))
+    xs = np.stack(xs)
+    xd = torch.from_numpy(xs).cuda()
+    cp = ps.proj_choi_to_completely_positive_batch(xd).cpu().numpy()
+    tp = ps.proj_choi_to_trace_preserving_batch(xd).cpu().numpy()
+    phys, counts = ps.proj_choi_to_physical_batch(xd, return_counts=True)
+    phys, counts = phys.cpu().numpy(), counts.cpu().numpy()
+    picks = range(batch) if n < 3 else range(3)
+    for b in picks:
+        assert relerr(cp[b], orc.proj_choi_to_completely_positive(xs[b])) < 1e-12
+        assert relerr(tp[b], orc.proj_choi_to_trace_preserving(xs[b])) < 1e-14
+        want, ne = orc.proj_choi_to_physical(xs[b], return_count=True)
+        assert relerr(phys[b], want) < TOL
+        assert abs(int(counts[b]) - ne) <= 1
+    # properties at every item: CP output PSD + idempotent; physical output CP and TP
+    assert np.linalg.eigvalsh(cp).min() > -1e-12
+    cp2 = ps.proj_choi_to_completely_positive_batch(torch.from_numpy(cp).cuda()).cpu().numpy()
+    assert max_relerr(cp2, cp) < 1e-12
+    pt = np.einsum("zijkj->zik", phys.reshape(batch, d, d, d, d))
+    assert np.abs(pt - np.eye(d)).max() < 1e-10
+    assert np.linalg.eigvalsh(phys).min() > -5e-3   # Dykstra stops at 1e-4 on squared norms
+
+
+def test_known_answers_and_dropin(torch):
+    """reference tests/test_project_superoperators.py:15-31, 79-90 (values re-derived)."""
+    from forest_benchmarking_b200 import operator_tools as ot
+    z = np.diag([1.0, -1.0]); x = np.array([[0, 1.0], [1, 0]]); y = np.array([[0, -1j], [1j, 0]])
+    for op in (z, x, y):
+        neg = -orc.kraus2choi([op])
+        assert np.allclose(ot.proj_choi_to_completely_positive(neg), 0, atol=1e-14)
+        pos = orc.kraus2choi([op])
+        assert np.allclose(ot.proj_choi_to_completely_positive(pos), pos, atol=1e-14)
+        assert np.allclose(ot.proj_choi_to_physical(pos), pos, atol=1e-12)
+        assert np.allclose(ot.proj_choi_to_trace_preserving(pos), pos, atol=1e-15)
+    bad = orc.kraus2choi([z]) * 1.3
+    assert np.allclose(ot.proj_choi_to_trace_non_increasing(bad), orc.proj_choi_to_trace_non_increasing(bad), atol=1e-13)
+    with pytest.raises(ValueError):
+        ot.proj_choi_to_completely_positive(np.full((4, 4), np.nan))
