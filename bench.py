@@ -322,8 +322,118 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def flop_model_pgdb(n, n_in, counters):
+    """eigh_calls*44 m^3 + (cost_evals + 2 outer)*F_A, F_A = 8 d^4 n_in + n_in*4*n*4^n."""
+    d, m = 2 ** n, 4 ** n
+    fa = 8.0 * d ** 4 * n_in + n_in * 4.0 * n * m
+    c = np.asarray(counters, dtype=np.float64)
+    return c[:, 2] * 44.0 * m ** 3 + (c[:, 1] + 2 * c[:, 0]) * fa
+
+
+def run_pgdb(args):
+    """BASELINE configs[2]: 3-qubit pgdb_process_estimate (64x64 Choi), batch 1024 per GPU, Pauli inputs."""
+    import torch
+    from forest_benchmarking_b200 import _lib, synthetic as sy, tomography as tm
+    rank, world, local = dist_info()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = {"pgdb3q": 3, "pgdb2q": 2, "pgdb1q": 1}[args.workload]
+    B = args.batch if args.batch != 4096 else 1024
+    codes, pidx, ex, cnt, _ = sy.process_tomography_batch(3003 + rank, B, n, in_basis=args.in_basis)
+    plan = tm.PgdbPlan(n, codes, pidx)
+    m = 4 ** n
+    ex_host, cnt_host = torch.from_numpy(ex).pin_memory(), torch.from_numpy(cnt).pin_memory()
+    ex_dev, cnt_dev = ex_host.cuda(), cnt_host.cuda()
+    out = torch.empty((B, m, m), dtype=torch.complex128, device="cuda")
+    out_host = torch.empty((B, m, m), dtype=torch.complex128).pin_memory()
+    gathered = torch.empty((world * B, m, m), dtype=torch.complex128, device="cuda") if world > 1 else None
+    nbytes = int(_lib.lib().qt_pgdb_workspace_bytes(plan._h, B))
+    ws = torch.empty((nbytes // 8,), dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device="cuda")
+    last = {}
+
+    def step_resident():
+        _, c = tm.pgdb_process_estimate_batch(plan, ex_dev, cnt_dev, True, out=out, return_counters=True, workspace=ws)
+        last["c"] = c
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(torch.float64), out.view(torch.float64))
+
+    def step_e2e():
+        e, c = ex_host.cuda(non_blocking=True), cnt_host.cuda(non_blocking=True)
+        tm.pgdb_process_estimate_batch(plan, e, c, True, out=out, workspace=ws)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered.view(torch.float64), out.view(torch.float64))
+        out_host.copy_(out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = []
+        for _ in range(steps):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); fn(); e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        tot = torch.tensor([sum(ms)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.barrier()
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        return float(tot.item()) / steps
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_res = timed(step_resident, args.steps, args.warmup)
+    ms_e2e = timed(step_e2e, args.steps, 1)
+    clocks = sampler.stop() if rank == 0 else None
+    counters = last["c"].cpu().numpy()
+    fp64_peak = measure_fp64_peak(torch, _lib.lib(), _lib)
+    flops = float(flop_model_pgdb(n, plan.n_in, counters).sum())
+    hbm_peak, _ = measured_peaks()
+    if rank == 0:
+        bytes_item = 2 * 8 * plan.S + 16 * m * m
+        line = {
+            "metric": METRIC, "value": world * B / (ms_res * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_res, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+            "config": {"workload": f"{n}-qubit pgdb_process_estimate (BASELINE configs[2]), {args.in_basis} inputs, "
+                                   f"{plan.S} settings x 1000 shots, Haar-random unitary truth",
+                       "batch_per_gpu": B, "global_batch": world * B, "l2": "flushed between timed iterations",
+                       "collective": "all_gather of reconstructed Choi matrices" if world > 1 else "none",
+                       "outer_mean": float(counters[:, 0].mean()), "cost_evals_mean": float(counters[:, 1].mean()),
+                       "eigh_calls_mean": float(counters[:, 2].mean())},
+            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(2 * ex_host.numel() * 8), "d2h_bytes_per_step": int(out_host.numel() * 16)},
+            "gpu_launches": args.steps, "clocks": clocks,
+            "roofline": {"kernel": f"pgdb_kernel<{n}> (fused PGD + Dykstra + Jacobi eigh, one experiment per "
+                                   f"{'block' if n == 3 else 'warp'})",
+                         "bound": "fp64", "achieved": flops / (ms_res * 1e-3) / 1e12, "peak": fp64_peak,
+                         "unit": "TFLOP/s", "frac": flops / (ms_res * 1e-3) / 1e12 / fp64_peak,
+                         "flop_model": "SURVEY.md 8(d): eigh*44m^3 + (cost_evals+2*outer)*F_A with the items' actual counters",
+                         "peak_source": "measured live: qt_fp64_probe", "traffic": None,
+                         "hbm_view": {"bound": "hbm", "achieved": B * bytes_item / (ms_res * 1e-3) / 1e9,
+                                      "peak": hbm_peak, "unit": "GB/s",
+                                      "frac": B * bytes_item / (ms_res * 1e-3) / 1e9 / hbm_peak,
+                                      "note": "compulsory bytes only"}},
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="mle2q", choices=["mle2q", "pgdb3q", "pgdb2q", "pgdb1q"])
+    ap.add_argument("--in-basis", default="pauli", choices=["pauli", "sic"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
@@ -334,6 +444,8 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload.startswith("pgdb"):
+        run_pgdb(args)
     else:
         run_ours(args)
 

@@ -13,6 +13,7 @@
 // All matrices are [B, d^2, d^2] interleaved complex128 row-major.  Reads and writes are fully coalesced
 // 16-byte accesses; permutations and butterflies go through shared memory.
 #include "qt_common.cuh"
+#include "qt_pauli.cuh"
 #include "../../include/qtomo.h"
 
 static constexpr int TILE_ELEMS = 4096;  // 64 KB of complex128 per block pass
@@ -155,79 +156,6 @@ extern "C" int qt_choi_superop_reshuffle_batch(int d, int64_t B, const void* in,
 // ---------------------------------------------------------------------------------------------
 // superop <-> Pauli-Liouville (PTM)
 // ---------------------------------------------------------------------------------------------
-// position p (2n bits: j bits high, i bits low; qubit 0 most significant in each half) <-> canonical
-// Pauli index with digit code (hi=j_q, lo=i_q): I=(0,0) X=(0,1) Y=(1,0) Z=(1,1) after the butterfly.
-__host__ __device__ __forceinline__ int pos_to_pauli(int p, int n) {
-  int idx = 0;
-  for (int q = 0; q < n; ++q) {
-    const int lo = (p >> (n - 1 - q)) & 1, hi = (p >> (2 * n - 1 - q)) & 1;
-    const int code = 2 * hi + lo;                   // 0:I 1:X 2:Y 3:Z
-    idx |= code << (2 * (n - 1 - q));
-  }
-  return idx;
-}
-__host__ __device__ __forceinline__ int pauli_to_pos(int idx, int n) {
-  int p = 0;
-  for (int q = 0; q < n; ++q) {
-    const int code = (idx >> (2 * (n - 1 - q))) & 3;
-    p |= (code & 1) << (n - 1 - q);
-    p |= (code >> 1) << (2 * n - 1 - q);
-  }
-  return p;
-}
-
-// One 4-point butterfly.  FWD: computational -> Pauli (F, or conj(F) when CONJ); !FWD: the adjoint.
-template <bool FWD, bool CONJ>
-__device__ __forceinline__ void bfly4(cplx& u00, cplx& u01, cplx& u10, cplx& u11) {
-  // argument order: (hi,lo) = (j,i) bit pair -> u[j i]; u01 means j=0,i=1, i.e. matrix element U[i=1][j=0].
-  // F row a, entry (i,j) = conj(sigma_a[i,j]).  sigma_y[i=0,j=1] = -i, sigma_y[i=1,j=0] = +i.
-  if (FWD) {
-    const cplx a = cadd(u00, u11), z = csub(u00, u11);
-    const cplx x = cadd(u01, u10);
-    // Y: conj(sy[1,0]) u(i=1,j=0) + conj(sy[0,1]) u(i=0,j=1) = -i*u01 + i*u10   (u01 = (j=0,i=1))
-    cplx y = csub(u10, u01);
-    y = CONJ ? cmake(y.y, -y.x) : cmake(-y.y, y.x);  // (+i or -i) * (u10 - u01)
-    u00 = a; u01 = x; u10 = y; u11 = z;
-  } else {
-    // adjoint: u(i,j) = sum_a sigma_a[i,j] v_a   (or its conjugate)
-    const cplx vi = u00, vx = u01, vy = u10, vz = u11;
-    cplx iy = CONJ ? cmake(vy.y, -vy.x) : cmake(-vy.y, vy.x);  // (+i or -i) * vy
-    u00 = cadd(vi, vz);
-    u11 = csub(vi, vz);
-    // element (i=1,j=0) = vx + sy[1,0] vy = vx + i vy ; element (i=0,j=1) = vx - i vy
-    u01 = cadd(vx, iy);
-    u10 = csub(vx, iy);
-  }
-}
-
-// In-place transform of `count` vectors of length L = 4^n held in shared memory.
-// Vector v, element p at  buf[v * vstride + p * estride].
-template <bool FWD, bool CONJ>
-__device__ void pauli_butterfly_smem(cplx* buf, int n, int count, int vstride, int estride, int tid, int nt) {
-  const int L = 1 << (2 * n);
-  const int quarter = L >> 2;
-  for (int q = 0; q < n; ++q) {
-    const int lo_bit = n - 1 - q, hi_bit = 2 * n - 1 - q;
-    for (int w = tid; w < count * quarter; w += nt) {
-      const int v = w / quarter;
-      int r = w % quarter;
-      // insert zero bits at lo_bit and hi_bit
-      int p = ((r >> lo_bit) << (lo_bit + 1)) | (r & ((1 << lo_bit) - 1));
-      p = ((p >> hi_bit) << (hi_bit + 1)) | (p & ((1 << hi_bit) - 1));
-      cplx* base = buf + v * vstride;
-      const int lo = 1 << lo_bit, hi = 1 << hi_bit;
-      cplx u00 = base[p * estride], u01 = base[(p | lo) * estride];
-      cplx u10 = base[(p | hi) * estride], u11 = base[(p | hi | lo) * estride];
-      bfly4<FWD, CONJ>(u00, u01, u10, u11);
-      base[p * estride] = u00;
-      base[(p | lo) * estride] = u01;
-      base[(p | hi) * estride] = u10;
-      base[(p | hi | lo) * estride] = u11;
-    }
-    __syncthreads();
-  }
-}
-
 // Fused kernel for n <= 3: whole matrices in shared memory.
 // FWD: out = (1/d) F S F^dagger, rows/cols permuted to canonical Pauli order.
 // !FWD: out = (1/d) F^dagger R F, input rows/cols gathered from canonical Pauli order.

@@ -1,0 +1,432 @@
+// Batched process tomography by projected gradient descent with backtracking (PGDB).
+//
+// Replaces, per experiment, forest/benchmarking/tomography.py:542-594 (pgdb_process_estimate) with
+// _extract_from_results (:494-539), _cost (:597-614) and _grad_cost (:617-633), and the Dykstra projection
+// proj_choi_to_physical (operator_tools/project_superoperators.py:87-144) it calls on every outer step.
+// One experiment = one warp (n <= 2) or one 256-thread block (n = 3), persistent over the batch.
+//
+// The reference's dense design matrix A (27216 x 4096 complex = 1.78 GB at n = 3) is never built.  With
+// R = PTM of the current estimate E (real for Hermitian E) and r_i[j] = Tr(P_j rho_i) the Pauli vector of
+// input state i (checked against the oracle to 1e-16):
+//     t_i[k]   = Tr(P_k E(rho_i)) = sum_j R[k,j] r_i[j]
+//     p_s(+-)  = (t_i[0] +- c_s t_i[k_s]) / (2 d^2)                       (== A vec(E), tomography.py:611)
+//     cost     = - sum_s n_s+ log clip(p_s+) + n_s- log clip(p_s-)         (:613-614, clip at 1e-6)
+//     gradient = -(1/d^2) pl2choi(Gp),  Gp[k,j] = sum_i w_i[k] r_i[j],
+//                w_i[0] = sum_{s in i} (eta+ + eta-)/2,  w_i[k_s] += c_s (eta+ - eta-)/2,  eta = n / clip(p)
+// Everything is linear in E, so the line search only needs T_est + alpha T_upd (one T build per outer step).
+#include "qt_choi.cuh"
+#include "qt_pauli.cuh"
+#include "../../include/qtomo.h"
+
+#include <algorithm>
+#include <map>
+#include <type_traits>
+#include <vector>
+
+struct qt_pgdb_plan {
+  int n, S, n_in, canonical;
+  int* d_state_id;    // [S]
+  int* d_pidx;        // [S]
+  double* d_coeff;    // [S]
+  double* d_svec;     // [n_in, 4^n]
+};
+
+struct PgdbView {
+  int S, n_in, canonical;
+  const int* state_id;
+  const int* pidx;
+  const double* coeff;
+  const double* svec;
+};
+
+template <int N>
+struct PgdbCfg {
+  static constexpr int NT = (N >= 3) ? 256 : 32;
+  static constexpr int GPB = (N >= 3) ? 1 : 4;
+  using Sync = typename std::conditional<(N >= 3), SyncBlock, SyncWarp>::type;
+  using G = ChoiGroup<N, NT, Sync>;
+  static constexpr size_t group_smem = (sizeof(cplx) * 2 * G::MM + sizeof(double) * G::SMALL_DOUBLES + 15) / 16 * 16;
+  // per-group global workspace, in doubles
+  static __host__ __device__ int64_t ws_doubles(int n_in) {
+    return 5LL * 2 * G::MM + 3LL * n_in * G::M;
+  }
+};
+
+template <int N>
+struct Pgdb {
+  using C = PgdbCfg<N>;
+  using G = typename C::G;
+  using Sync = typename C::Sync;
+  static constexpr int NT = C::NT, D = G::D, M = G::M, MM = G::MM;
+
+  // in-place choi <-> superop reshuffle of a shared M x M matrix (swap index digits 0 and 3)
+  static __device__ void reshuffle_inplace(cplx* X, int tid) {
+    for (int e = tid; e < MM; e += NT) {
+      const int r = e / M, c = e % M;
+      const int i0 = r / D, i1 = r % D, i2 = c / D, i3 = c % D;
+      if (i0 < i3) {
+        const int e2 = (i3 * D + i1) * M + i2 * D + i0;
+        const cplx a = X[e], b = X[e2];
+        X[e] = b;
+        X[e2] = a;
+      }
+    }
+    Sync::sync();
+  }
+
+  // X (shared, Choi) -> Pauli-Liouville coefficients left at butterfly positions: R[k][j] = X[pos(k)*M + pos(j)] / d
+  static __device__ void choi_to_pl_positions(cplx* X, int tid) {
+    reshuffle_inplace(X, tid);
+    pauli_butterfly_smem<true, true, Sync>(X, N, M, M, 1, tid, NT);
+    pauli_butterfly_smem<true, false, Sync>(X, N, M, 1, M, tid, NT);
+  }
+  // inverse: X holds PL coefficients at butterfly positions -> Choi (times d; caller scales)
+  static __device__ void pl_positions_to_choi(cplx* X, int tid) {
+    pauli_butterfly_smem<false, true, Sync>(X, N, M, M, 1, tid, NT);
+    pauli_butterfly_smem<false, false, Sync>(X, N, M, 1, M, tid, NT);
+    reshuffle_inplace(X, tid);
+  }
+
+  // T[i][k] = sum_j R[k][j] svec[i][j], R read from butterfly positions of X (real part) with scale 1/d
+  static __device__ void build_T(const cplx* X, const PgdbView& pv, double* T, int tid) {
+    const double scale = 1.0 / D;
+    for (int e = tid; e < pv.n_in * M; e += NT) {
+      const int i = e / M, k = e % M;
+      const cplx* row = X + pauli_to_pos(k, N) * M;
+      const double* sv = pv.svec + (int64_t)i * M;
+      double acc = 0.0;
+      for (int j = 0; j < M; ++j) acc = fma(row[pauli_to_pos(j, N)].x, sv[j], acc);
+      T[e] = acc * scale;
+    }
+    Sync::sync();
+  }
+
+  struct Data {
+    const double* ex;
+    const double* cnt;
+    double inv_total;
+  };
+
+  static __device__ __forceinline__ void setting_of(const PgdbView& pv, int s, int& i, int& k, double& c) {
+    if (pv.canonical) {
+      i = s / (M - 1);
+      k = s % (M - 1) + 1;
+      c = 1.0;
+    } else {
+      i = pv.state_id[s];
+      k = pv.pidx[s];
+      c = pv.coeff[s];
+    }
+  }
+
+  // cost of est + alpha * upd from the T arrays
+  static __device__ double cost(const PgdbView& pv, const Data& dt, const double* Te, const double* Tu, double alpha,
+                                double* red, int tid) {
+    const double h = 1.0 / (2.0 * D * D);
+    double acc = 0.0;
+    for (int s = tid; s < pv.S; s += NT) {
+      int i, k;
+      double c;
+      setting_of(pv, s, i, k, c);
+      const double t0 = fma(alpha, Tu[i * M], Te[i * M]);
+      const double tk = c * fma(alpha, Tu[i * M + k], Te[i * M + k]);
+      const double pp = fmax((t0 + tk) * h, 1e-6), pm = fmax((t0 - tk) * h, 1e-6);
+      const double plus = 0.5 * (1.0 + dt.ex[s]);
+      const double np_ = dt.cnt[s] * plus * dt.inv_total, nm = dt.cnt[s] * (1.0 - plus) * dt.inv_total;
+      acc -= np_ * log(pp) + nm * log(pm);
+    }
+    return group_sum<NT, Sync>(acc, red, tid);
+  }
+
+  // w_i[k] (global scratch W [n_in][M]) from the current T_est
+  static __device__ void build_w(const PgdbView& pv, const Data& dt, const double* Te, double* W, int tid) {
+    const double h = 1.0 / (2.0 * D * D);
+    if (pv.canonical) {
+      for (int i = tid; i < pv.n_in; i += NT) {
+        const double t0 = Te[i * M];
+        double w0 = 0.0;
+        for (int k = 1; k < M; ++k) {
+          const int s = i * (M - 1) + k - 1;
+          const double tk = Te[i * M + k];
+          const double pp = fmax((t0 + tk) * h, 1e-6), pm = fmax((t0 - tk) * h, 1e-6);
+          const double plus = 0.5 * (1.0 + dt.ex[s]);
+          const double ep = dt.cnt[s] * plus * dt.inv_total / pp, em = dt.cnt[s] * (1.0 - plus) * dt.inv_total / pm;
+          w0 += 0.5 * (ep + em);
+          W[i * M + k] = 0.5 * (ep - em);
+        }
+        W[i * M] = w0;
+      }
+    } else {
+      for (int e = tid; e < pv.n_in * M; e += NT) W[e] = 0.0;
+      Sync::sync();
+      for (int s = tid; s < pv.S; s += NT) {
+        int i, k;
+        double c;
+        setting_of(pv, s, i, k, c);
+        const double t0 = Te[i * M], tk = c * Te[i * M + k];
+        const double pp = fmax((t0 + tk) * h, 1e-6), pm = fmax((t0 - tk) * h, 1e-6);
+        const double plus = 0.5 * (1.0 + dt.ex[s]);
+        const double ep = dt.cnt[s] * plus * dt.inv_total / pp, em = dt.cnt[s] * (1.0 - plus) * dt.inv_total / pm;
+        atomicAdd(&W[i * M], 0.5 * (ep + em));
+        atomicAdd(&W[i * M + k], c * 0.5 * (ep - em));
+      }
+    }
+    __threadfence_block();
+    Sync::sync();
+  }
+
+  // One experiment.  EST = choi_out[b] (global).  ws: per-group workspace.  X, V, small: shared.
+  static __device__ void run(const PgdbView& pv, const Data& dt, bool make_tp, cplx* EST, double* ws, cplx* X,
+                             cplx* V, double* small, int* counters, int tid) {
+    cplx* Gr = reinterpret_cast<cplx*>(ws);
+    cplx* U = Gr + MM;
+    cplx* S = U + MM;
+    cplx* Q = S + MM;
+    cplx* CPREV = Q + MM;
+    double* Te = reinterpret_cast<double*>(CPREV + MM);
+    double* Tu = Te + (int64_t)pv.n_in * M;
+    double* W = Tu + (int64_t)pv.n_in * M;
+    double* red = small + G::SMALL_DOUBLES - 64;
+    const double mu = 3.0 / (2.0 * D * D), gamma = 0.3;
+
+    // est = I / d ; T_est from it
+    for (int e = tid; e < MM; e += NT) {
+      const cplx v = cmake((e / M == e % M) ? 1.0 / D : 0.0, 0.0);
+      EST[e] = v;
+      X[e] = v;
+    }
+    for (int e = tid; e < pv.n_in * M; e += NT) Tu[e] = 0.0;
+    Sync::sync();
+    choi_to_pl_positions(X, tid);
+    build_T(X, pv, Te, tid);
+    double old_cost = cost(pv, dt, Te, Tu, 0.0, red, tid);
+    int outer = 0, cost_evals = 1, eighs = 0;
+    while (true) {
+      ++outer;
+      // ---- gradient ----
+      build_w(pv, dt, Te, W, tid);
+      for (int e = tid; e < MM; e += NT) {
+        const int k = e / M, j = e % M;
+        double acc = 0.0;
+        for (int i = 0; i < pv.n_in; ++i) acc = fma(W[i * M + k], pv.svec[(int64_t)i * M + j], acc);
+        X[pauli_to_pos(k, N) * M + pauli_to_pos(j, N)] = cmake(acc, 0.0);
+      }
+      Sync::sync();
+      pl_positions_to_choi(X, tid);
+      // gradient = -(1/d^2) * (1/d) * X ; S = est - gradient / mu (Hermitian by construction up to rounding)
+      const double gs = -1.0 / ((double)D * D * D);
+      for (int e = tid; e < MM; e += NT) {
+        const int r = e / M, c = e % M;
+        const cplx x = X[e], y = X[c * M + r];
+        const cplx g = cmake(0.5 * gs * (x.x + y.x), 0.5 * gs * (x.y - y.y));
+        Gr[e] = g;
+        S[e] = csub(EST[e], cscale(g, 1.0 / mu));
+      }
+      Sync::sync();
+      // ---- projection ----
+      eighs += G::project_physical(S, Q, CPREV, X, V, small, make_tp, tid);
+      // ---- update direction, its PTM image, <update, gradient> ----
+      double ip = 0.0;
+      for (int e = tid; e < MM; e += NT) {
+        const cplx u = csub(S[e], EST[e]);
+        U[e] = u;
+        X[e] = u;
+        const cplx g = Gr[e];
+        ip += u.x * g.x + u.y * g.y;
+      }
+      ip = group_sum<NT, Sync>(ip, red, tid);
+      Sync::sync();
+      choi_to_pl_positions(X, tid);
+      build_T(X, pv, Tu, tid);
+      // ---- backtracking line search (tomography.py:574-585) ----
+      double alpha = 1.0;
+      double new_cost = cost(pv, dt, Te, Tu, alpha, red, tid);
+      ++cost_evals;
+      double change = gamma * alpha * ip;
+      while (new_cost > old_cost + change) {
+        alpha *= 0.5;
+        change *= 0.5;
+        new_cost = cost(pv, dt, Te, Tu, alpha, red, tid);
+        ++cost_evals;
+        if (alpha < 1e-15) break;
+      }
+      // ---- est += alpha * update ----
+      for (int e = tid; e < MM; e += NT) {
+        const cplx u = U[e];
+        cplx v = EST[e];
+        v.x = fma(alpha, u.x, v.x);
+        v.y = fma(alpha, u.y, v.y);
+        EST[e] = v;
+      }
+      for (int e = tid; e < pv.n_in * M; e += NT) Te[e] = fma(alpha, Tu[e], Te[e]);
+      __threadfence_block();
+      Sync::sync();
+      if (old_cost - new_cost < 1e-10 || outer >= 100000) break;
+      old_cost = new_cost;
+    }
+    if (tid == 0 && counters) {
+      counters[0] = outer;
+      counters[1] = cost_evals;
+      counters[2] = eighs;
+    }
+  }
+};
+
+template <int N>
+__global__ void pgdb_kernel(PgdbView pv, int64_t B, const double* __restrict__ expect,
+                            const double* __restrict__ counts, int make_tp, cplx* __restrict__ choi_out,
+                            int* __restrict__ counters, double* __restrict__ workspace) {
+  using C = PgdbCfg<N>;
+  using G = typename C::G;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int gib = threadIdx.x / C::NT, tid = threadIdx.x % C::NT;
+  cplx* X = reinterpret_cast<cplx*>(smem_raw + C::group_smem * gib);
+  cplx* V = X + G::MM;
+  double* small = reinterpret_cast<double*>(V + G::MM);
+  const int64_t group = (int64_t)blockIdx.x * C::GPB + gib;
+  const int64_t n_groups = (int64_t)gridDim.x * C::GPB;
+  double* ws = workspace + group * C::ws_doubles(pv.n_in);
+  double* red = small + G::SMALL_DOUBLES - 64;
+  for (int64_t b = group; b < B; b += n_groups) {
+    typename Pgdb<N>::Data dt;
+    dt.ex = expect + b * pv.S;
+    dt.cnt = counts + b * pv.S;
+    double tot = 0.0;
+    for (int s = tid; s < pv.S; s += C::NT) tot += dt.cnt[s];
+    tot = group_sum<C::NT, typename C::Sync>(tot, red, tid);
+    dt.inv_total = 1.0 / tot;
+    C::Sync::sync();
+    Pgdb<N>::run(pv, dt, make_tp != 0, choi_out + b * G::MM, ws, X, V, small, counters ? counters + 3 * b : nullptr,
+                 tid);
+    C::Sync::sync();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static void bloch_of_state(int code, double v[4]) {
+  static const double s2 = 1.4142135623730951, s6 = 2.449489742783178;
+  static const double tab[10][3] = {{1, 0, 0}, {-1, 0, 0}, {0, 1, 0}, {0, -1, 0}, {0, 0, 1}, {0, 0, -1},
+                                    {0, 0, 1}, {2 * s2 / 3, 0, -1.0 / 3}, {-s2 / 3, -s6 / 3, -1.0 / 3},
+                                    {-s2 / 3, s6 / 3, -1.0 / 3}};
+  v[0] = 1.0;
+  v[1] = tab[code][0];
+  v[2] = tab[code][1];
+  v[3] = tab[code][2];
+}
+
+extern "C" int qt_pgdb_plan_create(int n, int S, const int32_t* state_codes, const int32_t* pauli_idx,
+                                   const double* coeff, qt_pgdb_plan** plan_out) {
+  QT_REQUIRE(n >= 1 && n <= 3, "qt_pgdb_plan_create: n=%d out of range 1..3", n);
+  QT_REQUIRE(S >= 1 && state_codes && pauli_idx && coeff && plan_out, "qt_pgdb_plan_create: bad arguments");
+  const int M = 1 << (2 * n);
+  std::map<std::vector<int>, int> ids;
+  std::vector<std::vector<int>> states;
+  std::vector<int> sid(S);
+  for (int s = 0; s < S; ++s) {
+    std::vector<int> key(state_codes + (size_t)s * n, state_codes + (size_t)(s + 1) * n);
+    for (int q = 0; q < n; ++q)
+      QT_REQUIRE(key[q] >= 0 && key[q] <= 9, "qt_pgdb_plan_create: state code %d out of range 0..9", key[q]);
+    QT_REQUIRE(pauli_idx[s] >= 0 && pauli_idx[s] < M, "qt_pgdb_plan_create: pauli_idx[%d]=%d out of range", s,
+               pauli_idx[s]);
+    auto it = ids.find(key);
+    if (it == ids.end()) {
+      it = ids.emplace(key, (int)states.size()).first;
+      states.push_back(key);
+    }
+    sid[s] = it->second;
+  }
+  const int n_in = (int)states.size();
+  std::vector<double> svec((size_t)n_in * M);
+  for (int i = 0; i < n_in; ++i)
+    for (int j = 0; j < M; ++j) {
+      double v = 1.0;
+      for (int q = 0; q < n; ++q) {
+        double b4[4];
+        bloch_of_state(states[i][q], b4);
+        v *= b4[(j >> (2 * (n - 1 - q))) & 3];
+      }
+      svec[(size_t)i * M + j] = v;
+    }
+  int canonical = (S == n_in * (M - 1));
+  for (int s = 0; s < S && canonical; ++s)
+    canonical = (sid[s] == s / (M - 1)) && (pauli_idx[s] == s % (M - 1) + 1) && (coeff[s] == 1.0);
+  qt_pgdb_plan* p = new qt_pgdb_plan();
+  p->n = n; p->S = S; p->n_in = n_in; p->canonical = canonical;
+  p->d_state_id = nullptr; p->d_pidx = nullptr; p->d_coeff = nullptr; p->d_svec = nullptr;
+  QT_CUDA(cudaMalloc(&p->d_state_id, sizeof(int) * S));
+  QT_CUDA(cudaMalloc(&p->d_pidx, sizeof(int) * S));
+  QT_CUDA(cudaMalloc(&p->d_coeff, sizeof(double) * S));
+  QT_CUDA(cudaMalloc(&p->d_svec, sizeof(double) * svec.size()));
+  QT_CUDA(cudaMemcpy(p->d_state_id, sid.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+  QT_CUDA(cudaMemcpy(p->d_pidx, pauli_idx, sizeof(int) * S, cudaMemcpyHostToDevice));
+  QT_CUDA(cudaMemcpy(p->d_coeff, coeff, sizeof(double) * S, cudaMemcpyHostToDevice));
+  QT_CUDA(cudaMemcpy(p->d_svec, svec.data(), sizeof(double) * svec.size(), cudaMemcpyHostToDevice));
+  *plan_out = p;
+  return QT_OK;
+}
+
+extern "C" int qt_pgdb_plan_destroy(qt_pgdb_plan* p) {
+  if (!p) return QT_OK;
+  cudaFree(p->d_state_id);
+  cudaFree(p->d_pidx);
+  cudaFree(p->d_coeff);
+  cudaFree(p->d_svec);
+  delete p;
+  return QT_OK;
+}
+
+extern "C" int qt_pgdb_plan_info(const qt_pgdb_plan* p, int32_t* n_in_out, int32_t* canonical_out) {
+  QT_REQUIRE(p, "qt_pgdb_plan_info: null plan");
+  if (n_in_out) *n_in_out = p->n_in;
+  if (canonical_out) *canonical_out = p->canonical;
+  return QT_OK;
+}
+
+template <int N>
+static int64_t pgdb_grid(int64_t B) {
+  using C = PgdbCfg<N>;
+  const int per_sm = (N >= 3) ? 1 : 8;
+  return std::min<int64_t>((B + C::GPB - 1) / C::GPB, (int64_t)QT_NUM_SMS * per_sm);
+}
+
+extern "C" int64_t qt_pgdb_workspace_bytes(const qt_pgdb_plan* p, int64_t B) {
+  if (!p) return -1;
+  switch (p->n) {
+    case 1: return pgdb_grid<1>(B) * PgdbCfg<1>::GPB * PgdbCfg<1>::ws_doubles(p->n_in) * 8;
+    case 2: return pgdb_grid<2>(B) * PgdbCfg<2>::GPB * PgdbCfg<2>::ws_doubles(p->n_in) * 8;
+    default: return pgdb_grid<3>(B) * PgdbCfg<3>::GPB * PgdbCfg<3>::ws_doubles(p->n_in) * 8;
+  }
+}
+
+template <int N>
+static int launch_pgdb(const qt_pgdb_plan* p, int64_t B, const double* expect, const double* counts, int make_tp,
+                       void* choi_out, int* counters, void* ws, cudaStream_t st) {
+  using C = PgdbCfg<N>;
+  PgdbView pv{p->S, p->n_in, p->canonical, p->d_state_id, p->d_pidx, p->d_coeff, p->d_svec};
+  const size_t smem = C::group_smem * C::GPB;
+  QT_CUDA(cudaFuncSetAttribute(pgdb_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pgdb_kernel<N><<<(unsigned)pgdb_grid<N>(B), C::NT * C::GPB, smem, st>>>(pv, B, expect, counts, make_tp,
+                                                                          (cplx*)choi_out, counters, (double*)ws);
+  return qt_check_launch("pgdb_kernel");
+}
+
+extern "C" int qt_pgdb_process_batch(const qt_pgdb_plan* p, int64_t B, const double* expect, const double* counts,
+                                     int trace_preserving, void* choi_out, int32_t* counters_out, void* workspace,
+                                     int64_t workspace_bytes, void* stream) {
+  QT_REQUIRE(p, "qt_pgdb_process_batch: null plan");
+  if (B == 0) return QT_OK;
+  QT_REQUIRE(expect && counts && choi_out && workspace, "qt_pgdb_process_batch: null argument");
+  if (workspace_bytes < qt_pgdb_workspace_bytes(p, B)) {
+    qt_set_error("qt_pgdb_process_batch: workspace too small (%lld < %lld bytes)", (long long)workspace_bytes,
+                 (long long)qt_pgdb_workspace_bytes(p, B));
+    return QT_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (p->n) {
+    case 1: return launch_pgdb<1>(p, B, expect, counts, trace_preserving, choi_out, counters_out, workspace, st);
+    case 2: return launch_pgdb<2>(p, B, expect, counts, trace_preserving, choi_out, counters_out, workspace, st);
+    default: return launch_pgdb<3>(p, B, expect, counts, trace_preserving, choi_out, counters_out, workspace, st);
+  }
+}

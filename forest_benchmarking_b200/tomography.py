@@ -12,7 +12,7 @@ from typing import List, Sequence
 import numpy as np
 
 from . import _lib
-from .utils import flatten_state_results
+from .utils import flatten_process_results, flatten_state_results
 
 MAXITER = "maxiter"
 OPTIMAL = "optimal"
@@ -105,3 +105,81 @@ def iterative_mle_state_estimate(results: List, qubits: List[int], epsilon=.1, e
     if int(iters.item()) >= maxiter:
         warnings.warn('Maximum number of iterations reached before convergence.')
     return rho[0].cpu().numpy()
+
+
+# ==================================================================================================
+# PROCESS tomography
+# ==================================================================================================
+class PgdbPlan:
+    """Device-side description of one list of process-tomography settings (shared by the batch)."""
+
+    def __init__(self, n_qubits: int, state_codes, pauli_idx, coeffs=None):
+        _lib.require_cuda()
+        self.n = int(n_qubits)
+        codes = np.ascontiguousarray(state_codes, dtype=np.int32).reshape(-1, self.n)
+        idx = np.ascontiguousarray(pauli_idx, dtype=np.int32)
+        cf = np.ones(len(idx)) if coeffs is None else np.ascontiguousarray(coeffs, dtype=np.float64)
+        if len(codes) != len(idx) or len(cf) != len(idx):
+            raise ValueError("state_codes, pauli_idx and coeffs must have one entry per setting")
+        self.S = len(idx)
+        self._h = ctypes.c_void_p()
+        _lib.check(_lib.lib().qt_pgdb_plan_create(
+            self.n, self.S, codes.ctypes.data_as(ctypes.c_void_p), idx.ctypes.data_as(ctypes.c_void_p),
+            cf.ctypes.data_as(ctypes.c_void_p), ctypes.byref(self._h)), "qt_pgdb_plan_create")
+        n_in, canon = ctypes.c_int32(), ctypes.c_int32()
+        _lib.check(_lib.lib().qt_pgdb_plan_info(self._h, ctypes.byref(n_in), ctypes.byref(canon)), "qt_pgdb_plan_info")
+        self.n_in, self.canonical = n_in.value, bool(canon.value)
+
+    @classmethod
+    def complete(cls, n_qubits: int, in_basis="pauli"):
+        """The tomographically complete settings of generate_process_tomography_experiment
+        (reference tomography.py:71-123): product(input states) x all traceless Paulis."""
+        import itertools
+        codes = range(0, 6) if in_basis.lower() == "pauli" else range(6, 10)
+        k = 4 ** n_qubits - 1
+        states = np.array(list(itertools.product(codes, repeat=n_qubits)), dtype=np.int32)
+        return cls(n_qubits, np.repeat(states, k, axis=0), np.tile(np.arange(1, k + 1, dtype=np.int32), len(states)))
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                _lib.lib().qt_pgdb_plan_destroy(h)
+            except Exception:
+                pass
+
+
+def pgdb_process_estimate_batch(plan: PgdbPlan, expectations, counts, trace_preserving=True, out=None,
+                                return_counters=False, workspace=None):
+    """Batched PGDB.  expectations / counts: CUDA float64 [B, S].  Returns choi [B, 4^n, 4^n] complex128
+    (and, optionally, int32 [B, 3] counters: outer iterations, cost evaluations, eigh calls)."""
+    torch = _lib.require_cuda()
+    for t in (expectations, counts):
+        if t.dtype != torch.float64 or not t.is_cuda or t.dim() != 2 or t.shape[1] != plan.S:
+            raise ValueError(f"expectations and counts must be CUDA float64 tensors of shape [B, {plan.S}]")
+    expectations, counts = expectations.contiguous(), counts.contiguous()
+    b, m = expectations.shape[0], 4 ** plan.n
+    lib = _lib.lib()
+    if out is None:
+        out = torch.empty((b, m, m), dtype=torch.complex128, device=expectations.device)
+    counters = torch.zeros((b, 3), dtype=torch.int32, device=expectations.device)
+    nbytes = int(lib.qt_pgdb_workspace_bytes(plan._h, ctypes.c_int64(b)))
+    if workspace is None or workspace.numel() * workspace.element_size() < nbytes:
+        workspace = torch.empty((max(nbytes, 8) // 8,), dtype=torch.float64, device=expectations.device)
+    _lib.check(lib.qt_pgdb_process_batch(plan._h, ctypes.c_int64(b), _lib.ptr(expectations), _lib.ptr(counts),
+                                         ctypes.c_int(1 if trace_preserving else 0), _lib.ptr(out),
+                                         _lib.ptr(counters), _lib.ptr(workspace),
+                                         ctypes.c_int64(workspace.numel() * workspace.element_size()),
+                                         _lib.current_stream_ptr()), "qt_pgdb_process_batch")
+    return (out, counters) if return_counters else out
+
+
+def pgdb_process_estimate(results: List, qubits: List[int], trace_preserving=True) -> np.ndarray:
+    """Drop-in for reference tomography.py:542-594."""
+    torch = _lib.require_cuda()
+    codes, idx, cf, ex, cnt = flatten_process_results(results, qubits)
+    plan = PgdbPlan(len(qubits), codes, idx, cf)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    choi = pgdb_process_estimate_batch(plan, torch.from_numpy(ex[None, :]).to(dev),
+                                       torch.from_numpy(cnt[None, :]).to(dev), trace_preserving)
+    return choi[0].cpu().numpy()

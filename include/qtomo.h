@@ -86,6 +86,22 @@ int64_t qt_proj_physical_workspace_bytes(int n, int64_t B);
 int qt_proj_physical_batch(int n, int64_t B, const void* choi, void* out, int make_trace_preserving,
                            void* workspace, int64_t workspace_bytes, int32_t* eigh_calls_out, void* stream);
 
+/* ---- process tomography: pgdb_process_estimate (tomography.py:542-594) ------------------------- */
+typedef struct qt_pgdb_plan qt_pgdb_plan;
+/* One entry per result, in the order of `results`: state_codes_host[S*n] (per-qubit input-state codes,
+ * qubits[0] first), pauli_idx_host[S], coeff_host[S].  n = 1..3. */
+int qt_pgdb_plan_create(int n, int S, const int32_t* state_codes_host, const int32_t* pauli_idx_host,
+                        const double* coeff_host, qt_pgdb_plan** plan);
+int qt_pgdb_plan_destroy(qt_pgdb_plan* plan);
+/* number of distinct input states; canonical = settings are product(states) x all traceless Paulis */
+int qt_pgdb_plan_info(const qt_pgdb_plan* plan, int32_t* n_in_out, int32_t* canonical_out);
+int64_t qt_pgdb_workspace_bytes(const qt_pgdb_plan* plan, int64_t B);
+/* expect[B,S], counts[B,S] -> choi_out[B,4^n,4^n]; counters_out[B,3] (may be NULL) = outer iterations,
+ * cost evaluations, eigh calls (the trip counts of tomography.py:570, :576/:582 and project_superoperators.py:115) */
+int qt_pgdb_process_batch(const qt_pgdb_plan* plan, int64_t B, const double* expect, const double* counts,
+                          int trace_preserving, void* choi_out, int32_t* counters_out, void* workspace,
+                          int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,104 @@
+"""GPU parity: batched PGDB process tomography vs the reference goldens and the oracle."""
+import numpy as np
+import pytest
+
+from oracle import ref_numpy as orc
+from util import golden, relerr, max_relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def torch():
+    import torch
+    assert torch.cuda.is_available()
+    return torch
+
+
+def _run(torch, n, codes, pidx, ex, cnt, coeffs=None, tp=True):
+    from forest_benchmarking_b200 import tomography as tm
+    plan = tm.PgdbPlan(n, codes, pidx, coeffs)
+    choi, counters = tm.pgdb_process_estimate_batch(plan, torch.from_numpy(np.ascontiguousarray(ex)).cuda(),
+                                                    torch.from_numpy(np.ascontiguousarray(cnt)).cuda(), tp,
+                                                    return_counters=True)
+    torch.cuda.synchronize()
+    return plan, choi.cpu().numpy(), counters.cpu().numpy()
+
+
+@pytest.mark.parametrize("name", ["pgdb_1q_pauli", "pgdb_1q_sic", "pgdb_1q_pauli_tni", "pgdb_1q_pauli_mixed",
+                                  "pgdb_2q_pauli", "pgdb_2q_sic", "pgdb_2q_sic_mixed", "pgdb_3q_sic", "pgdb_3q_pauli"])
+def test_golden(torch, name):
+    g = golden(name)
+    n = int(g["n"])
+    plan, choi, counters = _run(torch, n, g["state_codes"], g["pauli_idx"], g["expectations"], g["counts"],
+                                tp=bool(g["trace_preserving"]))
+    assert plan.canonical
+    err = max_relerr(choi, g["choi_ref"])
+    print(name, "max rel err", err, "counters (outer, cost, eigh)", counters.tolist(), "ref (eigh, cost)",
+          g["counters_ref"].tolist())
+    assert err < TOL
+    # trip counts: same stopping rules; the decisions are threshold tests on rounded quantities, so allow a
+    # small slack and require most items to agree exactly
+    ref_eigh, ref_cost = g["counters_ref"][:, 0], g["counters_ref"][:, 1]
+    assert np.all(np.abs(counters[:, 2] - ref_eigh) <= np.maximum(3, 0.02 * ref_eigh))
+    # cost evaluations include the final noise-level backtracking (alpha halved until < 1e-15 when no step can
+    # improve the cost any more), whose length depends on comparisons of numbers that agree to ~1e-16
+    assert np.all(np.abs(counters[:, 1] - ref_cost) <= 15)
+
+
+def test_noncanonical_settings_and_coefficients(torch):
+    """Shuffled settings, a duplicated setting and a sign-flipped observable (coefficient -1)."""
+    rng = np.random.default_rng(8)
+    _, settings, ex, cnt = orc.synth_process_tomography(17, 2, 1, in_basis="pauli")
+    perm = rng.permutation(len(settings))
+    settings = [settings[i] for i in perm] + [settings[perm[0]]]
+    ex = np.concatenate([ex[:, perm], ex[:, perm[:1]]], axis=1)
+    cnt = np.concatenate([cnt[:, perm], cnt[:, perm[:1]] * 2], axis=1)
+    coeffs = np.ones(len(settings)); coeffs[3] = -1.0; ex[:, 3] *= -1.0
+    codes = np.array([s for s, _ in settings], dtype=np.int32)
+    pidx = np.array([k for _, k in settings], dtype=np.int32)
+    plan, choi, _ = _run(torch, 1, codes, pidx, ex, cnt, coeffs)
+    assert not plan.canonical and plan.n_in == 6
+    for b in range(2):
+        want = orc.pgdb_process_estimate(settings, coeffs, ex[b], cnt[b], 1)
+        assert relerr(choi[b], want) < TOL
+
+
+@pytest.mark.parametrize("n,basis,batch", [(1, "pauli", 64), (2, "sic", 12), (2, "pauli", 6)])
+def test_vs_oracle_batch(torch, n, basis, batch):
+    from forest_benchmarking_b200 import synthetic as sy
+    codes, pidx, ex, cnt, ptm = sy.process_tomography_batch(300 + n, batch, n, in_basis=basis)
+    plan, choi, counters = _run(torch, n, codes, pidx, ex, cnt)
+    settings = [(tuple(int(c) for c in s), int(k)) for s, k in zip(codes, pidx)]
+    picks = range(batch) if n == 1 else range(0, batch, 3)
+    for b in picks:
+        want, cn = orc.pgdb_process_estimate(settings, np.ones(len(settings)), ex[b], cnt[b], n, return_counters=True)
+        assert relerr(choi[b], want) < TOL
+        assert abs(counters[b, 0] - cn["outer"]) <= 1
+    # properties: CPTP to the Dykstra tolerance, close to the true channel
+    d = 2 ** n
+    pt = np.einsum("zijkj->zik", choi.reshape(batch, d, d, d, d))
+    assert np.abs(pt - np.eye(d)).max() < 1e-9
+    assert np.linalg.eigvalsh(choi).min() > -5e-3
+    truth = np.stack([orc.pauli_liouville2choi(p) for p in ptm])
+    assert max_relerr(choi, truth) < 0.25
+
+
+def test_dropin_signature(torch):
+    from forest_benchmarking_b200 import tomography as tm
+    from forest_benchmarking_b200.observable_estimation import (ExperimentResult, ExperimentSetting, plusX, minusX,
+                                                               plusY, minusY, plusZ, minusZ)
+    from forest_benchmarking_b200.utils import all_traceless_pauli_terms
+    qubits = [3]
+    _, settings, ex, cnt = orc.synth_process_tomography(23, 1, 1, in_basis="pauli")
+    fac = [plusX, minusX, plusY, minusY, plusZ, minusZ]
+    terms = all_traceless_pauli_terms(qubits)
+    res = [ExperimentResult(ExperimentSetting(fac[codes[0]](3), terms[k - 1]), e, int(c))
+           for (codes, k), e, c in zip(settings, ex[0], cnt[0])]
+    got = tm.pgdb_process_estimate(res, qubits)
+    want = orc.pgdb_process_estimate(settings, np.ones(len(settings)), ex[0], cnt[0], 1)
+    assert relerr(got, want) < TOL
+    got2 = tm.pgdb_process_estimate(res, qubits, trace_preserving=False)
+    want2 = orc.pgdb_process_estimate(settings, np.ones(len(settings)), ex[0], cnt[0], 1, trace_preserving=False)
+    assert relerr(got2, want2) < TOL
