@@ -195,6 +195,262 @@ __global__ void __launch_bounds__(32) mle_reg_kernel(int64_t B, int K, const int
 }
 
 // =============================================================================================
+// Quad kernel: one 2-qubit experiment per 4 lanes (8 experiments per warp), unit coefficients, vanilla MLE.
+//
+// With one experiment per thread a batch of 4096 fills only 128 warps (< 1 per SM sub-partition) and
+// every warp is latency-bound on its own dependency chains (ncu: 5 cycles per issued instruction, FP64
+// pipe 6 % busy -- profiles/r01_ncu_mle_reg_kernel_v0.md).  Splitting an experiment over the 4 lanes of a
+// quad cuts the per-warp critical path ~3x and puts a warp on ~86 % of the 592 sub-partitions.
+//
+// Lane c (= lane & 3) owns column c of rho' = M rho M.  To keep every register index static it works in
+// the frame permuted by the X-type Pauli Pi_c (row r -> r ^ c):  R_c = Pi_c rho Pi_c, M_c = Pi_c M Pi_c, so
+// that "column c" is always column 0:  v = M_c (R_c M_c[:,0]) = rho'[. ^ c, c].  Conjugation by Pi_c only
+// flips signs in the Pauli basis:  Pi_c P_j Pi_c = (-1)^{|z_j & c|} P_j,  hence
+//     Tr(P_j rho) = (-1)^{|z_j & c|} Tr(P_j R_c),     M_c = (1-eps) I + (eps/K) sum_j (-1)^{|z_j & c|} w_j P_j.
+// The likelihood ratios of the 16 Pauli slots are split 4 per lane (slot j = 4c + i) and all-gathered with
+// 32 shuffles; the new state is all-gathered with 18 (Hermitian: R_c[a][b] = shfl_xor(v[a ^ b], b)).
+// =============================================================================================
+__device__ __forceinline__ double flip_sign(double x, int mask) {
+  return __hiloint2double(__double2hiint(x) ^ mask, __double2loint(x));
+}
+__device__ __forceinline__ double shfl_xor_d(double x, int m) { return __shfl_xor_sync(0xffffffffu, x, m); }
+// 1/d to ~1 ulp: MUFU.RCP64H seed (20+ bits) + two Newton steps = 1 MUFU + 4 DFMA.  An IEEE division costs
+// ~133 issue cycles per warp on B200 (profiles/r01_ubench_fp64.txt) and was 46 % of the iteration.
+__device__ __forceinline__ double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+}
+
+__global__ void __launch_bounds__(32) mle_quad_kernel(int64_t B, int K, const int* __restrict__ slot_ptr,
+                                                      const int* __restrict__ member_col,
+                                                      const double* __restrict__ expect, double eps, double tol,
+                                                      int maxiter, cplx* __restrict__ rho_out,
+                                                      int* __restrict__ iters_out) {
+  constexpr int N = 2, D = 4, S = 16;
+  constexpr double TINY = 2.2250738585072014e-308;
+  const int lane = threadIdx.x;
+  const int c = lane & 3, qbase = lane & ~3;
+  const int64_t b = (int64_t)blockIdx.x * 8 + (lane >> 2);
+  const bool valid = b < B;
+
+  // this lane's 4 Pauli slots j = 4c + i: aggregated (1 +- m_k)/2 and the frame sign (-1)^{|z_j & c|}
+  double fp[4], fm[4];
+  int sgm[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int j = 4 * c + i;
+    double ap = 0.0, am = 0.0;
+    if (valid) {
+      for (int m = slot_ptr[j]; m < slot_ptr[j + 1]; ++m) {
+        const double e = expect[b * K + member_col[m]];
+        ap += 0.5 * (1.0 + e);
+        am += 0.5 * (1.0 - e);
+      }
+    }
+    fp[i] = ap;
+    fm[i] = am;
+    sgm[i] = (__popc(pauli_zmask(j, N) & c) & 1) ? (int)0x80000000 : 0;
+  }
+  const int m_z1 = (c & 1) ? (int)0x80000000 : 0, m_z2 = (c & 2) ? (int)0x80000000 : 0;
+  const double sc = 0.5 * eps / (double)K;
+  const double tol2 = tol * tol;
+
+  Herm<D> R;
+#pragma unroll
+  for (int r = 0; r < D; ++r)
+#pragma unroll
+    for (int k = 0; k < D; ++k) R.h[r][k] = (r == k) ? 1.0 / D : 0.0;
+
+  int it = 1;
+  bool done = !valid;
+  while (true) {
+    if (!done && it >= maxiter) {  // tomography.py:244 -- the state as it stands is the answer
+      cplx* out = rho_out + b * (D * D) + c * D;
+      out[c] = cmake(R.h[0][0], 0.0);
+#pragma unroll
+      for (int k = 1; k < D; ++k) out[k ^ c] = cmake(R.re(0, k), R.im(0, k));
+      if (c == 0) iters_out[b] = it;
+      done = true;
+    }
+    if (__all_sync(0xffffffffu, done)) break;
+
+    // ---- th[j] = Tr(P_j R_c) / 2 for all 16 Paulis (static butterfly on the Hermitian-packed state) ----
+    double th[S];
+    {
+      const double s01 = R.h[0][0] + R.h[1][1], m01 = R.h[0][0] - R.h[1][1];
+      const double s23 = R.h[2][2] + R.h[3][3], m23 = R.h[2][2] - R.h[3][3];
+      th[pauli_from_masks(0, 0, N)] = 0.5 * (s01 + s23);
+      th[pauli_from_masks(0, 1, N)] = 0.5 * (m01 + m23);
+      th[pauli_from_masks(0, 2, N)] = 0.5 * (s01 - s23);
+      th[pauli_from_masks(0, 3, N)] = 0.5 * (m01 - m23);
+    }
+#pragma unroll
+    for (int x = 1; x < D; ++x) {
+#pragma unroll
+      for (int z = 0; z < D; ++z) {
+        const int ph = popc_c(x & z) & 3;
+        const bool odd = ph & 1;
+        double acc = 0.0;
+        bool first = true;
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+          if (a < (a ^ x)) {
+            // pair (a, a^x): even phase -> +-2 Re, odd phase -> -+2 Im of element (a, a^x)
+            const bool neg = ((popc_c(z & a) & 1) != 0) != (odd ? (ph == 1) : (ph == 2));
+            const double v = odd ? R.im(a, a ^ x) : R.re(a, a ^ x);
+            if (first) acc = neg ? -v : v;
+            else acc = neg ? acc - v : acc + v;
+            first = false;
+          }
+        }
+        th[pauli_from_masks(x, z, N)] = acc;
+      }
+    }
+    // ---- this lane's 4 slots: likelihood ratios with ONE reciprocal per slot ----
+    double w[4], w0 = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double lo = (c & 1) ? th[4 + i] : th[i];
+      const double hi = (c & 1) ? th[12 + i] : th[8 + i];
+      const double tt = flip_sign((c & 2) ? hi : lo, sgm[i]);  // true-frame Tr(P_j rho)/2
+      const double pp = (0.5 + tt) + TINY, pm = (0.5 - tt) + TINY;
+      const double inv = fast_rcp(pp * pm);
+      const double ap = fp[i] * pm * inv, am = fm[i] * pp * inv;
+      w0 += ap + am;
+      w[i] = sc * (ap - am);
+    }
+    w0 += shfl_xor_d(w0, 1);
+    w0 += shfl_xor_d(w0, 2);
+    // ---- all-gather the 16 coefficients, move them to this lane's frame ----
+    double wf[S];
+#pragma unroll
+    for (int src = 0; src < 4; ++src)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int j = 4 * src + i;
+        const int z = pauli_zmask(j, N);
+        const int mask = ((z & 1) ? m_z1 : 0) ^ ((z & 2) ? m_z2 : 0);
+        const double v = __shfl_sync(0xffffffffu, w[i], qbase + src);
+        wf[j] = (z == 0) ? v : flip_sign(v, mask);
+      }
+    wf[0] = fma(sc, w0, wf[0]);
+    // ---- M_c = (1 - eps) I + sum_j wf_j P_j  (Hermitian packed) ----
+    Herm<D> M;
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int k = r; k < D; ++k) {
+        const int x = r ^ k;
+        double sre = 0.0, sim = 0.0;
+        bool fre = true, fim = true;
+#pragma unroll
+        for (int z = 0; z < D; ++z) {
+          const double wj = wf[pauli_from_masks(x, z, N)];
+          const int ph = popc_c(x & z) & 3;
+          const bool neg = ((popc_c(z & k) & 1) != 0) != (ph >= 2);  // P_j[r, k] = i^ph * sgn
+          if ((ph & 1) == 0) {
+            sre = fre ? (neg ? -wj : wj) : (neg ? sre - wj : sre + wj);
+            fre = false;
+          } else {
+            sim = fim ? (neg ? -wj : wj) : (neg ? sim - wj : sim + wj);
+            fim = false;
+          }
+        }
+        if (r == k) {
+          M.h[r][r] = (1.0 - eps) + sre;
+        } else {
+          M.h[r][k] = sre;
+          M.h[k][r] = sim;
+        }
+      }
+    // ---- u = R_c M_c[:, 0],  v = M_c u  (column 0 of M_c R_c M_c) ----
+    double ur[D], ui[D], vr[D], vi[D];
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      double ar = 0.0, ai = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const double pr = R.re(r, k), pi = R.im(r, k), mr = M.re(k, 0), mi = M.im(k, 0);
+        ar = fma(pr, mr, ar);
+        if (k != 0) ai = fma(pr, mi, ai);
+        if (r != k) {
+          if (k != 0) ar = fma(-pi, mi, ar);
+          ai = fma(pi, mr, ai);
+        }
+      }
+      ur[r] = ar;
+      ui[r] = ai;
+    }
+#pragma unroll
+    for (int r = 0; r < D; ++r) {
+      double ar = 0.0, ai = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const double mr = M.re(r, k), mi = M.im(r, k);
+        ar = fma(mr, ur[k], ar);
+        ai = fma(mr, ui[k], ai);
+        if (r != k) {
+          ar = fma(-mi, ui[k], ar);
+          ai = fma(mi, ur[k], ai);
+        }
+      }
+      vr[r] = ar;
+      vi[r] = ai;
+    }
+    // ---- all-gather the new (unnormalised) state in this lane's frame ----
+    Herm<D> nw;
+    nw.h[0][0] = vr[0];
+#pragma unroll
+    for (int k = 1; k < D; ++k) {  // element (0, k) = conj(v[k])
+      nw.h[0][k] = vr[k];
+      nw.h[k][0] = -vi[k];
+      nw.h[k][k] = shfl_xor_d(vr[0], k);
+    }
+#pragma unroll
+    for (int a = 1; a < D; ++a)
+#pragma unroll
+      for (int k = a + 1; k < D; ++k) {  // element (a, k) = v[a ^ k] of lane c ^ k
+        nw.h[a][k] = shfl_xor_d(vr[a ^ k], k);
+        nw.h[k][a] = shfl_xor_d(vi[a ^ k], k);
+      }
+    // trace and ||rho' - rho||_F^2 summed pairwise: invariant under the lanes' index relabelling
+    const double tr = (nw.h[0][0] + nw.h[1][1]) + (nw.h[2][2] + nw.h[3][3]);
+    const double inv = fast_rcp(tr);
+    double dd[D], dx[D];
+#pragma unroll
+    for (int x = 0; x < D; ++x) dx[x] = 0.0;
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        const double v = nw.h[r][k] * inv;
+        const double dlt = v - R.h[r][k];
+        if (r == k) dd[r] = dlt * dlt;
+        else dx[r ^ k] = fma(dlt, dlt, dx[r ^ k]);
+        R.h[r][k] = v;
+      }
+    const double diff = ((dd[0] + dd[1]) + (dd[2] + dd[3])) + 2.0 * ((dx[1] + dx[2]) + dx[3]);
+    const int conv = __shfl_sync(0xffffffffu, (int)(diff < tol2), qbase);
+    if (!done) {
+      if (conv) {
+        cplx* out = rho_out + b * (D * D) + c * D;
+        out[c] = cmake(R.h[0][0], 0.0);
+#pragma unroll
+        for (int k = 1; k < D; ++k) out[k ^ c] = cmake(R.re(0, k), R.im(0, k));
+        if (c == 0) iters_out[b] = it;
+        done = true;
+      } else {
+        ++it;
+      }
+    }
+  }
+}
+
+// =============================================================================================
 // Warp kernel: one experiment per warp, any n <= 5, arbitrary observable lists / coefficients,
 // vanilla + maximum-entropy + hedged variants (tomography.py:252-260).  State in shared memory.
 // =============================================================================================
@@ -560,6 +816,14 @@ extern "C" int qt_mle_state_batch(const qt_mle_plan* p, int64_t B, const double*
   const bool reg_ok = p->n <= 2 && p->unit_coeff && !variants;
   QT_REQUIRE(kernel_variant != QT_MLE_KERNEL_REGISTER || reg_ok,
              "qt_mle_state_batch: register kernel needs n<=2, unit coefficients, vanilla MLE");
+  QT_REQUIRE(kernel_variant != QT_MLE_KERNEL_QUAD || (reg_ok && p->n == 2),
+             "qt_mle_state_batch: quad kernel needs n==2, unit coefficients, vanilla MLE");
+  if (reg_ok && p->n == 2 && (kernel_variant == QT_MLE_KERNEL_QUAD || kernel_variant == QT_MLE_KERNEL_AUTO)) {
+    const unsigned blocks = (unsigned)((B + 7) / 8);
+    mle_quad_kernel<<<blocks, 32, 0, st>>>(B, p->K, p->d_slot_ptr, p->d_member_col, expect, epsilon, tol, maxiter, out,
+                                           iters_out);
+    return qt_check_launch("mle_quad_kernel");
+  }
   if (reg_ok && kernel_variant != QT_MLE_KERNEL_WARP) {
     const unsigned blocks = (unsigned)((B + 31) / 32);
     if (p->n == 1)

@@ -18,7 +18,7 @@ MAXITER = "maxiter"
 OPTIMAL = "optimal"
 FRO = "fro"
 
-KERNEL_AUTO, KERNEL_REGISTER, KERNEL_WARP = 0, 1, 2
+KERNEL_AUTO, KERNEL_REGISTER, KERNEL_WARP, KERNEL_QUAD = 0, 1, 2, 3
 
 
 class MlePlan:

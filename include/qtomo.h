@@ -44,6 +44,7 @@ int qt_mle_plan_destroy(qt_mle_plan* plan);
 #define QT_MLE_KERNEL_AUTO 0
 #define QT_MLE_KERNEL_REGISTER 1 /* one experiment per thread, n<=2, unit coefficients, vanilla MLE */
 #define QT_MLE_KERNEL_WARP 2     /* one experiment per warp, any n<=5, all variants */
+#define QT_MLE_KERNEL_QUAD 3     /* one experiment per 4 lanes, n==2, unit coefficients, vanilla MLE (AUTO picks it) */
 /* expect[B,K], counts[B,K] (may be NULL unless beta>0) -> rho_out[B,d,d] complex, iters_out[B]
  * iters_out = the reference's loop counter at exit (== maxiter when the cap was hit, tomography.py:244) */
 int qt_mle_state_batch(const qt_mle_plan* plan, int64_t B, const double* expect, const double* counts,

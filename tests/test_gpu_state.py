@@ -29,7 +29,7 @@ def _run_mle(torch, n, pidx, ex, cnt=None, coeffs=None, kernel=0, **kw):
 
 @pytest.mark.parametrize("name", ["mle_1q", "mle_2q", "mle_2q_tol1e-4", "mle_2q_maxiter200", "mle_3q_tol1e-5",
                                   "mle_2q_maxent", "mle_2q_hedged"])
-@pytest.mark.parametrize("kernel", [1, 2])
+@pytest.mark.parametrize("kernel", [1, 2, 3])
 def test_mle_golden(torch, name, kernel):
     g = golden(name)
     kw = eval(str(g["kwargs"]))
@@ -37,6 +37,8 @@ def test_mle_golden(torch, name, kernel):
     variants = bool(kw.get("entropy_penalty")) or bool(kw.get("beta"))
     if kernel == 1 and (n > 2 or variants):
         pytest.skip("register kernel: n<=2 vanilla only")
+    if kernel == 3 and (n != 2 or variants):
+        pytest.skip("quad kernel: n==2 vanilla only")
     rho, iters = _run_mle(torch, n, g["pauli_idx"], g["expectations"], g["counts"], kernel=kernel, **kw)
     assert max_relerr(rho, g["rho_ref"]) < TOL
     # iteration counters: identical stopping rule; allow +-1 only where ||drho|| sits within rounding of tol
@@ -45,7 +47,7 @@ def test_mle_golden(torch, name, kernel):
     assert np.all(np.abs(iters - g["iters_ref"]) <= 2)
 
 
-@pytest.mark.parametrize("n,kernel", [(1, 1), (1, 2), (2, 1), (2, 2), (3, 2)])
+@pytest.mark.parametrize("n,kernel", [(1, 1), (1, 2), (2, 1), (2, 2), (2, 3), (3, 2)])
 def test_mle_vs_oracle_batch(torch, n, kernel):
     _, pidx, ex, cnt = orc.synth_state_tomography(500 + n, 40, n)
     kw = dict(tol=1e-6, maxiter=3000)
@@ -57,6 +59,26 @@ def test_mle_vs_oracle_batch(torch, n, kernel):
     assert np.allclose(rho, rho.conj().transpose(0, 2, 1), atol=1e-13)
     assert np.allclose(np.trace(rho, axis1=1, axis2=2), 1, atol=1e-12)
     assert np.linalg.eigvalsh(rho).min() > -1e-12
+
+
+def test_mle_quad_kernel_ragged_batch_and_full_size(torch):
+    """quad kernel (4 lanes per experiment): batch sizes that do not fill a warp; full BASELINE batch vs the
+    register kernel (independent code path) and the size-independent properties."""
+    for batch in (1, 5, 13):
+        _, pidx, ex, cnt = orc.synth_state_tomography(700 + batch, batch, 2)
+        kw = dict(tol=1e-7, maxiter=1500)
+        rho, iters = _run_mle(torch, 2, pidx, ex, kernel=3, **kw)
+        want, witers = orc.mle_state_estimate_batch(pidx, np.ones(15), ex, 2, **kw)
+        assert max_relerr(rho, want) < TOL and np.all(np.abs(iters - witers) <= 2)
+    from forest_benchmarking_b200 import synthetic as sy
+    pidx, ex, _, _ = sy.state_tomography_batch(2002, 4096, 2)
+    rho3, it3 = _run_mle(torch, 2, pidx, ex, kernel=3)
+    rho1, it1 = _run_mle(torch, 2, pidx, ex, kernel=1)
+    assert max_relerr(rho3, rho1) < TOL
+    assert np.mean(it3 != it1) < 0.02 and np.all(np.abs(it3 - it1) <= 3)
+    assert np.allclose(rho3, rho3.conj().transpose(0, 2, 1), atol=1e-13)
+    assert np.allclose(np.trace(rho3, axis1=1, axis2=2), 1, atol=1e-12)
+    assert np.linalg.eigvalsh(rho3).min() > -1e-12
 
 
 def test_mle_4q_and_5q_warp_kernel(torch):
@@ -84,9 +106,10 @@ def test_mle_general_observable_lists(torch):
     coeffs1 = np.ones(len(pidx))
     rho1, _ = _run_mle(torch, 2, pidx, ex, None, coeffs=coeffs1, kernel=1, **kw)
     rho2, _ = _run_mle(torch, 2, pidx, ex, None, coeffs=coeffs1, kernel=2, **kw)
+    rho3, _ = _run_mle(torch, 2, pidx, ex, None, coeffs=coeffs1, kernel=3, **kw)
     for b in range(5):
         want, _ = orc.mle_state_estimate(pidx, coeffs1, ex[b], np.full(len(pidx), 50.), 2, **kw)
-        assert relerr(rho1[b], want) < TOL and relerr(rho2[b], want) < TOL
+        assert relerr(rho1[b], want) < TOL and relerr(rho2[b], want) < TOL and relerr(rho3[b], want) < TOL
 
 
 def test_mle_dropin_signature_and_errors(torch):
