@@ -6,13 +6,18 @@
 //   proj TNI  :37-59                                           C - kron((Tr_out C - clamp_le1(Tr_out C))/d, I)
 //   physical  :87-144   Dykstra alternating projections with the Birgin-Raydan stopping rule
 //
-// One Choi matrix (m = 4^n) is one GROUP's work: a warp for n <= 2, a 256-thread block for n = 3.
-// The eigensolver operands X, V live in shared memory; the Dykstra state (S = last_state, Q =
-// old_CP_change, CPREV = last_CP_projection) lives behind plain pointers (global/L2 or shared).
+// One Choi matrix (m = 4^n) is one GROUP's work: a warp for n <= 2, a 512-thread block for n = 3.
+// The eigensolver operands X, V and the basis-change temporary T live in shared memory with a padded
+// leading dimension LD; the Dykstra state (S = last_state, Q = old_CP_change, CPREV = last_CP_projection)
+// lives behind plain dense pointers (global/L2).
 // Structure used: both the TP and TNI corrections are -kron(E, I_d) with a d x d matrix E, so
 // old_TP_change is carried as E (d^2 numbers) and
 //   ||dTP||^2 = d ||E_new - E||_F^2,   <old_TP, S_new - S> = -sum conj(E) (Tr_out S_new - Tr_out S),
 //   new_CP_change - old_CP_change = CP - S   (so ||dCP||^2 = ||CP - S||_F^2).
+// Warm start: consecutive CP-projection inputs differ by a small kron-structured term
+// (pre_CP_{k+1} = pre_CP_k + kron(E_{k-1} - E_k, I)), so every eigendecomposition after the first starts
+// from the previous eigenbasis: A' = V^dagger A V (two 64^3 products) leaves ~1e-3 of the Frobenius mass
+// off the diagonal and Jacobi needs 2-3 sweeps instead of 9-10.
 #pragma once
 #include "qt_common.cuh"
 #include "qt_eigh.cuh"
@@ -21,59 +26,63 @@ template <int N, int NT, class Sync>
 struct ChoiGroup {
   static constexpr int D = 1 << N;
   static constexpr int M = D * D;
-  static constexpr int MM = M * M;
-  static constexpr int TS = (M >= 64) ? 4 : (M >= 16 ? 2 : 1);  // register tile of the recomposition
+  static constexpr int MM = M * M;                      // dense element count (global buffers)
+  static constexpr int LD = (M >= 16) ? M + 1 : M;      // padded leading dimension (shared buffers)
+  static constexpr int MP = M * LD;                     // padded element count
+  static constexpr int TR = (M >= 16) ? 2 : 1, TC = (M >= 16) ? 4 : 1;  // register tile of the recomposition
   // small shared scratch (doubles): ev[M] | jacobi scratch | E[2*D*D] | En[2*D*D] | ptS[2*D*D] | ptC[2*D*D] |
   //                                 small eigh: P[2*D*D] W[2*D*D] pev[D] + jacobi scratch<D> | red2[64]
   static constexpr int SMALL_DOUBLES = M + JacobiScratch<M>::doubles + 12 * D * D + D + JacobiScratch<D>::doubles + 64;
+  static constexpr size_t group_smem = (sizeof(cplx) * 3 * MP + sizeof(double) * SMALL_DOUBLES + 15) / 16 * 16;
 
-  // OUT (shared, M x M) = V max(ev,0) V^dagger, or PRE + V max(-ev,0) V^dagger when fewer negatives.
-  // PRE(e) is a callable returning the Hermitian matrix that was decomposed.
+  static __device__ __forceinline__ int sidx(int e) { return (e / M) * LD + e % M; }
+
+  // OUT (shared, padded) = V max(ev,0) V^dagger, or PRE + V max(-ev,0) V^dagger when fewer negatives.
+  // pre(r, c) is a callable returning the Hermitian matrix that was decomposed.
   template <class PreFn>
   static __device__ void recompose_psd(cplx* OUT, const cplx* V, const double* ev, PreFn pre, int tid) {
     int npos = 0;
     for (int k = 0; k < M; ++k) npos += (ev[k] > 0.0) ? 1 : 0;
     const bool use_pos = npos <= M / 2;
-    constexpr int T = M / TS;
-    for (int t = tid; t < T * T; t += NT) {
-      const int r0 = (t / T) * TS, c0 = (t % T) * TS;
-      cplx acc[TS][TS];
+    constexpr int NR = M / TR, NC = M / TC;
+    for (int t = tid; t < NR * NC; t += NT) {
+      const int tr = t / NC, tc = t % NC;
+      cplx acc[TR][TC];
 #pragma unroll
-      for (int i = 0; i < TS; ++i)
+      for (int i = 0; i < TR; ++i)
 #pragma unroll
-        for (int j = 0; j < TS; ++j) acc[i][j] = cmake(0.0, 0.0);
+        for (int j = 0; j < TC; ++j) acc[i][j] = cmake(0.0, 0.0);
       for (int k = 0; k < M; ++k) {
         const double lam = ev[k];
         const double w = use_pos ? fmax(lam, 0.0) : fmax(-lam, 0.0);
         if (w == 0.0) continue;
-        cplx vr[TS], vc[TS];
+        cplx vr[TR], vc[TC];
 #pragma unroll
-        for (int i = 0; i < TS; ++i) {
-          vr[i] = cscale(V[(r0 + i) * M + k], w);
-          vc[i] = V[(c0 + i) * M + k];
-        }
+        for (int i = 0; i < TR; ++i) vr[i] = cscale(V[(tr + i * NR) * LD + k], w);
 #pragma unroll
-        for (int i = 0; i < TS; ++i)
+        for (int j = 0; j < TC; ++j) vc[j] = V[(tc + j * NC) * LD + k];
 #pragma unroll
-          for (int j = 0; j < TS; ++j) cfma_conj(acc[i][j], vr[i], vc[j]);
+        for (int i = 0; i < TR; ++i)
+#pragma unroll
+          for (int j = 0; j < TC; ++j) cfma_conj(acc[i][j], vr[i], vc[j]);
       }
 #pragma unroll
-      for (int i = 0; i < TS; ++i)
+      for (int i = 0; i < TR; ++i)
 #pragma unroll
-        for (int j = 0; j < TS; ++j) {
-          const int e = (r0 + i) * M + c0 + j;
-          OUT[e] = use_pos ? acc[i][j] : cadd(pre(e), acc[i][j]);
+        for (int j = 0; j < TC; ++j) {
+          const int r = tr + i * NR, c = tc + j * NC;
+          OUT[r * LD + c] = use_pos ? acc[i][j] : cadd(pre(r, c), acc[i][j]);
         }
     }
     Sync::sync();
   }
 
-  // partial trace over the output factor: pt[a*D + c] = sum_b C[(a*D+b), (c*D+b)]
-  static __device__ void partial_trace_out(const cplx* C, cplx* pt, int tid) {
+  // partial trace over the output factor: pt[a*D + c] = sum_b C[(a*D+b), (c*D+b)]; C has leading dimension ldc
+  static __device__ void partial_trace_out(const cplx* C, int ldc, cplx* pt, int tid) {
     for (int e = tid; e < D * D; e += NT) {
       const int a = e / D, c = e % D;
       cplx s = cmake(0.0, 0.0);
-      for (int b = 0; b < D; ++b) s = cadd(s, C[(a * D + b) * M + c * D + b]);
+      for (int b = 0; b < D; ++b) s = cadd(s, C[(a * D + b) * ldc + c * D + b]);
       pt[e] = s;
     }
     Sync::sync();
@@ -111,11 +120,40 @@ struct ChoiGroup {
     Sync::sync();
   }
 
+  // Eigendecomposition of the Hermitian matrix held in X (padded, shared).  With a valid previous eigenbasis
+  // in V the matrix is first rotated into it (X <- V^dagger X V through T) and Jacobi continues from V.
+  static __device__ void eigh_warm(cplx* X, cplx* V, cplx* T, double* ev, double* jscr, bool& v_valid, int tid) {
+    if (v_valid) {
+      smem_matmul<M, NT, LD, 0>(T, X, V, tid);
+      Sync::sync();
+      smem_matmul<M, NT, LD, 1>(X, V, T, tid);
+      Sync::sync();
+      // restore exact Hermiticity (the two products round differently above and below the diagonal)
+      for (int e = tid; e < MM; e += NT) {
+        const int r = e / M, c = e % M;
+        if (r < c) {
+          const cplx a = X[r * LD + c], b = X[c * LD + r];
+          const cplx h = cmake(0.5 * (a.x + b.x), 0.5 * (a.y - b.y));
+          X[r * LD + c] = h;
+          X[c * LD + r] = cconj(h);
+        } else if (r == c) {
+          X[r * LD + r].y = 0.0;
+        }
+      }
+      Sync::sync();
+      jacobi_eigh<M, NT, Sync, true, LD>(X, V, ev, jscr, tid, /*init_v=*/false);
+    } else {
+      jacobi_eigh<M, NT, Sync, true, LD>(X, V, ev, jscr, tid, /*init_v=*/true);
+      v_valid = true;
+    }
+  }
+
   // Dykstra.  On entry S holds the (Hermitian) matrix to project; on exit S holds the projection.
-  // X, V: shared M x M work matrices; Q, CPREV: M x M state buffers (any address space); small: shared
-  // scratch of SMALL_DOUBLES doubles (16-byte aligned).  Returns the number of CP projections (eigh calls).
-  static __device__ int project_physical(cplx* S, cplx* Q, cplx* CPREV, cplx* X, cplx* V, double* small,
-                                         bool make_tp, int tid, int max_iter = 10000) {
+  // X, V, T: shared padded work matrices; S, Q, CPREV: dense M x M state buffers (any address space); small:
+  // shared scratch of SMALL_DOUBLES doubles (16-byte aligned).  v_valid: V holds an eigenbasis to warm-start
+  // from (kept up to date here).  Returns the number of CP projections (eigh calls).
+  static __device__ int project_physical(cplx* S, cplx* Q, cplx* CPREV, cplx* X, cplx* V, cplx* T, double* small,
+                                         bool make_tp, int tid, bool& v_valid, int max_iter = 10000) {
     double* ev = small;
     double* jscr = ev + M;
     cplx* E = reinterpret_cast<cplx*>(jscr + JacobiScratch<M>::doubles);
@@ -137,24 +175,24 @@ struct ChoiGroup {
     int n_eigh = 0;
     while (true) {
       // X = pre_CP = S - Q
-      for (int e = tid; e < MM; e += NT) X[e] = csub(S[e], Q[e]);
+      for (int e = tid; e < MM; e += NT) X[sidx(e)] = csub(S[e], Q[e]);
       Sync::sync();
-      jacobi_eigh<M, NT, Sync, true>(X, V, ev, jscr, tid);
+      eigh_warm(X, V, T, ev, jscr, v_valid, tid);
       ++n_eigh;
-      recompose_psd(X, V, ev, [&](int e) { return csub(S[e], Q[e]); }, tid);  // X = CP projection
+      recompose_psd(X, V, ev, [&](int r, int c) { return csub(S[r * M + c], Q[r * M + c]); }, tid);  // X = CP
       // criterion pieces + state update of Q, CPREV
       double n_dcp = 0.0;
       cplx ip_q = cmake(0.0, 0.0);
       for (int e = tid; e < MM; e += NT) {
-        const cplx cp = X[e], s = S[e], q = Q[e], cprev = CPREV[e];
+        const cplx cp = X[sidx(e)], s = S[e], q = Q[e], cprev = CPREV[e];
         const cplx d1 = csub(cp, s);
         n_dcp += cabs2(d1);
         cfma_conj(ip_q, csub(cp, cprev), q);  // conj(q) * (cp - cprev)
         Q[e] = cadd(d1, q);                   // new_CP_change = CP - pre_CP = CP - S + Q
         CPREV[e] = cp;
       }
-      partial_trace_out(S, ptS, tid);
-      partial_trace_out(X, ptC, tid);
+      partial_trace_out(S, M, ptS, tid);
+      partial_trace_out(X, LD, ptC, tid);
       // pre_TP = CP - old_TP_change = CP + kron(E, I):  Tr_out(pre_TP) = ptC + d E
       for (int e = tid; e < D * D; e += NT) ptC[e] = cadd(ptC[e], cscale(E[e], (double)D));
       Sync::sync();
@@ -162,7 +200,7 @@ struct ChoiGroup {
       // new_state = pre_TP - kron(En, I) = CP + kron(E - En, I)
       for (int e = tid; e < MM; e += NT) {
         const int r = e / M, c = e % M;
-        cplx v = X[e];
+        cplx v = X[r * LD + c];
         if ((r % D) == (c % D)) {
           const int a = r / D, cc = c / D;
           v = cadd(v, csub(E[a * D + cc], En[a * D + cc]));

@@ -74,6 +74,17 @@ __host__ __device__ __forceinline__ cplx cmul_ipow(cplx a, int k) {
   }
 }
 
+// 1/d to ~1 ulp: MUFU.RCP64H seed (20+ bits) + two Newton steps = 1 MUFU + 4 DFMA.  An IEEE division costs
+// ~133 issue cycles per warp on B200 (profiles/r01_ubench_fp64.txt).  d must be a normal, finite number.
+__device__ __forceinline__ double fast_rcp(double d) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-d, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-d, r, 1.0);
+  return fma(r, e, r);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Pauli bookkeeping.  Canonical index = base-4 number, digits I=0 X=1 Y=2 Z=3, first qubit most
 // significant (reference utils.py:146-156, 398-409).  A Pauli is i^{|x&z|} X^x Z^z with n-bit masks

@@ -1,11 +1,19 @@
 // Batched complex-Hermitian eigensolver: parallel cyclic two-sided Jacobi, matrix resident in shared
-// memory, one matrix per warp (M <= 32) or per thread block (M = 64 ...).
+// memory, one matrix per warp (M <= 32) or per thread block (M = 64).
 //
 // Stands in for the LAPACK calls the reference makes through scipy.linalg.eigh / np.linalg.eigh
 // (operator_tools/project_superoperators.py:31, calculational.py:88, superoperator_transformations.py:334).
 // Jacobi is used because every rotation of a round-robin step is independent (M/2 per step), the whole
-// matrix lives on-chip, and its results (V max(L,0) V^dagger, sum sqrt(l)) are gauge-independent, so
-// they agree with LAPACK to ~1e-14.
+// matrix lives on-chip, it can be WARM-STARTED from a previous eigenbasis (the Dykstra / PGD loops
+// decompose a slowly moving matrix hundreds of times), and its results (V max(L,0) V^dagger, sum sqrt(l))
+// are gauge-independent, so they agree with LAPACK to ~1e-14.
+//
+// Step pipeline (one round-robin step = M/2 disjoint rotations):
+//     A <- J^dagger A J   (all threads)                                   | sync
+//     rotation parameters of step+1 (warp 0)  ||  V <- V J (other warps)  | sync
+// so the latency-bound parameter phase (rsqrt / reciprocal chains) hides behind the V update.
+// Matrices may have a padded leading dimension LD (M + 1 for M >= 16): column accesses of the
+// recomposition / basis-change products are then bank-conflict free.
 #pragma once
 #include "qt_common.cuh"
 
@@ -26,26 +34,23 @@ __device__ __forceinline__ void rr_pair(int M, int s, int i, int& p, int& q) {
 }
 
 // Rotation J = [[c, s],[-conj(s), c]] (c real) that diagonalises [[alpha, beta],[conj(beta), gamma]].
-__device__ __forceinline__ void jacobi_rotation(double alpha, double gamma, cplx beta, double& c, cplx& s,
-                                                double& alpha_new, double& gamma_new) {
+// Square roots and the division go through MUFU seeds + Newton steps (rsqrt / fast_rcp): a correctly
+// rounded DDIV / DSQRT costs ~130 issue cycles per warp on B200 (profiles/r01_ubench_fp64.txt).
+__device__ __forceinline__ void jacobi_rotation(double alpha, double gamma, cplx beta, double& c, cplx& s) {
   const double ab2 = cabs2(beta);
   const double scale = fabs(alpha) + fabs(gamma);
   if (ab2 <= 1e-36 * scale * scale || ab2 == 0.0) {
     c = 1.0;
     s = cmake(0.0, 0.0);
-    alpha_new = alpha;
-    gamma_new = gamma;
     return;
   }
-  const double ab = sqrt(ab2);
-  const double tau = (gamma - alpha) / (2.0 * ab);
-  const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-  c = rsqrt(1.0 + t * t);
-  const double sn = t * c;
-  const double inv = sn / ab;
-  s = cmake(beta.x * inv, beta.y * inv);  // s * e^{i phi}
-  alpha_new = alpha - t * ab;
-  gamma_new = gamma + t * ab;
+  const double rab = rsqrt(ab2);  // 1 / |beta|
+  const double tau = 0.5 * (gamma - alpha) * rab;
+  const double q = fma(tau, tau, 1.0);
+  const double t = (tau >= 0.0 ? 1.0 : -1.0) * fast_rcp(fabs(tau) + q * rsqrt(q));
+  c = rsqrt(fma(t, t, 1.0));
+  const double inv = t * c * rab;
+  s = cmake(beta.x * inv, beta.y * inv);  // sin * e^{i phi}
 }
 
 struct SyncWarp {
@@ -69,27 +74,28 @@ __device__ __forceinline__ double group_sum(double v, double* red, int tid) {
   return tot;
 }
 
-// Scratch layout (doubles, 16-byte aligned base): rs[M/2] (complex) | rc[M/2] | red[32]
+// Scratch layout (doubles, 16-byte aligned base): rs[2][M/2] (complex) | rc[2][M/2] | red[32]
 template <int M>
 struct JacobiScratch {
-  static constexpr int doubles = M / 2 + M + 32;
+  static constexpr int doubles = 3 * M + 32;
 };
 
-// A: M x M Hermitian in shared memory (row-major, leading dimension M), overwritten (diagonal = eigenvalues).
-// V: M x M in shared memory; on exit column k is the eigenvector of ev[k].  If `init_v` the routine
-//    starts from V = I; otherwise V is taken as given and A must already be expressed in that basis
-//    (warm start: A = V0^dagger A0 V0).
-// Returns the number of sweeps performed.
-template <int M, int NT, class Sync, bool WANT_V>
+// A: M x M Hermitian in shared memory (row-major, leading dimension LD), overwritten (diagonal = eigenvalues).
+// V: M x M in shared memory (leading dimension LD); on exit column k is the eigenvector of ev[k].  If
+//    `init_v` the routine starts from V = I; otherwise V is taken as given and A must already be expressed
+//    in that basis (warm start: A = V0^dagger A0 V0).
+// Stops when  off(A)^2 <= tol_off * M^2 * ||A||_F^2.  Returns the number of sweeps performed.
+template <int M, int NT, class Sync, bool WANT_V, int LD = M>
 __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v = true,
-                           int max_sweeps = 30) {
-  constexpr int HP = M / 2;
+                           int max_sweeps = 30, double tol_off = 1e-30) {
+  constexpr int HP = (M / 2 > 0) ? M / 2 : 1;
+  static_assert(NT == 32 || HP <= 32, "parameter phase is one warp wide");
   cplx* rs = reinterpret_cast<cplx*>(scratch);  // scratch must be 16-byte aligned
-  double* rc = scratch + M;
-  double* red = scratch + M + HP;
+  double* rc = scratch + 4 * HP;
+  double* red = rc + 2 * HP;
 
   if (WANT_V && init_v) {
-    for (int e = tid; e < M * M; e += NT) V[e] = cmake((e / M == e % M) ? 1.0 : 0.0, 0.0);
+    for (int e = tid; e < M * M; e += NT) V[(e / M) * LD + e % M] = cmake((e / M == e % M) ? 1.0 : 0.0, 0.0);
   }
   Sync::sync();
   if (M == 1) {
@@ -97,38 +103,44 @@ __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int ti
     Sync::sync();
     return 0;
   }
+  auto params = [&](int step, int buf) {
+    for (int i = tid; i < HP; i += NT) {
+      int p, q;
+      rr_pair(M, step, i, p, q);
+      double c;
+      cplx s;
+      jacobi_rotation(A[p * LD + p].x, A[q * LD + q].x, A[p * LD + q], c, s);
+      rc[buf * HP + i] = c;
+      rs[buf * HP + i] = s;
+    }
+  };
   int sweep = 0;
   for (; sweep < max_sweeps; ++sweep) {
     double off = 0.0, tot = 0.0;
     for (int e = tid; e < M * M; e += NT) {
-      const double a2 = cabs2(A[e]);
+      const int r = e / M, c = e % M;
+      const double a2 = cabs2(A[r * LD + c]);
       tot += a2;
-      if (e / M != e % M) off += a2;
+      if (r != c) off += a2;
     }
     off = group_sum<NT, Sync>(off, red, tid);
     tot = group_sum<NT, Sync>(tot, red, tid);
-    if (off <= (1e-30 * M * M) * tot || tot == 0.0) break;
+    if (off <= (tol_off * M * M) * tot || tot == 0.0) break;
+    params(0, 0);
+    Sync::sync();
     for (int step = 0; step < M - 1; ++step) {
-      // ---- rotation parameters, one pair per thread ----
-      for (int i = tid; i < HP; i += NT) {
-        int p, q;
-        rr_pair(M, step, i, p, q);
-        double c, an, gn;
-        cplx s;
-        jacobi_rotation(A[p * M + p].x, A[q * M + q].x, A[p * M + q], c, s, an, gn);
-        rc[i] = c;
-        rs[i] = s;
-      }
-      Sync::sync();
+      const int cur = step & 1;
+      const double* rcc = rc + cur * HP;
+      const cplx* rsc = rs + cur * HP;
       // ---- A <- J^dagger A J, one 2x2 block (pair I rows, pair J cols) per work item ----
       for (int w = tid; w < HP * HP; w += NT) {
         const int I = w / HP, J = w % HP;
         int pi, qi, pj, qj;
         rr_pair(M, step, I, pi, qi);
         rr_pair(M, step, J, pj, qj);
-        const double cI = rc[I], cJ = rc[J];
-        const cplx sI = rs[I], sJ = rs[J];
-        const cplx b00 = A[pi * M + pj], b01 = A[pi * M + qj], b10 = A[qi * M + pj], b11 = A[qi * M + qj];
+        const double cI = rcc[I], cJ = rcc[J];
+        const cplx sI = rsc[I], sJ = rsc[J];
+        const cplx b00 = A[pi * LD + pj], b01 = A[pi * LD + qj], b10 = A[qi * LD + pj], b11 = A[qi * LD + qj];
         // X = B J_J
         const cplx csJ = cconj(sJ);
         cplx x00 = csub(cscale(b00, cJ), cmul(csJ, b01));
@@ -147,28 +159,35 @@ __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int ti
           y01 = cmake(0.0, 0.0);
           y10 = cmake(0.0, 0.0);
         }
-        A[pi * M + pj] = y00;
-        A[pi * M + qj] = y01;
-        A[qi * M + pj] = y10;
-        A[qi * M + qj] = y11;
+        A[pi * LD + pj] = y00;
+        A[pi * LD + qj] = y01;
+        A[qi * LD + pj] = y10;
+        A[qi * LD + qj] = y11;
       }
-      // ---- V <- V J ----
-      if (WANT_V) {
-        for (int w = tid; w < M * HP; w += NT) {
+      Sync::sync();
+      // ---- parameters of the next step (first warp)  ||  V <- V J (the other warps) ----
+      const bool split = (NT > 32) && WANT_V;
+      if (!split || tid < 32) {
+        if (step + 1 < M - 1) params(step + 1, cur ^ 1);
+      }
+      if (WANT_V && (!split || tid >= 32)) {
+        const int vt = split ? tid - 32 : tid;
+        constexpr int VNT = (NT > 32) ? NT - 32 : NT;
+        for (int w = vt; w < M * HP; w += VNT) {
           const int r = w / HP, J = w % HP;
           int pj, qj;
           rr_pair(M, step, J, pj, qj);
-          const double cJ = rc[J];
-          const cplx sJ = rs[J];
-          const cplx v0 = V[r * M + pj], v1 = V[r * M + qj];
-          V[r * M + pj] = csub(cscale(v0, cJ), cmul(cconj(sJ), v1));
-          V[r * M + qj] = cadd(cmul(sJ, v0), cscale(v1, cJ));
+          const double cJ = rcc[J];
+          const cplx sJ = rsc[J];
+          const cplx v0 = V[r * LD + pj], v1 = V[r * LD + qj];
+          V[r * LD + pj] = csub(cscale(v0, cJ), cmul(cconj(sJ), v1));
+          V[r * LD + qj] = cadd(cmul(sJ, v0), cscale(v1, cJ));
         }
       }
       Sync::sync();
     }
   }
-  for (int k = tid; k < M; k += NT) ev[k] = A[k * M + k].x;
+  for (int k = tid; k < M; k += NT) ev[k] = A[k * LD + k].x;
   Sync::sync();
   return sweep;
 }
@@ -178,4 +197,44 @@ __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int ti
 template <int D>
 __device__ __forceinline__ int jacobi_eigh_warp(cplx* A, cplx* V, double* ev, int lane) {
   return jacobi_eigh<D, 32, SyncWarp, true>(A, V, ev, ev + D, lane);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shared-memory M x M complex products with strided register tiles (TR x TC outputs per work item:
+// rows tr + i*M/TR, columns tc + j*M/TC -- so the lanes of a warp read consecutive columns and at most two
+// distinct rows: conflict-free with the padded leading dimension).
+//   MODE 0: C = A * B            MODE 1: C = A^dagger * B
+// C must not alias A or B.
+// ---------------------------------------------------------------------------------------------
+template <int M, int NT, int LD, int MODE>
+__device__ void smem_matmul(cplx* __restrict__ C, const cplx* __restrict__ A, const cplx* __restrict__ B, int tid) {
+  constexpr int TR = (M >= 16) ? 2 : 1, TC = (M >= 16) ? 4 : 1;
+  constexpr int NR = M / TR, NC = M / TC;  // tile grid
+  for (int t = tid; t < NR * NC; t += NT) {
+    const int tr = t / NC, tc = t % NC;
+    cplx acc[TR][TC];
+#pragma unroll
+    for (int i = 0; i < TR; ++i)
+#pragma unroll
+      for (int j = 0; j < TC; ++j) acc[i][j] = cmake(0.0, 0.0);
+#pragma unroll 4
+    for (int k = 0; k < M; ++k) {
+      cplx a[TR], b[TC];
+#pragma unroll
+      for (int i = 0; i < TR; ++i) {
+        const int r = tr + i * NR;
+        a[i] = (MODE == 0) ? A[r * LD + k] : cconj(A[k * LD + r]);
+      }
+#pragma unroll
+      for (int j = 0; j < TC; ++j) b[j] = B[k * LD + tc + j * NC];
+#pragma unroll
+      for (int i = 0; i < TR; ++i)
+#pragma unroll
+        for (int j = 0; j < TC; ++j) cfma(acc[i][j], a[i], b[j]);
+    }
+#pragma unroll
+    for (int i = 0; i < TR; ++i)
+#pragma unroll
+      for (int j = 0; j < TC; ++j) C[(tr + i * NR) * LD + tc + j * NC] = acc[i][j];
+  }
 }

@@ -214,16 +214,6 @@ __device__ __forceinline__ double flip_sign(double x, int mask) {
   return __hiloint2double(__double2hiint(x) ^ mask, __double2loint(x));
 }
 __device__ __forceinline__ double shfl_xor_d(double x, int m) { return __shfl_xor_sync(0xffffffffu, x, m); }
-// 1/d to ~1 ulp: MUFU.RCP64H seed (20+ bits) + two Newton steps = 1 MUFU + 4 DFMA.  An IEEE division costs
-// ~133 issue cycles per warp on B200 (profiles/r01_ubench_fp64.txt) and was 46 % of the iteration.
-__device__ __forceinline__ double fast_rcp(double d) {
-  double r;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
-  double e = fma(-d, r, 1.0);
-  r = fma(r, e, r);
-  e = fma(-d, r, 1.0);
-  return fma(r, e, r);
-}
 
 __global__ void __launch_bounds__(32) mle_quad_kernel(int64_t B, int K, const int* __restrict__ slot_ptr,
                                                       const int* __restrict__ member_col,

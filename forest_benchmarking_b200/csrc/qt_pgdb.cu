@@ -41,11 +41,11 @@ struct PgdbView {
 
 template <int N>
 struct PgdbCfg {
-  static constexpr int NT = (N >= 3) ? 256 : 32;
+  static constexpr int NT = (N >= 3) ? 512 : 32;
   static constexpr int GPB = (N >= 3) ? 1 : 4;
   using Sync = typename std::conditional<(N >= 3), SyncBlock, SyncWarp>::type;
   using G = ChoiGroup<N, NT, Sync>;
-  static constexpr size_t group_smem = (sizeof(cplx) * 2 * G::MM + sizeof(double) * G::SMALL_DOUBLES + 15) / 16 * 16;
+  static constexpr size_t group_smem = G::group_smem;  // X, V, T (padded) + small scratch
   // per-group global workspace, in doubles
   static __host__ __device__ int64_t ws_doubles(int n_in) {
     return 5LL * 2 * G::MM + 3LL * n_in * G::M;
@@ -57,7 +57,7 @@ struct Pgdb {
   using C = PgdbCfg<N>;
   using G = typename C::G;
   using Sync = typename C::Sync;
-  static constexpr int NT = C::NT, D = G::D, M = G::M, MM = G::MM;
+  static constexpr int NT = C::NT, D = G::D, M = G::M, MM = G::MM, LD = G::LD;
 
   // in-place choi <-> superop reshuffle of a shared M x M matrix (swap index digits 0 and 3)
   static __device__ void reshuffle_inplace(cplx* X, int tid) {
@@ -65,9 +65,9 @@ struct Pgdb {
       const int r = e / M, c = e % M;
       const int i0 = r / D, i1 = r % D, i2 = c / D, i3 = c % D;
       if (i0 < i3) {
-        const int e2 = (i3 * D + i1) * M + i2 * D + i0;
-        const cplx a = X[e], b = X[e2];
-        X[e] = b;
+        const int e1 = r * LD + c, e2 = (i3 * D + i1) * LD + i2 * D + i0;
+        const cplx a = X[e1], b = X[e2];
+        X[e1] = b;
         X[e2] = a;
       }
     }
@@ -77,13 +77,13 @@ struct Pgdb {
   // X (shared, Choi) -> Pauli-Liouville coefficients left at butterfly positions: R[k][j] = X[pos(k)*M + pos(j)] / d
   static __device__ void choi_to_pl_positions(cplx* X, int tid) {
     reshuffle_inplace(X, tid);
-    pauli_butterfly_smem<true, true, Sync>(X, N, M, M, 1, tid, NT);
-    pauli_butterfly_smem<true, false, Sync>(X, N, M, 1, M, tid, NT);
+    pauli_butterfly_smem<true, true, Sync>(X, N, M, LD, 1, tid, NT);
+    pauli_butterfly_smem<true, false, Sync>(X, N, M, 1, LD, tid, NT);
   }
   // inverse: X holds PL coefficients at butterfly positions -> Choi (times d; caller scales)
   static __device__ void pl_positions_to_choi(cplx* X, int tid) {
-    pauli_butterfly_smem<false, true, Sync>(X, N, M, M, 1, tid, NT);
-    pauli_butterfly_smem<false, false, Sync>(X, N, M, 1, M, tid, NT);
+    pauli_butterfly_smem<false, true, Sync>(X, N, M, LD, 1, tid, NT);
+    pauli_butterfly_smem<false, false, Sync>(X, N, M, 1, LD, tid, NT);
     reshuffle_inplace(X, tid);
   }
 
@@ -92,7 +92,7 @@ struct Pgdb {
     const double scale = 1.0 / D;
     for (int e = tid; e < pv.n_in * M; e += NT) {
       const int i = e / M, k = e % M;
-      const cplx* row = X + pauli_to_pos(k, N) * M;
+      const cplx* row = X + pauli_to_pos(k, N) * LD;
       const double* sv = pv.svec + (int64_t)i * M;
       double acc = 0.0;
       for (int j = 0; j < M; ++j) acc = fma(row[pauli_to_pos(j, N)].x, sv[j], acc);
@@ -177,7 +177,7 @@ struct Pgdb {
 
   // One experiment.  EST = choi_out[b] (global).  ws: per-group workspace.  X, V, small: shared.
   static __device__ void run(const PgdbView& pv, const Data& dt, bool make_tp, cplx* EST, double* ws, cplx* X,
-                             cplx* V, double* small, int* counters, int tid) {
+                             cplx* V, cplx* T, double* small, int* counters, int tid) {
     cplx* Gr = reinterpret_cast<cplx*>(ws);
     cplx* U = Gr + MM;
     cplx* S = U + MM;
@@ -193,7 +193,7 @@ struct Pgdb {
     for (int e = tid; e < MM; e += NT) {
       const cplx v = cmake((e / M == e % M) ? 1.0 / D : 0.0, 0.0);
       EST[e] = v;
-      X[e] = v;
+      X[G::sidx(e)] = v;
     }
     for (int e = tid; e < pv.n_in * M; e += NT) Tu[e] = 0.0;
     Sync::sync();
@@ -201,6 +201,7 @@ struct Pgdb {
     build_T(X, pv, Te, tid);
     double old_cost = cost(pv, dt, Te, Tu, 0.0, red, tid);
     int outer = 0, cost_evals = 1, eighs = 0;
+    bool v_valid = false;  // V keeps the last eigenbasis across Dykstra AND outer iterations (warm start)
     while (true) {
       ++outer;
       // ---- gradient ----
@@ -209,7 +210,7 @@ struct Pgdb {
         const int k = e / M, j = e % M;
         double acc = 0.0;
         for (int i = 0; i < pv.n_in; ++i) acc = fma(W[i * M + k], pv.svec[(int64_t)i * M + j], acc);
-        X[pauli_to_pos(k, N) * M + pauli_to_pos(j, N)] = cmake(acc, 0.0);
+        X[pauli_to_pos(k, N) * LD + pauli_to_pos(j, N)] = cmake(acc, 0.0);
       }
       Sync::sync();
       pl_positions_to_choi(X, tid);
@@ -217,20 +218,20 @@ struct Pgdb {
       const double gs = -1.0 / ((double)D * D * D);
       for (int e = tid; e < MM; e += NT) {
         const int r = e / M, c = e % M;
-        const cplx x = X[e], y = X[c * M + r];
+        const cplx x = X[r * LD + c], y = X[c * LD + r];
         const cplx g = cmake(0.5 * gs * (x.x + y.x), 0.5 * gs * (x.y - y.y));
         Gr[e] = g;
         S[e] = csub(EST[e], cscale(g, 1.0 / mu));
       }
       Sync::sync();
       // ---- projection ----
-      eighs += G::project_physical(S, Q, CPREV, X, V, small, make_tp, tid);
+      eighs += G::project_physical(S, Q, CPREV, X, V, T, small, make_tp, tid, v_valid);
       // ---- update direction, its PTM image, <update, gradient> ----
       double ip = 0.0;
       for (int e = tid; e < MM; e += NT) {
         const cplx u = csub(S[e], EST[e]);
         U[e] = u;
-        X[e] = u;
+        X[G::sidx(e)] = u;
         const cplx g = Gr[e];
         ip += u.x * g.x + u.y * g.y;
       }
@@ -273,7 +274,7 @@ struct Pgdb {
 };
 
 template <int N>
-__global__ void pgdb_kernel(PgdbView pv, int64_t B, const double* __restrict__ expect,
+__global__ void __launch_bounds__(PgdbCfg<N>::NT * PgdbCfg<N>::GPB) pgdb_kernel(PgdbView pv, int64_t B, const double* __restrict__ expect,
                             const double* __restrict__ counts, int make_tp, cplx* __restrict__ choi_out,
                             int* __restrict__ counters, double* __restrict__ workspace) {
   using C = PgdbCfg<N>;
@@ -281,8 +282,9 @@ __global__ void pgdb_kernel(PgdbView pv, int64_t B, const double* __restrict__ e
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int gib = threadIdx.x / C::NT, tid = threadIdx.x % C::NT;
   cplx* X = reinterpret_cast<cplx*>(smem_raw + C::group_smem * gib);
-  cplx* V = X + G::MM;
-  double* small = reinterpret_cast<double*>(V + G::MM);
+  cplx* V = X + G::MP;
+  cplx* T = V + G::MP;
+  double* small = reinterpret_cast<double*>(T + G::MP);
   const int64_t group = (int64_t)blockIdx.x * C::GPB + gib;
   const int64_t n_groups = (int64_t)gridDim.x * C::GPB;
   double* ws = workspace + group * C::ws_doubles(pv.n_in);
@@ -296,8 +298,8 @@ __global__ void pgdb_kernel(PgdbView pv, int64_t B, const double* __restrict__ e
     tot = group_sum<C::NT, typename C::Sync>(tot, red, tid);
     dt.inv_total = 1.0 / tot;
     C::Sync::sync();
-    Pgdb<N>::run(pv, dt, make_tp != 0, choi_out + b * G::MM, ws, X, V, small, counters ? counters + 3 * b : nullptr,
-                 tid);
+    Pgdb<N>::run(pv, dt, make_tp != 0, choi_out + b * G::MM, ws, X, V, T, small,
+                 counters ? counters + 3 * b : nullptr, tid);
     C::Sync::sync();
   }
 }

@@ -8,37 +8,37 @@
 
 template <int N>
 struct ProjCfg {
-  static constexpr int NT = (N >= 3) ? 256 : 32;           // threads per group
+  static constexpr int NT = (N >= 3) ? 512 : 32;           // threads per group
   static constexpr int GPB = (N >= 3) ? 1 : 4;             // groups per block
   using Sync = typename std::conditional<(N >= 3), SyncBlock, SyncWarp>::type;
   using G = ChoiGroup<N, NT, Sync>;
-  static constexpr size_t group_smem = (sizeof(cplx) * 2 * G::MM + sizeof(double) * G::SMALL_DOUBLES + 15) / 16 * 16;
+  static constexpr size_t group_smem = G::group_smem;      // X, V, T (padded) + small scratch
 };
 
 // ---- CP ---------------------------------------------------------------------------------------------
 template <int N>
-__global__ void proj_cp_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out) {
+__global__ void __launch_bounds__(ProjCfg<N>::NT * ProjCfg<N>::GPB)
+    proj_cp_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out) {
   using C = ProjCfg<N>;
   using G = typename C::G;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int gib = threadIdx.x / C::NT, tid = threadIdx.x % C::NT;
   cplx* X = reinterpret_cast<cplx*>(smem_raw + C::group_smem * gib);
-  cplx* V = X + G::MM;
-  double* small = reinterpret_cast<double*>(V + G::MM);
+  cplx* V = X + G::MP;
+  double* small = reinterpret_cast<double*>(V + 2 * G::MP);
   const int64_t b = (int64_t)blockIdx.x * C::GPB + gib;
   if (b >= B) return;
   const cplx* src = in + b * G::MM;
-  auto herm = [&](int e) {
-    const int r = e / G::M, c = e % G::M;
-    const cplx x = src[e], y = src[c * G::M + r];
+  auto herm = [&](int r, int c) {
+    const cplx x = src[r * G::M + c], y = src[c * G::M + r];
     return cmake(0.5 * (x.x + y.x), 0.5 * (x.y - y.y));
   };
-  for (int e = tid; e < G::MM; e += C::NT) X[e] = herm(e);
+  for (int e = tid; e < G::MM; e += C::NT) X[G::sidx(e)] = herm(e / G::M, e % G::M);
   C::Sync::sync();
-  jacobi_eigh<G::M, C::NT, typename C::Sync, true>(X, V, small, small + G::M, tid);
+  jacobi_eigh<G::M, C::NT, typename C::Sync, true, G::LD>(X, V, small, small + G::M, tid);
   G::recompose_psd(X, V, small, herm, tid);
   cplx* dst = out + b * G::MM;
-  for (int e = tid; e < G::MM; e += C::NT) dst[e] = X[e];
+  for (int e = tid; e < G::MM; e += C::NT) dst[e] = X[G::sidx(e)];
 }
 
 // ---- TP / TNI: streaming kernel, several items per block for small n --------------------------------
@@ -108,15 +108,17 @@ __global__ void proj_tp_kernel(int64_t B, const cplx* __restrict__ in, cplx* __r
 
 // ---- physical (Dykstra): persistent groups, S = out[b], Q / CPREV in the workspace -------------------
 template <int N>
-__global__ void proj_physical_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out, int make_tp,
-                                     cplx* __restrict__ workspace, int* __restrict__ eigh_calls) {
+__global__ void __launch_bounds__(ProjCfg<N>::NT * ProjCfg<N>::GPB)
+    proj_physical_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out, int make_tp,
+                         cplx* __restrict__ workspace, int* __restrict__ eigh_calls) {
   using C = ProjCfg<N>;
   using G = typename C::G;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int gib = threadIdx.x / C::NT, tid = threadIdx.x % C::NT;
   cplx* X = reinterpret_cast<cplx*>(smem_raw + C::group_smem * gib);
-  cplx* V = X + G::MM;
-  double* small = reinterpret_cast<double*>(V + G::MM);
+  cplx* V = X + G::MP;
+  cplx* T = V + G::MP;
+  double* small = reinterpret_cast<double*>(T + G::MP);
   const int64_t group = (int64_t)blockIdx.x * C::GPB + gib;
   const int64_t n_groups = (int64_t)gridDim.x * C::GPB;
   cplx* Q = workspace + group * 2 * G::MM;
@@ -130,10 +132,83 @@ __global__ void proj_physical_kernel(int64_t B, const cplx* __restrict__ in, cpl
       S[e] = cmake(0.5 * (x.x + y.x), 0.5 * (x.y - y.y));
     }
     C::Sync::sync();
-    const int calls = G::project_physical(S, Q, CPREV, X, V, small, make_tp != 0, tid);
+    bool v_valid = false;  // items are unrelated: the first decomposition of each starts cold
+    const int calls = G::project_physical(S, Q, CPREV, X, V, T, small, make_tp != 0, tid, v_valid);
     if (tid == 0 && eigh_calls) eigh_calls[b] = calls;
     C::Sync::sync();
   }
+}
+
+
+// ---- choi2kraus: eigh + sqrt(lambda) unvec(v) for |lambda| > tol ---------------------------------------
+// operator_tools/superoperator_transformations.py:325-336.  np.linalg.eigh reads the LOWER triangle and
+// returns ascending eigenvalues; the Kraus operators keep that order, compacted to the front of
+// kraus_out[b] (count_out[b] of them, the rest zero-filled).  Negative eigenvalues give i*sqrt(|lambda|)
+// (np.lib.scimath.sqrt).  Eigenvector phases are a gauge: compare through kraus2choi(choi2kraus(C)) == C.
+template <int N>
+__global__ void __launch_bounds__(ProjCfg<N>::NT * ProjCfg<N>::GPB)
+    choi2kraus_kernel(int64_t B, const cplx* __restrict__ in, double tol, double* __restrict__ evals_out,
+                      cplx* __restrict__ kraus_out, int* __restrict__ count_out) {
+  using C = ProjCfg<N>;
+  using G = typename C::G;
+  constexpr int M = G::M, D = G::D, LD = G::LD;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int gib = threadIdx.x / C::NT, tid = threadIdx.x % C::NT;
+  cplx* X = reinterpret_cast<cplx*>(smem_raw + C::group_smem * gib);
+  cplx* V = X + G::MP;
+  double* small = reinterpret_cast<double*>(V + 2 * G::MP);
+  double* ev = small;
+  int* pos = reinterpret_cast<int*>(small + M + JacobiScratch<M>::doubles);  // [M] slot of eigenpair k, or -1
+  int* rank = pos + M;                                                       // [M]
+  const int64_t b = (int64_t)blockIdx.x * C::GPB + gib;
+  if (b >= B) return;
+  const cplx* src = in + b * G::MM;
+  for (int e = tid; e < G::MM; e += C::NT) {
+    const int r = e / M, c = e % M;
+    cplx v = (r >= c) ? src[r * M + c] : cconj(src[c * M + r]);
+    if (r == c) v.y = 0.0;
+    X[r * LD + c] = v;
+  }
+  C::Sync::sync();
+  jacobi_eigh<M, C::NT, typename C::Sync, true, LD>(X, V, ev, small + M, tid);
+  for (int k = tid; k < M; k += C::NT) {
+    int rk = 0;
+    for (int j = 0; j < M; ++j) rk += (ev[j] < ev[k] || (ev[j] == ev[k] && j < k)) ? 1 : 0;
+    rank[k] = rk;
+  }
+  C::Sync::sync();
+  for (int k = tid; k < M; k += C::NT) {
+    int before = 0;
+    for (int j = 0; j < M; ++j) before += (rank[j] < rank[k] && fabs(ev[j]) > tol) ? 1 : 0;
+    pos[k] = (fabs(ev[k]) > tol) ? before : -1;
+    evals_out[b * M + rank[k]] = ev[k];
+  }
+  C::Sync::sync();
+  int kept = 0;
+  for (int k = 0; k < M; ++k) kept += (pos[k] >= 0) ? 1 : 0;
+  if (tid == 0) count_out[b] = kept;
+  cplx* dst = kraus_out + b * (int64_t)M * M;
+  for (int e = tid; e < (M - kept) * M; e += C::NT) dst[kept * M + e] = cmake(0.0, 0.0);
+  for (int e = tid; e < G::MM; e += C::NT) {
+    const int k = e / M, r = e % M;  // eigenpair k, vec index r = j*D + i  ->  K[i][j]
+    if (pos[k] < 0) continue;
+    const double lam = ev[k];
+    const double sq = sqrt(fabs(lam));
+    const cplx v = V[r * LD + k];
+    const cplx val = (lam >= 0.0) ? cscale(v, sq) : cmake(-sq * v.y, sq * v.x);
+    dst[pos[k] * M + (r % D) * D + (r / D)] = val;
+  }
+}
+
+template <int N>
+static int launch_choi2kraus(int64_t B, const void* in, double tol, double* evals, void* kraus, int* count,
+                             cudaStream_t st) {
+  using C = ProjCfg<N>;
+  const size_t smem = C::group_smem * C::GPB;
+  QT_CUDA(cudaFuncSetAttribute(choi2kraus_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  choi2kraus_kernel<N><<<(unsigned)((B + C::GPB - 1) / C::GPB), C::NT * C::GPB, smem, st>>>(
+      B, (const cplx*)in, tol, evals, (cplx*)kraus, count);
+  return qt_check_launch("choi2kraus_kernel");
 }
 
 template <int N>
@@ -234,6 +309,15 @@ extern "C" int qt_proj_physical_batch(int n, int64_t B, const void* choi, void* 
   QT_REQUIRE(choi && out && workspace, "qt_proj_physical_batch: null argument");
 #define CALL(N) \
   launch_physical<N>(B, choi, out, make_trace_preserving, workspace, workspace_bytes, eigh_calls_out, (cudaStream_t)stream)
+  DISPATCH_N3(n, CALL)
+#undef CALL
+}
+
+extern "C" int qt_choi2kraus_batch(int n, int64_t B, const void* choi, double tol, double* evals_out,
+                                   void* kraus_out, int32_t* count_out, void* stream) {
+  if (B == 0) return QT_OK;
+  QT_REQUIRE(choi && evals_out && kraus_out && count_out, "qt_choi2kraus_batch: null argument");
+#define CALL(N) launch_choi2kraus<N>(B, choi, tol, evals_out, kraus_out, count_out, (cudaStream_t)stream)
   DISPATCH_N3(n, CALL)
 #undef CALL
 }

@@ -13,7 +13,7 @@ from .. import _lib
 
 __all__ = ["vec", "unvec", "kraus2choi", "kraus2superop", "kraus2pauli_liouville", "choi2superop",
            "superop2choi", "superop2pauli_liouville", "pauli_liouville2superop", "choi2pauli_liouville",
-           "pauli_liouville2choi", "kraus2choi_batch", "kraus2superop_batch", "reshuffle_batch",
+           "pauli_liouville2choi", "choi2kraus", "choi2kraus_batch", "kraus2choi_batch", "kraus2superop_batch", "reshuffle_batch",
            "superop2pauli_liouville_batch", "pauli_liouville2superop_batch",
            "choi2pauli_liouville_batch", "pauli_liouville2choi_batch"]
 
@@ -112,6 +112,24 @@ def pauli_liouville2choi_batch(pl):
     return reshuffle_batch(pauli_liouville2superop_batch(pl))
 
 
+def choi2kraus_batch(choi, tol: float = 1e-9):
+    """choi [B, d^2, d^2] (n <= 3) -> (kraus [B, d^2, d, d], counts [B] int32, evals [B, d^2] ascending).
+    kraus[b, :counts[b]] are the operators sqrt(lambda) unvec(v) with |lambda| > tol in ascending-eigenvalue
+    order (reference :325-336); the remaining slots are zero."""
+    torch = _lib.require_cuda()
+    choi = _check_c128(choi, 3)
+    b, d2, _ = choi.shape
+    n = _nq(d2)
+    d = 2 ** n
+    kraus = torch.empty((b, d2, d, d), dtype=torch.complex128, device=choi.device)
+    evals = torch.empty((b, d2), dtype=torch.float64, device=choi.device)
+    counts = torch.empty((b,), dtype=torch.int32, device=choi.device)
+    _lib.check(_lib.lib().qt_choi2kraus_batch(ctypes.c_int(n), ctypes.c_int64(b), _lib.ptr(choi), ctypes.c_double(tol),
+                                              _lib.ptr(evals), _lib.ptr(kraus), _lib.ptr(counts),
+                                              _lib.current_stream_ptr()), "qt_choi2kraus_batch")
+    return kraus, counts, evals
+
+
 # ---- reference-named single-matrix functions -------------------------------------------------
 def _to_dev(x):
     torch = _lib.require_cuda()
@@ -158,6 +176,13 @@ def superop2pauli_liouville(superop: np.ndarray) -> np.ndarray:
 def pauli_liouville2superop(pl_matrix: np.ndarray) -> np.ndarray:
     """reference :301-312."""
     return pauli_liouville2superop_batch(_to_dev(pl_matrix)[None])[0].cpu().numpy()
+
+
+def choi2kraus(choi: np.ndarray, tol: float = 1e-9) -> List[np.ndarray]:
+    """reference :325-336 (ragged list: only operators whose |eigenvalue| exceeds tol)."""
+    kraus, counts, _ = choi2kraus_batch(_to_dev(choi)[None], tol)
+    k = int(counts[0].item())
+    return [m for m in kraus[0, :k].cpu().numpy()]
 
 
 def choi2pauli_liouville(choi: np.ndarray) -> np.ndarray:

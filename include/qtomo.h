@@ -66,6 +66,12 @@ int qt_choi_superop_reshuffle_batch(int d, int64_t B, const void* in, void* out,
  * workspace: NULL for n<=3; B*16^n*16 bytes of device memory for n = 4, 5 (two-pass path). */
 int qt_superop2pl_batch(int n, int64_t B, const void* superop, void* pl_out, void* workspace, void* stream);
 int qt_pl2superop_batch(int n, int64_t B, const void* pl, void* superop_out, void* workspace, void* stream);
+/* choi2kraus (:325-336), n = 1..3: eigh of the lower triangle; evals_out[B,4^n] ascending (np.linalg.eigh order);
+ * kraus_out[B,4^n,d,d]: sqrt(lambda_k) * unvec(v_k) for |lambda_k| > tol in ascending-eigenvalue order, compacted to
+ * the front (count_out[b] operators, the rest zero); negative lambda -> i*sqrt(|lambda|) like np.lib.scimath.sqrt.
+ * Eigenvector phases are a gauge: compare via kraus2choi(choi2kraus(C)) == C (the reference's own test). */
+int qt_choi2kraus_batch(int n, int64_t B, const void* choi, double tol, double* evals_out, void* kraus_out,
+                        int32_t* count_out, void* stream);
 
 /* ---- distance measures (distance_measures.py) -------------------------------------------------- */
 /* rho, sigma: [B, 2^n, 2^n]; out[B] doubles */

@@ -94,3 +94,40 @@ def test_dropin_functions(torch):
     assert np.allclose(ot.kraus2superop(ad), orc.kraus2superop(ad), atol=1e-16)
     assert np.array_equal(ot.vec(np.arange(4).reshape(2, 2)), np.array([[0], [2], [1], [3]]))
     assert np.array_equal(ot.unvec(ot.vec(np.arange(4).reshape(2, 2))), np.arange(4).reshape(2, 2))
+
+
+@pytest.mark.parametrize("n,batch", [(1, 257), (2, 61), (3, 9)])
+def test_choi2kraus(torch, n, batch):
+    """a17 choi2kraus: not element-wise comparable (eigenvector gauge) -- check what the reference's own test
+    checks (test_superoperator_transformations.py:263-271): kraus2choi(choi2kraus(C)) == C, plus sorted
+    eigenvalues vs np.linalg.eigh, the |lambda| > tol filter and the complex sqrt of negative eigenvalues."""
+    from forest_benchmarking_b200.operator_tools import superoperator_transformations as st
+    rng = np.random.default_rng(70 + n)
+    d, m = 2 ** n, 4 ** n
+    chois = []
+    for b in range(batch):
+        nk = 1 + b % 3
+        ks = [np.sqrt(1.0 / nk) * orc.haar_unitary(rng, d) for _ in range(nk)]
+        c = orc.kraus2choi(ks)
+        if b % 4 == 3:  # indefinite Hermitian input: negative eigenvalues -> imaginary sqrt
+            h = rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m))
+            c = c + 0.05 * (h + h.conj().T)
+        chois.append(c)
+    chois = np.stack(chois)
+    kraus, counts, evals = st.choi2kraus_batch(torch.from_numpy(chois).cuda())
+    kraus, counts, evals = kraus.cpu().numpy(), counts.cpu().numpy(), evals.cpu().numpy()
+    for b in range(batch):
+        w = np.linalg.eigvalsh(chois[b])
+        assert np.allclose(evals[b], w, atol=1e-12)
+        want = orc.choi2kraus(chois[b])
+        assert counts[b] == len(want) == int(np.sum(np.abs(w) > 1e-9))
+        assert np.all(kraus[b, counts[b]:] == 0)
+        # sum_k vec(K) vec(K)^T-with-scimath-sqrt reproduces C:  sqrt(l)^2 = l also for negative l
+        rec = np.zeros((m, m), dtype=complex)
+        for k, lam in zip(kraus[b, :counts[b]], w[np.abs(w) > 1e-9]):
+            v = orc.vec(k) / np.emath.sqrt(lam)
+            rec += lam * (v @ v.conj().T)
+        assert relerr(rec, chois[b]) < 1e-9
+    # drop-in signature: list of operators, round trip through kraus2choi
+    ks = st.choi2kraus(chois[0])
+    assert relerr(st.kraus2choi(ks), chois[0]) < 1e-9
