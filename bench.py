@@ -410,7 +410,8 @@ def run_pgdb(args):
                        "batch_per_gpu": B, "global_batch": world * B, "l2": "flushed between timed iterations",
                        "collective": "all_gather of reconstructed Choi matrices" if world > 1 else "none",
                        "outer_mean": float(counters[:, 0].mean()), "cost_evals_mean": float(counters[:, 1].mean()),
-                       "eigh_calls_mean": float(counters[:, 2].mean())},
+                       "eigh_calls_mean": float(counters[:, 2].mean()),
+                       "jacobi_sweeps_per_eigh": float(counters[:, 3].sum() / max(1, counters[:, 2].sum()))},
             "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": int(2 * ex_host.numel() * 8), "d2h_bytes_per_step": int(out_host.numel() * 16)},
             "gpu_launches": args.steps, "clocks": clocks,

@@ -122,7 +122,7 @@ struct ChoiGroup {
 
   // Eigendecomposition of the Hermitian matrix held in X (padded, shared).  With a valid previous eigenbasis
   // in V the matrix is first rotated into it (X <- V^dagger X V through T) and Jacobi continues from V.
-  static __device__ void eigh_warm(cplx* X, cplx* V, cplx* T, double* ev, double* jscr, bool& v_valid, int tid) {
+  static __device__ int eigh_warm(cplx* X, cplx* V, cplx* T, double* ev, double* jscr, bool& v_valid, int tid) {
     if (v_valid) {
       smem_matmul<M, NT, LD, 0>(T, X, V, tid);
       Sync::sync();
@@ -141,19 +141,20 @@ struct ChoiGroup {
         }
       }
       Sync::sync();
-      jacobi_eigh<M, NT, Sync, true, LD>(X, V, ev, jscr, tid, /*init_v=*/false);
-    } else {
-      jacobi_eigh<M, NT, Sync, true, LD>(X, V, ev, jscr, tid, /*init_v=*/true);
-      v_valid = true;
+      return jacobi_eigh<M, NT, Sync, true, LD>(X, V, ev, jscr, tid, /*init_v=*/false);
     }
+    v_valid = true;
+    return jacobi_eigh<M, NT, Sync, true, LD>(X, V, ev, jscr, tid, /*init_v=*/true);
   }
 
   // Dykstra.  On entry S holds the (Hermitian) matrix to project; on exit S holds the projection.
   // X, V, T: shared padded work matrices; S, Q, CPREV: dense M x M state buffers (any address space); small:
   // shared scratch of SMALL_DOUBLES doubles (16-byte aligned).  v_valid: V holds an eigenbasis to warm-start
-  // from (kept up to date here).  Returns the number of CP projections (eigh calls).
+  // from (kept up to date here).  Returns the number of CP projections (eigh calls); *sweeps_acc accumulates
+  // the Jacobi sweeps they took.
   static __device__ int project_physical(cplx* S, cplx* Q, cplx* CPREV, cplx* X, cplx* V, cplx* T, double* small,
-                                         bool make_tp, int tid, bool& v_valid, int max_iter = 10000) {
+                                         bool make_tp, int tid, bool& v_valid, int* sweeps_acc = nullptr,
+                                         int max_iter = 10000) {
     double* ev = small;
     double* jscr = ev + M;
     cplx* E = reinterpret_cast<cplx*>(jscr + JacobiScratch<M>::doubles);
@@ -177,7 +178,8 @@ struct ChoiGroup {
       // X = pre_CP = S - Q
       for (int e = tid; e < MM; e += NT) X[sidx(e)] = csub(S[e], Q[e]);
       Sync::sync();
-      eigh_warm(X, V, T, ev, jscr, v_valid, tid);
+      const int sw = eigh_warm(X, V, T, ev, jscr, v_valid, tid);
+      if (sweeps_acc) *sweeps_acc += sw;
       ++n_eigh;
       recompose_psd(X, V, ev, [&](int r, int c) { return csub(S[r * M + c], Q[r * M + c]); }, tid);  // X = CP
       // criterion pieces + state update of Q, CPREV

@@ -17,28 +17,29 @@
 #pragma once
 #include "qt_common.cuh"
 
-// Round-robin ("circle") pairing: M players, step s in [0, M-1), pair i in [0, M/2).
+// Round-robin ("circle") pairing: M players, step s in [0, M-1), pair i in [0, M/2):
+//   first(i) = (s + i) mod (M-1),   second(0) = M-1,   second(i) = (s - i) mod (M-1).
+// The pair is NOT ordered by index: consecutive pairs then touch consecutive (ascending / descending)
+// rows and columns, which keeps the 16-byte shared-memory accesses of a warp on distinct banks.
 __device__ __forceinline__ void rr_pair(int M, int s, int i, int& p, int& q) {
   const int m1 = M - 1;
-  int a = s + i;
-  if (a >= m1) a -= m1;
-  int b2;
-  if (i == 0) {
-    b2 = m1;
-  } else {
-    b2 = s - i;
-    if (b2 < 0) b2 += m1;
-  }
-  p = a < b2 ? a : b2;
-  q = a < b2 ? b2 : a;
+  p = s + i;
+  if (p >= m1) p -= m1;
+  q = s - i;
+  if (q < 0) q += m1;
+  if (i == 0) q = m1;
 }
 
-// Rotation J = [[c, s],[-conj(s), c]] (c real) that diagonalises [[alpha, beta],[conj(beta), gamma]].
+// Rotation J = [[c, s],[-conj(s), c]] (c real) that diagonalises [[alpha, beta],[conj(beta), gamma]];
+// the rotated diagonal is (alpha - t|beta|, gamma + t|beta|).
 // Square roots and the division go through MUFU seeds + Newton steps (rsqrt / fast_rcp): a correctly
 // rounded DDIV / DSQRT costs ~130 issue cycles per warp on B200 (profiles/r01_ubench_fp64.txt).
-__device__ __forceinline__ void jacobi_rotation(double alpha, double gamma, cplx beta, double& c, cplx& s) {
+__device__ __forceinline__ void jacobi_rotation(double alpha, double gamma, cplx beta, double& c, cplx& s,
+                                                double& alpha_new, double& gamma_new) {
   const double ab2 = cabs2(beta);
   const double scale = fabs(alpha) + fabs(gamma);
+  alpha_new = alpha;
+  gamma_new = gamma;
   if (ab2 <= 1e-36 * scale * scale || ab2 == 0.0) {
     c = 1.0;
     s = cmake(0.0, 0.0);
@@ -51,6 +52,9 @@ __device__ __forceinline__ void jacobi_rotation(double alpha, double gamma, cplx
   c = rsqrt(fma(t, t, 1.0));
   const double inv = t * c * rab;
   s = cmake(beta.x * inv, beta.y * inv);  // sin * e^{i phi}
+  const double tab = t * (ab2 * rab);     // t |beta|
+  alpha_new = alpha - tab;
+  gamma_new = gamma + tab;
 }
 
 struct SyncWarp {
@@ -81,6 +85,8 @@ struct JacobiScratch {
 };
 
 // A: M x M Hermitian in shared memory (row-major, leading dimension LD), overwritten (diagonal = eigenvalues).
+//    Both triangles are stored and kept exactly conjugate: only the blocks above the block diagonal are
+//    computed, their mirror images are written as conjugates; the 2x2 diagonal blocks are set analytically.
 // V: M x M in shared memory (leading dimension LD); on exit column k is the eigenvector of ev[k].  If
 //    `init_v` the routine starts from V = I; otherwise V is taken as given and A must already be expressed
 //    in that basis (warm start: A = V0^dagger A0 V0).
@@ -89,7 +95,14 @@ template <int M, int NT, class Sync, bool WANT_V, int LD = M>
 __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v = true,
                            int max_sweeps = 30, double tol_off = 1e-30) {
   constexpr int HP = (M / 2 > 0) ? M / 2 : 1;
+  constexpr int NOFF = HP * (HP - 1) / 2;                        // 2x2 blocks above the block diagonal
+  constexpr int NBA = (NOFF + NT - 1) / NT > 0 ? (NOFF + NT - 1) / NT : 1;
+  constexpr bool SPLIT = (NT > 32) && WANT_V;                    // warp 0: parameters, other warps: V update
+  constexpr int VNT = SPLIT ? NT - 32 : NT;
   static_assert(NT == 32 || HP <= 32, "parameter phase is one warp wide");
+  static_assert(VNT % HP == 0, "a thread keeps one column pair across its V rows");
+  constexpr int RSTRIDE = VNT / HP;                              // V rows covered per round
+  constexpr int NBV = (M + RSTRIDE - 1) / RSTRIDE;
   cplx* rs = reinterpret_cast<cplx*>(scratch);  // scratch must be 16-byte aligned
   double* rc = scratch + 4 * HP;
   double* red = rc + 2 * HP;
@@ -103,15 +116,39 @@ __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int ti
     Sync::sync();
     return 0;
   }
+  // static assignment of the off-diagonal blocks (I < J) to threads: w -> (I, J) in row-major triangular order
+  int bI[NBA], bJ[NBA];
+#pragma unroll
+  for (int k = 0; k < NBA; ++k) {
+    int w = tid + k * NT, I = -1, J = 0;
+    if (w < NOFF) {
+      I = 0;
+      while (w >= HP - 1 - I) {
+        w -= HP - 1 - I;
+        ++I;
+      }
+      J = I + 1 + w;
+    }
+    bI[k] = I;
+    bJ[k] = J;
+  }
+  const int vt = SPLIT ? tid - 32 : tid;
+  const int vJ = vt % HP, vr0 = vt / HP;
+
+  // rotation parameters of `step` into buffer `buf`; the pair's own 2x2 diagonal block is finished here
   auto params = [&](int step, int buf) {
     for (int i = tid; i < HP; i += NT) {
       int p, q;
       rr_pair(M, step, i, p, q);
-      double c;
+      double c, an, gn;
       cplx s;
-      jacobi_rotation(A[p * LD + p].x, A[q * LD + q].x, A[p * LD + q], c, s);
+      jacobi_rotation(A[p * LD + p].x, A[q * LD + q].x, A[p * LD + q], c, s, an, gn);
       rc[buf * HP + i] = c;
       rs[buf * HP + i] = s;
+      A[p * LD + p] = cmake(an, 0.0);
+      A[q * LD + q] = cmake(gn, 0.0);
+      A[p * LD + q] = cmake(0.0, 0.0);
+      A[q * LD + p] = cmake(0.0, 0.0);
     }
   };
   int sweep = 0;
@@ -132,56 +169,67 @@ __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int ti
       const int cur = step & 1;
       const double* rcc = rc + cur * HP;
       const cplx* rsc = rs + cur * HP;
-      // ---- A <- J^dagger A J, one 2x2 block (pair I rows, pair J cols) per work item ----
-      for (int w = tid; w < HP * HP; w += NT) {
-        const int I = w / HP, J = w % HP;
+      // ---- A <- J^dagger A J on the blocks above the block diagonal (+ conjugate mirror) ----
+#pragma unroll
+      for (int k = 0; k < NBA; ++k) {
+        const int I = bI[k], J = bJ[k];
+        if (I < 0) continue;
         int pi, qi, pj, qj;
         rr_pair(M, step, I, pi, qi);
         rr_pair(M, step, J, pj, qj);
+        const cplx b00 = A[pi * LD + pj], b01 = A[pi * LD + qj], b10 = A[qi * LD + pj], b11 = A[qi * LD + qj];
         const double cI = rcc[I], cJ = rcc[J];
         const cplx sI = rsc[I], sJ = rsc[J];
-        const cplx b00 = A[pi * LD + pj], b01 = A[pi * LD + qj], b10 = A[qi * LD + pj], b11 = A[qi * LD + qj];
         // X = B J_J
         const cplx csJ = cconj(sJ);
-        cplx x00 = csub(cscale(b00, cJ), cmul(csJ, b01));
-        cplx x01 = cadd(cmul(sJ, b00), cscale(b01, cJ));
-        cplx x10 = csub(cscale(b10, cJ), cmul(csJ, b11));
-        cplx x11 = cadd(cmul(sJ, b10), cscale(b11, cJ));
+        const cplx x00 = csub(cscale(b00, cJ), cmul(csJ, b01));
+        const cplx x01 = cadd(cmul(sJ, b00), cscale(b01, cJ));
+        const cplx x10 = csub(cscale(b10, cJ), cmul(csJ, b11));
+        const cplx x11 = cadd(cmul(sJ, b10), cscale(b11, cJ));
         // Y = J_I^dagger X
         const cplx csI = cconj(sI);
-        cplx y00 = csub(cscale(x00, cI), cmul(sI, x10));
-        cplx y01 = csub(cscale(x01, cI), cmul(sI, x11));
-        cplx y10 = cadd(cmul(csI, x00), cscale(x10, cI));
-        cplx y11 = cadd(cmul(csI, x01), cscale(x11, cI));
-        if (I == J) {  // exact diagonal block: real diagonal, zero off-diagonal
-          y00.y = 0.0;
-          y11.y = 0.0;
-          y01 = cmake(0.0, 0.0);
-          y10 = cmake(0.0, 0.0);
-        }
+        const cplx y00 = csub(cscale(x00, cI), cmul(sI, x10));
+        const cplx y01 = csub(cscale(x01, cI), cmul(sI, x11));
+        const cplx y10 = cadd(cmul(csI, x00), cscale(x10, cI));
+        const cplx y11 = cadd(cmul(csI, x01), cscale(x11, cI));
         A[pi * LD + pj] = y00;
         A[pi * LD + qj] = y01;
         A[qi * LD + pj] = y10;
         A[qi * LD + qj] = y11;
+        A[pj * LD + pi] = cconj(y00);
+        A[qj * LD + pi] = cconj(y01);
+        A[pj * LD + qi] = cconj(y10);
+        A[qj * LD + qi] = cconj(y11);
       }
       Sync::sync();
       // ---- parameters of the next step (first warp)  ||  V <- V J (the other warps) ----
-      const bool split = (NT > 32) && WANT_V;
-      if (!split || tid < 32) {
+      if (!SPLIT || tid < 32) {
         if (step + 1 < M - 1) params(step + 1, cur ^ 1);
       }
-      if (WANT_V && (!split || tid >= 32)) {
-        const int vt = split ? tid - 32 : tid;
-        constexpr int VNT = (NT > 32) ? NT - 32 : NT;
-        for (int w = vt; w < M * HP; w += VNT) {
-          const int r = w / HP, J = w % HP;
-          int pj, qj;
-          rr_pair(M, step, J, pj, qj);
-          const double cJ = rcc[J];
-          const cplx sJ = rsc[J];
-          const cplx v0 = V[r * LD + pj], v1 = V[r * LD + qj];
-          V[r * LD + pj] = csub(cscale(v0, cJ), cmul(cconj(sJ), v1));
-          V[r * LD + qj] = cadd(cmul(sJ, v0), cscale(v1, cJ));
+      if (WANT_V && (!SPLIT || tid >= 32) && vr0 < M) {
+        int pj, qj;
+        rr_pair(M, step, vJ, pj, qj);
+        const double cJ = rcc[vJ];
+        const cplx sJ = rsc[vJ], csJ = cconj(sJ);
+#pragma unroll
+        for (int k0 = 0; k0 < NBV; k0 += 4) {
+          cplx v0[4], v1[4];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int r = vr0 + (k0 + kk) * RSTRIDE;
+            if (k0 + kk < NBV && r < M) {
+              v0[kk] = V[r * LD + pj];
+              v1[kk] = V[r * LD + qj];
+            }
+          }
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const int r = vr0 + (k0 + kk) * RSTRIDE;
+            if (k0 + kk < NBV && r < M) {
+              V[r * LD + pj] = csub(cscale(v0[kk], cJ), cmul(csJ, v1[kk]));
+              V[r * LD + qj] = cadd(cmul(sJ, v0[kk]), cscale(v1[kk], cJ));
+            }
+          }
         }
       }
       Sync::sync();

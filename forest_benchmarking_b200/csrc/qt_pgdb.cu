@@ -200,7 +200,7 @@ struct Pgdb {
     choi_to_pl_positions(X, tid);
     build_T(X, pv, Te, tid);
     double old_cost = cost(pv, dt, Te, Tu, 0.0, red, tid);
-    int outer = 0, cost_evals = 1, eighs = 0;
+    int outer = 0, cost_evals = 1, eighs = 0, sweeps = 0;
     bool v_valid = false;  // V keeps the last eigenbasis across Dykstra AND outer iterations (warm start)
     while (true) {
       ++outer;
@@ -225,7 +225,7 @@ struct Pgdb {
       }
       Sync::sync();
       // ---- projection ----
-      eighs += G::project_physical(S, Q, CPREV, X, V, T, small, make_tp, tid, v_valid);
+      eighs += G::project_physical(S, Q, CPREV, X, V, T, small, make_tp, tid, v_valid, &sweeps);
       // ---- update direction, its PTM image, <update, gradient> ----
       double ip = 0.0;
       for (int e = tid; e < MM; e += NT) {
@@ -269,6 +269,7 @@ struct Pgdb {
       counters[0] = outer;
       counters[1] = cost_evals;
       counters[2] = eighs;
+      counters[3] = sweeps;
     }
   }
 };
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(PgdbCfg<N>::NT * PgdbCfg<N>::GPB) pgdb_kernel(
     dt.inv_total = 1.0 / tot;
     C::Sync::sync();
     Pgdb<N>::run(pv, dt, make_tp != 0, choi_out + b * G::MM, ws, X, V, T, small,
-                 counters ? counters + 3 * b : nullptr, tid);
+                 counters ? counters + 4 * b : nullptr, tid);
     C::Sync::sync();
   }
 }

@@ -152,7 +152,7 @@ class PgdbPlan:
 def pgdb_process_estimate_batch(plan: PgdbPlan, expectations, counts, trace_preserving=True, out=None,
                                 return_counters=False, workspace=None):
     """Batched PGDB.  expectations / counts: CUDA float64 [B, S].  Returns choi [B, 4^n, 4^n] complex128
-    (and, optionally, int32 [B, 3] counters: outer iterations, cost evaluations, eigh calls)."""
+    (and, optionally, int32 [B, 4] counters: outer iterations, cost evaluations, eigh calls, Jacobi sweeps)."""
     torch = _lib.require_cuda()
     for t in (expectations, counts):
         if t.dtype != torch.float64 or not t.is_cuda or t.dim() != 2 or t.shape[1] != plan.S:
@@ -162,7 +162,7 @@ def pgdb_process_estimate_batch(plan: PgdbPlan, expectations, counts, trace_pres
     lib = _lib.lib()
     if out is None:
         out = torch.empty((b, m, m), dtype=torch.complex128, device=expectations.device)
-    counters = torch.zeros((b, 3), dtype=torch.int32, device=expectations.device)
+    counters = torch.zeros((b, 4), dtype=torch.int32, device=expectations.device)
     nbytes = int(lib.qt_pgdb_workspace_bytes(plan._h, ctypes.c_int64(b)))
     if workspace is None or workspace.numel() * workspace.element_size() < nbytes:
         workspace = torch.empty((max(nbytes, 8) // 8,), dtype=torch.float64, device=expectations.device)

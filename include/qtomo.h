@@ -103,8 +103,9 @@ int qt_pgdb_plan_destroy(qt_pgdb_plan* plan);
 /* number of distinct input states; canonical = settings are product(states) x all traceless Paulis */
 int qt_pgdb_plan_info(const qt_pgdb_plan* plan, int32_t* n_in_out, int32_t* canonical_out);
 int64_t qt_pgdb_workspace_bytes(const qt_pgdb_plan* plan, int64_t B);
-/* expect[B,S], counts[B,S] -> choi_out[B,4^n,4^n]; counters_out[B,3] (may be NULL) = outer iterations,
- * cost evaluations, eigh calls (the trip counts of tomography.py:570, :576/:582 and project_superoperators.py:115) */
+/* expect[B,S], counts[B,S] -> choi_out[B,4^n,4^n]; counters_out[B,4] (may be NULL) = outer iterations,
+ * cost evaluations, eigh calls (the trip counts of tomography.py:570, :576/:582 and project_superoperators.py:115)
+ * and the total number of Jacobi sweeps those eigh calls took (a cost figure; no reference counterpart) */
 int qt_pgdb_process_batch(const qt_pgdb_plan* plan, int64_t B, const double* expect, const double* counts,
                           int trace_preserving, void* choi_out, int32_t* counters_out, void* workspace,
                           int64_t workspace_bytes, void* stream);
