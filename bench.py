@@ -342,6 +342,9 @@ def run_pgdb(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n = {"pgdb3q": 3, "pgdb2q": 2, "pgdb1q": 1}[args.workload]
+    if args.eigh_tol is not None:
+        import ctypes
+        _lib.check(_lib.lib().qt_set_eigh_tolerance(ctypes.c_double(args.eigh_tol)), "qt_set_eigh_tolerance")
     B = args.batch if args.batch != 4096 else 1024
     codes, pidx, ex, cnt, _ = sy.process_tomography_batch(3003 + rank, B, n, in_basis=args.in_basis)
     plan = tm.PgdbPlan(n, codes, pidx)
@@ -431,9 +434,47 @@ def run_pgdb(args):
         dist.destroy_process_group()
 
 
+def run_kernels(args):
+    """--workload streaming | convert | distances: per-kernel HBM-roofline tables (bench_kernels.py)."""
+    import torch
+    import bench_kernels as bk
+    rank, world, local = dist_info()
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    peak, peak_src = measured_peaks()
+    sampler = ClockSampler(local)
+    sampler.start()
+    if args.workload == "streaming":
+        rows = bk.streaming_rows(torch, peak)
+        headline = next(r for r in rows if r["kernel"].startswith("mle_step_kernel<2>"))
+        workload = "HBM-bound kernels of the path, one launch each over a 2 GiB working set (inputs > L2)"
+    elif args.workload == "convert":
+        rows = bk.convert_rows(torch, peak)
+        headline = next(r for r in rows if r["kernel"].startswith("superop2pauli_liouville n=3"))
+        workload = "BASELINE configs[3]: conversion sweep kraus<->choi<->pauli_liouville, n=1..5, batch 16384 (chunked)"
+    else:
+        pairs = 1_000_000 // world
+        rows = bk.distance_rows(torch, peak, pairs)
+        headline = rows[0]
+        workload = f"BASELINE configs[4]: fidelity + trace_distance, 10^6 4-qubit pairs / {world} GPU(s)"
+    clocks = sampler.stop()
+    if rank == 0:
+        print(json.dumps({
+            "metric": "kernel roofline sweep", "value": headline["items_per_s"], "unit": "items/s (headline kernel)",
+            "n_gpus": world, "steps": 5, "warmup": 3, "ms_per_step": headline["ms"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",
+            "config": {"workload": workload, "l2": "inputs larger than the 126 MB L2"},
+            "clocks": clocks,
+            "roofline": {"kernel": headline["kernel"], "bound": "hbm", "achieved": headline["achieved_gbs"],
+                         "peak": peak, "unit": "GB/s", "frac": headline["frac_of_hbm_peak"], "peak_source": peak_src,
+                         "traffic": None},
+            "kernels": rows}))
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="mle2q", choices=["mle2q", "pgdb3q", "pgdb2q", "pgdb1q"])
+    ap.add_argument("--workload", default="mle2q", choices=["mle2q", "pgdb3q", "pgdb2q", "pgdb1q", "streaming",
+                                                            "convert", "distances"])
     ap.add_argument("--in-basis", default="pauli", choices=["pauli", "sic"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -441,12 +482,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--eigh-tol", type=float, default=None, help="experiment: qt_set_eigh_tolerance value")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference_arm(args)
     elif args.workload.startswith("pgdb"):
         run_pgdb(args)
+    elif args.workload in ("streaming", "convert", "distances"):
+        run_kernels(args)
     else:
         run_ours(args)
 

@@ -122,7 +122,8 @@ struct ChoiGroup {
 
   // Eigendecomposition of the Hermitian matrix held in X (padded, shared).  With a valid previous eigenbasis
   // in V the matrix is first rotated into it (X <- V^dagger X V through T) and Jacobi continues from V.
-  static __device__ int eigh_warm(cplx* X, cplx* V, cplx* T, double* ev, double* jscr, bool& v_valid, int tid) {
+  static __device__ int eigh_warm(cplx* X, cplx* V, cplx* T, double* ev, double* jscr, bool& v_valid, int tid,
+                                  double rel2) {
     if (v_valid) {
       smem_matmul<M, NT, LD, 0>(T, X, V, tid);
       Sync::sync();
@@ -141,10 +142,10 @@ struct ChoiGroup {
         }
       }
       Sync::sync();
-      return jacobi_eigh<M, NT, Sync, true, LD>(X, V, ev, jscr, tid, /*init_v=*/false);
+      return jacobi_eigh<M, NT, Sync, true, LD>(X, V, ev, jscr, tid, /*init_v=*/false, 30, rel2);
     }
     v_valid = true;
-    return jacobi_eigh<M, NT, Sync, true, LD>(X, V, ev, jscr, tid, /*init_v=*/true);
+    return jacobi_eigh<M, NT, Sync, true, LD>(X, V, ev, jscr, tid, /*init_v=*/true, 30, rel2);
   }
 
   // Dykstra.  On entry S holds the (Hermitian) matrix to project; on exit S holds the projection.
@@ -154,7 +155,7 @@ struct ChoiGroup {
   // the Jacobi sweeps they took.
   static __device__ int project_physical(cplx* S, cplx* Q, cplx* CPREV, cplx* X, cplx* V, cplx* T, double* small,
                                          bool make_tp, int tid, bool& v_valid, int* sweeps_acc = nullptr,
-                                         int max_iter = 10000) {
+                                         double rel2 = 0.0, int max_iter = 10000) {
     double* ev = small;
     double* jscr = ev + M;
     cplx* E = reinterpret_cast<cplx*>(jscr + JacobiScratch<M>::doubles);
@@ -178,7 +179,7 @@ struct ChoiGroup {
       // X = pre_CP = S - Q
       for (int e = tid; e < MM; e += NT) X[sidx(e)] = csub(S[e], Q[e]);
       Sync::sync();
-      const int sw = eigh_warm(X, V, T, ev, jscr, v_valid, tid);
+      const int sw = eigh_warm(X, V, T, ev, jscr, v_valid, tid, rel2);
       if (sweeps_acc) *sweeps_acc += sw;
       ++n_eigh;
       recompose_psd(X, V, ev, [&](int r, int c) { return csub(S[r * M + c], Q[r * M + c]); }, tid);  // X = CP

@@ -17,6 +17,7 @@ typedef double2 cplx;  // .x = real, .y = imag
 #define QT_ERR_WORKSPACE (-4)
 
 void qt_set_error(const char* fmt, ...);
+double qt_eigh_rel2();  // squared relative off-diagonal tolerance of the Dykstra/PGDB eigensolver (0 = default)
 int qt_check_launch(const char* what);
 
 #define QT_REQUIRE(cond, ...)                \

@@ -90,10 +90,11 @@ struct JacobiScratch {
 // V: M x M in shared memory (leading dimension LD); on exit column k is the eigenvector of ev[k].  If
 //    `init_v` the routine starts from V = I; otherwise V is taken as given and A must already be expressed
 //    in that basis (warm start: A = V0^dagger A0 V0).
-// Stops when  off(A)^2 <= tol_off * M^2 * ||A||_F^2.  Returns the number of sweeps performed.
+// Stops when  off(A)^2 <= rel2 * ||A||_F^2  (rel2 <= 0: the default 1e-30 * M^2, i.e. a relative off-diagonal
+// Frobenius norm of 1e-15 * M).  Returns the number of sweeps performed.
 template <int M, int NT, class Sync, bool WANT_V, int LD = M>
 __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v = true,
-                           int max_sweeps = 30, double tol_off = 1e-30) {
+                           int max_sweeps = 30, double rel2 = 0.0) {
   constexpr int HP = (M / 2 > 0) ? M / 2 : 1;
   constexpr int NOFF = HP * (HP - 1) / 2;                        // 2x2 blocks above the block diagonal
   constexpr int NBA = (NOFF + NT - 1) / NT > 0 ? (NOFF + NT - 1) / NT : 1;
@@ -162,7 +163,7 @@ __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int ti
     }
     off = group_sum<NT, Sync>(off, red, tid);
     tot = group_sum<NT, Sync>(tot, red, tid);
-    if (off <= (tol_off * M * M) * tot || tot == 0.0) break;
+    if (off <= (rel2 > 0.0 ? rel2 : 1e-30 * M * M) * tot || tot == 0.0) break;
     params(0, 0);
     Sync::sync();
     for (int step = 0; step < M - 1; ++step) {

@@ -255,19 +255,19 @@ __global__ void __launch_bounds__(32) mle_quad_kernel(int64_t B, int K, const in
 #pragma unroll
     for (int k = 0; k < D; ++k) R.h[r][k] = (r == k) ? 1.0 / D : 0.0;
 
+  // Loop bookkeeping with ONE exit/store site (at the bottom): the reference tests `iteration >= maxiter` at the
+  // top of the next trip (tomography.py:244), which is the same as testing it right after the increment.
   int it = 1;
   bool done = !valid;
-  while (true) {
-    if (!done && it >= maxiter) {  // tomography.py:244 -- the state as it stands is the answer
-      cplx* out = rho_out + b * (D * D) + c * D;
-      out[c] = cmake(R.h[0][0], 0.0);
+  if (valid && it >= maxiter) {  // maxiter <= 1: the maximally mixed start is the answer
+    cplx* out = rho_out + b * (D * D) + c * D;
 #pragma unroll
-      for (int k = 1; k < D; ++k) out[k ^ c] = cmake(R.re(0, k), R.im(0, k));
-      if (c == 0) iters_out[b] = it;
-      done = true;
-    }
-    if (__all_sync(0xffffffffu, done)) break;
-
+    for (int k = 0; k < D; ++k) out[k] = cmake((k == c) ? 1.0 / D : 0.0, 0.0);
+    if (c == 0) iters_out[b] = it;
+    done = true;
+  }
+#pragma unroll 2
+  while (!__all_sync(0xffffffffu, done)) {
     // ---- th[j] = Tr(P_j R_c) / 2 for all 16 Paulis (static butterfly on the Hermitian-packed state) ----
     double th[S];
     {
@@ -425,17 +425,14 @@ __global__ void __launch_bounds__(32) mle_quad_kernel(int64_t B, int K, const in
       }
     const double diff = ((dd[0] + dd[1]) + (dd[2] + dd[3])) + 2.0 * ((dx[1] + dx[2]) + dx[3]);
     const int conv = __shfl_sync(0xffffffffu, (int)(diff < tol2), qbase);
-    if (!done) {
-      if (conv) {
-        cplx* out = rho_out + b * (D * D) + c * D;
-        out[c] = cmake(R.h[0][0], 0.0);
+    if (!done && !conv) ++it;
+    if (!done && (conv || it >= maxiter)) {
+      cplx* out = rho_out + b * (D * D) + c * D;
+      out[c] = cmake(R.h[0][0], 0.0);
 #pragma unroll
-        for (int k = 1; k < D; ++k) out[k ^ c] = cmake(R.re(0, k), R.im(0, k));
-        if (c == 0) iters_out[b] = it;
-        done = true;
-      } else {
-        ++it;
-      }
+      for (int k = 1; k < D; ++k) out[k ^ c] = cmake(R.re(0, k), R.im(0, k));
+      if (c == 0) iters_out[b] = it;
+      done = true;
     }
   }
 }
@@ -668,8 +665,12 @@ __global__ void mle_step_kernel(int64_t B, int K, const double* __restrict__ exp
       }
       const double t = cmul_ipow(acc, popc_c(x & z) & 3).x;
       const double e = expect_canon[(int64_t)(j - 1) * B + b0 + tid];
-      const double ap = (0.5 * (1.0 + e)) / (0.5 * (1.0 + t) + TINY);
-      const double am = (0.5 * (1.0 - e)) / (0.5 * (1.0 - t) + TINY);
+      // one reciprocal for both ratios (a correctly rounded DDIV costs ~133 issue cycles per warp and made
+      // this streaming kernel FP64-bound instead of HBM-bound)
+      const double pp = 0.5 * (1.0 + t) + TINY, pm = 0.5 * (1.0 - t) + TINY;
+      const double ipm = fast_rcp(pp * pm);
+      const double ap = (0.5 * (1.0 + e)) * pm * ipm;
+      const double am = (0.5 * (1.0 - e)) * pp * ipm;
       w0 += 0.5 * (ap + am);
       w[j] = 0.5 * (ap - am);
     }
@@ -712,7 +713,7 @@ __global__ void mle_step_kernel(int64_t B, int K, const double* __restrict__ exp
         r[i][c] = acc;
         if (i == c) tr += acc.x;
       }
-    const double inv = 1.0 / tr;
+    const double inv = fast_rcp(tr);
 #pragma unroll
     for (int i = 0; i < D; ++i)
 #pragma unroll

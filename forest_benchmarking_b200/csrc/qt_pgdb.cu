@@ -177,7 +177,7 @@ struct Pgdb {
 
   // One experiment.  EST = choi_out[b] (global).  ws: per-group workspace.  X, V, small: shared.
   static __device__ void run(const PgdbView& pv, const Data& dt, bool make_tp, cplx* EST, double* ws, cplx* X,
-                             cplx* V, cplx* T, double* small, int* counters, int tid) {
+                             cplx* V, cplx* T, double* small, int* counters, int tid, double rel2) {
     cplx* Gr = reinterpret_cast<cplx*>(ws);
     cplx* U = Gr + MM;
     cplx* S = U + MM;
@@ -225,7 +225,7 @@ struct Pgdb {
       }
       Sync::sync();
       // ---- projection ----
-      eighs += G::project_physical(S, Q, CPREV, X, V, T, small, make_tp, tid, v_valid, &sweeps);
+      eighs += G::project_physical(S, Q, CPREV, X, V, T, small, make_tp, tid, v_valid, &sweeps, rel2);
       // ---- update direction, its PTM image, <update, gradient> ----
       double ip = 0.0;
       for (int e = tid; e < MM; e += NT) {
@@ -277,7 +277,7 @@ struct Pgdb {
 template <int N>
 __global__ void __launch_bounds__(PgdbCfg<N>::NT * PgdbCfg<N>::GPB) pgdb_kernel(PgdbView pv, int64_t B, const double* __restrict__ expect,
                             const double* __restrict__ counts, int make_tp, cplx* __restrict__ choi_out,
-                            int* __restrict__ counters, double* __restrict__ workspace) {
+                            int* __restrict__ counters, double* __restrict__ workspace, double rel2) {
   using C = PgdbCfg<N>;
   using G = typename C::G;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -287,10 +287,19 @@ __global__ void __launch_bounds__(PgdbCfg<N>::NT * PgdbCfg<N>::GPB) pgdb_kernel(
   cplx* T = V + G::MP;
   double* small = reinterpret_cast<double*>(T + G::MP);
   const int64_t group = (int64_t)blockIdx.x * C::GPB + gib;
-  const int64_t n_groups = (int64_t)gridDim.x * C::GPB;
-  double* ws = workspace + group * C::ws_doubles(pv.n_in);
+  // workspace = [ 256-byte header: work-queue counter | per-group scratch ... ]
+  unsigned long long* queue = reinterpret_cast<unsigned long long*>(workspace);
+  double* ws = workspace + 32 + group * C::ws_doubles(pv.n_in);
   double* red = small + G::SMALL_DOUBLES - 64;
-  for (int64_t b = group; b < B; b += n_groups) {
+  long long* next = reinterpret_cast<long long*>(red + 48);
+  // Experiments take 0.6x .. 1.5x the mean time (data-dependent trip counts), so groups pull the next
+  // experiment from a global counter instead of owning a fixed stride of the batch.
+  while (true) {
+    if (tid == 0) *next = (long long)atomicAdd(queue, 1ULL);
+    C::Sync::sync();
+    const int64_t b = *next;
+    C::Sync::sync();
+    if (b >= B) break;
     typename Pgdb<N>::Data dt;
     dt.ex = expect + b * pv.S;
     dt.cnt = counts + b * pv.S;
@@ -300,7 +309,7 @@ __global__ void __launch_bounds__(PgdbCfg<N>::NT * PgdbCfg<N>::GPB) pgdb_kernel(
     dt.inv_total = 1.0 / tot;
     C::Sync::sync();
     Pgdb<N>::run(pv, dt, make_tp != 0, choi_out + b * G::MM, ws, X, V, T, small,
-                 counters ? counters + 4 * b : nullptr, tid);
+                 counters ? counters + 4 * b : nullptr, tid, rel2);
     C::Sync::sync();
   }
 }
@@ -397,9 +406,9 @@ static int64_t pgdb_grid(int64_t B) {
 extern "C" int64_t qt_pgdb_workspace_bytes(const qt_pgdb_plan* p, int64_t B) {
   if (!p) return -1;
   switch (p->n) {
-    case 1: return pgdb_grid<1>(B) * PgdbCfg<1>::GPB * PgdbCfg<1>::ws_doubles(p->n_in) * 8;
-    case 2: return pgdb_grid<2>(B) * PgdbCfg<2>::GPB * PgdbCfg<2>::ws_doubles(p->n_in) * 8;
-    default: return pgdb_grid<3>(B) * PgdbCfg<3>::GPB * PgdbCfg<3>::ws_doubles(p->n_in) * 8;
+    case 1: return 256 + pgdb_grid<1>(B) * PgdbCfg<1>::GPB * PgdbCfg<1>::ws_doubles(p->n_in) * 8;
+    case 2: return 256 + pgdb_grid<2>(B) * PgdbCfg<2>::GPB * PgdbCfg<2>::ws_doubles(p->n_in) * 8;
+    default: return 256 + pgdb_grid<3>(B) * PgdbCfg<3>::GPB * PgdbCfg<3>::ws_doubles(p->n_in) * 8;
   }
 }
 
@@ -409,9 +418,10 @@ static int launch_pgdb(const qt_pgdb_plan* p, int64_t B, const double* expect, c
   using C = PgdbCfg<N>;
   PgdbView pv{p->S, p->n_in, p->canonical, p->d_state_id, p->d_pidx, p->d_coeff, p->d_svec};
   const size_t smem = C::group_smem * C::GPB;
+  QT_CUDA(cudaMemsetAsync(ws, 0, 256, st));  // work-queue counter
   QT_CUDA(cudaFuncSetAttribute(pgdb_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pgdb_kernel<N><<<(unsigned)pgdb_grid<N>(B), C::NT * C::GPB, smem, st>>>(pv, B, expect, counts, make_tp,
-                                                                          (cplx*)choi_out, counters, (double*)ws);
+                                                                          (cplx*)choi_out, counters, (double*)ws, qt_eigh_rel2());
   return qt_check_launch("pgdb_kernel");
 }
 

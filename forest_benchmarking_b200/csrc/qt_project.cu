@@ -110,7 +110,7 @@ __global__ void proj_tp_kernel(int64_t B, const cplx* __restrict__ in, cplx* __r
 template <int N>
 __global__ void __launch_bounds__(ProjCfg<N>::NT * ProjCfg<N>::GPB)
     proj_physical_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out, int make_tp,
-                         cplx* __restrict__ workspace, int* __restrict__ eigh_calls) {
+                         cplx* __restrict__ workspace, int* __restrict__ eigh_calls, double rel2) {
   using C = ProjCfg<N>;
   using G = typename C::G;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(ProjCfg<N>::NT * ProjCfg<N>::GPB)
     }
     C::Sync::sync();
     bool v_valid = false;  // items are unrelated: the first decomposition of each starts cold
-    const int calls = G::project_physical(S, Q, CPREV, X, V, T, small, make_tp != 0, tid, v_valid);
+    const int calls = G::project_physical(S, Q, CPREV, X, V, T, small, make_tp != 0, tid, v_valid, nullptr, rel2);
     if (tid == 0 && eigh_calls) eigh_calls[b] = calls;
     C::Sync::sync();
   }
@@ -255,7 +255,7 @@ static int launch_physical(int64_t B, const void* in, void* out, int make_tp, vo
   const size_t smem = C::group_smem * C::GPB;
   QT_CUDA(cudaFuncSetAttribute(proj_physical_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   proj_physical_kernel<N><<<(unsigned)blocks, C::NT * C::GPB, smem, st>>>(B, (const cplx*)in, (cplx*)out, make_tp,
-                                                                          (cplx*)ws, eigh_calls);
+                                                                          (cplx*)ws, eigh_calls, qt_eigh_rel2());
   return qt_check_launch("proj_physical_kernel");
 }
 

@@ -33,6 +33,10 @@ int qt_version(void);
 /* copies the last error message of this thread into buf (NUL-terminated, truncated to len) */
 int qt_last_error(char* buf, int len);
 
+/* Process-wide tuning knob: relative off-diagonal Frobenius norm at which the Jacobi eigensolver inside
+ * qt_proj_physical_batch / qt_pgdb_process_batch declares convergence (default 1e-9; 0 = tight 1e-15 * 4^n). */
+int qt_set_eigh_tolerance(double rel_off);
+
 /* FP64 FMA throughput probe (bench utility): blocks*threads*8*iters FMAs; scratch = 1 double on device */
 int qt_fp64_probe(int blocks, int threads, int iters, double* scratch, void* stream);
 
