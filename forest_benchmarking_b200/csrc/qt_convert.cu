@@ -99,168 +99,228 @@ extern "C" int qt_kraus2superop_batch(int d, int n_kraus, int64_t B, const void*
 }
 
 // ---------------------------------------------------------------------------------------------
-// choi <-> superop reshuffle:  out[(i0,i1),(i2,i3)] = in[(i3,i1),(i2,i0)]
-// A work unit is (item, i1, chunk of i2): the d x C2 x d block in[(i3,i1),(i2,i0)] is read with i0
-// fastest (runs of d contiguous elements, C2*d when C2 == d), transposed in shared memory and written
-// with i3 fastest.  Several units per block when a unit is smaller than the 64 KB tile.
+// choi <-> superop reshuffle:  out[(i0,i1),(i2,i3)] = in[(i3,i1),(i2,i0)]   (d = 2^LOGD)
+// A work unit is (item, i1, chunk of C2 values of i2): the d x C2 x d block in[(i3,i1),(i2,i0)] is read with
+// (i2,i0) fastest (runs of C2*d contiguous elements), transposed through padded shared memory and written with
+// (i2,i3) fastest.  Everything is a compile-time power of two: index math is shifts and masks.
 // ---------------------------------------------------------------------------------------------
-__global__ void reshuffle_kernel(int d, int c2, int64_t n_units, const cplx* __restrict__ in,
-                                 cplx* __restrict__ out, int units_per_block) {
+template <int LOGD>
+struct ReshuffleCfg {
+  static constexpr int D = 1 << LOGD;
+  static constexpr int TILE = 2048;                                   // elements per block (32 KB)
+  static constexpr int C2 = (TILE / (D * D) >= D) ? D : (TILE / (D * D) >= 1 ? TILE / (D * D) : 1);
+  static constexpr int UNIT = D * C2 * D;                             // elements per unit
+  static constexpr int UPB = (TILE / UNIT >= 1) ? TILE / UNIT : 1;    // units per block
+  static constexpr int RS = C2 * D + 1;                               // padded row stride in shared memory
+  static constexpr int CHUNKS = D / C2;
+  static constexpr size_t smem = sizeof(cplx) * UPB * D * RS;
+  static constexpr int NT = 256;
+};
+
+template <int LOGD>
+__global__ void __launch_bounds__(256) reshuffle_kernel(int64_t n_units, const cplx* __restrict__ in,
+                                                        cplx* __restrict__ out) {
+  using C = ReshuffleCfg<LOGD>;
+  constexpr int D = C::D, C2 = C::C2, UNIT = C::UNIT, RS = C::RS, CHUNKS = C::CHUNKS;
   extern __shared__ __align__(16) cplx tile[];
-  const int d2 = d * d;
-  const int chunks = d / c2;
-  const int unit_elems = d * c2 * d;
-  const int row_stride = c2 * d + 1;  // +1 element of padding: conflict-free transposed reads
-  const int unit_smem = d * row_stride;
-  const int64_t u0 = (int64_t)blockIdx.x * units_per_block;
-  const int nu = (int)min((int64_t)units_per_block, n_units - u0);
-  for (int e = threadIdx.x; e < nu * unit_elems; e += blockDim.x) {
-    const int ul = e / unit_elems, w = e % unit_elems;
-    const int i0 = w % d, i2l = (w / d) % c2, i3 = w / (d * c2);
-    const int64_t u = u0 + ul;
-    const int chunk = (int)(u % chunks), i1 = (int)((u / chunks) % d);
-    const int64_t b = u / ((int64_t)chunks * d);
-    const int i2 = chunk * c2 + i2l;
-    tile[ul * unit_smem + i3 * row_stride + i2l * d + i0] =
-        in[(b * d2 + (i3 * d + i1)) * d2 + i2 * d + i0];
+  const int64_t u0 = (int64_t)blockIdx.x * C::UPB;
+  const int nu = (int)min((int64_t)C::UPB, n_units - u0);
+  constexpr int PER = (C::UPB * UNIT + C::NT - 1) / C::NT;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int e = threadIdx.x + k * C::NT;
+    if (e < nu * UNIT) {
+      const int ul = e / UNIT, w = e % UNIT;
+      const int i0 = w % D, i2l = (w / D) % C2, i3 = w / (D * C2);
+      const int64_t u = u0 + ul;
+      const int chunk = (int)(u % CHUNKS), i1 = (int)((u / CHUNKS) % D);
+      const int64_t b = u / (CHUNKS * D);
+      const int i2 = chunk * C2 + i2l;
+      tile[ul * (D * RS) + i3 * RS + i2l * D + i0] = in[((b * D + i3) * D + i1) * (D * D) + i2 * D + i0];
+    }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < nu * unit_elems; e += blockDim.x) {
-    const int ul = e / unit_elems, w = e % unit_elems;
-    const int i3 = w % d, i2l = (w / d) % c2, i0 = w / (d * c2);
-    const int64_t u = u0 + ul;
-    const int chunk = (int)(u % chunks), i1 = (int)((u / chunks) % d);
-    const int64_t b = u / ((int64_t)chunks * d);
-    const int i2 = chunk * c2 + i2l;
-    out[(b * d2 + (i0 * d + i1)) * d2 + i2 * d + i3] = tile[ul * unit_smem + i3 * row_stride + i2l * d + i0];
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int e = threadIdx.x + k * C::NT;
+    if (e < nu * UNIT) {
+      const int ul = e / UNIT, w = e % UNIT;
+      const int i3 = w % D, i2l = (w / D) % C2, i0 = w / (D * C2);
+      const int64_t u = u0 + ul;
+      const int chunk = (int)(u % CHUNKS), i1 = (int)((u / CHUNKS) % D);
+      const int64_t b = u / (CHUNKS * D);
+      const int i2 = chunk * C2 + i2l;
+      out[((b * D + i0) * D + i1) * (D * D) + i2 * D + i3] = tile[ul * (D * RS) + i3 * RS + i2l * D + i0];
+    }
   }
 }
 
-extern "C" int qt_choi_superop_reshuffle_batch(int d, int64_t B, const void* in, void* out, void* stream) {
-  QT_REQUIRE(d >= 1 && d <= 32 && (d & (d - 1)) == 0 && in && out && in != out,
-             "qt_choi_superop_reshuffle_batch: bad arguments (d power of two <= 32, out-of-place)");
-  if (B == 0) return QT_OK;
-  int c2 = d;
-  while ((int64_t)d * c2 * d > TILE_ELEMS) c2 /= 2;
-  const int unit_elems = d * c2 * d;
-  const int upb = max(1, TILE_ELEMS / unit_elems);
-  const int64_t n_units = B * d * (d / c2);
-  const size_t smem = (size_t)upb * d * (c2 * d + 1) * sizeof(cplx);
-  QT_CUDA(cudaFuncSetAttribute(reshuffle_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  const int64_t blocks = (n_units + upb - 1) / upb;
-  reshuffle_kernel<<<(unsigned)blocks, 256, smem, (cudaStream_t)stream>>>(d, c2, n_units, (const cplx*)in,
-                                                                           (cplx*)out, upb);
+template <int LOGD>
+static int launch_reshuffle(int64_t B, const void* in, void* out, cudaStream_t st) {
+  using C = ReshuffleCfg<LOGD>;
+  const int64_t n_units = B * C::D * C::CHUNKS;
+  const int64_t blocks = (n_units + C::UPB - 1) / C::UPB;
+  reshuffle_kernel<LOGD><<<(unsigned)blocks, C::NT, C::smem, st>>>(n_units, (const cplx*)in, (cplx*)out);
   return qt_check_launch("reshuffle_kernel");
+}
+
+extern "C" int qt_choi_superop_reshuffle_batch(int d, int64_t B, const void* in, void* out, void* stream) {
+  QT_REQUIRE(d >= 2 && d <= 32 && (d & (d - 1)) == 0 && in && out && in != out,
+             "qt_choi_superop_reshuffle_batch: bad arguments (d = 2, 4, 8, 16 or 32, out-of-place)");
+  if (B == 0) return QT_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (d) {
+    case 2: return launch_reshuffle<1>(B, in, out, st);
+    case 4: return launch_reshuffle<2>(B, in, out, st);
+    case 8: return launch_reshuffle<3>(B, in, out, st);
+    case 16: return launch_reshuffle<4>(B, in, out, st);
+    default: return launch_reshuffle<5>(B, in, out, st);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
 // superop <-> Pauli-Liouville (PTM)
 // ---------------------------------------------------------------------------------------------
-// Fused kernel for n <= 3: whole matrices in shared memory.
-// FWD: out = (1/d) F S F^dagger, rows/cols permuted to canonical Pauli order.
-// !FWD: out = (1/d) F^dagger R F, input rows/cols gathered from canonical Pauli order.
-template <bool FWD>
-__global__ void pl_fused_kernel(int n, int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out,
-                                int items_per_block) {
+// FWD : out = (1/d) F S F^dagger, rows/cols delivered in canonical Pauli order.
+// !FWD: out = (1/d) F^dagger R F, rows/cols of the input are in canonical Pauli order.
+// F = kron_q F_q; F_q is a 4-point add-only butterfly on the bit pair (j_q, i_q) of the vec index.  The inner
+// (column-index) transform and the outer (row-index) transform commute and so do different qubits, so the
+// work is cut into two kinds of shared-memory passes:
+//   pass A: tiles of 4^RQN full rows (all combinations of the first RQN row qubits): all N inner stages +
+//           the outer stages of those RQN qubits.  n <= 3: RQN = N, the whole matrix is one tile -> one pass.
+//   pass B: tiles of 4^(N-RQN) rows x W columns: the remaining outer stages, the row permutation and the scale.
+// Between the passes the matrix lives in `workspace` with rows in "position" order (row index bits
+// (j_0..j_{n-1}, i_0..i_{n-1}); Pauli digits of not-yet-transformed qubits sit at their (j, i) bit positions).
+// Row runs are >= 256 B in every pass; every shared buffer row is padded by one element.
+template <int N>
+struct PlCfg {
+  static constexpr int L = 1 << (2 * N);
+  static constexpr int RQN = (N <= 3) ? N : 1;                    // row qubits handled by pass A
+  static constexpr int TRA = 1 << (2 * RQN);                      // tile rows of pass A
+  static constexpr int IPB = (2048 / (TRA * L) >= 1) ? 2048 / (TRA * L) : 1;  // tiles per block (small n)
+  static constexpr int LDA = L + 1;
+  static constexpr size_t smem_a = sizeof(cplx) * IPB * TRA * LDA;
+  static constexpr int NTA = (TRA * L * IPB >= 4096) ? 512 : 256;
+  static constexpr int TRB = 1 << (2 * (N - RQN));                // tile rows of pass B
+  static constexpr int W = (N == 4) ? 32 : 16;                    // tile columns of pass B
+  static constexpr int LDB = W + 1;
+  static constexpr size_t smem_b = sizeof(cplx) * TRB * LDB;
+  static constexpr int NTB = (TRB * W >= 4096) ? 512 : 256;
+};
+
+template <int N, bool FWD>
+__global__ void __launch_bounds__(PlCfg<N>::NTA) pl_pass_a_kernel(int64_t n_tiles, const cplx* __restrict__ in,
+                                                                  cplx* __restrict__ out) {
+  using C = PlCfg<N>;
+  constexpr int L = C::L, RQN = C::RQN, TRA = C::TRA, LDA = C::LDA, NT = C::NTA;
+  constexpr int REST = 1 << (2 * (N - RQN));  // combinations of the row qubits NOT in this tile
+  constexpr bool SINGLE = (RQN == N);
   extern __shared__ __align__(16) cplx buf[];
-  const int L = 1 << (2 * n);
-  const int ld = L + 1;  // padded leading dimension
-  const int msz = L * ld;
-  const int64_t b0 = (int64_t)blockIdx.x * items_per_block;
-  const int nb = (int)min((int64_t)items_per_block, B - b0);
-  const double scale = 1.0 / (double)(1 << n);
-  for (int e = threadIdx.x; e < nb * L * L; e += blockDim.x) {
-    const int bi = e / (L * L), r = (e / L) % L, c = e % L;
-    const cplx v = in[b0 * L * L + e];
-    if (FWD) buf[bi * msz + r * ld + c] = v;
-    else buf[bi * msz + pauli_to_pos(r, n) * ld + pauli_to_pos(c, n)] = v;
+  const int64_t t0 = (int64_t)blockIdx.x * C::IPB;
+  const int nt_here = (int)min((int64_t)C::IPB, n_tiles - t0);
+  const double scale = SINGLE ? 1.0 / (double)(1 << N) : 1.0;
+  // load: tile row t <-> Pauli-digit row index idx = t * REST + fixed  (position row = pauli_to_pos(idx))
+  for (int e = threadIdx.x; e < nt_here * TRA * L; e += NT) {
+    const int c = e % L, t = (e / L) % TRA, tl = e / (L * TRA);
+    const int64_t tile_id = t0 + tl;
+    const int64_t b = tile_id / REST;
+    const int idx = t * REST + (int)(tile_id % REST);
+    const int row = FWD ? pauli_to_pos(idx, N) : idx;
+    const cplx v = in[(b * L + row) * L + c];
+    buf[(tl * TRA + t) * LDA + (FWD ? c : pauli_to_pos(c, N))] = v;
   }
   __syncthreads();
-  // along columns index (within each row): right factor.  FWD: Y = X F^dagger -> conj butterfly.
-  pauli_butterfly_smem<FWD, true>(buf, n, nb * L, /*vstride*/ ld, /*estride*/ 1, threadIdx.x, blockDim.x);
-  // along row index (for each column): left factor.  vector v = (item, column)
-  for (int bi = 0; bi < nb; ++bi)
-    pauli_butterfly_smem<FWD, false>(buf + bi * msz, n, L, /*vstride*/ 1, /*estride*/ ld, threadIdx.x, blockDim.x);
-  for (int e = threadIdx.x; e < nb * L * L; e += blockDim.x) {
-    const int bi = e / (L * L), r = (e / L) % L, c = e % L;
-    cplx v;
-    if (FWD) v = buf[bi * msz + pauli_to_pos(r, n) * ld + pauli_to_pos(c, n)];
-    else v = buf[bi * msz + r * ld + c];
-    out[b0 * L * L + e] = cscale(v, scale);
+  // inner transform (right factor, conjugated butterfly), all N qubits, vectors = tile rows
+#pragma unroll
+  for (int q = 0; q < N; ++q) {
+    bfly_stage<FWD, true, false>(buf, 2 * N, N - 1 - q, 2 * N - 1 - q, nt_here * TRA, LDA, 1, threadIdx.x, NT);
+    __syncthreads();
+  }
+  // outer transform (left factor) on the tile's row qubits: tile row t has digit layout (hi, lo adjacent)
+#pragma unroll
+  for (int q = 0; q < RQN; ++q) {
+    for (int tl = 0; tl < nt_here; ++tl)
+      bfly_stage<FWD, false, true>(buf + tl * TRA * LDA, 2 * RQN, 2 * (RQN - 1 - q), 2 * (RQN - 1 - q) + 1, L, 1, LDA,
+                                   threadIdx.x, NT);
+    __syncthreads();
+  }
+  for (int e = threadIdx.x; e < nt_here * TRA * L; e += NT) {
+    const int c = e % L, t = (e / L) % TRA, tl = e / (L * TRA);
+    const int64_t tile_id = t0 + tl;
+    const int64_t b = tile_id / REST;
+    const int idx = t * REST + (int)(tile_id % REST);
+    // FWD: columns leave in Pauli order; rows in Pauli order if this is the only pass, else position order.
+    // !FWD: columns are back in position order; rows leave in position order.
+    const int row = FWD ? (SINGLE ? idx : pauli_to_pos(idx, N)) : pauli_to_pos(idx, N);
+    const cplx v = buf[(tl * TRA + t) * LDA + (FWD ? pauli_to_pos(c, N) : c)];
+    out[(b * L + row) * L + c] = SINGLE ? cscale(v, scale) : v;
   }
 }
 
-// Two-pass path for n >= 4 (matrix larger than shared memory).
-// Pass ROWS: transform along the contiguous (column-index) axis, `rows_per_block` full rows per block.
-template <bool FWD>
-__global__ void pl_rows_kernel(int n, int64_t total_rows, const cplx* __restrict__ in, cplx* __restrict__ out,
-                               int rows_per_block) {
+template <int N, bool FWD>
+__global__ void __launch_bounds__(PlCfg<N>::NTB) pl_pass_b_kernel(int64_t B, const cplx* __restrict__ in,
+                                                                  cplx* __restrict__ out) {
+  using C = PlCfg<N>;
+  constexpr int L = C::L, RQN = C::RQN, TRB = C::TRB, W = C::W, LDB = C::LDB, NT = C::NTB;
+  constexpr int TOPS = 1 << (2 * RQN), PANELS = L / W;
   extern __shared__ __align__(16) cplx buf[];
-  const int L = 1 << (2 * n);
-  const int ld = L + 1;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  const int nr = (int)min((int64_t)rows_per_block, total_rows - r0);
-  for (int e = threadIdx.x; e < nr * L; e += blockDim.x) {
-    const int rr = e / L, c = e % L;
-    const cplx v = in[r0 * L + e];
-    buf[rr * ld + (FWD ? c : pauli_to_pos(c, n))] = v;
-  }
-  __syncthreads();
-  pauli_butterfly_smem<FWD, true>(buf, n, nr, ld, 1, threadIdx.x, blockDim.x);
-  for (int e = threadIdx.x; e < nr * L; e += blockDim.x) {
-    const int rr = e / L, c = e % L;
-    out[r0 * L + e] = buf[rr * ld + (FWD ? pauli_to_pos(c, n) : c)];
-  }
-}
-// Pass COLS: transform along the row-index axis for a panel of `w` columns (all L rows) of one item,
-// row permutation folded into the global addressing; applies the 1/d scale.
-template <bool FWD>
-__global__ void pl_cols_kernel(int n, int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out, int w) {
-  extern __shared__ __align__(16) cplx buf[];
-  const int L = 1 << (2 * n);
-  const int panels = L / w;
-  const int64_t b = blockIdx.x / panels;
-  const int c0 = (int)(blockIdx.x % panels) * w;
-  const int ld = w + 1;
-  const double scale = 1.0 / (double)(1 << n);
+  const int64_t tile_id = blockIdx.x;
+  const int panel = (int)(tile_id % PANELS);
+  const int top = (int)((tile_id / PANELS) % TOPS);
+  const int64_t b = tile_id / ((int64_t)PANELS * TOPS);
+  const int c0 = panel * W;
+  const double scale = 1.0 / (double)(1 << N);
   const cplx* src = in + b * L * L;
   cplx* dst = out + b * L * L;
-  for (int e = threadIdx.x; e < L * w; e += blockDim.x) {
-    const int r = e / w, c = e % w;
-    buf[(FWD ? r : pauli_to_pos(r, n)) * ld + c] = src[(int64_t)r * L + c0 + c];
+  for (int e = threadIdx.x; e < TRB * W; e += NT) {
+    const int cc = e % W, t = e / W;
+    const int idx = top * TRB + t;
+    buf[t * LDB + cc] = src[(int64_t)pauli_to_pos(idx, N) * L + c0 + cc];
   }
   __syncthreads();
-  pauli_butterfly_smem<FWD, false>(buf, n, w, /*vstride*/ 1, /*estride*/ ld, threadIdx.x, blockDim.x);
-  for (int e = threadIdx.x; e < L * w; e += blockDim.x) {
-    const int r = e / w, c = e % w;
-    dst[(int64_t)r * L + c0 + c] = cscale(buf[(FWD ? pauli_to_pos(r, n) : r) * ld + c], scale);
+#pragma unroll
+  for (int q = RQN; q < N; ++q) {
+    bfly_stage<FWD, false, true>(buf, 2 * (N - RQN), 2 * (N - 1 - q), 2 * (N - 1 - q) + 1, W, 1, LDB, threadIdx.x, NT);
+    __syncthreads();
   }
+  for (int e = threadIdx.x; e < TRB * W; e += NT) {
+    const int cc = e % W, t = e / W;
+    const int idx = top * TRB + t;
+    const int row = FWD ? idx : pauli_to_pos(idx, N);
+    dst[(int64_t)row * L + c0 + cc] = cscale(buf[t * LDB + cc], scale);
+  }
+}
+
+template <int N, bool FWD>
+static int launch_pl_n(int64_t B, const void* in, void* out, void* workspace, cudaStream_t st) {
+  using C = PlCfg<N>;
+  constexpr int REST = 1 << (2 * (N - C::RQN));
+  const int64_t n_tiles = B * REST;
+  const int64_t blocks_a = (n_tiles + C::IPB - 1) / C::IPB;
+  QT_CUDA(cudaFuncSetAttribute(pl_pass_a_kernel<N, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_a));
+  if (C::RQN == N) {
+    pl_pass_a_kernel<N, FWD><<<(unsigned)blocks_a, C::NTA, C::smem_a, st>>>(n_tiles, (const cplx*)in, (cplx*)out);
+    return qt_check_launch("pl_pass_a_kernel");
+  }
+  QT_REQUIRE(workspace, "superop<->pauli_liouville with n >= 4 needs a workspace of B*16^n*16 bytes");
+  pl_pass_a_kernel<N, FWD><<<(unsigned)blocks_a, C::NTA, C::smem_a, st>>>(n_tiles, (const cplx*)in, (cplx*)workspace);
+  int rc = qt_check_launch("pl_pass_a_kernel");
+  if (rc) return rc;
+  QT_CUDA(cudaFuncSetAttribute(pl_pass_b_kernel<N, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_b));
+  const int64_t blocks_b = B * (1 << (2 * C::RQN)) * (C::L / C::W);
+  pl_pass_b_kernel<N, FWD><<<(unsigned)blocks_b, C::NTB, C::smem_b, st>>>(B, (const cplx*)workspace, (cplx*)out);
+  return qt_check_launch("pl_pass_b_kernel");
 }
 
 template <bool FWD>
 static int launch_pl(int n, int64_t B, const void* in, void* out, void* workspace, cudaStream_t st) {
-  const int L = 1 << (2 * n);
-  if (n <= 3) {
-    const int ipb = max(1, TILE_ELEMS / (L * L));
-    const size_t smem = (size_t)ipb * L * (L + 1) * sizeof(cplx);
-    QT_CUDA(cudaFuncSetAttribute(pl_fused_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pl_fused_kernel<FWD><<<(unsigned)((B + ipb - 1) / ipb), 256, smem, st>>>(n, B, (const cplx*)in, (cplx*)out, ipb);
-    return qt_check_launch("pl_fused_kernel");
+  switch (n) {
+    case 1: return launch_pl_n<1, FWD>(B, in, out, workspace, st);
+    case 2: return launch_pl_n<2, FWD>(B, in, out, workspace, st);
+    case 3: return launch_pl_n<3, FWD>(B, in, out, workspace, st);
+    case 4: return launch_pl_n<4, FWD>(B, in, out, workspace, st);
+    default: return launch_pl_n<5, FWD>(B, in, out, workspace, st);
   }
-  QT_REQUIRE(workspace, "superop<->pauli_liouville with n >= 4 needs a workspace of B*16^n*16 bytes");
-  const int rpb = max(1, TILE_ELEMS / L);
-  const size_t smem_r = (size_t)rpb * (L + 1) * sizeof(cplx);
-  QT_CUDA(cudaFuncSetAttribute(pl_rows_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_r));
-  const int64_t total_rows = B * L;
-  pl_rows_kernel<FWD><<<(unsigned)((total_rows + rpb - 1) / rpb), 256, smem_r, st>>>(n, total_rows, (const cplx*)in,
-                                                                                     (cplx*)workspace, rpb);
-  int rc = qt_check_launch("pl_rows_kernel");
-  if (rc) return rc;
-  const int w = max(1, 2 * TILE_ELEMS / L);  // n=4: 32 columns (512 B runs), n=5: 8 columns (128 B runs)
-  const size_t smem_c = (size_t)L * (w + 1) * sizeof(cplx);
-  QT_CUDA(cudaFuncSetAttribute(pl_cols_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_c));
-  pl_cols_kernel<FWD><<<(unsigned)(B * (L / w)), 256, smem_c, st>>>(n, B, (const cplx*)workspace, (cplx*)out, w);
-  return qt_check_launch("pl_cols_kernel");
 }
 
 extern "C" int qt_superop2pl_batch(int n, int64_t B, const void* superop, void* pl_out, void* workspace,

@@ -55,24 +55,28 @@ __global__ void purity_kernel(int64_t B, const cplx* __restrict__ rho, double* _
   if (lane == 0) out[b] = acc;
 }
 
-// shared memory per warp: 3 matrices + eigenvalues + Jacobi scratch
+// shared memory per warp: 3 matrices (leading dimension LD = D + 1 for D >= 8: the Jacobi block updates and the
+// products read columns, which an unpadded power-of-two row stride maps onto the same banks) + eigenvalues +
+// Jacobi scratch
 template <int D>
 struct FidSmem {
+  static constexpr int LD = (D >= 8) ? D + 1 : D;
+  static constexpr int MP = D * LD;
   static constexpr size_t bytes =
-      (sizeof(cplx) * D * D * 3 + sizeof(double) * (D + JacobiScratch<D>::doubles) + 15) / 16 * 16;
+      (sizeof(cplx) * MP * 3 + sizeof(double) * (D + JacobiScratch<D>::doubles) + 15) / 16 * 16;
 };
 
 // MODE 0: fidelity.  MODE 1: nuclear-norm trace distance.
 template <int D, int MODE>
 __global__ void fidelity_kernel(int64_t B, const cplx* __restrict__ rho, const cplx* __restrict__ sigma,
                                 double* __restrict__ out) {
-  constexpr int DD = D * D;
+  constexpr int DD = D * D, LD = FidSmem<D>::LD, MP = FidSmem<D>::MP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   cplx* A = reinterpret_cast<cplx*>(smem_raw + FidSmem<D>::bytes * wib);
-  cplx* V = A + DD;
-  cplx* W = V + DD;
-  double* ev = reinterpret_cast<double*>(W + DD);
+  cplx* V = A + MP;
+  cplx* W = V + MP;
+  double* ev = reinterpret_cast<double*>(W + MP);
   const int64_t b = (int64_t)blockIdx.x * wpb + wib;
   if (b >= B) return;
   const cplx* r = rho + b * DD;
@@ -82,10 +86,10 @@ __global__ void fidelity_kernel(int64_t B, const cplx* __restrict__ rho, const c
       // Hermitian part of rho - sigma
       const int i = e / D, j = e % D;
       const cplx d1 = csub(r[e], s[e]), d2 = csub(r[j * D + i], s[j * D + i]);
-      A[e] = cmake(0.5 * (d1.x + d2.x), 0.5 * (d1.y - d2.y));
+      A[i * LD + j] = cmake(0.5 * (d1.x + d2.x), 0.5 * (d1.y - d2.y));
     }
     __syncwarp();
-    jacobi_eigh<D, 32, SyncWarp, false>(A, nullptr, ev, ev + D, lane);
+    jacobi_eigh<D, 32, SyncWarp, false, LD>(A, nullptr, ev, ev + D, lane);
     double acc = 0.0;
     for (int k = lane; k < D; k += 32) acc += fabs(ev[k]);
     acc = warp_sum(acc);
@@ -97,45 +101,45 @@ __global__ void fidelity_kernel(int64_t B, const cplx* __restrict__ rho, const c
     const int i = e / D, j = e % D;
     cplx v = (i >= j) ? r[e] : cconj(r[j * D + i]);
     if (i == j) v.y = 0.0;
-    A[e] = v;
+    A[i * LD + j] = v;
   }
   __syncwarp();
-  jacobi_eigh<D, 32, SyncWarp, true>(A, V, ev, ev + D, lane);
+  jacobi_eigh<D, 32, SyncWarp, true, LD>(A, V, ev, ev + D, lane);
   // S = V sqrt(max(ev,0)) V^dagger  -> A
   for (int e = lane; e < DD; e += 32) {
     const int i = e / D, j = e % D;
     cplx acc = cmake(0.0, 0.0);
     for (int k = 0; k < D; ++k) {
       const double w = sqrt(fmax(ev[k], 0.0));
-      cfma_conj(acc, cscale(V[i * D + k], w), V[j * D + k]);
+      cfma_conj(acc, cscale(V[i * LD + k], w), V[j * LD + k]);
     }
-    A[e] = acc;
+    A[i * LD + j] = acc;
   }
   __syncwarp();
   // W = S sigma
   for (int e = lane; e < DD; e += 32) {
     const int i = e / D, j = e % D;
     cplx acc = cmake(0.0, 0.0);
-    for (int k = 0; k < D; ++k) cfma(acc, A[i * D + k], s[k * D + j]);
-    W[e] = acc;
+    for (int k = 0; k < D; ++k) cfma(acc, A[i * LD + k], s[k * D + j]);
+    W[i * LD + j] = acc;
   }
   __syncwarp();
   // V = W S, then the Hermitian matrix eigh would see (lower triangle)
   for (int e = lane; e < DD; e += 32) {
     const int i = e / D, j = e % D;
     cplx acc = cmake(0.0, 0.0);
-    for (int k = 0; k < D; ++k) cfma(acc, W[i * D + k], A[k * D + j]);
-    V[e] = acc;
+    for (int k = 0; k < D; ++k) cfma(acc, W[i * LD + k], A[k * LD + j]);
+    V[i * LD + j] = acc;
   }
   __syncwarp();
   for (int e = lane; e < DD; e += 32) {
     const int i = e / D, j = e % D;
-    cplx v = (i >= j) ? V[e] : cconj(V[j * D + i]);
+    cplx v = (i >= j) ? V[i * LD + j] : cconj(V[j * LD + i]);
     if (i == j) v.y = 0.0;
-    W[e] = v;
+    W[i * LD + j] = v;
   }
   __syncwarp();
-  jacobi_eigh<D, 32, SyncWarp, false>(W, nullptr, ev, ev + D, lane);
+  jacobi_eigh<D, 32, SyncWarp, false, LD>(W, nullptr, ev, ev + D, lane);
   double acc = 0.0;
   for (int k = lane; k < D; k += 32) acc += sqrt(fmax(ev[k], 0.0));
   acc = warp_sum(acc);

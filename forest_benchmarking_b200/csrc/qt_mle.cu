@@ -95,8 +95,10 @@ __global__ void __launch_bounds__(32) mle_reg_kernel(int64_t B, int K, const int
         else v = rho.im(c, r);
         t += sgn * v;
       }
-      const double ap = fp[j][tid] / (0.5 * (1.0 + t) + TINY);
-      const double am = fm[j][tid] / (0.5 * (1.0 - t) + TINY);
+      // one MUFU-seeded reciprocal for both ratios (an IEEE DDIV costs ~133 issue cycles per warp)
+      const double pp = 0.5 * (1.0 + t) + TINY, pm = 0.5 * (1.0 - t) + TINY;
+      const double ipm = fast_rcp(pp * pm);
+      const double ap = fp[j][tid] * pm * ipm, am = fm[j][tid] * pp * ipm;
       w0 += 0.5 * (ap + am);
       w[j] = 0.5 * (ap - am);
     }
@@ -172,7 +174,7 @@ __global__ void __launch_bounds__(32) mle_reg_kernel(int64_t B, int K, const int
           nw.h[c][r] = ai;
         }
       }
-    const double inv = 1.0 / tr;
+    const double inv = fast_rcp(tr);
     double diff = 0.0;
 #pragma unroll
     for (int r = 0; r < D; ++r)
@@ -809,7 +811,10 @@ extern "C" int qt_mle_state_batch(const qt_mle_plan* p, int64_t B, const double*
              "qt_mle_state_batch: register kernel needs n<=2, unit coefficients, vanilla MLE");
   QT_REQUIRE(kernel_variant != QT_MLE_KERNEL_QUAD || (reg_ok && p->n == 2),
              "qt_mle_state_batch: quad kernel needs n==2, unit coefficients, vanilla MLE");
-  if (reg_ok && p->n == 2 && (kernel_variant == QT_MLE_KERNEL_QUAD || kernel_variant == QT_MLE_KERNEL_AUTO)) {
+  // AUTO at n = 2: 4 lanes per experiment while the batch cannot fill the FP64 pipes with one thread each
+  // (the quad kernel executes ~1.8x the FP64 instructions per experiment but has 4x the parallelism)
+  const bool auto_quad = kernel_variant == QT_MLE_KERNEL_AUTO && B < (int64_t)QT_NUM_SMS * 4 * 32;
+  if (reg_ok && p->n == 2 && (kernel_variant == QT_MLE_KERNEL_QUAD || auto_quad)) {
     const unsigned blocks = (unsigned)((B + 7) / 8);
     mle_quad_kernel<<<blocks, 32, 0, st>>>(B, p->K, p->d_slot_ptr, p->d_member_col, expect, epsilon, tol, maxiter, out,
                                            iters_out);

@@ -77,3 +77,28 @@ __device__ void pauli_butterfly_smem(cplx* buf, int n, int count, int vstride, i
   }
 }
 
+
+// One butterfly stage on the bit pair (lo_bit < hi_bit) of the element index of `count` vectors of
+// 2^len_bits elements (element e of vector v at buf[v * vstride + e * estride]).  VEC_FASTEST: consecutive
+// threads walk the vector id first (use when vstride == 1 so that a warp touches consecutive addresses).
+// No trailing synchronisation.
+template <bool FWD, bool CONJ, bool VEC_FASTEST>
+__device__ __forceinline__ void bfly_stage(cplx* buf, int len_bits, int lo_bit, int hi_bit, int count, int vstride,
+                                           int estride, int tid, int nt) {
+  const int quarter = 1 << (len_bits - 2);
+  const int lo = 1 << lo_bit, hi = 1 << hi_bit;
+  for (int w = tid; w < count * quarter; w += nt) {
+    const int v = VEC_FASTEST ? w % count : w / quarter;
+    const int r = VEC_FASTEST ? w / count : w % quarter;
+    int p = ((r >> lo_bit) << (lo_bit + 1)) | (r & (lo - 1));  // insert zero bits at lo_bit and hi_bit
+    p = ((p >> hi_bit) << (hi_bit + 1)) | (p & (hi - 1));
+    cplx* base = buf + v * vstride;
+    cplx u00 = base[p * estride], u01 = base[(p | lo) * estride];
+    cplx u10 = base[(p | hi) * estride], u11 = base[(p | hi | lo) * estride];
+    bfly4<FWD, CONJ>(u00, u01, u10, u11);
+    base[p * estride] = u00;
+    base[(p | lo) * estride] = u01;
+    base[(p | hi) * estride] = u10;
+    base[(p | hi | lo) * estride] = u11;
+  }
+}
