@@ -86,6 +86,17 @@ __device__ __forceinline__ double fast_rcp(double d) {
   return fma(r, e, r);
 }
 
+// 1/sqrt(d) to ~1 ulp, branch-free: MUFU.RSQ64H seed + two Newton steps.  CUDA's rsqrt() carries a slow-path
+// CALL for special inputs, which splits the caller's basic block (see qt_eigh.cuh).  d must be normal, > 0.
+__device__ __forceinline__ double fast_rsqrt(double d) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+  double e = fma(-(d * r), r, 1.0);
+  r = fma(0.5 * r, e, r);
+  e = fma(-(d * r), r, 1.0);
+  return fma(0.5 * r, e, r);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Pauli bookkeeping.  Canonical index = base-4 number, digits I=0 X=1 Y=2 Z=3, first qubit most
 // significant (reference utils.py:146-156, 398-409).  A Pauli is i^{|x&z|} X^x Z^z with n-bit masks

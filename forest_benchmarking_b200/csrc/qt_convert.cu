@@ -63,8 +63,74 @@ __global__ void kraus_outer_kernel(int d, int nk, int64_t B, const cplx* __restr
   }
 }
 
+// kraus2choi fast path for d = 2^LOGD: a block produces 4096 output elements (64 KB), consecutive threads write
+// consecutive elements, and all index math is compile-time shifts and masks.
+template <int LOGD>
+struct K2cCfg {
+  static constexpr int D = 1 << LOGD, D2 = D * D;
+  static constexpr int64_t O = (int64_t)D2 * D2;
+  static constexpr int OUT_PER_BLOCK = 4096;
+  static constexpr int IPB = (O >= OUT_PER_BLOCK) ? 1 : (int)(OUT_PER_BLOCK / O);
+  static constexpr int ROWS = (O >= OUT_PER_BLOCK) ? OUT_PER_BLOCK / D2 : D2;
+  static constexpr int RCHUNKS = D2 / ROWS;
+  static constexpr int UNITS = IPB * ROWS * (D2 / 4);
+};
+
+template <int LOGD>
+__global__ void __launch_bounds__(256) kraus2choi_kernel(int nk, int64_t B, const cplx* __restrict__ kraus,
+                                                         cplx* __restrict__ out) {
+  using C = K2cCfg<LOGD>;
+  constexpr int D = C::D, D2 = C::D2, ROWS = C::ROWS;
+  extern __shared__ __align__(16) cplx ks[];  // [IPB][nk][D2] in vec order: v_k[j*D + i] = K_k[i][j]
+  const int64_t b0 = (int64_t)(blockIdx.x / C::RCHUNKS) * C::IPB;
+  const int row0 = (int)(blockIdx.x % C::RCHUNKS) * ROWS;
+  const int nb = (int)min((int64_t)C::IPB, B - b0);
+  for (int e = threadIdx.x; e < nb * nk * D2; e += 256) {
+    const int within = e % D2, which = e / D2;
+    ks[which * D2 + (within % D) * D + within / D] = kraus[b0 * nk * D2 + e];
+  }
+  __syncthreads();
+  // consecutive threads -> consecutive output elements (fully coalesced 16-byte stores)
+  constexpr int PER = C::IPB * ROWS * D2 / 256;
+#pragma unroll 4
+  for (int k = 0; k < PER; ++k) {
+    const int e = threadIdx.x + k * 256;
+    const int c = e % D2, rr = (e / D2) % ROWS, bi = e / (ROWS * D2);
+    if (bi < nb) {
+      const int r = row0 + rr;
+      const cplx* kb = ks + bi * nk * D2;
+      cplx acc = cmake(0.0, 0.0);
+      for (int q = 0; q < nk; ++q) cfma_conj(acc, kb[q * D2 + r], kb[q * D2 + c]);
+      out[((b0 + bi) * D2 + r) * D2 + c] = acc;
+    }
+  }
+}
+
+template <int LOGD>
+static int launch_kraus2choi_fast(int nk, int64_t B, const void* kraus, void* out, cudaStream_t st) {
+  using C = K2cCfg<LOGD>;
+  const size_t smem = sizeof(cplx) * C::IPB * nk * C::D2;
+  QT_CUDA(cudaFuncSetAttribute(kraus2choi_kernel<LOGD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks = ((B + C::IPB - 1) / C::IPB) * C::RCHUNKS;
+  kraus2choi_kernel<LOGD><<<(unsigned)blocks, 256, smem, st>>>(nk, B, (const cplx*)kraus, (cplx*)out);
+  return qt_check_launch("kraus2choi_kernel");
+}
+
 static int launch_kraus_outer(int mode, int d, int nk, int64_t B, const void* kraus, void* out, cudaStream_t st) {
   const int d2 = d * d;
+  if (mode == 0 && (d & (d - 1)) == 0 && d >= 2) {
+    const int ipb = (d2 * d2 >= 4096) ? 1 : 4096 / (d2 * d2);
+    if ((size_t)ipb * nk * d2 * sizeof(cplx) <= 96 * 1024) {
+      switch (d) {
+        case 2: return launch_kraus2choi_fast<1>(nk, B, kraus, out, st);
+        case 4: return launch_kraus2choi_fast<2>(nk, B, kraus, out, st);
+        case 8: return launch_kraus2choi_fast<3>(nk, B, kraus, out, st);
+        case 16: return launch_kraus2choi_fast<4>(nk, B, kraus, out, st);
+        case 32: return launch_kraus2choi_fast<5>(nk, B, kraus, out, st);
+        default: break;
+      }
+    }
+  }
   const int64_t d4 = (int64_t)d2 * d2;
   int ipb = 1, rpt = d2;
   if (d4 <= TILE_ELEMS) ipb = (int)(TILE_ELEMS / d4);

@@ -36,25 +36,24 @@ __device__ __forceinline__ void rr_pair(int M, int s, int i, int& p, int& q) {
 // rounded DDIV / DSQRT costs ~130 issue cycles per warp on B200 (profiles/r01_ubench_fp64.txt).
 __device__ __forceinline__ void jacobi_rotation(double alpha, double gamma, cplx beta, double& c, cplx& s,
                                                 double& alpha_new, double& gamma_new) {
+  // branch-free (the caller's instruction stream stays one basic block, so independent work can be scheduled
+  // into the latency of this dependent chain): a negligible off-diagonal element runs the arithmetic on a
+  // dummy value and selects the identity at the end
   const double ab2 = cabs2(beta);
   const double scale = fabs(alpha) + fabs(gamma);
-  alpha_new = alpha;
-  gamma_new = gamma;
-  if (ab2 <= 1e-36 * scale * scale || ab2 == 0.0) {
-    c = 1.0;
-    s = cmake(0.0, 0.0);
-    return;
-  }
-  const double rab = rsqrt(ab2);  // 1 / |beta|
+  const bool skip = (ab2 <= 1e-36 * scale * scale) || (ab2 == 0.0);
+  const double ab2s = skip ? 1.0 : ab2;
+  const double rab = fast_rsqrt(ab2s);  // 1 / |beta|
   const double tau = 0.5 * (gamma - alpha) * rab;
   const double q = fma(tau, tau, 1.0);
-  const double t = (tau >= 0.0 ? 1.0 : -1.0) * fast_rcp(fabs(tau) + q * rsqrt(q));
-  c = rsqrt(fma(t, t, 1.0));
-  const double inv = t * c * rab;
-  s = cmake(beta.x * inv, beta.y * inv);  // sin * e^{i phi}
-  const double tab = t * (ab2 * rab);     // t |beta|
-  alpha_new = alpha - tab;
-  gamma_new = gamma + tab;
+  const double t = (tau >= 0.0 ? 1.0 : -1.0) * fast_rcp(fabs(tau) + q * fast_rsqrt(q));
+  const double cc = fast_rsqrt(fma(t, t, 1.0));
+  const double inv = t * cc * rab;
+  const double tab = t * (ab2s * rab);  // t |beta|
+  c = skip ? 1.0 : cc;
+  s = skip ? cmake(0.0, 0.0) : cmake(beta.x * inv, beta.y * inv);  // sin * e^{i phi}
+  alpha_new = skip ? alpha : alpha - tab;
+  gamma_new = skip ? gamma : gamma + tab;
 }
 
 struct SyncWarp {
@@ -84,6 +83,10 @@ struct JacobiScratch {
   static constexpr int doubles = 3 * M + 32;
 };
 
+template <int LD>
+__device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v,
+                                   int max_sweeps, double rel2);
+
 // A: M x M Hermitian in shared memory (row-major, leading dimension LD), overwritten (diagonal = eigenvalues).
 //    Both triangles are stored and kept exactly conjugate: only the blocks above the block diagonal are
 //    computed, their mirror images are written as conjugates; the 2x2 diagonal blocks are set analytically.
@@ -95,6 +98,9 @@ struct JacobiScratch {
 template <int M, int NT, class Sync, bool WANT_V, int LD = M>
 __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v = true,
                            int max_sweeps = 30, double rel2 = 0.0) {
+  if constexpr (M == 64 && NT == 512 && WANT_V) {
+    return jacobi_eigh_block64<LD>(A, V, ev, scratch, tid, init_v, max_sweeps, rel2);
+  }
   constexpr int HP = (M / 2 > 0) ? M / 2 : 1;
   constexpr int NOFF = HP * (HP - 1) / 2;                        // 2x2 blocks above the block diagonal
   constexpr int NBA = (NOFF + NT - 1) / NT > 0 ? (NOFF + NT - 1) / NT : 1;
@@ -238,6 +244,171 @@ __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int ti
   }
   for (int k = tid; k < M; k += NT) ev[k] = A[k * LD + k].x;
   Sync::sync();
+  return sweep;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Block-wide eigensolver for M = 64 with 512 threads: ONE barrier per round-robin step.
+//
+// The generic routine above spends most of its time at its two barriers per step and in the serial
+// parameter phase (profiles/r01_ncu_pgdb3_kernel_v5.md: barrier 23 % of samples, FP64 pipe 29 % busy).  Here:
+//  * every warp computes the 32 rotations of the step itself (lane i = pair i; 16x redundant, ~60 DFMA-class
+//    instructions per thread) from the pair's off-diagonal element and its diagonal entries -- no separate
+//    parameter phase, no second barrier; a thread fetches the rotations of its block (I, J) by shuffle;
+//  * diagonal entries and the eigenvector matrix V live in REGISTERS (warp w: rows 4w..4w+3 of V, lane i: the two
+//    columns of pair i) and travel one position along the round-robin ring after each step
+//    (p_i <- p_{i+1}, q_i <- q_{i-1}, q_31 -> p_31, p_0 -> q_1, index 63 stays in lane 0);
+//  * of A only the 2x2 blocks above the block diagonal are kept (496 blocks = 496 threads): element (x, y) is
+//    valid at the position written by the block that last produced it.  One step later that is the direct
+//    position for every element a block needs except (p_I, q_J) with J = I+1, which is read transposed, and
+//    the three elements whose two indices formed a pair in the previous step (annihilated: read as zero).
+// ---------------------------------------------------------------------------------------------
+template <int LD>
+__device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v,
+                                   int max_sweeps, double rel2) {
+  constexpr int M = 64, HP = 32, NT = 512, M1 = 63, NOFF = HP * (HP - 1) / 2, RV = 4;
+  double* red = scratch;  // >= 16 doubles
+  const int lane = tid & 31, wid = tid >> 5;
+  if (init_v) {
+    for (int e = tid; e < M * M; e += NT) V[(e / M) * LD + e % M] = cmake((e / M == e % M) ? 1.0 : 0.0, 0.0);
+  }
+  __syncthreads();
+  // static block assignment: thread t < 496 -> block (I, J), I < J, row-major triangular order; the 16 spare
+  // threads shadow block (0, 1) with their stores predicated off (keeps the step free of branches)
+  const bool has_block = tid < NOFF;
+  int bI = 0, bJ = 1;
+  if (has_block) {
+    int w = tid, I = 0;
+    while (w >= HP - 1 - I) {
+      w -= HP - 1 - I;
+      ++I;
+    }
+    bI = I;
+    bJ = I + 1 + w;
+  }
+  const bool near1 = (bJ == bI + 1), near2 = (bJ == bI + 2), last2 = (bI == HP - 2), first2 = (bI == 0 && bJ == 1);
+  // V in registers.  The V update of a step is applied one step LATE (it only needs that step's rotation, so it
+  // is scheduled into the latency of the next step's rotation chain); the columns are therefore loaded in the
+  // arrangement of step M-2 (== step -1) and the first deferred update is the identity followed by the shift.
+  int p62, q62;
+  rr_pair(M, M1 - 1, lane, p62, q62);
+  cplx vp[RV], vq[RV];
+#pragma unroll
+  for (int k = 0; k < RV; ++k) {
+    vp[k] = V[(RV * wid + k) * LD + p62];
+    vq[k] = V[(RV * wid + k) * LD + q62];
+  }
+  const int col0q = (lane == 0) ? M1 : M1 - lane;  // step-0 arrangement: pair i = (i, 63 - i), pair 0 = (0, 63)
+  double dp = A[lane * LD + lane].x, dq = A[col0q * LD + col0q].x;
+  double c_prev = 1.0;
+  cplx s_prev = cmake(0.0, 0.0);
+  bool fresh = true;  // both triangles of A valid, nothing annihilated yet
+
+  auto v_update = [&]() {  // V <- V J(previous step), then every column moves one position along the ring
+    const cplx cs = cconj(s_prev);
+#pragma unroll
+    for (int k = 0; k < RV; ++k) {
+      const cplx np = csub(cscale(vp[k], c_prev), cmul(cs, vq[k]));
+      const cplx nq = cadd(cmul(s_prev, vp[k]), cscale(vq[k], c_prev));
+      const cplx up = (lane == 0) ? np : nq;  // lane 0 hands its first column to lane 1's second slot
+      cplx rp, rq;
+      rp.x = __shfl_down_sync(0xffffffffu, np.x, 1);
+      rp.y = __shfl_down_sync(0xffffffffu, np.y, 1);
+      rq.x = __shfl_up_sync(0xffffffffu, up.x, 1);
+      rq.y = __shfl_up_sync(0xffffffffu, up.y, 1);
+      vp[k] = (lane == 31) ? nq : rp;
+      vq[k] = (lane == 0) ? nq : rq;
+    }
+  };
+
+  int sweep = 0;
+  for (; sweep < max_sweeps; ++sweep) {
+    // ---- off-diagonal / total Frobenius mass from the valid elements (arrangement of step 0) ----
+    int p = lane, q = col0q;                       // this lane's pair
+    int pi, qi, pj, qj;                            // this thread's block
+    rr_pair(M, 0, bI, pi, qi);
+    rr_pair(M, 0, bJ, pj, qj);
+    {
+      cplx b00 = A[pi * LD + pj];
+      cplx b01 = near1 ? A[qj * LD + pi] : A[pi * LD + qj];
+      const cplx b10 = A[qi * LD + pj];
+      cplx b11 = A[qi * LD + qj];
+      if (!fresh && near2) b01 = cmake(0.0, 0.0);
+      if (!fresh && last2) b00 = cmake(0.0, 0.0);
+      if (!fresh && first2) b11 = cmake(0.0, 0.0);
+      double off = has_block ? cabs2(b00) + cabs2(b01) + cabs2(b10) + cabs2(b11) : 0.0;
+      if (wid == 0) off += cabs2(A[q * LD + p]);  // the off-diagonal element of pair `lane` itself
+      const double dg = (wid == 0) ? dp * dp + dq * dq : 0.0;
+      off = 2.0 * group_sum<NT, SyncBlock>(off, red, tid);
+      const double tot = off + group_sum<NT, SyncBlock>(dg, red, tid);
+      if (off <= (rel2 > 0.0 ? rel2 : 1e-30 * M * M) * tot || tot == 0.0) break;
+    }
+#pragma unroll 3
+    for (int step = 0; step < M1; ++step) {
+      // ---- loads of this step: the pair's off-diagonal element and the thread's 2x2 block ----
+      const cplx beta = cconj(A[q * LD + p]);
+      cplx b00 = A[pi * LD + pj];
+      cplx b01 = near1 ? cconj(A[qj * LD + pi]) : A[pi * LD + qj];
+      const cplx b10 = A[qi * LD + pj];
+      cplx b11 = A[qi * LD + qj];
+      b01 = (!fresh && near2) ? cmake(0.0, 0.0) : b01;
+      b00 = (!fresh && last2) ? cmake(0.0, 0.0) : b00;
+      b11 = (!fresh && first2) ? cmake(0.0, 0.0) : b11;
+      // ---- deferred V update of the previous step (independent of everything below) ----
+      v_update();
+      // ---- rotation of pair `lane` (every warp computes all 32) ----
+      double c, an, gn;
+      cplx s;
+      jacobi_rotation(dp, dq, beta, c, s, an, gn);
+      // ---- A <- J^dagger A J on this thread's block (rotations of pairs I and J fetched by shuffle) ----
+      const double cI = __shfl_sync(0xffffffffu, c, bI), cJ = __shfl_sync(0xffffffffu, c, bJ);
+      cplx sI, sJ;
+      sI.x = __shfl_sync(0xffffffffu, s.x, bI);
+      sI.y = __shfl_sync(0xffffffffu, s.y, bI);
+      sJ.x = __shfl_sync(0xffffffffu, s.x, bJ);
+      sJ.y = __shfl_sync(0xffffffffu, s.y, bJ);
+      const cplx csJ = cconj(sJ), csI = cconj(sI);
+      const cplx x00 = csub(cscale(b00, cJ), cmul(csJ, b01));
+      const cplx x01 = cadd(cmul(sJ, b00), cscale(b01, cJ));
+      const cplx x10 = csub(cscale(b10, cJ), cmul(csJ, b11));
+      const cplx x11 = cadd(cmul(sJ, b10), cscale(b11, cJ));
+      const cplx y00 = csub(cscale(x00, cI), cmul(sI, x10));
+      const cplx y01 = csub(cscale(x01, cI), cmul(sI, x11));
+      const cplx y10 = cadd(cmul(csI, x00), cscale(x10, cI));
+      const cplx y11 = cadd(cmul(csI, x01), cscale(x11, cI));
+      if (has_block) {
+        A[pi * LD + pj] = y00;
+        A[pi * LD + qj] = y01;
+        A[qi * LD + pj] = y10;
+        A[qi * LD + qj] = y11;
+      }
+      // ---- diagonal entries move along the ring; next step's indices ----
+      {
+        const double upd = (lane == 0) ? an : gn;
+        const double rp = __shfl_down_sync(0xffffffffu, an, 1), rq = __shfl_up_sync(0xffffffffu, upd, 1);
+        dp = (lane == 31) ? gn : rp;
+        dq = (lane == 0) ? gn : rq;
+      }
+      c_prev = c;
+      s_prev = s;
+      fresh = false;
+      rr_pair(M, step + 1 == M1 ? 0 : step + 1, lane, p, q);
+      rr_pair(M, step + 1 == M1 ? 0 : step + 1, bI, pi, qi);
+      rr_pair(M, step + 1 == M1 ? 0 : step + 1, bJ, pj, qj);
+      __syncthreads();
+    }
+  }
+  v_update();  // the last executed step's rotation (or the identity) + shift: columns are in step-0 slots again
+#pragma unroll
+  for (int k = 0; k < RV; ++k) {
+    V[(RV * wid + k) * LD + lane] = vp[k];
+    V[(RV * wid + k) * LD + col0q] = vq[k];
+  }
+  if (wid == 0) {
+    ev[lane] = dp;
+    ev[col0q] = dq;
+  }
+  __syncthreads();
   return sweep;
 }
 

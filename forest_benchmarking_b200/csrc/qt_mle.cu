@@ -813,7 +813,7 @@ extern "C" int qt_mle_state_batch(const qt_mle_plan* p, int64_t B, const double*
              "qt_mle_state_batch: quad kernel needs n==2, unit coefficients, vanilla MLE");
   // AUTO at n = 2: 4 lanes per experiment while the batch cannot fill the FP64 pipes with one thread each
   // (the quad kernel executes ~1.8x the FP64 instructions per experiment but has 4x the parallelism)
-  const bool auto_quad = kernel_variant == QT_MLE_KERNEL_AUTO && B < (int64_t)QT_NUM_SMS * 4 * 32;
+  const bool auto_quad = kernel_variant == QT_MLE_KERNEL_AUTO && B <= 8192;  // measured crossover, profiles/r01_exp_mle_batch.txt
   if (reg_ok && p->n == 2 && (kernel_variant == QT_MLE_KERNEL_QUAD || auto_quad)) {
     const unsigned blocks = (unsigned)((B + 7) / 8);
     mle_quad_kernel<<<blocks, 32, 0, st>>>(B, p->K, p->d_slot_ptr, p->d_member_col, expect, epsilon, tol, maxiter, out,

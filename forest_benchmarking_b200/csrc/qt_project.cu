@@ -41,6 +41,108 @@ __global__ void __launch_bounds__(ProjCfg<N>::NT * ProjCfg<N>::GPB)
   for (int e = tid; e < G::MM; e += C::NT) dst[e] = X[G::sidx(e)];
 }
 
+// ---- CP for n = 1: one 4x4 matrix per THREAD, Jacobi entirely in registers --------------------------------
+// A warp per 4x4 matrix (the generic kernel above) leaves 3/4 of the lanes idle and pays shared-memory
+// latency on every rotation: 1.8 % of the HBM roofline (profiles/r01_bench_streaming_v1.json).  Here the
+// Hermitian matrix is kept as diagonal d[4] + upper triangle o[r][c] (r < c), V as 16 complex registers, and
+// the three round-robin steps (0,1)(2,3) | (0,2)(1,3) | (0,3)(1,2) are unrolled with compile-time indices.
+template <int R, int C>
+__device__ __forceinline__ cplx hget(const cplx (&o)[4][4]) {
+  if constexpr (R < C) return o[R][C];
+  else return cconj(o[C][R]);
+}
+template <int R, int C>
+__device__ __forceinline__ void hset(cplx (&o)[4][4], cplx v) {
+  if constexpr (R < C) o[R][C] = v;
+  else o[C][R] = cconj(v);
+}
+template <int P, int Q, int K>
+__device__ __forceinline__ void rot4_k(cplx (&o)[4][4], double c, cplx s) {
+  if constexpr (K != P && K != Q) {
+    const cplx a = hget<K, P>(o), b = hget<K, Q>(o);
+    hset<K, P>(o, csub(cscale(a, c), cmul(cconj(s), b)));
+    hset<K, Q>(o, cadd(cmul(s, a), cscale(b, c)));
+  }
+}
+template <int P, int Q>
+__device__ __forceinline__ void rot4(double (&d)[4], cplx (&o)[4][4], cplx (&v)[4][4]) {
+  double c, an, gn;
+  cplx s;
+  jacobi_rotation(d[P], d[Q], o[P][Q], c, s, an, gn);
+  d[P] = an;
+  d[Q] = gn;
+  o[P][Q] = cmake(0.0, 0.0);
+  rot4_k<P, Q, 0>(o, c, s);
+  rot4_k<P, Q, 1>(o, c, s);
+  rot4_k<P, Q, 2>(o, c, s);
+  rot4_k<P, Q, 3>(o, c, s);
+  const cplx cs = cconj(s);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const cplx v0 = v[r][P], v1 = v[r][Q];
+    v[r][P] = csub(cscale(v0, c), cmul(cs, v1));
+    v[r][Q] = cadd(cmul(s, v0), cscale(v1, c));
+  }
+}
+
+__global__ void __launch_bounds__(128) proj_cp4_thread_kernel(int64_t B, const cplx* __restrict__ in,
+                                                              cplx* __restrict__ out) {
+  __shared__ cplx tile[16 * 128];  // element-major: tile[e * 128 + item] -> conflict-free per-thread access
+  const int tid = threadIdx.x;
+  const int64_t b0 = (int64_t)blockIdx.x * 128;
+  const int nb = (int)min((int64_t)128, B - b0);
+  for (int e = tid; e < nb * 16; e += 128) tile[(e % 16) * 128 + e / 16] = in[b0 * 16 + e];
+  __syncthreads();
+  if (tid < nb) {
+    double d[4];
+    cplx o[4][4], v[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      d[r] = tile[(r * 4 + r) * 128 + tid].x;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        v[r][c] = cmake(r == c ? 1.0 : 0.0, 0.0);
+        if (r < c) {  // Hermitian part (C + C^dagger) / 2, project_superoperators.py:30
+          const cplx x = tile[(r * 4 + c) * 128 + tid], y = tile[(c * 4 + r) * 128 + tid];
+          o[r][c] = cmake(0.5 * (x.x + y.x), 0.5 * (x.y - y.y));
+        }
+      }
+    }
+    for (int sweep = 0; sweep < 30; ++sweep) {
+      double off = 0.0, tot = 0.0;
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        tot = fma(d[r], d[r], tot);
+#pragma unroll
+        for (int c = r + 1; c < 4; ++c) off += cabs2(o[r][c]);
+      }
+      off *= 2.0;
+      tot += off;
+      if (off <= (1e-30 * 16) * tot || tot == 0.0) break;
+      rot4<0, 1>(d, o, v);
+      rot4<2, 3>(d, o, v);
+      rot4<0, 2>(d, o, v);
+      rot4<1, 3>(d, o, v);
+      rot4<0, 3>(d, o, v);
+      rot4<1, 2>(d, o, v);
+    }
+    // OUT = V max(lambda, 0) V^dagger (upper triangle computed, lower mirrored)
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = r; c < 4; ++c) {
+        cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) cfma_conj(acc, cscale(v[r][k], fmax(d[k], 0.0)), v[c][k]);
+        if (r == c) acc.y = 0.0;
+        tile[(r * 4 + c) * 128 + tid] = acc;
+        if (r != c) tile[(c * 4 + r) * 128 + tid] = cconj(acc);
+      }
+  }
+  __syncthreads();
+  for (int e = tid; e < nb * 16; e += 128) out[b0 * 16 + e] = tile[(e % 16) * 128 + e / 16];
+}
+
 // ---- TP / TNI: streaming kernel, several items per block for small n --------------------------------
 template <int N>
 __global__ void proj_tp_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out, int make_tp,
@@ -272,6 +374,11 @@ static int launch_physical(int64_t B, const void* in, void* out, int make_tp, vo
 extern "C" int qt_proj_cp_batch(int n, int64_t B, const void* choi, void* out, void* stream) {
   if (B == 0) return QT_OK;
   QT_REQUIRE(choi && out, "qt_proj_cp_batch: null argument");
+  if (n == 1) {
+    proj_cp4_thread_kernel<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(B, (const cplx*)choi,
+                                                                                          (cplx*)out);
+    return qt_check_launch("proj_cp4_thread_kernel");
+  }
 #define CALL(N) launch_cp<N>(B, choi, out, (cudaStream_t)stream)
   DISPATCH_N3(n, CALL)
 #undef CALL
