@@ -22,6 +22,11 @@
 #include "qt_common.cuh"
 #include "qt_eigh.cuh"
 
+// threads of the block that owns one 64 x 64 Choi matrix (n = 3): 256 or 512 (see jacobi_eigh_block64)
+#ifndef QT_N3_THREADS
+#define QT_N3_THREADS 512
+#endif
+
 template <int N, int NT, class Sync>
 struct ChoiGroup {
   static constexpr int D = 1 << N;

@@ -69,7 +69,7 @@ template <int LOGD>
 struct K2cCfg {
   static constexpr int D = 1 << LOGD, D2 = D * D;
   static constexpr int64_t O = (int64_t)D2 * D2;
-  static constexpr int OUT_PER_BLOCK = 4096;
+  static constexpr int OUT_PER_BLOCK = (D2 >= 1024) ? 16384 : 4096;  // n = 5: amortise the 32 KB Kraus staging
   static constexpr int IPB = (O >= OUT_PER_BLOCK) ? 1 : (int)(OUT_PER_BLOCK / O);
   static constexpr int ROWS = (O >= OUT_PER_BLOCK) ? OUT_PER_BLOCK / D2 : D2;
   static constexpr int RCHUNKS = D2 / ROWS;
@@ -87,7 +87,12 @@ __global__ void __launch_bounds__(256) kraus2choi_kernel(int nk, int64_t B, cons
   const int nb = (int)min((int64_t)C::IPB, B - b0);
   for (int e = threadIdx.x; e < nb * nk * D2; e += 256) {
     const int within = e % D2, which = e / D2;
-    ks[which * D2 + (within % D) * D + within / D] = kraus[b0 * nk * D2 + e];
+    if (D >= 16) {
+      // transpose on the (L2-resident) read side: a transposed shared-memory write would put 32 lanes on one bank
+      ks[e] = kraus[b0 * nk * D2 + which * D2 + (within % D) * D + within / D];
+    } else {
+      ks[which * D2 + (within % D) * D + within / D] = kraus[b0 * nk * D2 + e];
+    }
   }
   __syncthreads();
   // consecutive threads -> consecutive output elements (fully coalesced 16-byte stores)
@@ -119,7 +124,7 @@ static int launch_kraus2choi_fast(int nk, int64_t B, const void* kraus, void* ou
 static int launch_kraus_outer(int mode, int d, int nk, int64_t B, const void* kraus, void* out, cudaStream_t st) {
   const int d2 = d * d;
   if (mode == 0 && (d & (d - 1)) == 0 && d >= 2) {
-    const int ipb = (d2 * d2 >= 4096) ? 1 : 4096 / (d2 * d2);
+    const int ipb = (d2 * d2 >= 4096) ? 1 : 4096 / (d2 * d2);  // K2cCfg::IPB
     if ((size_t)ipb * nk * d2 * sizeof(cplx) <= 96 * 1024) {
       switch (d) {
         case 2: return launch_kraus2choi_fast<1>(nk, B, kraus, out, st);

@@ -83,7 +83,7 @@ struct JacobiScratch {
   static constexpr int doubles = 3 * M + 32;
 };
 
-template <int LD>
+template <int LD, int NT>
 __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v,
                                    int max_sweeps, double rel2);
 
@@ -98,8 +98,8 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
 template <int M, int NT, class Sync, bool WANT_V, int LD = M>
 __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v = true,
                            int max_sweeps = 30, double rel2 = 0.0) {
-  if constexpr (M == 64 && NT == 512 && WANT_V) {
-    return jacobi_eigh_block64<LD>(A, V, ev, scratch, tid, init_v, max_sweeps, rel2);
+  if constexpr (M == 64 && (NT == 512 || NT == 256) && WANT_V) {
+    return jacobi_eigh_block64<LD, NT>(A, V, ev, scratch, tid, init_v, max_sweeps, rel2);
   }
   constexpr int HP = (M / 2 > 0) ? M / 2 : 1;
   constexpr int NOFF = HP * (HP - 1) / 2;                        // 2x2 blocks above the block diagonal
@@ -248,7 +248,7 @@ __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int ti
 }
 
 // ---------------------------------------------------------------------------------------------
-// Block-wide eigensolver for M = 64 with 512 threads: ONE barrier per round-robin step.
+// Block-wide eigensolver for M = 64 with 256 or 512 threads: ONE barrier per round-robin step.
 //
 // The generic routine above spends most of its time at its two barriers per step and in the serial
 // parameter phase (profiles/r01_ncu_pgdb3_kernel_v5.md: barrier 23 % of samples, FP64 pipe 29 % busy).  Here:
@@ -263,30 +263,40 @@ __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int ti
 //    position for every element a block needs except (p_I, q_J) with J = I+1, which is read transposed, and
 //    the three elements whose two indices formed a pair in the previous step (annihilated: read as zero).
 // ---------------------------------------------------------------------------------------------
-template <int LD>
+template <int LD, int NT>
 __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v,
                                    int max_sweeps, double rel2) {
-  constexpr int M = 64, HP = 32, NT = 512, M1 = 63, NOFF = HP * (HP - 1) / 2, RV = 4;
+  constexpr int M = 64, HP = 32, M1 = 63, NOFF = HP * (HP - 1) / 2;
+  constexpr int NW = NT / 32, RV = M / NW;        // V rows per warp
+  constexpr int NB = (NOFF + NT - 1) / NT;        // 2x2 blocks per thread
   double* red = scratch;  // >= 16 doubles
   const int lane = tid & 31, wid = tid >> 5;
   if (init_v) {
     for (int e = tid; e < M * M; e += NT) V[(e / M) * LD + e % M] = cmake((e / M == e % M) ? 1.0 : 0.0, 0.0);
   }
   __syncthreads();
-  // static block assignment: thread t < 496 -> block (I, J), I < J, row-major triangular order; the 16 spare
-  // threads shadow block (0, 1) with their stores predicated off (keeps the step free of branches)
-  const bool has_block = tid < NOFF;
-  int bI = 0, bJ = 1;
-  if (has_block) {
-    int w = tid, I = 0;
-    while (w >= HP - 1 - I) {
-      w -= HP - 1 - I;
-      ++I;
+  // static block assignment: block w = tid + k NT < 496 -> (I, J), I < J, row-major triangular order; spare
+  // slots shadow block (0, 1) with their stores predicated off (keeps the step free of branches)
+  bool has_block[NB], near1[NB], near2[NB], last2[NB], first2[NB];
+  int bI[NB], bJ[NB];
+#pragma unroll
+  for (int k = 0; k < NB; ++k) {
+    int w = tid + k * NT, I = 0, J = 1;
+    has_block[k] = w < NOFF;
+    if (has_block[k]) {
+      while (w >= HP - 1 - I) {
+        w -= HP - 1 - I;
+        ++I;
+      }
+      J = I + 1 + w;
     }
-    bI = I;
-    bJ = I + 1 + w;
+    bI[k] = I;
+    bJ[k] = J;
+    near1[k] = (J == I + 1);
+    near2[k] = (J == I + 2);
+    last2[k] = (I == HP - 2);
+    first2[k] = (I == 0 && J == 1);
   }
-  const bool near1 = (bJ == bI + 1), near2 = (bJ == bI + 2), last2 = (bI == HP - 2), first2 = (bI == 0 && bJ == 1);
   // V in registers.  The V update of a step is applied one step LATE (it only needs that step's rotation, so it
   // is scheduled into the latency of the next step's rotation chain); the columns are therefore loaded in the
   // arrangement of step M-2 (== step -1) and the first deferred update is the identity followed by the shift.
@@ -325,18 +335,22 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
   for (; sweep < max_sweeps; ++sweep) {
     // ---- off-diagonal / total Frobenius mass from the valid elements (arrangement of step 0) ----
     int p = lane, q = col0q;                       // this lane's pair
-    int pi, qi, pj, qj;                            // this thread's block
-    rr_pair(M, 0, bI, pi, qi);
-    rr_pair(M, 0, bJ, pj, qj);
+    int pi[NB], qi[NB], pj[NB], qj[NB];            // this thread's blocks
     {
-      cplx b00 = A[pi * LD + pj];
-      cplx b01 = near1 ? A[qj * LD + pi] : A[pi * LD + qj];
-      const cplx b10 = A[qi * LD + pj];
-      cplx b11 = A[qi * LD + qj];
-      if (!fresh && near2) b01 = cmake(0.0, 0.0);
-      if (!fresh && last2) b00 = cmake(0.0, 0.0);
-      if (!fresh && first2) b11 = cmake(0.0, 0.0);
-      double off = has_block ? cabs2(b00) + cabs2(b01) + cabs2(b10) + cabs2(b11) : 0.0;
+      double off = 0.0;
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        rr_pair(M, 0, bI[k], pi[k], qi[k]);
+        rr_pair(M, 0, bJ[k], pj[k], qj[k]);
+        cplx b00 = A[pi[k] * LD + pj[k]];
+        cplx b01 = near1[k] ? A[qj[k] * LD + pi[k]] : A[pi[k] * LD + qj[k]];
+        const cplx b10 = A[qi[k] * LD + pj[k]];
+        cplx b11 = A[qi[k] * LD + qj[k]];
+        if (!fresh && near2[k]) b01 = cmake(0.0, 0.0);
+        if (!fresh && last2[k]) b00 = cmake(0.0, 0.0);
+        if (!fresh && first2[k]) b11 = cmake(0.0, 0.0);
+        if (has_block[k]) off += cabs2(b00) + cabs2(b01) + cabs2(b10) + cabs2(b11);
+      }
       if (wid == 0) off += cabs2(A[q * LD + p]);  // the off-diagonal element of pair `lane` itself
       const double dg = (wid == 0) ? dp * dp + dq * dq : 0.0;
       off = 2.0 * group_sum<NT, SyncBlock>(off, red, tid);
@@ -345,42 +359,49 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
     }
 #pragma unroll 3
     for (int step = 0; step < M1; ++step) {
-      // ---- loads of this step: the pair's off-diagonal element and the thread's 2x2 block ----
+      // ---- loads of this step: the pair's off-diagonal element and the thread's 2x2 blocks ----
       const cplx beta = cconj(A[q * LD + p]);
-      cplx b00 = A[pi * LD + pj];
-      cplx b01 = near1 ? cconj(A[qj * LD + pi]) : A[pi * LD + qj];
-      const cplx b10 = A[qi * LD + pj];
-      cplx b11 = A[qi * LD + qj];
-      b01 = (!fresh && near2) ? cmake(0.0, 0.0) : b01;
-      b00 = (!fresh && last2) ? cmake(0.0, 0.0) : b00;
-      b11 = (!fresh && first2) ? cmake(0.0, 0.0) : b11;
+      cplx b00[NB], b01[NB], b10[NB], b11[NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        b00[k] = A[pi[k] * LD + pj[k]];
+        b01[k] = near1[k] ? cconj(A[qj[k] * LD + pi[k]]) : A[pi[k] * LD + qj[k]];
+        b10[k] = A[qi[k] * LD + pj[k]];
+        b11[k] = A[qi[k] * LD + qj[k]];
+        b01[k] = (!fresh && near2[k]) ? cmake(0.0, 0.0) : b01[k];
+        b00[k] = (!fresh && last2[k]) ? cmake(0.0, 0.0) : b00[k];
+        b11[k] = (!fresh && first2[k]) ? cmake(0.0, 0.0) : b11[k];
+      }
       // ---- deferred V update of the previous step (independent of everything below) ----
       v_update();
       // ---- rotation of pair `lane` (every warp computes all 32) ----
       double c, an, gn;
       cplx s;
       jacobi_rotation(dp, dq, beta, c, s, an, gn);
-      // ---- A <- J^dagger A J on this thread's block (rotations of pairs I and J fetched by shuffle) ----
-      const double cI = __shfl_sync(0xffffffffu, c, bI), cJ = __shfl_sync(0xffffffffu, c, bJ);
-      cplx sI, sJ;
-      sI.x = __shfl_sync(0xffffffffu, s.x, bI);
-      sI.y = __shfl_sync(0xffffffffu, s.y, bI);
-      sJ.x = __shfl_sync(0xffffffffu, s.x, bJ);
-      sJ.y = __shfl_sync(0xffffffffu, s.y, bJ);
-      const cplx csJ = cconj(sJ), csI = cconj(sI);
-      const cplx x00 = csub(cscale(b00, cJ), cmul(csJ, b01));
-      const cplx x01 = cadd(cmul(sJ, b00), cscale(b01, cJ));
-      const cplx x10 = csub(cscale(b10, cJ), cmul(csJ, b11));
-      const cplx x11 = cadd(cmul(sJ, b10), cscale(b11, cJ));
-      const cplx y00 = csub(cscale(x00, cI), cmul(sI, x10));
-      const cplx y01 = csub(cscale(x01, cI), cmul(sI, x11));
-      const cplx y10 = cadd(cmul(csI, x00), cscale(x10, cI));
-      const cplx y11 = cadd(cmul(csI, x01), cscale(x11, cI));
-      if (has_block) {
-        A[pi * LD + pj] = y00;
-        A[pi * LD + qj] = y01;
-        A[qi * LD + pj] = y10;
-        A[qi * LD + qj] = y11;
+      // ---- A <- J^dagger A J on this thread's blocks (rotations of pairs I and J fetched by shuffle) ----
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        const double cI = __shfl_sync(0xffffffffu, c, bI[k]), cJ = __shfl_sync(0xffffffffu, c, bJ[k]);
+        cplx sI, sJ;
+        sI.x = __shfl_sync(0xffffffffu, s.x, bI[k]);
+        sI.y = __shfl_sync(0xffffffffu, s.y, bI[k]);
+        sJ.x = __shfl_sync(0xffffffffu, s.x, bJ[k]);
+        sJ.y = __shfl_sync(0xffffffffu, s.y, bJ[k]);
+        const cplx csJ = cconj(sJ), csI = cconj(sI);
+        const cplx x00 = csub(cscale(b00[k], cJ), cmul(csJ, b01[k]));
+        const cplx x01 = cadd(cmul(sJ, b00[k]), cscale(b01[k], cJ));
+        const cplx x10 = csub(cscale(b10[k], cJ), cmul(csJ, b11[k]));
+        const cplx x11 = cadd(cmul(sJ, b10[k]), cscale(b11[k], cJ));
+        const cplx y00 = csub(cscale(x00, cI), cmul(sI, x10));
+        const cplx y01 = csub(cscale(x01, cI), cmul(sI, x11));
+        const cplx y10 = cadd(cmul(csI, x00), cscale(x10, cI));
+        const cplx y11 = cadd(cmul(csI, x01), cscale(x11, cI));
+        if (has_block[k]) {
+          A[pi[k] * LD + pj[k]] = y00;
+          A[pi[k] * LD + qj[k]] = y01;
+          A[qi[k] * LD + pj[k]] = y10;
+          A[qi[k] * LD + qj[k]] = y11;
+        }
       }
       // ---- diagonal entries move along the ring; next step's indices ----
       {
@@ -392,9 +413,13 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
       c_prev = c;
       s_prev = s;
       fresh = false;
-      rr_pair(M, step + 1 == M1 ? 0 : step + 1, lane, p, q);
-      rr_pair(M, step + 1 == M1 ? 0 : step + 1, bI, pi, qi);
-      rr_pair(M, step + 1 == M1 ? 0 : step + 1, bJ, pj, qj);
+      const int nxt = (step + 1 == M1) ? 0 : step + 1;
+      rr_pair(M, nxt, lane, p, q);
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        rr_pair(M, nxt, bI[k], pi[k], qi[k]);
+        rr_pair(M, nxt, bJ[k], pj[k], qj[k]);
+      }
       __syncthreads();
     }
   }

@@ -41,7 +41,7 @@ struct PgdbView {
 
 template <int N>
 struct PgdbCfg {
-  static constexpr int NT = (N >= 3) ? 512 : 32;
+  static constexpr int NT = (N >= 3) ? QT_N3_THREADS : 32;
   static constexpr int GPB = (N >= 3) ? 1 : 4;
   using Sync = typename std::conditional<(N >= 3), SyncBlock, SyncWarp>::type;
   using G = ChoiGroup<N, NT, Sync>;

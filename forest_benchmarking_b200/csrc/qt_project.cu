@@ -8,7 +8,7 @@
 
 template <int N>
 struct ProjCfg {
-  static constexpr int NT = (N >= 3) ? 512 : 32;           // threads per group
+  static constexpr int NT = (N >= 3) ? QT_N3_THREADS : 32;           // threads per group
   static constexpr int GPB = (N >= 3) ? 1 : 4;             // groups per block
   using Sync = typename std::conditional<(N >= 3), SyncBlock, SyncWarp>::type;
   using G = ChoiGroup<N, NT, Sync>;
