@@ -83,7 +83,9 @@ struct JacobiScratch {
   static constexpr int doubles = 3 * M + 32;
 };
 
-template <int LD, int NT>
+// ABL: ablation mask for scripts/ubench_jacobi.cu only (1: no V update, 2: no block update, 4: no rotation
+// chain, 8: no barrier); 0 in every product instantiation.
+template <int LD, int NT, int ABL = 0>
 __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v,
                                    int max_sweeps, double rel2);
 
@@ -247,6 +249,25 @@ __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int ti
   return sweep;
 }
 
+// Split-phase CTA barrier on an mbarrier in shared memory: arrive (release) right after the last shared-memory
+// store of a step, wait (acquire) right before the first load of the next one; the register-only V update sits
+// in between, so a warp that is ahead does useful work instead of idling at the barrier.
+__device__ __forceinline__ void mbar_init(double* slot, int count) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(slot);
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(double* slot) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(slot);
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}" ::"r"(a) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(double* slot, unsigned parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(slot);
+  asm volatile(
+      "{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n"
+      " bra WAIT_%=;\n DONE_%=:\n}" ::"r"(a), "r"(parity)
+      : "memory");
+}
+
 // ---------------------------------------------------------------------------------------------
 // Block-wide eigensolver for M = 64 with 256 or 512 threads: ONE barrier per round-robin step.
 //
@@ -263,7 +284,7 @@ __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int ti
 //    position for every element a block needs except (p_I, q_J) with J = I+1, which is read transposed, and
 //    the three elements whose two indices formed a pair in the previous step (annihilated: read as zero).
 // ---------------------------------------------------------------------------------------------
-template <int LD, int NT>
+template <int LD, int NT, int ABL>
 __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v,
                                    int max_sweeps, double rel2) {
   constexpr int M = 64, HP = 32, M1 = 63, NOFF = HP * (HP - 1) / 2;
@@ -297,24 +318,31 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
     last2[k] = (I == HP - 2);
     first2[k] = (I == 0 && J == 1);
   }
-  // V in registers.  The V update of a step is applied one step LATE (it only needs that step's rotation, so it
-  // is scheduled into the latency of the next step's rotation chain); the columns are therefore loaded in the
-  // arrangement of step M-2 (== step -1) and the first deferred update is the identity followed by the shift.
-  int p62, q62;
-  rr_pair(M, M1 - 1, lane, p62, q62);
+  // V in registers, columns in the arrangement of step 0: pair i = (i, 63 - i), pair 0 = (0, 63)
+  const int col0q = (lane == 0) ? M1 : M1 - lane;
   cplx vp[RV], vq[RV];
 #pragma unroll
   for (int k = 0; k < RV; ++k) {
-    vp[k] = V[(RV * wid + k) * LD + p62];
-    vq[k] = V[(RV * wid + k) * LD + q62];
+    vp[k] = V[(RV * wid + k) * LD + lane];
+    vq[k] = V[(RV * wid + k) * LD + col0q];
   }
-  const int col0q = (lane == 0) ? M1 : M1 - lane;  // step-0 arrangement: pair i = (i, 63 - i), pair 0 = (0, 63)
   double dp = A[lane * LD + lane].x, dq = A[col0q * LD + col0q].x;
-  double c_prev = 1.0;
-  cplx s_prev = cmake(0.0, 0.0);
   bool fresh = true;  // both triangles of A valid, nothing annihilated yet
+  // split-phase barrier state: `pending` = an arrive of this thread has not been matched by a wait yet
+  double* mbar = scratch + 32;
+  unsigned parity = 0;
+  bool pending = false;
+  if (tid == 0) mbar_init(mbar, NT);
+  __syncthreads();
+  auto wait_pending = [&]() {
+    if (pending) {
+      if constexpr (!(ABL & 8)) mbar_wait(mbar, parity);
+      parity ^= 1u;
+      pending = false;
+    }
+  };
 
-  auto v_update = [&]() {  // V <- V J(previous step), then every column moves one position along the ring
+  auto v_update = [&](double c_prev, cplx s_prev) {  // V <- V J, then every column moves one ring position
     const cplx cs = cconj(s_prev);
 #pragma unroll
     for (int k = 0; k < RV; ++k) {
@@ -334,6 +362,7 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
   int sweep = 0;
   for (; sweep < max_sweeps; ++sweep) {
     // ---- off-diagonal / total Frobenius mass from the valid elements (arrangement of step 0) ----
+    wait_pending();
     int p = lane, q = col0q;                       // this lane's pair
     int pi[NB], qi[NB], pj[NB], qj[NB];            // this thread's blocks
     {
@@ -360,6 +389,7 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
 #pragma unroll 3
     for (int step = 0; step < M1; ++step) {
       // ---- loads of this step: the pair's off-diagonal element and the thread's 2x2 blocks ----
+      wait_pending();
       const cplx beta = cconj(A[q * LD + p]);
       cplx b00[NB], b01[NB], b10[NB], b11[NB];
 #pragma unroll
@@ -372,21 +402,32 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
         b00[k] = (!fresh && last2[k]) ? cmake(0.0, 0.0) : b00[k];
         b11[k] = (!fresh && first2[k]) ? cmake(0.0, 0.0) : b11[k];
       }
-      // ---- deferred V update of the previous step (independent of everything below) ----
-      v_update();
       // ---- rotation of pair `lane` (every warp computes all 32) ----
       double c, an, gn;
       cplx s;
-      jacobi_rotation(dp, dq, beta, c, s, an, gn);
+      if constexpr (ABL & 4) {
+        c = 0.8;
+        s = cmake(0.36 + 1e-9 * beta.x, 0.48);
+        an = dp;
+        gn = dq;
+      } else {
+        jacobi_rotation(dp, dq, beta, c, s, an, gn);
+      }
       // ---- A <- J^dagger A J on this thread's blocks (rotations of pairs I and J fetched by shuffle) ----
 #pragma unroll
-      for (int k = 0; k < NB; ++k) {
-        const double cI = __shfl_sync(0xffffffffu, c, bI[k]), cJ = __shfl_sync(0xffffffffu, c, bJ[k]);
+      for (int k = 0; k < ((ABL & 2) ? 0 : NB); ++k) {
+        double cI, cJ;
         cplx sI, sJ;
-        sI.x = __shfl_sync(0xffffffffu, s.x, bI[k]);
-        sI.y = __shfl_sync(0xffffffffu, s.y, bI[k]);
-        sJ.x = __shfl_sync(0xffffffffu, s.x, bJ[k]);
-        sJ.y = __shfl_sync(0xffffffffu, s.y, bJ[k]);
+        if constexpr (ABL & 16) {
+          cI = c; cJ = c; sI = s; sJ = cconj(s);
+        } else {
+          cI = __shfl_sync(0xffffffffu, c, bI[k]);
+          cJ = __shfl_sync(0xffffffffu, c, bJ[k]);
+          sI.x = __shfl_sync(0xffffffffu, s.x, bI[k]);
+          sI.y = __shfl_sync(0xffffffffu, s.y, bI[k]);
+          sJ.x = __shfl_sync(0xffffffffu, s.x, bJ[k]);
+          sJ.y = __shfl_sync(0xffffffffu, s.y, bJ[k]);
+        }
         const cplx csJ = cconj(sJ), csI = cconj(sI);
         const cplx x00 = csub(cscale(b00[k], cJ), cmul(csJ, b01[k]));
         const cplx x01 = cadd(cmul(sJ, b00[k]), cscale(b01[k], cJ));
@@ -396,13 +437,17 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
         const cplx y01 = csub(cscale(x01, cI), cmul(sI, x11));
         const cplx y10 = cadd(cmul(csI, x00), cscale(x10, cI));
         const cplx y11 = cadd(cmul(csI, x01), cscale(x11, cI));
-        if (has_block[k]) {
+        if (has_block[k] && (!(ABL & 32) || y00.x == 1.2345)) {
           A[pi[k] * LD + pj[k]] = y00;
           A[pi[k] * LD + qj[k]] = y01;
           A[qi[k] * LD + pj[k]] = y10;
           A[qi[k] * LD + qj[k]] = y11;
         }
       }
+      // ---- all shared-memory stores of the step are issued: arrive, then do the register-only work ----
+      if constexpr (!(ABL & 8)) mbar_arrive(mbar);
+      pending = true;
+      if constexpr (!(ABL & 1)) v_update(c, s);
       // ---- diagonal entries move along the ring; next step's indices ----
       {
         const double upd = (lane == 0) ? an : gn;
@@ -410,8 +455,6 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
         dp = (lane == 31) ? gn : rp;
         dq = (lane == 0) ? gn : rq;
       }
-      c_prev = c;
-      s_prev = s;
       fresh = false;
       const int nxt = (step + 1 == M1) ? 0 : step + 1;
       rr_pair(M, nxt, lane, p, q);
@@ -420,10 +463,10 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
         rr_pair(M, nxt, bI[k], pi[k], qi[k]);
         rr_pair(M, nxt, bJ[k], pj[k], qj[k]);
       }
-      __syncthreads();
     }
   }
-  v_update();  // the last executed step's rotation (or the identity) + shift: columns are in step-0 slots again
+  wait_pending();
+  // a whole number of sweeps returns every column to its step-0 slot
 #pragma unroll
   for (int k = 0; k < RV; ++k) {
     V[(RV * wid + k) * LD + lane] = vp[k];
@@ -434,6 +477,10 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
     ev[col0q] = dq;
   }
   __syncthreads();
+  if (tid == 0) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(mbar);
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(a) : "memory");
+  }
   return sweep;
 }
 

@@ -22,6 +22,27 @@ __global__ void dfma_chain(int iters, double* out, long long* cyc) {
   if (threadIdx.x == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
 }
 
+template <int OP>
+__global__ void dop_tput(int iters, double* out) {
+  double a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 1.0 + threadIdx.x + i;
+  const double m = 0.999999, c = 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (OP == 0) a[i] = fma(a[i], m, c);
+      if (OP == 1) a[i] = a[i] * m;
+      if (OP == 2) a[i] = a[i] + c;
+      if (OP == 3) { a[i] = a[i] * m; a[i] = a[i] + c; }
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == 42.0) out[0] = s;
+}
+
 __global__ void ddiv_chain(int iters, double* out, long long* cyc) {
   double a = 1.0 + threadIdx.x, b = 3.0 + threadIdx.x;
   long long t0 = clock64();
@@ -88,6 +109,23 @@ int main() {
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     double fl = 148.0 * 32 * wps * 8 * 200000 * 2;
     printf("DFMA tput %2d warps/SM: %.2f TFLOP/s\n", wps, fl / ms / 1e9);
+  }
+  const char* names[4] = {"DFMA", "DMUL", "DADD", "DMUL+DADD (2 ops)"};
+  for (int op = 0; op < 4; ++op) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float ms;
+    auto launch = [&](int it) {
+      if (op == 0) dop_tput<0><<<148, 512>>>(it, out);
+      if (op == 1) dop_tput<1><<<148, 512>>>(it, out);
+      if (op == 2) dop_tput<2><<<148, 512>>>(it, out);
+      if (op == 3) dop_tput<3><<<148, 512>>>(it, out);
+    };
+    launch(1000);
+    cudaEventRecord(e0); launch(100000); cudaEventRecord(e1); cudaDeviceSynchronize();
+    cudaEventElapsedTime(&ms, e0, e1);
+    double ops = 148.0 * 512 * 8 * 100000 * (op == 3 ? 2 : 1);
+    printf("%-20s 16 warps/SM: %.2f T ops/s  (%.2f cycles per warp-instruction per SMSP)\n", names[op], ops / ms / 1e9,
+           ms * 1e-3 * 1.965e9 / (100000.0 * 8 * (op == 3 ? 2 : 1) * 4));
   }
   return 0;
 }
