@@ -24,6 +24,7 @@ struct qt_mle_plan {
   int* d_slot_ptr;        // [S+1]  CSR over canonical Pauli slots
   int* d_member_col;      // [K]    column of `expect` for each member
   double* d_member_coeff; // [K]
+  double* d_member_linw;  // [K]    linear-inversion weight c_k / (d * sum_{k' in slot} c_k'^2)
   int* d_mask2idx;        // [S]    (x*D + z) -> canonical Pauli index
 };
 
@@ -726,6 +727,40 @@ __global__ void mle_step_kernel(int64_t B, int K, const double* __restrict__ exp
 }
 
 // =============================================================================================
+// Linear inversion (tomography.py:130-165): rho = unvec(pinv(M) e) + I/d with rows M_k = c_k vec(P_k)^dagger.
+// Distinct Paulis are orthogonal, so M^dagger M is diagonal in the Pauli basis and the pseudo-inverse is a
+// per-slot weighted average:  rho = I/d + sum_j [ sum_{k in j} c_k e_k / (d sum_{k in j} c_k^2) ] P_j
+// for ANY list of Pauli observables (duplicates, missing terms, non-unit coefficients) -- one inverse Pauli
+// transform per experiment, no SVD.  One block per experiment.
+// =============================================================================================
+template <int N>
+__global__ void linear_inv_kernel(int64_t B, int K, const int* __restrict__ slot_ptr, const int* __restrict__ member_col,
+                                  const double* __restrict__ member_linw, const int* __restrict__ mask2idx,
+                                  const double* __restrict__ expect, cplx* __restrict__ rho_out) {
+  constexpr int D = 1 << N, S = 1 << (2 * N), DD = D * D;
+  __shared__ double w[S];
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    const double* ex = expect + b * K;
+    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+      double acc = 0.0;
+      for (int m = slot_ptr[j]; m < slot_ptr[j + 1]; ++m) acc = fma(member_linw[m], ex[member_col[m]], acc);
+      w[j] = acc;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < DD; e += blockDim.x) {
+      const int r = e / D, c = e % D, x = r ^ c;
+      cplx acc = cmake(r == c ? 1.0 / D : 0.0, 0.0);
+      for (int z = 0; z < D; ++z) {
+        const cplx term = cmul_ipow(cmake(w[mask2idx[x * D + z]], 0.0), __popc(x & z) & 3);
+        if (__popc(z & c) & 1) acc = csub(acc, term); else acc = cadd(acc, term);
+      }
+      rho_out[b * DD + e] = acc;
+    }
+    __syncthreads();
+  }
+}
+
+// =============================================================================================
 // C ABI
 // =============================================================================================
 extern "C" int qt_mle_plan_create(int n, int K, const int32_t* pauli_idx, const double* coeff,
@@ -734,7 +769,7 @@ extern "C" int qt_mle_plan_create(int n, int K, const int32_t* pauli_idx, const 
   QT_REQUIRE(K >= 1 && pauli_idx && coeff && plan_out, "qt_mle_plan_create: bad arguments");
   const int S = 1 << (2 * n), D = 1 << n;
   std::vector<int> slot_ptr(S + 1, 0), col(K), cursor(S, 0), m2i(S);
-  std::vector<double> cf(K);
+  std::vector<double> cf(K), linw(K), slot_c2(S, 0.0);
   int unit = 1;
   for (int k = 0; k < K; ++k) {
     QT_REQUIRE(pauli_idx[k] >= 0 && pauli_idx[k] < S, "qt_mle_plan_create: pauli_idx[%d]=%d out of range", k,
@@ -748,12 +783,18 @@ extern "C" int qt_mle_plan_create(int n, int K, const int32_t* pauli_idx, const 
     int pos = slot_ptr[s] + cursor[s]++;
     col[pos] = k;
     cf[pos] = coeff[k];
+    slot_c2[s] += coeff[k] * coeff[k];
   }
+  for (int s = 0; s < S; ++s)
+    for (int m = slot_ptr[s]; m < slot_ptr[s + 1]; ++m) linw[m] = slot_c2[s] > 0.0 ? cf[m] / (D * slot_c2[s]) : 0.0;
   for (int x = 0; x < D; ++x)
     for (int z = 0; z < D; ++z) m2i[x * D + z] = pauli_from_masks(x, z, n);
   qt_mle_plan* p = new qt_mle_plan();
   p->n = n; p->K = K; p->S = S; p->unit_coeff = unit;
   p->d_slot_ptr = nullptr; p->d_member_col = nullptr; p->d_member_coeff = nullptr; p->d_mask2idx = nullptr;
+  p->d_member_linw = nullptr;
+  QT_CUDA(cudaMalloc(&p->d_member_linw, sizeof(double) * K));
+  QT_CUDA(cudaMemcpy(p->d_member_linw, linw.data(), sizeof(double) * K, cudaMemcpyHostToDevice));
   QT_CUDA(cudaMalloc(&p->d_slot_ptr, sizeof(int) * (S + 1)));
   QT_CUDA(cudaMalloc(&p->d_member_col, sizeof(int) * K));
   QT_CUDA(cudaMalloc(&p->d_member_coeff, sizeof(double) * K));
@@ -771,6 +812,7 @@ extern "C" int qt_mle_plan_destroy(qt_mle_plan* p) {
   cudaFree(p->d_slot_ptr);
   cudaFree(p->d_member_col);
   cudaFree(p->d_member_coeff);
+  cudaFree(p->d_member_linw);
   cudaFree(p->d_mask2idx);
   delete p;
   return QT_OK;
@@ -851,4 +893,26 @@ extern "C" int qt_mle_step_batch(int n, int64_t B, const double* expect_canon, c
   else
     mle_step_kernel<2><<<blocks, 128, 0, st>>>(B, K, expect_canon, (const cplx*)rho_in, epsilon, (cplx*)rho_out);
   return qt_check_launch("mle_step_kernel");
+}
+
+extern "C" int qt_linear_inv_state_batch(const qt_mle_plan* p, int64_t B, const double* expect, void* rho_out,
+                                         void* stream) {
+  QT_REQUIRE(p, "qt_linear_inv_state_batch: null plan");
+  if (B == 0) return QT_OK;
+  QT_REQUIRE(expect && rho_out, "qt_linear_inv_state_batch: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)std::min<int64_t>(B, (int64_t)QT_NUM_SMS * 16);
+  const int threads = p->n <= 2 ? 32 : 256;
+#define LAUNCH(N)                                                                                                  \
+  linear_inv_kernel<N><<<blocks, threads, 0, st>>>(B, p->K, p->d_slot_ptr, p->d_member_col, p->d_member_linw, \
+                                                   p->d_mask2idx, expect, (cplx*)rho_out)
+  switch (p->n) {
+    case 1: LAUNCH(1); break;
+    case 2: LAUNCH(2); break;
+    case 3: LAUNCH(3); break;
+    case 4: LAUNCH(4); break;
+    default: LAUNCH(5); break;
+  }
+#undef LAUNCH
+  return qt_check_launch("linear_inv_kernel");
 }

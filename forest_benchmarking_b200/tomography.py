@@ -76,6 +76,30 @@ def iterative_mle_state_estimate_batch(plan: MlePlan, expectations, counts=None,
     return out, iters_out
 
 
+def linear_inv_state_estimate_batch(plan: MlePlan, expectations, out=None):
+    """Batched linear inversion.  expectations: CUDA float64 [B, K] -> rho [B, d, d] complex128 (CUDA)."""
+    torch = _lib.require_cuda()
+    if expectations.dtype != torch.float64 or not expectations.is_cuda or expectations.dim() != 2 \
+            or expectations.shape[1] != plan.K:
+        raise ValueError(f"expectations must be a CUDA float64 tensor of shape [B, {plan.K}]")
+    expectations = expectations.contiguous()
+    b, d = expectations.shape[0], 2 ** plan.n
+    if out is None:
+        out = torch.empty((b, d, d), dtype=torch.complex128, device=expectations.device)
+    _lib.check(_lib.lib().qt_linear_inv_state_batch(plan._h, ctypes.c_int64(b), _lib.ptr(expectations), _lib.ptr(out),
+                                                    _lib.current_stream_ptr()), "qt_linear_inv_state_batch")
+    return out
+
+
+def linear_inv_state_estimate(results: List, qubits: List[int]) -> np.ndarray:
+    """Drop-in for reference tomography.py:130-165."""
+    torch = _lib.require_cuda()
+    idx, cf, ex, _ = flatten_state_results(results, qubits)
+    plan = MlePlan(len(qubits), idx, cf)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    return linear_inv_state_estimate_batch(plan, torch.from_numpy(ex[None, :]).to(dev))[0].cpu().numpy()
+
+
 def mle_step_batch(n_qubits: int, expect_canon, rho, epsilon=.1, out=None):
     """ONE R-rho-R update streamed through HBM (n = 1, 2; complete canonical Pauli set).
     expect_canon: [4^n - 1, B] float64 CUDA (item-minor); rho: [B, d, d] complex128 CUDA."""

@@ -34,7 +34,7 @@ int qt_version(void);
 int qt_last_error(char* buf, int len);
 
 /* Process-wide tuning knob: relative off-diagonal Frobenius norm at which the Jacobi eigensolver inside
- * qt_proj_physical_batch / qt_pgdb_process_batch declares convergence (default 1e-9; 0 = tight 1e-15 * 4^n). */
+ * qt_proj_physical_batch / qt_pgdb_process_batch declares convergence (default 1e-8; 0 = tight 1e-15 * 4^n). */
 int qt_set_eigh_tolerance(double rel_off);
 
 /* FP64 FMA throughput probe (bench utility): blocks*threads*8*iters FMAs; scratch = 1 double on device */
@@ -54,6 +54,9 @@ int qt_mle_plan_destroy(qt_mle_plan* plan);
 int qt_mle_state_batch(const qt_mle_plan* plan, int64_t B, const double* expect, const double* counts,
                        double epsilon, double entropy_penalty, double beta, double tol, int maxiter,
                        int kernel_variant, void* rho_out, int32_t* iters_out, void* stream);
+/* linear_inv_state_estimate (tomography.py:130-165): expect[B,K] -> rho_out[B,d,d].  Uses the plan's observable
+ * list; valid for any list of Pauli observables (the pseudo-inverse is diagonal in the Pauli basis). */
+int qt_linear_inv_state_batch(const qt_mle_plan* plan, int64_t B, const double* expect, void* rho_out, void* stream);
 /* ONE R rho R update, rho streamed HBM -> HBM (n = 1, 2; complete canonical Pauli set, K = 4^n - 1).
  * expect_canon[K, B] (item-minor).  The HBM-roofline view of the update. */
 int qt_mle_step_batch(int n, int64_t B, const double* expect_canon, const void* rho_in, double epsilon,

@@ -10,7 +10,7 @@ codes3, pidx3, ex3, cnt3, _ = sy.process_tomography_batch(3003, 148, 3)
 plan3 = tm.PgdbPlan(3, codes3, pidx3)
 e3, c3 = torch.from_numpy(ex3).cuda(), torch.from_numpy(cnt3).cuda()
 base = None
-for tol in (0.0, 1e-12, 1e-11, 1e-10, 1e-9, 1e-8):
+for tol in (0.0, 1e-9, 1e-8, 1e-7, 1e-6, 1e-5, 1e-4):
     _lib.check(lib.qt_set_eigh_tolerance(ctypes.c_double(tol)), "tol")
     line = [f"tol={tol:g}"]
     for name in ("pgdb_3q_pauli", "pgdb_3q_sic", "pgdb_2q_pauli", "pgdb_2q_sic_mixed", "pgdb_1q_pauli"):

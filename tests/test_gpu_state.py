@@ -185,3 +185,30 @@ def test_distance_known_answers_and_dropin(torch):
     assert abs(dm.fidelity(z0, z1)) < 1e-15 and abs(dm.fidelity(z0, z0) - 1) < 1e-14
     assert abs(dm.purity(np.eye(2) / 2, dim_renorm=False) - 0.5) < 1e-15
     assert abs(dm.infidelity(z0, z0)) < 1e-14
+
+
+def test_linear_inv_state_estimate(torch):
+    """a4 / BASELINE configs[0]: linear inversion vs the oracle's pinv, complete and general observable lists."""
+    from forest_benchmarking_b200 import tomography as tm
+    from forest_benchmarking_b200.observable_estimation import ExperimentResult, ExperimentSetting, zeros_state
+    from forest_benchmarking_b200.utils import all_traceless_pauli_terms
+    for n in (1, 2, 3):
+        _, pidx, ex, cnt = orc.synth_state_tomography(1001 + n, 33, n)
+        plan = tm.MlePlan(n, pidx)
+        rho = tm.linear_inv_state_estimate_batch(plan, torch.from_numpy(ex).cuda()).cpu().numpy()
+        want = np.stack([orc.linear_inv_state_estimate(pidx, np.ones(len(pidx)), ex[b], n) for b in range(33)])
+        assert max_relerr(rho, want) < 1e-12
+    # duplicates, identity, missing terms, non-unit coefficients: the pseudo-inverse is still diagonal in the Pauli basis
+    rng = np.random.default_rng(5)
+    pidx = np.array([0, 7, 7, 12, 3, 1, 9, 9, 9], dtype=np.int32)
+    coeffs = np.array([1.0, -1.0, 0.5, 1.0, 1.0, 2.0, 1.0, 1.0, -3.0])
+    ex = rng.uniform(-.6, .6, size=(4, len(pidx)))
+    rho = tm.linear_inv_state_estimate_batch(tm.MlePlan(2, pidx, coeffs), torch.from_numpy(ex).cuda()).cpu().numpy()
+    for b in range(4):
+        assert relerr(rho[b], orc.linear_inv_state_estimate(pidx, coeffs, ex[b], 2)) < 1e-12
+    # drop-in signature (config 1: 1 qubit, X Y Z)
+    qubits = [3]
+    _, pidx, ex, cnt = orc.synth_state_tomography(1001, 1, 1)
+    res = [ExperimentResult(ExperimentSetting(zeros_state(qubits), t), e, int(c))
+           for t, e, c in zip(all_traceless_pauli_terms(qubits), ex[0], cnt[0])]
+    assert relerr(tm.linear_inv_state_estimate(res, qubits), orc.linear_inv_state_estimate(pidx, np.ones(3), ex[0], 1)) < 1e-12
