@@ -146,6 +146,86 @@ __global__ void fidelity_kernel(int64_t B, const cplx* __restrict__ rho, const c
   if (lane == 0) out[b] = acc * acc;
 }
 
+// project_state_matrix_to_physical (operator_tools/project_state_matrix.py:6-52), one state per warp:
+// rho / tr(rho) -> eigh (lower triangle, like scipy) -> if any eigenvalue is negative, zero the smallest ones and
+// spread their mass evenly over the rest (water filling) -> V diag(l') V^dagger.  A matrix that is already PSD
+// is returned as rho / tr(rho) unchanged, exactly like the reference.
+template <int D>
+__global__ void project_state_kernel(int64_t B, const cplx* __restrict__ rho, cplx* __restrict__ out) {
+  constexpr int DD = D * D, LD = FidSmem<D>::LD, MP = FidSmem<D>::MP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  cplx* A = reinterpret_cast<cplx*>(smem_raw + FidSmem<D>::bytes * wib);
+  cplx* V = A + MP;
+  cplx* R = V + MP;  // rho / tr(rho), kept for the already-physical case
+  double* ev = reinterpret_cast<double*>(R + MP);
+  const int64_t b = (int64_t)blockIdx.x * wpb + wib;
+  if (b >= B) return;
+  const cplx* r = rho + b * DD;
+  cplx tr = cmake(0.0, 0.0);
+  for (int k = lane; k < D; k += 32) tr = cadd(tr, r[k * D + k]);
+  tr.x = warp_sum(tr.x);
+  tr.y = warp_sum(tr.y);
+  const double n2 = cabs2(tr);
+  const cplx itr = cmake(tr.x / n2, -tr.y / n2);
+  for (int e = lane; e < DD; e += 32) R[(e / D) * LD + e % D] = cmul(r[e], itr);
+  __syncwarp();
+  for (int e = lane; e < DD; e += 32) {
+    const int i = e / D, j = e % D;
+    cplx v = (i >= j) ? R[i * LD + j] : cconj(R[j * LD + i]);
+    if (i == j) v.y = 0.0;
+    A[i * LD + j] = v;
+  }
+  __syncwarp();
+  jacobi_eigh<D, 32, SyncWarp, true, LD>(A, V, ev, ev + D, lane);
+  double mn = 1e300;
+  for (int k = 0; k < D; ++k) mn = fmin(mn, ev[k]);
+  cplx* dst = out + b * DD;
+  if (mn >= 0.0) {
+    for (int e = lane; e < DD; e += 32) dst[e] = R[(e / D) * LD + e % D];
+    return;
+  }
+  // rank of each eigenvalue in DESCENDING order (ties broken by index), then the water-filling scan
+  double* desc = ev + D;      // the Jacobi scratch (3 D + 32 doubles) is free now
+  double* wgt = ev + 2 * D;   // new eigenvalue of eigenpair k
+  __syncwarp();
+  for (int k = lane; k < D; k += 32) {
+    int rk = 0;
+    for (int j = 0; j < D; ++j) rk += (ev[j] > ev[k] || (ev[j] == ev[k] && j < k)) ? 1 : 0;
+    desc[rk] = ev[k];
+  }
+  __syncwarp();
+  int i = D;
+  double acc = 0.0;
+  while (i > 1 && desc[i - 1] + acc / (double)i < 0.0) {
+    acc += desc[i - 1];
+    --i;
+  }
+  const double shift = acc / (double)i;  // the i largest eigenvalues are kept and shifted
+  for (int k = lane; k < D; k += 32) {
+    int rk = 0;
+    for (int j = 0; j < D; ++j) rk += (ev[j] > ev[k] || (ev[j] == ev[k] && j < k)) ? 1 : 0;
+    wgt[k] = (rk < i) ? ev[k] + shift : 0.0;
+  }
+  __syncwarp();
+  for (int e = lane; e < DD; e += 32) {
+    const int a = e / D, c = e % D;
+    cplx s = cmake(0.0, 0.0);
+    for (int k = 0; k < D; ++k) cfma_conj(s, cscale(V[a * LD + k], wgt[k]), V[c * LD + k]);
+    dst[e] = s;
+  }
+}
+
+template <int D>
+static int launch_project_state(int64_t B, const void* rho, void* out, cudaStream_t st) {
+  const size_t per_warp = FidSmem<D>::bytes;
+  int wpb = (int)max((size_t)1, min((size_t)8, (size_t)(100 * 1024) / per_warp));
+  const size_t smem = per_warp * wpb;
+  QT_CUDA(cudaFuncSetAttribute(project_state_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  project_state_kernel<D><<<(unsigned)((B + wpb - 1) / wpb), 32 * wpb, smem, st>>>(B, (const cplx*)rho, (cplx*)out);
+  return qt_check_launch("project_state_kernel");
+}
+
 template <int D>
 static int launch_td(int64_t B, const void* rho, const void* sigma, double* out, cudaStream_t st) {
   const int wpb = 8;
@@ -212,6 +292,14 @@ extern "C" int qt_purity_batch(int n, int64_t B, const void* rho, double* out, v
   QT_REQUIRE(rho && out, "qt_purity_batch: null argument");
   if (B == 0) return QT_OK;
 #define CALL(D) launch_purity<D>(B, rho, out, (cudaStream_t)stream)
+  DISPATCH_D(n, CALL)
+#undef CALL
+}
+
+extern "C" int qt_project_state_batch(int n, int64_t B, const void* rho, void* out, void* stream) {
+  QT_REQUIRE(rho && out, "qt_project_state_batch: null argument");
+  if (B == 0) return QT_OK;
+#define CALL(D) launch_project_state<D>(B, rho, out, (cudaStream_t)stream)
   DISPATCH_D(n, CALL)
 #undef CALL
 }

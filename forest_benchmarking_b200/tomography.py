@@ -131,6 +131,68 @@ def iterative_mle_state_estimate(results: List, qubits: List[int], epsilon=.1, e
     return rho[0].cpu().numpy()
 
 
+def _resample_expectations_with_beta(expectations, counts, n_resamples, prior_counts=1):
+    """reference tomography.py:378-409 for n_resamples bootstrap replicas at once: expectation -> (+1, -1)
+    counts -> Beta(n+ + prior, n- + prior) -> expectation.  Draws come from NumPy's global RNG in the order the
+    reference consumes them (replica-major, result-minor), so a seeded run reproduces the reference's samples."""
+    num_plus = ((expectations + 1) / 2) * counts
+    num_minus = counts - num_plus
+    alpha = np.broadcast_to(num_plus + prior_counts, (n_resamples, len(expectations)))
+    beta = np.broadcast_to(num_minus + prior_counts, (n_resamples, len(expectations)))
+    return 2 * np.random.beta(alpha, beta) - 1
+
+
+def estimate_variance(results: List, qubits: List[int], tomo_estimator, functional, target_state=None,
+                      n_resamples: int = 40, project_to_physical: bool = False):
+    """Drop-in for reference tomography.py:412-453 (bootstrap error bar on a functional of the state).
+    The n_resamples replicas are ONE batch: when ``tomo_estimator`` is this module's
+    ``iterative_mle_state_estimate`` / ``linear_inv_state_estimate`` and ``functional`` one of this package's
+    distance measures, everything after the host-side resampling runs as batched kernels; any other callable
+    is applied replica by replica like the reference does."""
+    from . import distance_measures as dm
+    from .operator_tools.project_state_matrix import project_state_matrix_to_physical_batch
+    torch = _lib.require_cuda()
+    if functional != dm.purity and target_state is None:
+        raise ValueError("You're not using the `purity` functional. Please specify a target state.")
+    idx, cf, ex, cnt = flatten_state_results(results, qubits)
+    resampled = _resample_expectations_with_beta(ex, cnt, n_resamples)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if tomo_estimator in (iterative_mle_state_estimate, linear_inv_state_estimate):
+        plan = MlePlan(len(qubits), idx, cf)
+        e = torch.from_numpy(np.ascontiguousarray(resampled)).to(dev)
+        if tomo_estimator is linear_inv_state_estimate:
+            rho = linear_inv_state_estimate_batch(plan, e)
+        else:
+            c = torch.from_numpy(np.tile(cnt, (n_resamples, 1))).to(dev)
+            rho, iters = iterative_mle_state_estimate_batch(plan, e, c)
+            if bool((iters >= 10_000).any().item()):
+                warnings.warn('Maximum number of iterations reached before convergence.')
+    else:
+        from .observable_estimation import ExperimentResult
+        rhos = []
+        for row in resampled:
+            rs = [ExperimentResult(r.setting, float(x), r.total_counts, getattr(r, "std_err", None))
+                  for r, x in zip(results, row)]
+            rhos.append(np.asarray(tomo_estimator(rs, qubits), dtype=np.complex128))
+        rho = torch.from_numpy(np.stack(rhos)).to(dev)
+    if project_to_physical:
+        rho = project_state_matrix_to_physical_batch(rho)
+    if functional == dm.purity:
+        sample = dm.purity_batch(rho).cpu().numpy()
+    elif functional in (dm.fidelity, dm.infidelity, dm.trace_distance):
+        tgt = torch.from_numpy(np.ascontiguousarray(np.asarray(target_state, dtype=np.complex128))).to(dev)
+        tgt = tgt.expand(rho.shape[0], -1, -1).contiguous()
+        if functional == dm.trace_distance:
+            sample = dm.trace_distance_batch(tgt, rho).cpu().numpy()
+        else:
+            sample = dm.fidelity_batch(tgt, rho).cpu().numpy()
+            if functional == dm.infidelity:
+                sample = 1 - sample
+    else:
+        sample = np.array([np.real(functional(target_state, r)) for r in rho.cpu().numpy()])
+    return np.mean(sample), np.var(sample)
+
+
 # ==================================================================================================
 # PROCESS tomography
 # ==================================================================================================

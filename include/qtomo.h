@@ -88,6 +88,8 @@ int qt_trace_distance_batch(int n, int64_t B, const void* rho, const void* sigma
 /* textbook 0.5 * nuclear norm (extra; not the reference's behaviour) */
 int qt_trace_distance_nuclear_batch(int n, int64_t B, const void* rho, const void* sigma, double* out, void* stream);
 int qt_purity_batch(int n, int64_t B, const void* rho, double* out, void* stream);                             /* :14-37 */
+/* project_state_matrix_to_physical (operator_tools/project_state_matrix.py:6-52): closest trace-one PSD matrix */
+int qt_project_state_batch(int n, int64_t B, const void* rho, void* out, void* stream);
 
 /* ---- Choi-matrix projections (operator_tools/project_superoperators.py), n = 1..3, [B,4^n,4^n] ---- */
 int qt_proj_cp_batch(int n, int64_t B, const void* choi, void* out, void* stream);   /* :19-34 */

@@ -296,6 +296,38 @@ def purity(rho, dim_renorm=False):
     return float(p)
 
 
+def project_state_matrix_to_physical(rho):
+    """Smolin "wizard" projection onto trace-one PSD matrices, operator_tools/project_state_matrix.py:6-52:
+    normalise the trace, eigh, and if any eigenvalue is negative zero the smallest ones while spreading their
+    (negative) mass evenly over the eigenvalues that stay (water filling from the bottom)."""
+    rho = np.asarray(rho, dtype=complex)
+    rho = rho / np.trace(rho)
+    w, v = sla.eigh(rho)
+    if w.min() >= 0:
+        return rho
+    d = len(w)
+    desc = list(w[::-1])
+    new = [0.0] * d
+    i, acc = d, 0.0
+    while desc[i - 1] + acc / float(i) < 0:
+        acc += desc[i - 1]
+        i -= 1
+    for j in range(i):
+        new[j] = desc[j] + acc / float(i)
+    new.reverse()
+    return (v * np.array(new)) @ v.conj().T
+
+
+def resample_expectations_with_beta(expectations, counts, prior_counts=1):
+    """tomography.py:378-409 on arrays: one np.random.beta draw per result, in order (global NumPy RNG)."""
+    out = np.empty(len(expectations))
+    for k, (e, n) in enumerate(zip(expectations, counts)):
+        num_plus = ((e + 1) / 2) * n
+        num_minus = n - num_plus
+        out[k] = 2 * np.random.beta(num_plus + prior_counts, num_minus + prior_counts) - 1
+    return out
+
+
 # --------------------------------------------------------------------------------------------
 # State tomography  (tomography.py:130-338)
 # --------------------------------------------------------------------------------------------

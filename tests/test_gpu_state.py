@@ -212,3 +212,61 @@ def test_linear_inv_state_estimate(torch):
     res = [ExperimentResult(ExperimentSetting(zeros_state(qubits), t), e, int(c))
            for t, e, c in zip(all_traceless_pauli_terms(qubits), ex[0], cnt[0])]
     assert relerr(tm.linear_inv_state_estimate(res, qubits), orc.linear_inv_state_estimate(pidx, np.ones(3), ex[0], 1)) < 1e-12
+
+
+def test_project_state_matrix_and_estimate_variance(torch):
+    """"next" row 1: wizard projection vs the oracle, and the bootstrap estimate_variance as ONE batch
+    vs a replica-by-replica NumPy restatement with the same seeded RNG stream (tomography.py:412-453)."""
+    from forest_benchmarking_b200 import distance_measures as dm, tomography as tm
+    from forest_benchmarking_b200.operator_tools import project_state_matrix as psm
+    from forest_benchmarking_b200.observable_estimation import ExperimentResult, ExperimentSetting, zeros_state
+    from forest_benchmarking_b200.utils import all_traceless_pauli_terms
+    rng = np.random.default_rng(21)
+    for d in (2, 4, 8, 16, 32):
+        mats = []
+        for k in range(40):
+            g = rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d))
+            h = (g + g.conj().T) / 2
+            h = h / np.trace(h).real + 0.03 * rng.standard_normal() * np.eye(d)
+            mats.append(h if k % 3 else 2.5 * orc.ginibre_state(rng, d))  # every third one is already physical
+        mats = np.stack(mats)
+        got = psm.project_state_matrix_to_physical_batch(torch.from_numpy(mats).cuda()).cpu().numpy()
+        want = np.stack([orc.project_state_matrix_to_physical(m) for m in mats])
+        assert max_relerr(got, want) < 1e-10
+        assert np.allclose(np.trace(got, axis1=1, axis2=2), 1, atol=1e-12)
+        assert np.linalg.eigvalsh(got).min() > -1e-12
+    eigs = np.diag(np.array(list(reversed([3.0 / 5, 1.0 / 2, 7.0 / 20, 1.0 / 10, -11.0 / 20]))))
+    # the reference's own known answer needs d = 5 (not a qubit dimension): embed it in d = 8
+    emb = np.zeros((8, 8)); emb[:5, :5] = eigs
+    assert np.allclose(psm.project_state_matrix_to_physical(emb)[:5, :5], np.diag([0, 0, 1.0 / 5, 7.0 / 20, 9.0 / 20]))
+
+    qubits = [0, 1]
+    truth, pidx, ex, cnt = orc.synth_state_tomography(31, 1, 2, shots=200)
+    res = [ExperimentResult(ExperimentSetting(zeros_state(qubits), t), e, int(c))
+           for t, e, c in zip(all_traceless_pauli_terms(qubits), ex[0], cnt[0])]
+    for est, oest, functional, tgt, proj in (
+            (tm.linear_inv_state_estimate, "lin", dm.purity, None, True),
+            (tm.linear_inv_state_estimate, "lin", dm.fidelity, truth[0], True),
+            (tm.iterative_mle_state_estimate, "mle", dm.trace_distance, truth[0], False)):
+        np.random.seed(9)
+        mean, var = tm.estimate_variance(res, qubits, est, functional, target_state=tgt, n_resamples=12,
+                                         project_to_physical=proj)
+        np.random.seed(9)
+        vals = []
+        for _ in range(12):
+            e = orc.resample_expectations_with_beta(ex[0], cnt[0])
+            if oest == "lin":
+                rho = orc.linear_inv_state_estimate(pidx, np.ones(15), e, 2)
+            else:
+                rho, _ = orc.mle_state_estimate(pidx, np.ones(15), e, cnt[0], 2)
+            if proj:
+                rho = orc.project_state_matrix_to_physical(rho)
+            if functional == dm.purity:
+                vals.append(orc.purity(rho, dim_renorm=False))
+            elif functional == dm.fidelity:
+                vals.append(orc.fidelity(tgt, rho))
+            else:
+                vals.append(orc.trace_distance(tgt, rho))
+        assert abs(mean - np.mean(vals)) < 1e-8 and abs(var - np.var(vals)) < 1e-8
+    with pytest.raises(ValueError):
+        tm.estimate_variance(res, qubits, tm.linear_inv_state_estimate, dm.fidelity)

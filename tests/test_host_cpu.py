@@ -66,3 +66,15 @@ def test_flatten_results():
     assert utils.in_state_codes(SIC2(3), [3]) == (8,)
     with pytest.raises(ValueError):
         utils.pauli_term_to_index(sZ(7), [0, 1])
+
+
+def test_bootstrap_resampling_consumes_the_reference_rng_stream():
+    """estimate_variance's vectorised Beta resampling == the reference's per-result scalar draws (same seed)."""
+    from forest_benchmarking_b200.tomography import _resample_expectations_with_beta
+    from oracle import ref_numpy as orc
+    _, pidx, ex, cnt = orc.synth_state_tomography(77, 1, 2)
+    np.random.seed(5)
+    got = _resample_expectations_with_beta(ex[0], cnt[0], 3)
+    np.random.seed(5)
+    want = np.stack([orc.resample_expectations_with_beta(ex[0], cnt[0]) for _ in range(3)])
+    assert np.array_equal(got, want)

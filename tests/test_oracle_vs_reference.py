@@ -148,3 +148,31 @@ def test_pgdb(ref, n, basis, tp):
     assert relerr(got, want) < 1e-10
     assert relerr(orc.linear_inv_process_estimate(settings, coeffs, ex[0], n),
                   ref.tomo.linear_inv_process_estimate(res, qubits)) < 1e-11
+
+
+def test_project_state_matrix_to_physical(ref):
+    from forest.benchmarking.operator_tools.project_state_matrix import project_state_matrix_to_physical as ref_proj
+    rng = np.random.default_rng(11)
+    # the reference's own known answer (tests/test_project_state_matrix.py:12-14)
+    eigs = np.diag(np.array(list(reversed([3.0 / 5, 1.0 / 2, 7.0 / 20, 1.0 / 10, -11.0 / 20]))))
+    phys = orc.project_state_matrix_to_physical(eigs)
+    assert np.allclose(phys, np.diag([0, 0, 1.0 / 5, 7.0 / 20, 9.0 / 20]))
+    for d in (2, 4, 8, 16):
+        for _ in range(6):
+            g = rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d))
+            h = (g + g.conj().T) / 2
+            h = h / np.trace(h).real + 0.05 * np.eye(d) * rng.standard_normal()
+            assert relerr(orc.project_state_matrix_to_physical(h), ref_proj(h)) < 1e-12
+        rho = orc.ginibre_state(rng, d)
+        assert relerr(orc.project_state_matrix_to_physical(3.0 * rho), ref_proj(3.0 * rho)) < 1e-13
+
+
+def test_resample_matches_reference_stream(ref):
+    from forest.benchmarking.tomography import _resample_expectations_with_beta
+    _, pidx, ex, cnt = orc.synth_state_tomography(77, 1, 2)
+    results = rb.state_results(ref, pidx, np.ones(15), ex[0], cnt[0], [0, 1])
+    np.random.seed(5)
+    want = [r.expectation for r in _resample_expectations_with_beta(results)]
+    np.random.seed(5)
+    got = orc.resample_expectations_with_beta(ex[0], cnt[0])
+    assert np.array_equal(np.array(want), got)
