@@ -267,6 +267,7 @@ template <int N>
 struct PlCfg {
   static constexpr int L = 1 << (2 * N);
   static constexpr int RQN = (N <= 3) ? N : 1;                    // row qubits handled by pass A
+  static constexpr bool RADIX16 = (N == 2 || N == 4);             // two butterfly stages per shared-memory pass
   static constexpr int TRA = 1 << (2 * RQN);                      // tile rows of pass A
   static constexpr int IPB = (2048 / (TRA * L) >= 1) ? 2048 / (TRA * L) : 1;  // tiles per block (small n)
   static constexpr int LDA = L + 1;
@@ -301,19 +302,50 @@ __global__ void __launch_bounds__(PlCfg<N>::NTA) pl_pass_a_kernel(int64_t n_tile
     buf[(tl * TRA + t) * LDA + (FWD ? c : pauli_to_pos(c, N))] = v;
   }
   __syncthreads();
-  // inner transform (right factor, conjugated butterfly), all N qubits, vectors = tile rows
+  // N inner stages (right factor F^dagger: conjugated butterfly on column bits (N-1-q, 2N-1-q)) and RQN outer
+  // stages (left factor F on the tile-row digit q).  Radix 16 (two stages per pass over shared memory, 16
+  // elements per work item in registers) where it measured faster (n = 2, 4), radix 4 otherwise
+  // (profiles/r01_bench_convert_v4.json vs _v5.json).  The tiles of a block are stacked along the row index.
+  if constexpr (C::RADIX16) {
+    {
+      constexpr int NS = N + RQN;
+      const int n_el = nt_here * TRA * L;
+      auto lo_of = [](int st) { return st < N ? N - 1 - st : 2 * N + 2 * (RQN - 1 - (st - N)); };
+      auto hi_of = [](int st) { return st < N ? 2 * N - 1 - st : 2 * N + 2 * (RQN - 1 - (st - N)) + 1; };
 #pragma unroll
-  for (int q = 0; q < N; ++q) {
-    bfly_stage<FWD, true, false>(buf, 2 * N, N - 1 - q, 2 * N - 1 - q, nt_here * TRA, LDA, 1, threadIdx.x, NT);
-    __syncthreads();
-  }
-  // outer transform (left factor) on the tile's row qubits: tile row t has digit layout (hi, lo adjacent)
+      for (int st = 0; st + 1 < NS; st += 2) {
+        const bool in1 = st < N, in2 = st + 1 < N;
+        if (in1 && in2)
+          flat_stage2<FWD, true, true>(buf, n_el / 16, 2 * N, LDA, lo_of(st), hi_of(st), lo_of(st + 1), hi_of(st + 1),
+                                       threadIdx.x, NT);
+        else if (in1)
+          flat_stage2<FWD, true, false>(buf, n_el / 16, 2 * N, LDA, lo_of(st), hi_of(st), lo_of(st + 1), hi_of(st + 1),
+                                        threadIdx.x, NT);
+        else
+          flat_stage2<FWD, false, false>(buf, n_el / 16, 2 * N, LDA, lo_of(st), hi_of(st), lo_of(st + 1), hi_of(st + 1),
+                                         threadIdx.x, NT);
+        __syncthreads();
+      }
+      if (NS & 1) {
+        constexpr int st = NS - 1;
+        if (st < N) flat_stage1<FWD, true>(buf, n_el / 4, 2 * N, LDA, lo_of(st), hi_of(st), threadIdx.x, NT);
+        else flat_stage1<FWD, false>(buf, n_el / 4, 2 * N, LDA, lo_of(st), hi_of(st), threadIdx.x, NT);
+        __syncthreads();
+      }
+    }
+  } else {
 #pragma unroll
-  for (int q = 0; q < RQN; ++q) {
-    for (int tl = 0; tl < nt_here; ++tl)
-      bfly_stage<FWD, false, true>(buf + tl * TRA * LDA, 2 * RQN, 2 * (RQN - 1 - q), 2 * (RQN - 1 - q) + 1, L, 1, LDA,
-                                   threadIdx.x, NT);
-    __syncthreads();
+    for (int q = 0; q < N; ++q) {
+      bfly_stage<FWD, true, false>(buf, 2 * N, N - 1 - q, 2 * N - 1 - q, nt_here * TRA, LDA, 1, threadIdx.x, NT);
+      __syncthreads();
+    }
+#pragma unroll
+    for (int q = 0; q < RQN; ++q) {
+      for (int tl = 0; tl < nt_here; ++tl)
+        bfly_stage<FWD, false, true>(buf + tl * TRA * LDA, 2 * RQN, 2 * (RQN - 1 - q), 2 * (RQN - 1 - q) + 1, L, 1, LDA,
+                                     threadIdx.x, NT);
+      __syncthreads();
+    }
   }
   for (int e = threadIdx.x; e < nt_here * TRA * L; e += NT) {
     const int c = e % L, t = (e / L) % TRA, tl = e / (L * TRA);
@@ -349,10 +381,30 @@ __global__ void __launch_bounds__(PlCfg<N>::NTB) pl_pass_b_kernel(int64_t B, con
     buf[t * LDB + cc] = src[(int64_t)pauli_to_pos(idx, N) * L + c0 + cc];
   }
   __syncthreads();
+  // outer stages of the remaining qubits q = RQN..N-1: digit q of the tile row t sits at bits
+  // log2(W) + 2(N-1-q), +1 of the flat index t * W + cc
+  if constexpr (C::RADIX16) {
+    {
+      constexpr int NS = N - RQN;
+      constexpr int WB = (W == 32) ? 5 : 4;
+      auto lo_of = [](int st) { return WB + 2 * (N - 1 - (RQN + st)); };
 #pragma unroll
-  for (int q = RQN; q < N; ++q) {
-    bfly_stage<FWD, false, true>(buf, 2 * (N - RQN), 2 * (N - 1 - q), 2 * (N - 1 - q) + 1, W, 1, LDB, threadIdx.x, NT);
-    __syncthreads();
+      for (int st = 0; st + 1 < NS; st += 2) {
+        flat_stage2<FWD, false, false>(buf, TRB * W / 16, WB, LDB, lo_of(st), lo_of(st) + 1, lo_of(st + 1),
+                                       lo_of(st + 1) + 1, threadIdx.x, NT);
+        __syncthreads();
+      }
+      if (NS & 1) {
+        flat_stage1<FWD, false>(buf, TRB * W / 4, WB, LDB, lo_of(NS - 1), lo_of(NS - 1) + 1, threadIdx.x, NT);
+        __syncthreads();
+      }
+    }
+  } else {
+#pragma unroll
+    for (int q = RQN; q < N; ++q) {
+      bfly_stage<FWD, false, true>(buf, 2 * (N - RQN), 2 * (N - 1 - q), 2 * (N - 1 - q) + 1, W, 1, LDB, threadIdx.x, NT);
+      __syncthreads();
+    }
   }
   for (int e = threadIdx.x; e < TRB * W; e += NT) {
     const int cc = e % W, t = e / W;

@@ -102,3 +102,65 @@ __device__ __forceinline__ void bfly_stage(cplx* buf, int len_bits, int lo_bit, 
     base[(p | hi | lo) * estride] = u11;
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Flat-index butterflies for the PTM kernels.  A shared tile of 2^total_bits elements is addressed by a flat
+// index f whose low `colbits` bits are the column and whose remaining bits are the row of the (padded, leading
+// dimension ld) buffer.  A stage acts on one bit pair (lo, hi) of f.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int flat_addr(int f, int colbits, int ld) {
+  return (f >> colbits) * ld + (f & ((1 << colbits) - 1));
+}
+__device__ __forceinline__ int insert_zero_bit(int x, int pos) {
+  return ((x >> pos) << (pos + 1)) | (x & ((1 << pos) - 1));
+}
+
+template <bool FWD, bool CONJ>
+__device__ __forceinline__ void flat_stage1(cplx* buf, int n_items4, int colbits, int ld, int lo, int hi, int tid,
+                                            int nt) {
+  for (int w = tid; w < n_items4; w += nt) {
+    const int f = insert_zero_bit(insert_zero_bit(w, lo), hi);  // lo < hi
+    const int a00 = flat_addr(f, colbits, ld), a01 = flat_addr(f | (1 << lo), colbits, ld);
+    const int a10 = flat_addr(f | (1 << hi), colbits, ld), a11 = flat_addr(f | (1 << hi) | (1 << lo), colbits, ld);
+    cplx u00 = buf[a00], u01 = buf[a01], u10 = buf[a10], u11 = buf[a11];
+    bfly4<FWD, CONJ>(u00, u01, u10, u11);
+    buf[a00] = u00;
+    buf[a01] = u01;
+    buf[a10] = u10;
+    buf[a11] = u11;
+  }
+}
+
+// Two stages in one pass over shared memory: 16 elements per work item held in registers (radix 16).
+template <bool FWD, bool CONJ1, bool CONJ2>
+__device__ __forceinline__ void flat_stage2(cplx* buf, int n_items16, int colbits, int ld, int lo1, int hi1, int lo2,
+                                            int hi2, int tid, int nt) {
+  // the four bit positions in ascending order (for the zero-bit insertion)
+  int p0 = lo1, p1 = hi1, p2 = lo2, p3 = hi2, t;
+  if (p0 > p2) { t = p0; p0 = p2; p2 = t; }
+  if (p1 > p3) { t = p1; p1 = p3; p3 = t; }
+  if (p0 > p1) { t = p0; p0 = p1; p1 = t; }
+  if (p2 > p3) { t = p2; p2 = p3; p3 = t; }
+  if (p1 > p2) { t = p1; p1 = p2; p2 = t; }
+  for (int w = tid; w < n_items16; w += nt) {
+    const int f = insert_zero_bit(insert_zero_bit(insert_zero_bit(insert_zero_bit(w, p0), p1), p2), p3);
+    cplx u[4][4];
+    int addr[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const int g = f | ((a >> 1) << hi1) | ((a & 1) << lo1) | ((b >> 1) << hi2) | ((b & 1) << lo2);
+        addr[a][b] = flat_addr(g, colbits, ld);
+        u[a][b] = buf[addr[a][b]];
+      }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) bfly4<FWD, CONJ1>(u[0][b], u[1][b], u[2][b], u[3][b]);
+#pragma unroll
+    for (int a = 0; a < 4; ++a) bfly4<FWD, CONJ2>(u[a][0], u[a][1], u[a][2], u[a][3]);
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) buf[addr[a][b]] = u[a][b];
+  }
+}

@@ -13,7 +13,9 @@ from .. import _lib
 
 __all__ = ["vec", "unvec", "kraus2choi", "kraus2superop", "kraus2pauli_liouville", "choi2superop",
            "superop2choi", "superop2pauli_liouville", "pauli_liouville2superop", "choi2pauli_liouville",
-           "pauli_liouville2choi", "choi2kraus", "choi2kraus_batch", "kraus2choi_batch", "kraus2superop_batch", "reshuffle_batch",
+           "pauli_liouville2choi", "choi2kraus", "choi2kraus_batch", "kraus2chi", "chi2choi", "chi2pauli_liouville",
+           "chi2superop", "chi2kraus", "choi2chi", "superop2chi", "pauli_liouville2chi", "superop2kraus",
+           "pauli_liouville2kraus", "kraus2chi_batch", "chi2choi_batch", "kraus2choi_batch", "kraus2superop_batch", "reshuffle_batch",
            "superop2pauli_liouville_batch", "pauli_liouville2superop_batch",
            "choi2pauli_liouville_batch", "pauli_liouville2choi_batch"]
 
@@ -130,6 +132,19 @@ def choi2kraus_batch(choi, tol: float = 1e-9):
     return kraus, counts, evals
 
 
+def kraus2chi_batch(kraus):
+    """kraus [B, K, d, d] -> chi [B, d^2, d^2] = c2p (sum_k vec K vec K^dagger) c2p^dagger (reference :82-97).
+    c2p X c2p^dagger is the PTM butterfly kernel's (1/d) F X F^dagger divided by d."""
+    d = kraus.shape[-1]
+    return superop2pauli_liouville_batch(kraus2choi_batch(kraus)) / d
+
+
+def chi2choi_batch(chi):
+    """chi [B, d^2, d^2] -> choi = p2c chi p2c^dagger (reference :217-226) = d * (1/d) F^dagger chi F."""
+    d = int(round(np.sqrt(chi.shape[-1])))
+    return pauli_liouville2superop_batch(chi) * d
+
+
 # ---- reference-named single-matrix functions -------------------------------------------------
 def _to_dev(x):
     torch = _lib.require_cuda()
@@ -183,6 +198,57 @@ def choi2kraus(choi: np.ndarray, tol: float = 1e-9) -> List[np.ndarray]:
     kraus, counts, _ = choi2kraus_batch(_to_dev(choi)[None], tol)
     k = int(counts[0].item())
     return [m for m in kraus[0, :k].cpu().numpy()]
+
+
+def superop2kraus(superop: np.ndarray) -> List[np.ndarray]:
+    """reference :229-238."""
+    return choi2kraus(superop2choi(superop))
+
+
+def pauli_liouville2kraus(pl_matrix: np.ndarray) -> List[np.ndarray]:
+    """reference :280-288."""
+    return choi2kraus(pauli_liouville2choi(pl_matrix))
+
+
+def kraus2chi(kraus_ops: Sequence[np.ndarray]) -> np.ndarray:
+    """reference :82-97."""
+    return kraus2chi_batch(_to_dev(_kraus_stack(kraus_ops)[None]))[0].cpu().numpy()
+
+
+def chi2choi(chi_matrix: np.ndarray) -> np.ndarray:
+    """reference :217-226."""
+    return chi2choi_batch(_to_dev(chi_matrix)[None])[0].cpu().numpy()
+
+
+def chi2pauli_liouville(chi_matrix: np.ndarray) -> np.ndarray:
+    """reference :185-192."""
+    return choi2pauli_liouville_batch(chi2choi_batch(_to_dev(chi_matrix)[None]))[0].cpu().numpy()
+
+
+def chi2superop(chi_matrix: np.ndarray) -> np.ndarray:
+    """reference :207-214."""
+    return reshuffle_batch(chi2choi_batch(_to_dev(chi_matrix)[None]))[0].cpu().numpy()
+
+
+def chi2kraus(chi_matrix: np.ndarray) -> List[np.ndarray]:
+    """reference :195-204."""
+    return choi2kraus(chi2choi(chi_matrix))
+
+
+def choi2chi(choi: np.ndarray) -> np.ndarray:
+    """reference :339-348: kraus2chi(choi2kraus(choi)) -- eigenvalues below 1e-9 in magnitude are dropped and
+    negative ones enter with their absolute value, exactly like the reference's round trip through Kraus form."""
+    return kraus2chi(choi2kraus(choi))
+
+
+def superop2chi(superop: np.ndarray) -> np.ndarray:
+    """reference :241-250."""
+    return choi2chi(superop2choi(superop))
+
+
+def pauli_liouville2chi(pl_matrix: np.ndarray) -> np.ndarray:
+    """reference :291-298."""
+    return choi2chi(pauli_liouville2choi(pl_matrix))
 
 
 def choi2pauli_liouville(choi: np.ndarray) -> np.ndarray:

@@ -199,6 +199,44 @@ def choi2kraus(choi, tol=1e-9):
     return out
 
 
+def kraus2chi(kraus_ops):
+    """chi (process) matrix: sum_k c_k c_k^dagger with c_k = c2p vec(K_k), :82-97."""
+    ks = _as_kraus_list(kraus_ops)
+    c2p = computational2pauli_basis_matrix(ks[0].shape[0])
+    return sum((c2p @ vec(k)) @ (c2p @ vec(k)).conj().T for k in ks)
+
+
+def chi2choi(chi):
+    """p2c chi p2c^dagger, :217-226."""
+    p2c = pauli2computational_basis_matrix(int(np.sqrt(np.asarray(chi).shape[0])))
+    return p2c @ np.asarray(chi) @ p2c.conj().T
+
+
+def chi2pauli_liouville(chi):
+    """:185-192."""
+    return choi2pauli_liouville(chi2choi(chi))
+
+
+def chi2superop(chi):
+    """:207-214."""
+    return pauli_liouville2superop(chi2pauli_liouville(chi))
+
+
+def choi2chi(choi):
+    """kraus2chi(choi2kraus(choi)), :339-348 (drops |eigenvalue| <= 1e-9, takes |.| of negative ones)."""
+    return kraus2chi(choi2kraus(choi))
+
+
+def superop2chi(s):
+    """:241-250."""
+    return choi2chi(reshuffle(s))
+
+
+def pauli_liouville2chi(pl):
+    """:291-298."""
+    return choi2chi(pauli_liouville2choi(pl))
+
+
 # --------------------------------------------------------------------------------------------
 # Projections  (operator_tools/project_superoperators.py, calculational.py)
 # --------------------------------------------------------------------------------------------

@@ -131,3 +131,33 @@ def test_choi2kraus(torch, n, batch):
     # drop-in signature: list of operators, round trip through kraus2choi
     ks = st.choi2kraus(chois[0])
     assert relerr(st.kraus2choi(ks), chois[0]) < 1e-9
+
+
+def test_chi_matrix_family(torch):
+    """chi-matrix conversions as compositions of the conversion kernels, vs the oracle and the
+    reference's known answers (test_superoperator_transformations.py:139-145, 184-189)."""
+    from forest_benchmarking_b200.operator_tools import superoperator_transformations as st
+    had = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+    had_chi = 0.5 * np.array([[0, 0, 0, 0], [0, 1, 0, 1], [0, 0, 0, 0], [0, 1, 0, 1]])
+    assert np.allclose(st.kraus2chi(had), had_chi)
+    p = 0.1
+    ad = [np.array([[1, 0], [0, np.sqrt(1 - p)]]), np.array([[0, np.sqrt(p)], [0, 0]])]
+    assert np.allclose(st.kraus2chi(ad), orc.kraus2chi(ad))
+    assert np.allclose(st.chi2pauli_liouville(orc.kraus2chi(ad)), orc.kraus2pauli_liouville(ad))
+    rng = np.random.default_rng(90)
+    for n, batch in ((1, 50), (2, 20), (3, 4)):
+        d = 2 ** n
+        kraus = np.stack([[np.sqrt(.7) * orc.haar_unitary(rng, d), np.sqrt(.3) * orc.haar_unitary(rng, d)]
+                          for _ in range(batch)])
+        chi = st.kraus2chi_batch(torch.from_numpy(kraus).cuda())
+        want = np.stack([orc.kraus2chi(list(k)) for k in kraus])
+        assert max_relerr(chi.cpu().numpy(), want) < 1e-12
+        choi = st.chi2choi_batch(chi).cpu().numpy()
+        assert max_relerr(choi, np.stack([orc.kraus2choi(list(k)) for k in kraus])) < 1e-12
+        c0 = orc.kraus2choi(list(kraus[0]))
+        assert relerr(st.chi2superop(want[0]), orc.chi2superop(want[0])) < 1e-12
+        assert relerr(st.choi2chi(c0), orc.choi2chi(c0)) < 1e-9
+        assert relerr(st.superop2chi(orc.reshuffle(c0)), orc.superop2chi(orc.reshuffle(c0))) < 1e-9
+        assert relerr(st.pauli_liouville2chi(orc.choi2pauli_liouville(c0)), want[0]) < 1e-9
+        ks = st.chi2kraus(want[0])
+        assert relerr(st.kraus2choi(ks), c0) < 1e-9

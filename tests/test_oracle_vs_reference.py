@@ -176,3 +176,21 @@ def test_resample_matches_reference_stream(ref):
     np.random.seed(5)
     got = orc.resample_expectations_with_beta(ex[0], cnt[0])
     assert np.array_equal(np.array(want), got)
+
+
+@pytest.mark.parametrize("n", [1, 2])
+def test_chi_family(ref, n):
+    ot = ref.ot
+    rng = np.random.default_rng(40 + n)
+    d = 2 ** n
+    ks = [np.sqrt(.6) * orc.haar_unitary(rng, d), np.sqrt(.4) * orc.haar_unitary(rng, d)]
+    chi = orc.kraus2chi(ks)
+    assert relerr(chi, ot.kraus2chi(ks)) < 1e-13
+    assert relerr(orc.chi2choi(chi), ot.chi2choi(chi)) < 1e-13
+    assert relerr(orc.chi2pauli_liouville(chi), ot.chi2pauli_liouville(chi)) < 1e-13
+    assert relerr(orc.chi2superop(chi), ot.chi2superop(chi)) < 1e-13
+    choi = orc.kraus2choi(ks)
+    assert relerr(orc.choi2chi(choi), ot.choi2chi(choi)) < 1e-12
+    assert relerr(orc.superop2chi(orc.reshuffle(choi)), ot.superop2chi(orc.reshuffle(choi))) < 1e-12
+    pl = orc.choi2pauli_liouville(choi)
+    assert relerr(orc.pauli_liouville2chi(pl), ot.pauli_liouville2chi(pl)) < 1e-12
