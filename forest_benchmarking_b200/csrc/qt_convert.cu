@@ -266,15 +266,15 @@ extern "C" int qt_choi_superop_reshuffle_batch(int d, int64_t B, const void* in,
 template <int N>
 struct PlCfg {
   static constexpr int L = 1 << (2 * N);
-  static constexpr int RQN = (N <= 3) ? N : 1;                    // row qubits handled by pass A
-  static constexpr bool RADIX16 = (N == 2 || N == 4);             // two butterfly stages per shared-memory pass
+  static constexpr int RQN = (N <= 3) ? N : (N == 4 ? 2 : 1);     // row qubits handled by pass A
+  static constexpr bool RADIX16 = (N == 2);                       // two butterfly stages per shared-memory pass
   static constexpr int TRA = 1 << (2 * RQN);                      // tile rows of pass A
   static constexpr int IPB = (2048 / (TRA * L) >= 1) ? 2048 / (TRA * L) : 1;  // tiles per block (small n)
   static constexpr int LDA = L + 1;
   static constexpr size_t smem_a = sizeof(cplx) * IPB * TRA * LDA;
   static constexpr int NTA = (TRA * L * IPB >= 4096) ? 512 : 256;
   static constexpr int TRB = 1 << (2 * (N - RQN));                // tile rows of pass B
-  static constexpr int W = (N == 4) ? 32 : 16;                    // tile columns of pass B
+  static constexpr int W = (N == 4) ? 256 : 16;                   // tile columns of pass B (n = 4: full rows)
   static constexpr int LDB = W + 1;
   static constexpr size_t smem_b = sizeof(cplx) * TRB * LDB;
   static constexpr int NTB = (TRB * W >= 4096) ? 512 : 256;
@@ -304,7 +304,7 @@ __global__ void __launch_bounds__(PlCfg<N>::NTA) pl_pass_a_kernel(int64_t n_tile
   __syncthreads();
   // N inner stages (right factor F^dagger: conjugated butterfly on column bits (N-1-q, 2N-1-q)) and RQN outer
   // stages (left factor F on the tile-row digit q).  Radix 16 (two stages per pass over shared memory, 16
-  // elements per work item in registers) where it measured faster (n = 2, 4), radix 4 otherwise
+  // elements per work item in registers) where it measured faster (n = 2), radix 4 otherwise
   // (profiles/r01_bench_convert_v4.json vs _v5.json).  The tiles of a block are stacked along the row index.
   if constexpr (C::RADIX16) {
     {
@@ -336,7 +336,12 @@ __global__ void __launch_bounds__(PlCfg<N>::NTA) pl_pass_a_kernel(int64_t n_tile
   } else {
 #pragma unroll
     for (int q = 0; q < N; ++q) {
-      bfly_stage<FWD, true, false>(buf, 2 * N, N - 1 - q, 2 * N - 1 - q, nt_here * TRA, LDA, 1, threadIdx.x, NT);
+      // consecutive threads walk the ROWS (odd leading dimension: conflict-free) when a warp's worth exists;
+      // walking the row would put the 4 partners of lanes 0 and 4 on the same banks (2-way conflict)
+      if (TRA * C::IPB >= 8)
+        bfly_stage<FWD, true, true>(buf, 2 * N, N - 1 - q, 2 * N - 1 - q, nt_here * TRA, LDA, 1, threadIdx.x, NT);
+      else
+        bfly_stage<FWD, true, false>(buf, 2 * N, N - 1 - q, 2 * N - 1 - q, nt_here * TRA, LDA, 1, threadIdx.x, NT);
       __syncthreads();
     }
 #pragma unroll
@@ -386,7 +391,7 @@ __global__ void __launch_bounds__(PlCfg<N>::NTB) pl_pass_b_kernel(int64_t B, con
   if constexpr (C::RADIX16) {
     {
       constexpr int NS = N - RQN;
-      constexpr int WB = (W == 32) ? 5 : 4;
+      constexpr int WB = (W == 256) ? 8 : (W == 32 ? 5 : 4);
       auto lo_of = [](int st) { return WB + 2 * (N - 1 - (RQN + st)); };
 #pragma unroll
       for (int st = 0; st + 1 < NS; st += 2) {
