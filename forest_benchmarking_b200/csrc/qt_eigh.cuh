@@ -43,15 +43,17 @@ __device__ __forceinline__ void jacobi_rotation(double alpha, double gamma, cplx
   const double scale = fabs(alpha) + fabs(gamma);
   const bool skip = (ab2 <= 1e-36 * scale * scale) || (ab2 == 0.0);
   const double ab2s = skip ? 1.0 : ab2;
-  const double rab = fast_rsqrt(ab2s);  // 1 / |beta|
-  const double tau = 0.5 * (gamma - alpha) * rab;
-  const double q = fma(tau, tau, 1.0);
-  const double t = (tau >= 0.0 ? 1.0 : -1.0) * fast_rcp(fabs(tau) + q * fast_rsqrt(q));
-  const double cc = fast_rsqrt(fma(t, t, 1.0));
-  const double inv = t * cc * rab;
-  const double tab = t * (ab2s * rab);  // t |beta|
-  c = skip ? 1.0 : cc;
-  s = skip ? cmake(0.0, 0.0) : cmake(beta.x * inv, beta.y * inv);  // sin * e^{i phi}
+  // half-angle form (two dependent rsqrt instead of rsqrt -> rsqrt -> rcp -> rsqrt):
+  //   cos 2t = |D| / r,  r = sqrt(D^2 + 4|b|^2),  D = gamma - alpha   (|t| <= pi/4, sign t = sign D)
+  //   c = sqrt((1 + cos 2t) / 2),   sin t = sign(D) |b| / (r c),   t|b| = sign(D) |b|^2 / (r c^2)
+  const double dlt = gamma - alpha;
+  const double ir = fast_rsqrt(fma(dlt, dlt, 4.0 * ab2s));  // 1 / r
+  const double h = fma(0.5 * fabs(dlt), ir, 0.5);           // c^2
+  const double ic = fast_rsqrt(h);                           // 1 / c
+  const double sg = (dlt >= 0.0) ? ir * ic : -(ir * ic);     // sign(D) / (r c)
+  const double tab = ab2s * sg * ic;                         // tan(t) |beta|
+  c = skip ? 1.0 : h * ic;
+  s = skip ? cmake(0.0, 0.0) : cmake(beta.x * sg, beta.y * sg);  // sin(t) e^{i phi}
   alpha_new = skip ? alpha : alpha - tab;
   gamma_new = skip ? gamma : gamma + tab;
 }
@@ -395,7 +397,8 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
         b00[k] = A[pi[k] * LD + pj[k]];
-        b01[k] = near1[k] ? cconj(A[qj[k] * LD + pi[k]]) : A[pi[k] * LD + qj[k]];
+        b01[k] = A[near1[k] ? qj[k] * LD + pi[k] : pi[k] * LD + qj[k]];  // one load, address selected
+        b01[k].y = near1[k] ? -b01[k].y : b01[k].y;
         b10[k] = A[qi[k] * LD + pj[k]];
         b11[k] = A[qi[k] * LD + qj[k]];
         b01[k] = (!fresh && near2[k]) ? cmake(0.0, 0.0) : b01[k];
