@@ -86,7 +86,10 @@ def streaming_rows(torch, peak, budget_bytes=2 << 30):
         rows.append(_row(f"trace_distance_kernel<{d}>", b, 32 * d * d + 8, ms, peak))
         ms = _time(torch, lambda: dm.purity_batch(r, out=o))
         rows.append(_row(f"purity_kernel<{d}>", b, 16 * d * d + 8, ms, peak))
-        del r, s, o
+        oc = torch.empty((b,), dtype=torch.complex128, device="cuda")
+        ms = _time(torch, lambda: dm.hilbert_schmidt_ip_batch(r, s, out=oc))
+        rows.append(_row(f"hs_inner_kernel d={d} (hilbert_schmidt_ip / process_fidelity)", b, 32 * d * d + 16, ms, peak))
+        del r, s, o, oc
     return rows
 
 

@@ -11,6 +11,8 @@
 #include "qt_eigh.cuh"
 #include "../../include/qtomo.h"
 
+#include <algorithm>
+
 template <int D>
 __global__ void trace_distance_kernel(int64_t B, const cplx* __restrict__ rho, const cplx* __restrict__ sigma,
                                       double* __restrict__ out) {
@@ -226,6 +228,42 @@ static int launch_project_state(int64_t B, const void* rho, void* out, cudaStrea
   return qt_check_launch("project_state_kernel");
 }
 
+// Hilbert-Schmidt inner product tr(A^dagger B) per pair (distance_measures.py:198-216); the kernel behind
+// entanglement_fidelity / process_fidelity (:271-375).  Pure streaming: one warp per pair for small matrices, one
+// block per pair otherwise.  out[b] is complex.
+__global__ void hs_inner_kernel(int64_t elems, int64_t B, const cplx* __restrict__ a, const cplx* __restrict__ b,
+                                cplx* __restrict__ out, int block_per_pair) {
+  __shared__ double red[2][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  if (!block_per_pair) {
+    const int64_t p = (int64_t)blockIdx.x * wpb + wib;
+    if (p >= B) return;
+    cplx acc = cmake(0.0, 0.0);
+    for (int64_t e = lane; e < elems; e += 32) cfma(acc, cconj(a[p * elems + e]), b[p * elems + e]);
+    acc.x = warp_sum(acc.x);
+    acc.y = warp_sum(acc.y);
+    if (lane == 0) out[p] = acc;
+    return;
+  }
+  for (int64_t p = blockIdx.x; p < B; p += gridDim.x) {
+    cplx acc = cmake(0.0, 0.0);
+    for (int64_t e = threadIdx.x; e < elems; e += blockDim.x) cfma(acc, cconj(a[p * elems + e]), b[p * elems + e]);
+    acc.x = warp_sum(acc.x);
+    acc.y = warp_sum(acc.y);
+    __syncthreads();
+    if (lane == 0) {
+      red[0][wib] = acc.x;
+      red[1][wib] = acc.y;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      cplx t = cmake(0.0, 0.0);
+      for (int w = 0; w < wpb; ++w) t = cadd(t, cmake(red[0][w], red[1][w]));
+      out[p] = t;
+    }
+  }
+}
+
 template <int D>
 static int launch_td(int64_t B, const void* rho, const void* sigma, double* out, cudaStream_t st) {
   const int wpb = 8;
@@ -302,4 +340,16 @@ extern "C" int qt_project_state_batch(int n, int64_t B, const void* rho, void* o
 #define CALL(D) launch_project_state<D>(B, rho, out, (cudaStream_t)stream)
   DISPATCH_D(n, CALL)
 #undef CALL
+}
+
+extern "C" int qt_hs_inner_batch(int64_t rows, int64_t cols, int64_t B, const void* a, const void* b, void* out,
+                                 void* stream) {
+  QT_REQUIRE(rows > 0 && cols > 0 && a && b && out, "qt_hs_inner_batch: bad arguments");
+  if (B == 0) return QT_OK;
+  const int64_t elems = rows * cols;
+  const int block_per_pair = elems > 1024;
+  const int64_t blocks = block_per_pair ? std::min<int64_t>(B, (int64_t)QT_NUM_SMS * 8) : (B + 7) / 8;
+  hs_inner_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(elems, B, (const cplx*)a, (const cplx*)b,
+                                                                      (cplx*)out, block_per_pair);
+  return qt_check_launch("hs_inner_kernel");
 }

@@ -174,7 +174,8 @@ __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int ti
     off = group_sum<NT, Sync>(off, red, tid);
     tot = group_sum<NT, Sync>(tot, red, tid);
     if (off <= (rel2 > 0.0 ? rel2 : 1e-30 * M * M) * tot || tot == 0.0) break;
-    params(0, 0);
+    Sync::sync();  // the norm pass above read all of A (a warp-wide group_sum is shuffle-only): order it before
+    params(0, 0);  // the diagonal-block writes of the first parameter phase (racecheck: WAR hazard otherwise)
     Sync::sync();
     for (int step = 0; step < M - 1; ++step) {
       const int cur = step & 1;
@@ -299,7 +300,7 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
   }
   __syncthreads();
   // static block assignment: block w = tid + k NT < 496 -> (I, J), I < J, row-major triangular order; spare
-  // slots shadow block (0, 1) with their stores predicated off (keeps the step free of branches)
+  // slots run the same instructions on element (0, 0) with their stores predicated off (no branches in the step)
   bool has_block[NB], near1[NB], near2[NB], last2[NB], first2[NB];
   int bI[NB], bJ[NB];
 #pragma unroll
@@ -336,9 +337,16 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
   bool pending = false;
   if (tid == 0) mbar_init(mbar, NT);
   __syncthreads();
+  // QT_JACOBI_PLAIN_BARRIER (validation builds only, scripts/ubench_jacobi.cu): the split-phase barrier becomes a
+  // plain __syncthreads() at the wait point, which compute-sanitizer's racecheck can follow (it does not model
+  // mbarrier ordering and reports every step-to-step dependency of the default build as a hazard).
   auto wait_pending = [&]() {
     if (pending) {
+#ifdef QT_JACOBI_PLAIN_BARRIER
+      __syncthreads();
+#else
       if constexpr (!(ABL & 8)) mbar_wait(mbar, parity);
+#endif
       parity ^= 1u;
       pending = false;
     }
@@ -373,6 +381,7 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
       for (int k = 0; k < NB; ++k) {
         rr_pair(M, 0, bI[k], pi[k], qi[k]);
         rr_pair(M, 0, bJ[k], pj[k], qj[k]);
+        if (!has_block[k]) pi[k] = qi[k] = pj[k] = qj[k] = 0;
         cplx b00 = A[pi[k] * LD + pj[k]];
         cplx b01 = near1[k] ? A[qj[k] * LD + pi[k]] : A[pi[k] * LD + qj[k]];
         const cplx b10 = A[qi[k] * LD + pj[k]];
@@ -448,7 +457,9 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
         }
       }
       // ---- all shared-memory stores of the step are issued: arrive, then do the register-only work ----
+#ifndef QT_JACOBI_PLAIN_BARRIER
       if constexpr (!(ABL & 8)) mbar_arrive(mbar);
+#endif
       pending = true;
       if constexpr (!(ABL & 1)) v_update(c, s);
       // ---- diagonal entries move along the ring; next step's indices ----
@@ -465,6 +476,7 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
       for (int k = 0; k < NB; ++k) {
         rr_pair(M, nxt, bI[k], pi[k], qi[k]);
         rr_pair(M, nxt, bJ[k], pj[k], qj[k]);
+        if (!has_block[k]) pi[k] = qi[k] = pj[k] = qj[k] = 0;  // spare slot: read A[0][0], which no step writes
       }
     }
   }
@@ -503,7 +515,9 @@ __device__ __forceinline__ int jacobi_eigh_warp(cplx* A, cplx* V, double* ev, in
 // ---------------------------------------------------------------------------------------------
 template <int M, int NT, int LD, int MODE>
 __device__ void smem_matmul(cplx* __restrict__ C, const cplx* __restrict__ A, const cplx* __restrict__ B, int tid) {
-  constexpr int TR = (M >= 16) ? 2 : 1, TC = (M >= 16) ? 4 : 1;
+  // M = 64: 4x4 tiles on 256 work items -- 8 shared loads per 16 complex FMAs keeps the LDS pipe (4 cycles per
+  // 16-byte warp load) level with the FP64 pipe; 2x4 tiles on 512 threads were LDS-bound
+  constexpr int TR = (M >= 64) ? 4 : (M >= 16 ? 2 : 1), TC = (M >= 16) ? 4 : 1;
   constexpr int NR = M / TR, NC = M / TC;  // tile grid
   for (int t = tid; t < NR * NC; t += NT) {
     const int tr = t / NC, tc = t % NC;

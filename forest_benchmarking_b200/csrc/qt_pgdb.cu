@@ -87,16 +87,23 @@ struct Pgdb {
     reshuffle_inplace(X, tid);
   }
 
-  // T[i][k] = sum_j R[k][j] svec[i][j], R read from butterfly positions of X (real part) with scale 1/d
-  static __device__ void build_T(const cplx* X, const PgdbView& pv, double* T, int tid) {
+  // T[i][k] = sum_j R[k][j] svec[i][j], R read from butterfly positions of X (real part) with scale 1/d.
+  // The real PTM is first compacted (transposed, Pauli order) into `rt` (M*M doubles of shared scratch) so that
+  // the dot products read consecutive words: lanes walk k, svec[i][j] is a broadcast.
+  static __device__ void build_T(const cplx* X, const PgdbView& pv, double* T, double* rt, int tid) {
     const double scale = 1.0 / D;
+    for (int e = tid; e < MM; e += NT) {
+      const int j = e / M, k = e % M;
+      rt[e] = X[pauli_to_pos(k, N) * LD + pauli_to_pos(j, N)].x * scale;  // rt[j][k] = R[k][j] / d
+    }
+    Sync::sync();
     for (int e = tid; e < pv.n_in * M; e += NT) {
       const int i = e / M, k = e % M;
-      const cplx* row = X + pauli_to_pos(k, N) * LD;
       const double* sv = pv.svec + (int64_t)i * M;
       double acc = 0.0;
-      for (int j = 0; j < M; ++j) acc = fma(row[pauli_to_pos(j, N)].x, sv[j], acc);
-      T[e] = acc * scale;
+#pragma unroll 8
+      for (int j = 0; j < M; ++j) acc = fma(rt[j * M + k], sv[j], acc);
+      T[e] = acc;
     }
     Sync::sync();
   }
@@ -198,7 +205,7 @@ struct Pgdb {
     for (int e = tid; e < pv.n_in * M; e += NT) Tu[e] = 0.0;
     Sync::sync();
     choi_to_pl_positions(X, tid);
-    build_T(X, pv, Te, tid);
+    build_T(X, pv, Te, reinterpret_cast<double*>(T), tid);
     double old_cost = cost(pv, dt, Te, Tu, 0.0, red, tid);
     int outer = 0, cost_evals = 1, eighs = 0, sweeps = 0;
     bool v_valid = false;  // V keeps the last eigenbasis across Dykstra AND outer iterations (warm start)
@@ -238,7 +245,7 @@ struct Pgdb {
       ip = group_sum<NT, Sync>(ip, red, tid);
       Sync::sync();
       choi_to_pl_positions(X, tid);
-      build_T(X, pv, Tu, tid);
+      build_T(X, pv, Tu, reinterpret_cast<double*>(T), tid);
       // ---- backtracking line search (tomography.py:574-585) ----
       double alpha = 1.0;
       double new_cost = cost(pv, dt, Te, Tu, alpha, red, tid);

@@ -81,3 +81,53 @@ def purity(rho: np.ndarray, dim_renorm=True, tol: float = 1000) -> float:
         d = np.asarray(rho).shape[0]
         p = (d / (d - 1.0)) * (p - 1.0 / d)
     return p
+
+
+def hilbert_schmidt_ip_batch(a, b, out=None):
+    """tr(A^dagger B) for every pair of [B, r, c] complex128 CUDA tensors -> complex128 [B]."""
+    torch = _lib.require_cuda()
+    if a.shape != b.shape or a.dim() != 3 or a.dtype != torch.complex128 or b.dtype != torch.complex128:
+        raise ValueError("a and b must be complex128 CUDA tensors of identical shape [B, r, c]")
+    a, b = a.contiguous(), b.contiguous()
+    if out is None:
+        out = torch.empty((a.shape[0],), dtype=torch.complex128, device=a.device)
+    _lib.check(_lib.lib().qt_hs_inner_batch(ctypes.c_int64(a.shape[1]), ctypes.c_int64(a.shape[2]),
+                                            ctypes.c_int64(a.shape[0]), _lib.ptr(a), _lib.ptr(b), _lib.ptr(out),
+                                            _lib.current_stream_ptr()), "qt_hs_inner_batch")
+    return out
+
+
+def _real_if_close_item(z, tol=1000):
+    return np.ndarray.item(np.real_if_close(np.asarray(z), tol))
+
+
+def hilbert_schmidt_ip(A: np.ndarray, B: np.ndarray, tol: float = 1000) -> float:
+    """reference distance_measures.py:198-216."""
+    return _real_if_close_item(hilbert_schmidt_ip_batch(_one(A), _one(B)).cpu().numpy()[0], tol)
+
+
+def entanglement_fidelity_batch(pl0, pl1):
+    """F_e = tr(E^dagger F) / dim^2 for Pauli-Liouville matrices [B, dim^2, dim^2] -> complex128 [B]."""
+    return hilbert_schmidt_ip_batch(pl0, pl1) / pl0.shape[1]
+
+
+def entanglement_fidelity(pauli_lio0: np.ndarray, pauli_lio1: np.ndarray, tol: float = 1000) -> float:
+    """reference distance_measures.py:271-303."""
+    assert pauli_lio0.shape == pauli_lio1.shape
+    assert pauli_lio0.shape[0] == pauli_lio1.shape[1]
+    dim = int(np.sqrt(pauli_lio0.shape[0]))
+    fe = hilbert_schmidt_ip_batch(_one(pauli_lio0), _one(pauli_lio1)).cpu().numpy()[0] / (dim ** 2)
+    return _real_if_close_item(fe, tol)
+
+
+def process_fidelity(pauli_lio0: np.ndarray, pauli_lio1: np.ndarray) -> float:
+    """reference distance_measures.py:306-361: (dim F_e + 1) / (dim + 1)."""
+    assert pauli_lio0.shape == pauli_lio1.shape
+    assert pauli_lio0.shape[0] == pauli_lio1.shape[1]
+    dim = int(np.sqrt(pauli_lio0.shape[0]))
+    return (dim * entanglement_fidelity(pauli_lio0, pauli_lio1) + 1) / (dim + 1)
+
+
+def process_infidelity(pauli_lio0: np.ndarray, pauli_lio1: np.ndarray) -> float:
+    """reference distance_measures.py:364-375."""
+    return 1 - process_fidelity(pauli_lio0, pauli_lio1)

@@ -88,6 +88,9 @@ int qt_trace_distance_batch(int n, int64_t B, const void* rho, const void* sigma
 /* textbook 0.5 * nuclear norm (extra; not the reference's behaviour) */
 int qt_trace_distance_nuclear_batch(int n, int64_t B, const void* rho, const void* sigma, double* out, void* stream);
 int qt_purity_batch(int n, int64_t B, const void* rho, double* out, void* stream);                             /* :14-37 */
+/* hilbert_schmidt_ip tr(A^dagger B) per pair (:198-216), a, b: [B, rows, cols], out[B] complex; entanglement_fidelity /
+ * process_fidelity (:271-375) are this number on Pauli-Liouville matrices, rescaled on the host */
+int qt_hs_inner_batch(int64_t rows, int64_t cols, int64_t B, const void* a, const void* b, void* out, void* stream);
 /* project_state_matrix_to_physical (operator_tools/project_state_matrix.py:6-52): closest trace-one PSD matrix */
 int qt_project_state_batch(int n, int64_t B, const void* rho, void* out, void* stream);
 

@@ -325,6 +325,22 @@ def trace_distance(rho, sigma):
     return 0.5 * float(np.max(np.sum(np.abs(np.asarray(rho) - np.asarray(sigma)), axis=0)))
 
 
+def hilbert_schmidt_ip(a, b):
+    """tr(A^dagger B), distance_measures.py:198-216."""
+    return np.trace(np.asarray(a).conj().T @ np.asarray(b))
+
+
+def entanglement_fidelity(pl0, pl1):
+    """tr(E^dagger F) / dim^2, distance_measures.py:271-303."""
+    return hilbert_schmidt_ip(pl0, pl1) / np.asarray(pl0).shape[0]
+
+
+def process_fidelity(pl0, pl1):
+    """(dim F_e + 1) / (dim + 1), distance_measures.py:306-361."""
+    dim = int(np.sqrt(np.asarray(pl0).shape[0]))
+    return (dim * entanglement_fidelity(pl0, pl1) + 1) / (dim + 1)
+
+
 def purity(rho, dim_renorm=False):
     """distance_measures.py:14-37."""
     p = np.real(np.trace(rho @ rho))

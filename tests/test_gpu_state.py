@@ -270,3 +270,25 @@ def test_project_state_matrix_and_estimate_variance(torch):
         assert abs(mean - np.mean(vals)) < 1e-8 and abs(var - np.var(vals)) < 1e-8
     with pytest.raises(ValueError):
         tm.estimate_variance(res, qubits, tm.linear_inv_state_estimate, dm.fidelity)
+
+
+def test_hilbert_schmidt_and_process_fidelity(torch):
+    """tr(A^dagger B) streaming kernel and the process-fidelity family built on it (distance_measures.py:198-375)."""
+    from forest_benchmarking_b200 import distance_measures as dm
+    rng = np.random.default_rng(17)
+    for m, batch in ((4, 100), (16, 37), (64, 9), (256, 3)):
+        a = rng.standard_normal((batch, m, m)) + 1j * rng.standard_normal((batch, m, m))
+        b = rng.standard_normal((batch, m, m)) + 1j * rng.standard_normal((batch, m, m))
+        got = dm.hilbert_schmidt_ip_batch(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()).cpu().numpy()
+        want = np.array([orc.hilbert_schmidt_ip(x, y) for x, y in zip(a, b)])
+        assert np.allclose(got, want, rtol=1e-12, atol=1e-10)
+    for n in (1, 2, 3):
+        d = 2 ** n
+        u, v = orc.haar_unitary(rng, d), orc.haar_unitary(rng, d)
+        p0, p1 = orc.kraus2pauli_liouville([u]), orc.kraus2pauli_liouville([np.sqrt(.9) * u, np.sqrt(.1) * v])
+        assert abs(dm.entanglement_fidelity(p0, p1) - orc.entanglement_fidelity(p0, p1).real) < 1e-12
+        assert abs(dm.process_fidelity(p0, p1) - orc.process_fidelity(p0, p1).real) < 1e-12
+        assert abs(dm.process_fidelity(p0, p0) - 1.0) < 1e-12
+        assert abs(dm.process_infidelity(p0, p1) - (1 - orc.process_fidelity(p0, p1).real)) < 1e-12
+        rho, sig = orc.ginibre_state(rng, d), orc.ginibre_state(rng, d)
+        assert abs(dm.hilbert_schmidt_ip(rho, sig) - orc.hilbert_schmidt_ip(rho, sig).real) < 1e-13

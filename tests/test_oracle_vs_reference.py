@@ -194,3 +194,14 @@ def test_chi_family(ref, n):
     assert relerr(orc.superop2chi(orc.reshuffle(choi)), ot.superop2chi(orc.reshuffle(choi))) < 1e-12
     pl = orc.choi2pauli_liouville(choi)
     assert relerr(orc.pauli_liouville2chi(pl), ot.pauli_liouville2chi(pl)) < 1e-12
+
+
+def test_process_fidelities(ref):
+    rng = np.random.default_rng(8)
+    for n in (1, 2):
+        d = 2 ** n
+        u, v = orc.haar_unitary(rng, d), orc.haar_unitary(rng, d)
+        p0, p1 = orc.kraus2pauli_liouville([u]), orc.kraus2pauli_liouville([np.sqrt(.9) * u, np.sqrt(.1) * v])
+        assert abs(orc.hilbert_schmidt_ip(p0, p1) - ref.dm.hilbert_schmidt_ip(p0, p1)) < 1e-12
+        assert abs(orc.entanglement_fidelity(p0, p1) - ref.dm.entanglement_fidelity(p0, p1)) < 1e-13
+        assert abs(orc.process_fidelity(p0, p1) - ref.dm.process_fidelity(p0, p1)) < 1e-13
