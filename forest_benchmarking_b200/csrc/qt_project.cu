@@ -144,9 +144,8 @@ __global__ void __launch_bounds__(128) proj_cp4_thread_kernel(int64_t B, const c
 }
 
 // ---- TP / TNI: streaming kernel, several items per block for small n --------------------------------
-template <int N>
-__global__ void proj_tp_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out, int make_tp,
-                               int items_per_block) {
+template <int N, bool make_tp>
+__global__ void proj_tp_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out, int items_per_block) {
   constexpr int D = 1 << N, M = D * D, MM = M * M;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   cplx* tile = reinterpret_cast<cplx*>(smem_raw);         // [items][MM]
@@ -156,7 +155,7 @@ __global__ void proj_tp_kernel(int64_t B, const cplx* __restrict__ in, cplx* __r
   const int nb = (int)min((int64_t)items_per_block, B - b0);
   for (int e = threadIdx.x; e < nb * MM; e += blockDim.x) tile[e] = in[b0 * MM + e];
   __syncthreads();
-  if (make_tp) {
+  if constexpr (make_tp) {
     for (int w = threadIdx.x; w < nb * D * D; w += blockDim.x) {
       const int bi = w / (D * D), a = (w / D) % D, c = w % D;
       const cplx* Cm = tile + (size_t)bi * MM;
@@ -164,6 +163,65 @@ __global__ void proj_tp_kernel(int64_t B, const cplx* __restrict__ in, cplx* __r
       for (int bb = 0; bb < D; ++bb) s = cadd(s, Cm[(a * D + bb) * M + c * D + bb]);
       if (a == c) s.x -= 1.0;
       Eall[w] = cscale(s, 1.0 / D);
+    }
+  } else if constexpr (D <= 4) {
+    // n <= 2: one THREAD per item -- partial trace, d x d eigendecomposition (Jacobi unrolled in registers) and
+    // the correction; a warp per 2x2 / 4x4 problem left this streaming kernel at 0.17 of the HBM roof
+    for (int bi = threadIdx.x; bi < nb; bi += blockDim.x) {
+      const cplx* Cm = tile + (size_t)bi * MM;
+      cplx pt[4][4];
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          cplx sacc = cmake(0.0, 0.0);
+#pragma unroll
+          for (int bb = 0; bb < D; ++bb) sacc = cadd(sacc, Cm[(a * D + bb) * M + c * D + bb]);
+          pt[a][c] = sacc;
+        }
+      double dg[4];
+      cplx o[4][4], v[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        dg[a] = (a < D) ? pt[a][a].x : 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          v[a][c] = cmake(a == c ? 1.0 : 0.0, 0.0);
+          o[a][c] = cmake(0.0, 0.0);
+          if (a < c && c < D) o[a][c] = cmake(0.5 * (pt[a][c].x + pt[c][a].x), 0.5 * (pt[a][c].y - pt[c][a].y));
+        }
+      }
+      if constexpr (D == 2) {
+        rot4<0, 1>(dg, o, v);  // a 2x2 Hermitian matrix is diagonalised by one rotation
+      } else {
+        for (int sweep = 0; sweep < 30; ++sweep) {
+          double off = 0.0, tot = 0.0;
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            tot = fma(dg[a], dg[a], tot);
+#pragma unroll
+            for (int c = a + 1; c < 4; ++c) off += cabs2(o[a][c]);
+          }
+          off *= 2.0;
+          tot += off;
+          if (off <= (1e-30 * 16) * tot || tot == 0.0) break;
+          rot4<0, 1>(dg, o, v);
+          rot4<2, 3>(dg, o, v);
+          rot4<0, 2>(dg, o, v);
+          rot4<1, 3>(dg, o, v);
+          rot4<0, 3>(dg, o, v);
+          rot4<1, 2>(dg, o, v);
+        }
+      }
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+          for (int k = 0; k < D; ++k) cfma_conj(acc, cscale(v[a][k], fmin(dg[k], 1.0)), v[c][k]);
+          Eall[bi * D * D + a * D + c] = cscale(csub(pt[a][c], acc), 1.0 / D);
+        }
     }
   } else {
     // one warp per item computes pt, its eigen-decomposition and the correction
@@ -337,9 +395,17 @@ static int launch_tp(int64_t B, const void* in, void* out, int make_tp, cudaStre
   const int ipb = make_tp ? std::max(1, 4096 / MM) : std::max(1, std::min(64, 4096 / MM));
   constexpr int PER = 3 * D * D * 2 + D + JacobiScratch<D>::doubles + (D % 2);
   const size_t smem = sizeof(cplx) * ((size_t)ipb * MM + (size_t)ipb * D * D) +
-                      (make_tp ? 0 : sizeof(double) * (size_t)ipb * ((PER + 1) / 2 * 2));
-  QT_CUDA(cudaFuncSetAttribute(proj_tp_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  proj_tp_kernel<N><<<(unsigned)((B + ipb - 1) / ipb), 256, smem, st>>>(B, (const cplx*)in, (cplx*)out, make_tp, ipb);
+                      ((make_tp || D <= 4) ? 0 : sizeof(double) * (size_t)ipb * ((PER + 1) / 2 * 2));
+  const unsigned blocks = (unsigned)((B + ipb - 1) / ipb);
+  if (make_tp) {
+    QT_CUDA(cudaFuncSetAttribute(proj_tp_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    proj_tp_kernel<N, true><<<blocks, 256, smem, st>>>(B, (const cplx*)in, (cplx*)out, ipb);
+  } else {
+    QT_CUDA(cudaFuncSetAttribute(proj_tp_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // n <= 2: the per-item eigendecomposition runs on one thread with ~200 registers; small blocks keep several
+    // resident per SM
+    proj_tp_kernel<N, false><<<blocks, (D <= 4) ? 64 : 256, smem, st>>>(B, (const cplx*)in, (cplx*)out, ipb);
+  }
   return qt_check_launch("proj_tp_kernel");
 }
 
