@@ -136,7 +136,7 @@ def distance_rows(torch, peak, pairs, n=4):
     reps = -(-pairs // chunk)
     rows = []
     ms = _time(torch, lambda: dm.fidelity_batch(rho, sig, out=o))
-    rows.append(_row(f"fidelity_kernel<{d}> (2 warp-Jacobi eigh + 3 products per pair; FP64-bound)", chunk,
+    rows.append(_row(f"fidelity_kernel<{d}> (Cholesky + one values-only warp-Jacobi eigh per pair; FP64/latency-bound)", chunk,
                      32 * d * d + 8, ms, peak, {"batch_ms": round(ms * reps, 3), "pairs_total": pairs}))
     ms = _time(torch, lambda: dm.trace_distance_batch(rho, sig, out=o))
     rows.append(_row(f"trace_distance_kernel<{d}>", chunk, 32 * d * d + 8, ms, peak,

@@ -99,13 +99,83 @@ __global__ void fidelity_kernel(int64_t B, const cplx* __restrict__ rho, const c
     return;
   }
   // scipy.linalg.eigh reads the lower triangle only: build the Hermitian matrix it sees
-  for (int e = lane; e < DD; e += 32) {
-    const int i = e / D, j = e % D;
-    cplx v = (i >= j) ? r[e] : cconj(r[j * D + i]);
-    if (i == j) v.y = 0.0;
-    A[i * LD + j] = v;
+  auto load_rho = [&]() {
+    for (int e = lane; e < DD; e += 32) {
+      const int i = e / D, j = e % D;
+      cplx v = (i >= j) ? r[e] : cconj(r[j * D + i]);
+      if (i == j) v.y = 0.0;
+      A[i * LD + j] = v;
+    }
+    __syncwarp();
+  };
+  load_rho();
+  // Fast path for a numerically positive-definite rho: rho = L L^dagger (Cholesky), and the eigenvalues of
+  // L^dagger sigma L are those of sqrt(rho) sigma sqrt(rho) (similar matrices), so ONE values-only
+  // eigendecomposition replaces eigh(rho) with vectors + sqrtm + the second eigh.  A pivot that is not safely
+  // positive (rank-deficient or non-PSD input, where the reference's clamping in sqrtm_psd matters) falls back to
+  // the reference's own sequence below.
+  if constexpr (D >= 4) {
+    double dmax = 0.0;
+    for (int k = 0; k < D; ++k) dmax = fmax(dmax, A[k * LD + k].x);
+    const double thr = 1e-10 * dmax;
+    bool ok = dmax > 0.0;
+    for (int j = 0; j < D && ok; ++j) {
+      const double piv = A[j * LD + j].x;
+      if (!(piv > thr)) {
+        ok = false;
+        break;
+      }
+      const double inv = rsqrt(piv);
+      __syncwarp();
+      for (int i = j + lane; i < D; i += 32) A[i * LD + j] = (i == j) ? cmake(piv * inv, 0.0) : cscale(A[i * LD + j], inv);
+      __syncwarp();
+      const int nt = D - j - 1;
+      for (int e = lane; e < nt * nt; e += 32) {
+        const int i = j + 1 + e / nt, k = j + 1 + e % nt;
+        if (k <= i) {
+          const cplx li = A[i * LD + j], lk = A[k * LD + j];
+          cplx v = A[i * LD + k];
+          v.x -= li.x * lk.x + li.y * lk.y;  // v -= li * conj(lk)
+          v.y -= li.y * lk.x - li.x * lk.y;
+          if (i == k) v.y = 0.0;
+          A[i * LD + k] = v;
+        }
+      }
+      __syncwarp();
+    }
+    if (ok) {
+      // W = sigma L  (L lower triangular in A)
+      for (int e = lane; e < DD; e += 32) {
+        const int i = e / D, j = e % D;
+        cplx acc = cmake(0.0, 0.0);
+        for (int k = j; k < D; ++k) cfma(acc, s[i * D + k], A[k * LD + j]);
+        W[i * LD + j] = acc;
+      }
+      __syncwarp();
+      // V = L^dagger W, then the Hermitian matrix an eigensolver reading the lower triangle would see
+      for (int e = lane; e < DD; e += 32) {
+        const int i = e / D, j = e % D;
+        cplx acc = cmake(0.0, 0.0);
+        for (int k = i; k < D; ++k) cfma(acc, cconj(A[k * LD + i]), W[k * LD + j]);
+        V[i * LD + j] = acc;
+      }
+      __syncwarp();
+      for (int e = lane; e < DD; e += 32) {
+        const int i = e / D, j = e % D;
+        cplx v = (i >= j) ? V[i * LD + j] : cconj(V[j * LD + i]);
+        if (i == j) v.y = 0.0;
+        W[i * LD + j] = v;
+      }
+      __syncwarp();
+      jacobi_eigh<D, 32, SyncWarp, false, LD>(W, nullptr, ev, ev + D, lane);
+      double acc = 0.0;
+      for (int k = lane; k < D; k += 32) acc += sqrt(fmax(ev[k], 0.0));
+      acc = warp_sum(acc);
+      if (lane == 0) out[b] = acc * acc;
+      return;
+    }
+    load_rho();  // the factorisation overwrote A
   }
-  __syncwarp();
   jacobi_eigh<D, 32, SyncWarp, true, LD>(A, V, ev, ev + D, lane);
   // S = V sqrt(max(ev,0)) V^dagger  -> A
   for (int e = lane; e < DD; e += 32) {
@@ -221,7 +291,7 @@ __global__ void project_state_kernel(int64_t B, const cplx* __restrict__ rho, cp
 template <int D>
 static int launch_project_state(int64_t B, const void* rho, void* out, cudaStream_t st) {
   const size_t per_warp = FidSmem<D>::bytes;
-  int wpb = (int)max((size_t)1, min((size_t)8, (size_t)(100 * 1024) / per_warp));
+  int wpb = (int)max((size_t)1, min((size_t)8, (size_t)(112 * 1024) / per_warp));
   const size_t smem = per_warp * wpb;
   QT_CUDA(cudaFuncSetAttribute(project_state_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   project_state_kernel<D><<<(unsigned)((B + wpb - 1) / wpb), 32 * wpb, smem, st>>>(B, (const cplx*)rho, (cplx*)out);
@@ -280,7 +350,7 @@ static int launch_purity(int64_t B, const void* rho, double* out, cudaStream_t s
 template <int D, int MODE>
 static int launch_fid(int64_t B, const void* rho, const void* sigma, double* out, cudaStream_t st) {
   const size_t per_warp = FidSmem<D>::bytes;
-  int wpb = (int)max((size_t)1, min((size_t)8, (size_t)(100 * 1024) / per_warp));
+  int wpb = (int)max((size_t)1, min((size_t)8, (size_t)(112 * 1024) / per_warp));
   const size_t smem = per_warp * wpb;
   QT_CUDA(cudaFuncSetAttribute(fidelity_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fidelity_kernel<D, MODE><<<(unsigned)((B + wpb - 1) / wpb), 32 * wpb, smem, st>>>(B, (const cplx*)rho,

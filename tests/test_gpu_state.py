@@ -292,3 +292,34 @@ def test_hilbert_schmidt_and_process_fidelity(torch):
         assert abs(dm.process_infidelity(p0, p1) - (1 - orc.process_fidelity(p0, p1).real)) < 1e-12
         rho, sig = orc.ginibre_state(rng, d), orc.ginibre_state(rng, d)
         assert abs(dm.hilbert_schmidt_ip(rho, sig) - orc.hilbert_schmidt_ip(rho, sig).real) < 1e-13
+
+
+def test_fidelity_cholesky_fast_path_and_fallback(torch):
+    """fidelity: positive-definite rho goes through the Cholesky fast path, rank-deficient / non-PSD rho through the
+    reference's eigh + sqrtm_psd sequence; both must match the oracle (distance_measures.py:64-84)."""
+    from forest_benchmarking_b200 import distance_measures as dm
+    rng = np.random.default_rng(77)
+    for n in (2, 3, 4, 5):
+        d = 2 ** n
+        rho, sig = [], []
+        for b in range(24):
+            if b % 4 == 0:      # pure state: Cholesky pivots vanish -> fallback
+                r = orc.ginibre_state(rng, d, rank=1)
+            elif b % 4 == 1:    # slightly non-PSD Hermitian, unit trace (e.g. a linear-inversion estimate)
+                r = orc.ginibre_state(rng, d)
+                h = rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d))
+                r = r + 0.3 / d * (h + h.conj().T)
+                r = r / np.trace(r).real
+            elif b % 4 == 2:    # ill-conditioned but positive definite
+                r = 0.999 * orc.ginibre_state(rng, d, rank=1) + 0.001 * np.eye(d) / d
+            else:
+                r = orc.ginibre_state(rng, d)
+            rho.append(r)
+            sig.append(orc.ginibre_state(rng, d))
+        rho, sig = np.stack(rho), np.stack(sig)
+        fid = dm.fidelity_batch(torch.from_numpy(rho).cuda(), torch.from_numpy(sig).cuda()).cpu().numpy()
+        for b in range(24):
+            want = np.real(orc.fidelity(rho[b], sig[b]))
+            assert abs(fid[b] - want) < 1e-6 * max(abs(want), 1e-3), (n, b, fid[b], want)
+            if b % 4 == 3:
+                assert abs(fid[b] - want) < 1e-10
