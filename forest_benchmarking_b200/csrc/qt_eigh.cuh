@@ -15,6 +15,7 @@
 // Matrices may have a padded leading dimension LD (M + 1 for M >= 16): column accesses of the
 // recomposition / basis-change products are then bank-conflict free.
 #pragma once
+#include <type_traits>
 #include "qt_common.cuh"
 
 // Round-robin ("circle") pairing: M players, step s in [0, M-1), pair i in [0, M/2):
@@ -87,9 +88,9 @@ struct JacobiScratch {
 
 // ABL: ablation mask for scripts/ubench_jacobi.cu only (1: no V update, 2: no block update, 4: no rotation
 // chain, 8: no barrier); 0 in every product instantiation.
-template <int LD, int NT, int ABL = 0>
-__device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v,
-                                   int max_sweeps, double rel2);
+template <int M, int NT, int LD, bool WANT_V, int ABL = 0>
+__device__ int jacobi_eigh_ring(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v,
+                                int max_sweeps, double rel2);
 
 // A: M x M Hermitian in shared memory (row-major, leading dimension LD), overwritten (diagonal = eigenvalues).
 //    Both triangles are stored and kept exactly conjugate: only the blocks above the block diagonal are
@@ -102,8 +103,8 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
 template <int M, int NT, class Sync, bool WANT_V, int LD = M>
 __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v = true,
                            int max_sweeps = 30, double rel2 = 0.0) {
-  if constexpr (M == 64 && (NT == 512 || NT == 256) && WANT_V) {
-    return jacobi_eigh_block64<LD, NT>(A, V, ev, scratch, tid, init_v, max_sweeps, rel2);
+  if constexpr ((M == 64 && (NT == 512 || NT == 256) && WANT_V) || ((M == 16 || M == 8) && NT == 32)) {
+    return jacobi_eigh_ring<M, NT, LD, WANT_V>(A, V, ev, scratch, tid, init_v, max_sweeps, rel2);
   }
   constexpr int HP = (M / 2 > 0) ? M / 2 : 1;
   constexpr int NOFF = HP * (HP - 1) / 2;                        // 2x2 blocks above the block diagonal
@@ -272,34 +273,43 @@ __device__ __forceinline__ void mbar_wait(double* slot, unsigned parity) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Block-wide eigensolver for M = 64 with 256 or 512 threads: ONE barrier per round-robin step.
+// Ring eigensolver: ONE barrier per round-robin step, rotations / diagonal / V in registers.
+//   M = 64 with 256 or 512 threads (one matrix per block, split-phase mbarrier), and
+//   M = 16 or 8 with 32 threads (one matrix per warp, __syncwarp).
 //
 // The generic routine above spends most of its time at its two barriers per step and in the serial
-// parameter phase (profiles/r01_ncu_pgdb3_kernel_v5.md: barrier 23 % of samples, FP64 pipe 29 % busy).  Here:
-//  * every warp computes the 32 rotations of the step itself (lane i = pair i; 16x redundant, ~60 DFMA-class
-//    instructions per thread) from the pair's off-diagonal element and its diagonal entries -- no separate
-//    parameter phase, no second barrier; a thread fetches the rotations of its block (I, J) by shuffle;
-//  * diagonal entries and the eigenvector matrix V live in REGISTERS (warp w: rows 4w..4w+3 of V, lane i: the two
-//    columns of pair i) and travel one position along the round-robin ring after each step
-//    (p_i <- p_{i+1}, q_i <- q_{i-1}, q_31 -> p_31, p_0 -> q_1, index 63 stays in lane 0);
-//  * of A only the 2x2 blocks above the block diagonal are kept (496 blocks = 496 threads): element (x, y) is
-//    valid at the position written by the block that last produced it.  One step later that is the direct
-//    position for every element a block needs except (p_I, q_J) with J = I+1, which is read transposed, and
-//    the three elements whose two indices formed a pair in the previous step (annihilated: read as zero).
+// parameter phase (profiles/r01_ncu_pgdb3_kernel_v5.md: barrier 23 % of samples, FP64 pipe 29 % busy).  Here,
+// with HP = M/2 pairs per step and the NT threads split into NT/HP segments of HP consecutive threads:
+//  * every segment computes the HP rotations of the step itself (thread pr of a segment = pair pr; redundant
+//    across segments, ~60 DFMA-class instructions per thread) from the pair's off-diagonal element and its
+//    diagonal entries -- no separate parameter phase, no second barrier; a thread fetches the rotations of its
+//    block (I, J) by shuffle;
+//  * diagonal entries and the eigenvector matrix V live in REGISTERS (segment g: rows RV g .. RV g + RV-1 of V,
+//    thread pr: the two columns of pair pr) and travel one position along the round-robin ring after each step
+//    (p_i <- p_{i+1}, q_i <- q_{i-1}, q_{HP-1} -> p_{HP-1}, p_0 -> q_1, index M-1 stays in pair 0);
+//  * of A only the 2x2 blocks above the block diagonal are kept (HP (HP-1) / 2 blocks, one or two per thread):
+//    element (x, y) is valid at the position written by the block that last produced it.  One step later that is
+//    the direct position for every element a block needs except (p_I, q_J) with J = I+1, which is read
+//    transposed, and the three elements whose two indices formed a pair in the previous step (annihilated: read
+//    as zero).  A's diagonal is NOT maintained: the eigenvalues are returned in `ev` only.
 // ---------------------------------------------------------------------------------------------
-template <int LD, int NT, int ABL>
-__device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v,
-                                   int max_sweeps, double rel2) {
-  constexpr int M = 64, HP = 32, M1 = 63, NOFF = HP * (HP - 1) / 2;
-  constexpr int NW = NT / 32, RV = M / NW;        // V rows per warp
+template <int M, int NT, int LD, bool WANT_V, int ABL>
+__device__ int jacobi_eigh_ring(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v,
+                                int max_sweeps, double rel2) {
+  constexpr int HP = M / 2, M1 = M - 1, NOFF = HP * (HP - 1) / 2;
+  constexpr bool WARP = (NT == 32);               // one matrix per warp: __syncwarp instead of the mbarrier
+  static_assert(HP <= 32 && (HP & (HP - 1)) == 0 && NT % HP == 0 && (WARP || HP == 32), "segment = shuffle group");
+  constexpr int NSEG = NT / HP, RV = WANT_V ? M / NSEG : 1;  // V rows per segment
+  static_assert(!WANT_V || (M % NSEG == 0 && M >= NSEG), "V rows divide over the segments");
   constexpr int NB = (NOFF + NT - 1) / NT;        // 2x2 blocks per thread
-  double* red = scratch;  // >= 16 doubles
-  const int lane = tid & 31, wid = tid >> 5;
-  if (init_v) {
+  using Sync = typename std::conditional<WARP, SyncWarp, SyncBlock>::type;
+  double* red = scratch;  // >= 16 doubles (block-wide variant only)
+  const int lane = tid & 31, pr = tid % HP, seg = tid / HP;
+  if (WANT_V && init_v) {
     for (int e = tid; e < M * M; e += NT) V[(e / M) * LD + e % M] = cmake((e / M == e % M) ? 1.0 : 0.0, 0.0);
   }
-  __syncthreads();
-  // static block assignment: block w = tid + k NT < 496 -> (I, J), I < J, row-major triangular order; spare
+  Sync::sync();
+  // static block assignment: block w = tid + k NT < NOFF -> (I, J), I < J, row-major triangular order; spare
   // slots run the same instructions on element (0, 0) with their stores predicated off (no branches in the step)
   bool has_block[NB], near1[NB], near2[NB], last2[NB], first2[NB];
   int bI[NB], bJ[NB];
@@ -321,32 +331,40 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
     last2[k] = (I == HP - 2);
     first2[k] = (I == 0 && J == 1);
   }
-  // V in registers, columns in the arrangement of step 0: pair i = (i, 63 - i), pair 0 = (0, 63)
-  const int col0q = (lane == 0) ? M1 : M1 - lane;
+  // V in registers, columns in the arrangement of step 0: pair i = (i, M-1 - i), pair 0 = (0, M-1)
+  const int col0q = (pr == 0) ? M1 : M1 - pr;
   cplx vp[RV], vq[RV];
+  if constexpr (WANT_V) {
 #pragma unroll
-  for (int k = 0; k < RV; ++k) {
-    vp[k] = V[(RV * wid + k) * LD + lane];
-    vq[k] = V[(RV * wid + k) * LD + col0q];
+    for (int k = 0; k < RV; ++k) {
+      vp[k] = V[(RV * seg + k) * LD + pr];
+      vq[k] = V[(RV * seg + k) * LD + col0q];
+    }
   }
-  double dp = A[lane * LD + lane].x, dq = A[col0q * LD + col0q].x;
+  double dp = A[pr * LD + pr].x, dq = A[col0q * LD + col0q].x;
   bool fresh = true;  // both triangles of A valid, nothing annihilated yet
   // split-phase barrier state: `pending` = an arrive of this thread has not been matched by a wait yet
   double* mbar = scratch + 32;
   unsigned parity = 0;
   bool pending = false;
-  if (tid == 0) mbar_init(mbar, NT);
-  __syncthreads();
+  if constexpr (!WARP) {
+    if (tid == 0) mbar_init(mbar, NT);
+    __syncthreads();
+  }
   // QT_JACOBI_PLAIN_BARRIER (validation builds only, scripts/ubench_jacobi.cu): the split-phase barrier becomes a
   // plain __syncthreads() at the wait point, which compute-sanitizer's racecheck can follow (it does not model
   // mbarrier ordering and reports every step-to-step dependency of the default build as a hazard).
   auto wait_pending = [&]() {
     if (pending) {
+      if constexpr (WARP) {
+        __syncwarp();
+      } else {
 #ifdef QT_JACOBI_PLAIN_BARRIER
-      __syncthreads();
+        __syncthreads();
 #else
-      if constexpr (!(ABL & 8)) mbar_wait(mbar, parity);
+        if constexpr (!(ABL & 8)) mbar_wait(mbar, parity);
 #endif
+      }
       parity ^= 1u;
       pending = false;
     }
@@ -358,14 +376,14 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
     for (int k = 0; k < RV; ++k) {
       const cplx np = csub(cscale(vp[k], c_prev), cmul(cs, vq[k]));
       const cplx nq = cadd(cmul(s_prev, vp[k]), cscale(vq[k], c_prev));
-      const cplx up = (lane == 0) ? np : nq;  // lane 0 hands its first column to lane 1's second slot
+      const cplx up = (pr == 0) ? np : nq;  // pair 0 hands its first column to pair 1's second slot
       cplx rp, rq;
-      rp.x = __shfl_down_sync(0xffffffffu, np.x, 1);
-      rp.y = __shfl_down_sync(0xffffffffu, np.y, 1);
-      rq.x = __shfl_up_sync(0xffffffffu, up.x, 1);
-      rq.y = __shfl_up_sync(0xffffffffu, up.y, 1);
-      vp[k] = (lane == 31) ? nq : rp;
-      vq[k] = (lane == 0) ? nq : rq;
+      rp.x = __shfl_down_sync(0xffffffffu, np.x, 1, HP);
+      rp.y = __shfl_down_sync(0xffffffffu, np.y, 1, HP);
+      rq.x = __shfl_up_sync(0xffffffffu, up.x, 1, HP);
+      rq.y = __shfl_up_sync(0xffffffffu, up.y, 1, HP);
+      vp[k] = (pr == HP - 1) ? nq : rp;
+      vq[k] = (pr == 0) ? nq : rq;
     }
   };
 
@@ -373,7 +391,7 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
   for (; sweep < max_sweeps; ++sweep) {
     // ---- off-diagonal / total Frobenius mass from the valid elements (arrangement of step 0) ----
     wait_pending();
-    int p = lane, q = col0q;                       // this lane's pair
+    int p = pr, q = col0q;                         // this thread's pair
     int pi[NB], qi[NB], pj[NB], qj[NB];            // this thread's blocks
     {
       double off = 0.0;
@@ -391,10 +409,10 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
         if (!fresh && first2[k]) b11 = cmake(0.0, 0.0);
         if (has_block[k]) off += cabs2(b00) + cabs2(b01) + cabs2(b10) + cabs2(b11);
       }
-      if (wid == 0) off += cabs2(A[q * LD + p]);  // the off-diagonal element of pair `lane` itself
-      const double dg = (wid == 0) ? dp * dp + dq * dq : 0.0;
-      off = 2.0 * group_sum<NT, SyncBlock>(off, red, tid);
-      const double tot = off + group_sum<NT, SyncBlock>(dg, red, tid);
+      if (seg == 0) off += cabs2(A[q * LD + p]);  // the off-diagonal element of pair `pr` itself
+      const double dg = (seg == 0) ? dp * dp + dq * dq : 0.0;
+      off = 2.0 * group_sum<NT, Sync>(off, red, tid);
+      const double tot = off + group_sum<NT, Sync>(dg, red, tid);
       if (off <= (rel2 > 0.0 ? rel2 : 1e-30 * M * M) * tot || tot == 0.0) break;
     }
 #pragma unroll 3
@@ -414,7 +432,7 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
         b00[k] = (!fresh && last2[k]) ? cmake(0.0, 0.0) : b00[k];
         b11[k] = (!fresh && first2[k]) ? cmake(0.0, 0.0) : b11[k];
       }
-      // ---- rotation of pair `lane` (every warp computes all 32) ----
+      // ---- rotation of pair `pr` (every segment computes all HP) ----
       double c, an, gn;
       cplx s;
       if constexpr (ABL & 4) {
@@ -425,7 +443,8 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
       } else {
         jacobi_rotation(dp, dq, beta, c, s, an, gn);
       }
-      // ---- A <- J^dagger A J on this thread's blocks (rotations of pairs I and J fetched by shuffle) ----
+      // ---- A <- J^dagger A J on this thread's blocks (rotations of pairs I and J fetched by shuffle from the
+      //      first segment of the warp: lane index = pair index) ----
 #pragma unroll
       for (int k = 0; k < ((ABL & 2) ? 0 : NB); ++k) {
         double cI, cJ;
@@ -457,21 +476,23 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
         }
       }
       // ---- all shared-memory stores of the step are issued: arrive, then do the register-only work ----
+      if constexpr (!WARP) {
 #ifndef QT_JACOBI_PLAIN_BARRIER
-      if constexpr (!(ABL & 8)) mbar_arrive(mbar);
+        if constexpr (!(ABL & 8)) mbar_arrive(mbar);
 #endif
+      }
       pending = true;
-      if constexpr (!(ABL & 1)) v_update(c, s);
+      if constexpr (WANT_V && !(ABL & 1)) v_update(c, s);
       // ---- diagonal entries move along the ring; next step's indices ----
       {
-        const double upd = (lane == 0) ? an : gn;
-        const double rp = __shfl_down_sync(0xffffffffu, an, 1), rq = __shfl_up_sync(0xffffffffu, upd, 1);
-        dp = (lane == 31) ? gn : rp;
-        dq = (lane == 0) ? gn : rq;
+        const double upd = (pr == 0) ? an : gn;
+        const double rp = __shfl_down_sync(0xffffffffu, an, 1, HP), rq = __shfl_up_sync(0xffffffffu, upd, 1, HP);
+        dp = (pr == HP - 1) ? gn : rp;
+        dq = (pr == 0) ? gn : rq;
       }
       fresh = false;
       const int nxt = (step + 1 == M1) ? 0 : step + 1;
-      rr_pair(M, nxt, lane, p, q);
+      rr_pair(M, nxt, pr, p, q);
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
         rr_pair(M, nxt, bI[k], pi[k], qi[k]);
@@ -482,20 +503,25 @@ __device__ int jacobi_eigh_block64(cplx* A, cplx* V, double* ev, double* scratch
   }
   wait_pending();
   // a whole number of sweeps returns every column to its step-0 slot
+  if constexpr (WANT_V) {
 #pragma unroll
-  for (int k = 0; k < RV; ++k) {
-    V[(RV * wid + k) * LD + lane] = vp[k];
-    V[(RV * wid + k) * LD + col0q] = vq[k];
+    for (int k = 0; k < RV; ++k) {
+      V[(RV * seg + k) * LD + pr] = vp[k];
+      V[(RV * seg + k) * LD + col0q] = vq[k];
+    }
   }
-  if (wid == 0) {
-    ev[lane] = dp;
+  if (seg == 0) {
+    ev[pr] = dp;
     ev[col0q] = dq;
   }
-  __syncthreads();
-  if (tid == 0) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(mbar);
-    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(a) : "memory");
+  Sync::sync();
+  if constexpr (!WARP) {
+    if (tid == 0) {
+      const unsigned a = (unsigned)__cvta_generic_to_shared(mbar);
+      asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(a) : "memory");
+    }
   }
+  (void)lane;
   return sweep;
 }
 

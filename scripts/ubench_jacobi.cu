@@ -17,7 +17,7 @@ __global__ void __launch_bounds__(NT) jac_kernel(const cplx* in, double* evout, 
   for (int e = tid; e < M * M; e += NT) A[(e / M) * LD + e % M] = in[(size_t)blockIdx.x * M * M + e];
   __syncthreads();
   long long t0 = clock64();
-  jacobi_eigh_block64<LD, NT, ABL>(A, V, ev, scr, tid, true, sweeps, 1e-300);
+  jacobi_eigh_ring<64, NT, LD, true, ABL>(A, V, ev, scr, tid, true, sweeps, 1e-300);
   long long t1 = clock64();
   if (tid < M) evout[blockIdx.x * M + tid] = ev[tid] + V[tid * LD + 3].x;
   if (tid == 0 && blockIdx.x == 0) cyc[0] = t1 - t0;
