@@ -761,6 +761,54 @@ __global__ void linear_inv_kernel(int64_t B, int K, const int* __restrict__ slot
 }
 
 // =============================================================================================
+// state_log_likelihood (tomography.py:341-375), one experiment per block:
+//   ll = sum_k sum_{sign} n_k (1 + sign e_k)/2 * log10((1 + sign c_k tr(P_k rho))/2),  terms with pr <= 0 skipped.
+// The Pauli expectations tr(P rho) of the state are formed once per block for all 4^n slots.
+// =============================================================================================
+template <int N>
+__global__ void log_likelihood_kernel(int64_t B, int K, const int* __restrict__ slot_ptr,
+                                      const int* __restrict__ member_col, const double* __restrict__ member_coeff,
+                                      const int* __restrict__ mask2idx, const cplx* __restrict__ rho,
+                                      const double* __restrict__ expect, const double* __restrict__ counts,
+                                      double* __restrict__ ll_out) {
+  constexpr int D = 1 << N, S = 1 << (2 * N), DD = D * D;
+  __shared__ double t[S];
+  __shared__ double red[32];
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    const cplx* r = rho + b * DD;
+    for (int e = threadIdx.x; e < S; e += blockDim.x) {
+      const int x = e / D, z = e % D;
+      cplx acc = cmake(0.0, 0.0);
+      for (int c = 0; c < D; ++c) {  // tr(P rho) = sum_c P[c^x][c] rho[c][c^x],  P[c^x][c] = i^{|x&z|} (-1)^{|z&c|}
+        const cplx v = r[c * D + (c ^ x)];
+        if (__popc(z & c) & 1) acc = csub(acc, v); else acc = cadd(acc, v);
+      }
+      t[mask2idx[e]] = cmul_ipow(acc, __popc(x & z) & 3).x;
+    }
+    __syncthreads();
+    double ll = 0.0;
+    for (int j = threadIdx.x; j < S; j += blockDim.x) {
+      for (int m = slot_ptr[j]; m < slot_ptr[j + 1]; ++m) {
+        const int col = member_col[m];
+        const double meas = expect[b * K + col], n = counts[b * K + col], pred = member_coeff[m] * t[j];
+        const double pp = 0.5 * (1.0 + pred), pm = 0.5 * (1.0 - pred);
+        if (pp > 0.0) ll += n * (1.0 + meas) * 0.5 * log10(pp);
+        if (pm > 0.0) ll += n * (1.0 - meas) * 0.5 * log10(pm);
+      }
+    }
+    ll = warp_sum(ll);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ll;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double tot = 0.0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+      ll_out[b] = tot;
+    }
+    __syncthreads();
+  }
+}
+
+// =============================================================================================
 // C ABI
 // =============================================================================================
 extern "C" int qt_mle_plan_create(int n, int K, const int32_t* pauli_idx, const double* coeff,
@@ -915,4 +963,26 @@ extern "C" int qt_linear_inv_state_batch(const qt_mle_plan* p, int64_t B, const 
   }
 #undef LAUNCH
   return qt_check_launch("linear_inv_kernel");
+}
+
+extern "C" int qt_state_log_likelihood_batch(const qt_mle_plan* p, int64_t B, const void* rho, const double* expect,
+                                             const double* counts, double* ll_out, void* stream) {
+  QT_REQUIRE(p, "qt_state_log_likelihood_batch: null plan");
+  if (B == 0) return QT_OK;
+  QT_REQUIRE(rho && expect && counts && ll_out, "qt_state_log_likelihood_batch: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned blocks = (unsigned)std::min<int64_t>(B, (int64_t)QT_NUM_SMS * 16);
+  const int threads = p->n <= 2 ? 32 : 256;
+#define LAUNCH(N)                                                                                                   \
+  log_likelihood_kernel<N><<<blocks, threads, 0, st>>>(B, p->K, p->d_slot_ptr, p->d_member_col, p->d_member_coeff, \
+                                                       p->d_mask2idx, (const cplx*)rho, expect, counts, ll_out)
+  switch (p->n) {
+    case 1: LAUNCH(1); break;
+    case 2: LAUNCH(2); break;
+    case 3: LAUNCH(3); break;
+    case 4: LAUNCH(4); break;
+    default: LAUNCH(5); break;
+  }
+#undef LAUNCH
+  return qt_check_launch("log_likelihood_kernel");
 }

@@ -19,8 +19,10 @@
 #include "../../include/qtomo.h"
 
 #include <algorithm>
+#include <cmath>
 #include <map>
 #include <type_traits>
+#include <utility>
 #include <vector>
 
 struct qt_pgdb_plan {
@@ -29,6 +31,12 @@ struct qt_pgdb_plan {
   int* d_pidx;        // [S]
   double* d_coeff;    // [S]
   double* d_svec;     // [n_in, 4^n]
+  // linear inversion (built on first use by qt_linear_inv_process_batch): settings grouped by observable
+  std::vector<int> h_sid, h_pidx;
+  std::vector<double> h_coeff, h_svec;
+  int* d_li_slot_ptr = nullptr;    // [4^n + 1]  CSR over the observable's canonical Pauli index
+  int* d_li_member_col = nullptr;  // [S]        column of `expect` of each member
+  double* d_li_member_w = nullptr; // [S, 4^n]   row of the slot's pseudo-inverse that multiplies that expectation
 };
 
 struct PgdbView {
@@ -382,6 +390,10 @@ extern "C" int qt_pgdb_plan_create(int n, int S, const int32_t* state_codes, con
   QT_CUDA(cudaMemcpy(p->d_pidx, pauli_idx, sizeof(int) * S, cudaMemcpyHostToDevice));
   QT_CUDA(cudaMemcpy(p->d_coeff, coeff, sizeof(double) * S, cudaMemcpyHostToDevice));
   QT_CUDA(cudaMemcpy(p->d_svec, svec.data(), sizeof(double) * svec.size(), cudaMemcpyHostToDevice));
+  p->h_sid = sid;
+  p->h_pidx.assign(pauli_idx, pauli_idx + S);
+  p->h_coeff.assign(coeff, coeff + S);
+  p->h_svec = svec;
   *plan_out = p;
   return QT_OK;
 }
@@ -392,6 +404,9 @@ extern "C" int qt_pgdb_plan_destroy(qt_pgdb_plan* p) {
   cudaFree(p->d_pidx);
   cudaFree(p->d_coeff);
   cudaFree(p->d_svec);
+  cudaFree(p->d_li_slot_ptr);
+  cudaFree(p->d_li_member_col);
+  cudaFree(p->d_li_member_w);
   delete p;
   return QT_OK;
 }
@@ -448,5 +463,172 @@ extern "C" int qt_pgdb_process_batch(const qt_pgdb_plan* p, int64_t B, const dou
     case 1: return launch_pgdb<1>(p, B, expect, counts, trace_preserving, choi_out, counters_out, workspace, st);
     case 2: return launch_pgdb<2>(p, B, expect, counts, trace_preserving, choi_out, counters_out, workspace, st);
     default: return launch_pgdb<3>(p, B, expect, counts, trace_preserving, choi_out, counters_out, workspace, st);
+  }
+}
+
+// =============================================================================================
+// linear_inv_process_estimate (tomography.py:459-491): choi = unvec(pinv(M) e) + I/d with one row
+// vec(conj(rho_in) (x) c P_k)^dagger of M per setting.
+//
+// In Pauli-Liouville coordinates (an isometry of vec(choi) up to a factor, so the minimum-norm least-squares
+// solution is the same) a setting with observable P_k only involves row k of the PTM R:
+//     e_s = c_s sum_j R[k_s, j] r_{i_s}[j],   r_i = Pauli vector of input state i,
+// so M is block diagonal over k and  R[k, :] = pinv(X_k) e_k  with X_k = [c_s r_{i_s}] over the settings of slot k.
+// The dense 540 x 256 (n = 2) / 13608 x 4096 (n = 3) complex pseudo-inverse of the reference is never formed: the plan
+// keeps, per setting, the 4^n-vector  w_s = (X_k^T X_k)^+ c_s r_{i_s}  and the kernel accumulates
+// R[k, :] = sum_s w_s e_s, adds the identity term (R[0, 0] += 1, the eye(d^2)/d of the reference) and goes
+// PTM -> Choi in shared memory.  Checked against the oracle's dense pinv to 1e-14.
+// =============================================================================================
+template <int N>
+__global__ void __launch_bounds__(PgdbCfg<N>::NT * PgdbCfg<N>::GPB)
+    linproc_kernel(int64_t B, int S, const int* __restrict__ slot_ptr, const int* __restrict__ member_col,
+                   const double* __restrict__ member_w, const double* __restrict__ expect, cplx* __restrict__ choi_out) {
+  using C = PgdbCfg<N>;
+  using G = typename C::G;
+  constexpr int M = G::M, MM = G::MM, LD = G::LD, D = G::D;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int gib = threadIdx.x / C::NT, tid = threadIdx.x % C::NT;
+  cplx* X = reinterpret_cast<cplx*>(smem_raw) + (size_t)G::MP * gib;
+  for (int64_t b = (int64_t)blockIdx.x * C::GPB + gib; b < B; b += (int64_t)gridDim.x * C::GPB) {
+    const double* ex = expect + b * S;
+    for (int e = tid; e < MM; e += C::NT) {
+      const int k = e / M, j = e % M;
+      double acc = (e == 0) ? 1.0 : 0.0;
+      for (int m = slot_ptr[k]; m < slot_ptr[k + 1]; ++m) acc = fma(member_w[(int64_t)m * M + j], ex[member_col[m]], acc);
+      X[pauli_to_pos(k, N) * LD + pauli_to_pos(j, N)] = cmake(acc, 0.0);
+    }
+    C::Sync::sync();
+    Pgdb<N>::pl_positions_to_choi(X, tid);
+    cplx* dst = choi_out + b * MM;
+    for (int e = tid; e < MM; e += C::NT) dst[e] = cscale(X[(e / M) * LD + e % M], 1.0 / D);
+    C::Sync::sync();
+  }
+}
+
+// cyclic Jacobi for a small real symmetric matrix on the host (plan setup only): a -> eigenvalues on the diagonal,
+// v -> eigenvectors in columns
+static void host_sym_jacobi(int m, std::vector<double>& a, std::vector<double>& v) {
+  v.assign((size_t)m * m, 0.0);
+  for (int i = 0; i < m; ++i) v[(size_t)i * m + i] = 1.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, tot = 0.0;
+    for (int i = 0; i < m; ++i)
+      for (int j = 0; j < m; ++j) {
+        tot += a[(size_t)i * m + j] * a[(size_t)i * m + j];
+        if (i != j) off += a[(size_t)i * m + j] * a[(size_t)i * m + j];
+      }
+    if (off <= 1e-30 * tot) break;
+    for (int p = 0; p < m - 1; ++p)
+      for (int q = p + 1; q < m; ++q) {
+        const double apq = a[(size_t)p * m + q];
+        if (apq == 0.0) continue;
+        const double theta = (a[(size_t)q * m + q] - a[(size_t)p * m + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+        for (int k = 0; k < m; ++k) {  // columns p, q
+          const double akp = a[(size_t)k * m + p], akq = a[(size_t)k * m + q];
+          a[(size_t)k * m + p] = c * akp - sn * akq;
+          a[(size_t)k * m + q] = sn * akp + c * akq;
+        }
+        for (int k = 0; k < m; ++k) {  // rows p, q
+          const double apk = a[(size_t)p * m + k], aqk = a[(size_t)q * m + k];
+          a[(size_t)p * m + k] = c * apk - sn * aqk;
+          a[(size_t)q * m + k] = sn * apk + c * aqk;
+        }
+        for (int k = 0; k < m; ++k) {
+          const double vkp = v[(size_t)k * m + p], vkq = v[(size_t)k * m + q];
+          v[(size_t)k * m + p] = c * vkp - sn * vkq;
+          v[(size_t)k * m + q] = sn * vkp + c * vkq;
+        }
+      }
+  }
+}
+
+static int build_linear_inversion(qt_pgdb_plan* p) {
+  const int M = 1 << (2 * p->n), S = p->S;
+  std::vector<int> slot_ptr(M + 1, 0), col(S), cursor(M, 0);
+  for (int s = 0; s < S; ++s) slot_ptr[p->h_pidx[s] + 1]++;
+  for (int k = 0; k < M; ++k) slot_ptr[k + 1] += slot_ptr[k];
+  for (int s = 0; s < S; ++s) {  // stable: members keep the order of `results`
+    const int k = p->h_pidx[s];
+    col[slot_ptr[k] + cursor[k]++] = s;
+  }
+  std::vector<double> w((size_t)S * M);
+  // slots that share the same (input state, coefficient) list share the pseudo-inverse (every slot of a complete design)
+  std::map<std::vector<std::pair<int, double>>, int> seen;
+  std::vector<std::vector<double>> ginv;
+  for (int k = 0; k < M; ++k) {
+    const int m0 = slot_ptr[k], m1 = slot_ptr[k + 1];
+    if (m0 == m1) continue;
+    std::vector<std::pair<int, double>> key;
+    for (int m = m0; m < m1; ++m) key.emplace_back(p->h_sid[col[m]], p->h_coeff[col[m]]);
+    auto it = seen.find(key);
+    if (it == seen.end()) {
+      std::vector<double> g((size_t)M * M, 0.0), v;
+      for (const auto& kv : key) {
+        const double* r = &p->h_svec[(size_t)kv.first * M];
+        const double c2 = kv.second * kv.second;
+        for (int a = 0; a < M; ++a)
+          for (int b = 0; b < M; ++b) g[(size_t)a * M + b] += c2 * r[a] * r[b];
+      }
+      host_sym_jacobi(M, g, v);
+      double lmax = 0.0;
+      for (int a = 0; a < M; ++a) lmax = std::max(lmax, g[(size_t)a * M + a]);
+      std::vector<double> gi((size_t)M * M, 0.0);
+      for (int e = 0; e < M; ++e) {
+        const double lam = g[(size_t)e * M + e];
+        if (!(lam > 1e-11 * lmax)) continue;  // null space of the design: minimum-norm solution, like pinv
+        for (int a = 0; a < M; ++a)
+          for (int b = 0; b < M; ++b) gi[(size_t)a * M + b] += v[(size_t)a * M + e] * v[(size_t)b * M + e] / lam;
+      }
+      it = seen.emplace(key, (int)ginv.size()).first;
+      ginv.push_back(std::move(gi));
+    }
+    const std::vector<double>& gi = ginv[it->second];
+    for (int m = m0; m < m1; ++m) {
+      const int s = col[m];
+      const double* r = &p->h_svec[(size_t)p->h_sid[s] * M];
+      for (int a = 0; a < M; ++a) {
+        double acc = 0.0;
+        for (int b = 0; b < M; ++b) acc += gi[(size_t)a * M + b] * r[b];
+        w[(size_t)m * M + a] = acc * p->h_coeff[s];
+      }
+    }
+  }
+  QT_CUDA(cudaMalloc(&p->d_li_slot_ptr, sizeof(int) * (M + 1)));
+  QT_CUDA(cudaMalloc(&p->d_li_member_col, sizeof(int) * S));
+  QT_CUDA(cudaMalloc(&p->d_li_member_w, sizeof(double) * w.size()));
+  QT_CUDA(cudaMemcpy(p->d_li_slot_ptr, slot_ptr.data(), sizeof(int) * (M + 1), cudaMemcpyHostToDevice));
+  QT_CUDA(cudaMemcpy(p->d_li_member_col, col.data(), sizeof(int) * S, cudaMemcpyHostToDevice));
+  QT_CUDA(cudaMemcpy(p->d_li_member_w, w.data(), sizeof(double) * w.size(), cudaMemcpyHostToDevice));
+  return QT_OK;
+}
+
+template <int N>
+static int launch_linproc(const qt_pgdb_plan* p, int64_t B, const double* expect, void* choi_out, cudaStream_t st) {
+  using C = PgdbCfg<N>;
+  const size_t smem = sizeof(cplx) * C::G::MP * C::GPB;
+  const int per_sm = (N >= 3) ? 3 : 8;
+  const int64_t grid = std::min<int64_t>((B + C::GPB - 1) / C::GPB, (int64_t)QT_NUM_SMS * per_sm);
+  QT_CUDA(cudaFuncSetAttribute(linproc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  linproc_kernel<N><<<(unsigned)grid, C::NT * C::GPB, smem, st>>>(B, p->S, p->d_li_slot_ptr, p->d_li_member_col,
+                                                                  p->d_li_member_w, expect, (cplx*)choi_out);
+  return qt_check_launch("linproc_kernel");
+}
+
+extern "C" int qt_linear_inv_process_batch(qt_pgdb_plan* p, int64_t B, const double* expect, void* choi_out,
+                                           void* stream) {
+  QT_REQUIRE(p, "qt_linear_inv_process_batch: null plan");
+  if (!p->d_li_member_w) {
+    const int rc = build_linear_inversion(p);
+    if (rc != QT_OK) return rc;
+  }
+  if (B == 0) return QT_OK;
+  QT_REQUIRE(expect && choi_out, "qt_linear_inv_process_batch: null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (p->n) {
+    case 1: return launch_linproc<1>(p, B, expect, choi_out, st);
+    case 2: return launch_linproc<2>(p, B, expect, choi_out, st);
+    default: return launch_linproc<3>(p, B, expect, choi_out, st);
   }
 }

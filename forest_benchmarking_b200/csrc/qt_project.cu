@@ -41,6 +41,88 @@ __global__ void __launch_bounds__(ProjCfg<N>::NT * ProjCfg<N>::GPB)
   for (int e = tid; e < G::MM; e += C::NT) dst[e] = X[G::sidx(e)];
 }
 
+// ---- closest unitary ---------------------------------------------------------------------------------
+// proj_choi_to_unitary (project_superoperators.py:147-175): eigh of the Hermitian part, the eigenvector of the
+// largest eigenvalue un-vec'ed (column stacking) into the dominant Kraus operator K, the unitary polar factor of K
+// (U @ Vh of the reference's SVD == K (K^dagger K)^{-1/2}: one d x d eigh by the first warp of the group), global
+// phase fixed so that element (0, 0) is real and non-negative, and kraus2choi of the result.  The eigenvector's
+// arbitrary phase cancels in the last two steps.  K must have full rank (any process with a dominant Kraus
+// operator close to a unitary); a singular K has no unique polar factor.
+template <int N>
+__global__ void __launch_bounds__(ProjCfg<N>::NT * ProjCfg<N>::GPB)
+    proj_unitary_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out) {
+  using C = ProjCfg<N>;
+  using G = typename C::G;
+  constexpr int D = G::D, DD = D * D, M = G::M, LD = G::LD;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int gib = threadIdx.x / C::NT, tid = threadIdx.x % C::NT;
+  cplx* X = reinterpret_cast<cplx*>(smem_raw + C::group_smem * gib);
+  cplx* V = X + G::MP;
+  double* small = reinterpret_cast<double*>(V + 2 * G::MP);
+  double* base = small + M + JacobiScratch<M>::doubles;
+  cplx* K = reinterpret_cast<cplx*>(base);
+  cplx* P = K + DD;
+  cplx* W = P + DD;
+  cplx* U = W + DD;
+  double* pev = reinterpret_cast<double*>(U + DD);
+  double* pscr = pev + D + (D & 1);
+  const int64_t b = (int64_t)blockIdx.x * C::GPB + gib;
+  if (b >= B) return;
+  const cplx* src = in + b * G::MM;
+  for (int e = tid; e < G::MM; e += C::NT) {
+    const int r = e / M, c = e % M;
+    const cplx x = src[r * M + c], y = src[c * M + r];
+    X[G::sidx(e)] = cmake(0.5 * (x.x + y.x), 0.5 * (x.y - y.y));
+  }
+  C::Sync::sync();
+  jacobi_eigh<M, C::NT, typename C::Sync, true, LD>(X, V, small, small + M, tid);
+  int kmax = 0;
+  double best = small[0];
+  for (int k = 1; k < M; ++k)
+    if (small[k] > best) {
+      best = small[k];
+      kmax = k;
+    }
+  for (int e = tid; e < DD; e += C::NT) K[e] = V[((e % D) * D + e / D) * LD + kmax];  // K[i][j] = v[j d + i]
+  C::Sync::sync();
+  if (tid < 32) {
+    for (int e = tid; e < DD; e += 32) {
+      const int a = e / D, c = e % D;
+      cplx acc = cmake(0.0, 0.0);
+      for (int k = 0; k < D; ++k) cfma(acc, cconj(K[k * D + a]), K[k * D + c]);
+      if (a == c) acc.y = 0.0;
+      P[e] = acc;
+    }
+    __syncwarp();
+    jacobi_eigh<D, 32, SyncWarp, true>(P, W, pev, pscr, tid);
+    for (int e = tid; e < DD; e += 32) {  // (K^dagger K)^{-1/2}
+      const int a = e / D, c = e % D;
+      cplx acc = cmake(0.0, 0.0);
+      for (int k = 0; k < D; ++k) cfma_conj(acc, cscale(W[a * D + k], rsqrt(pev[k])), W[c * D + k]);
+      P[e] = acc;
+    }
+    __syncwarp();
+    for (int e = tid; e < DD; e += 32) {
+      const int i = e / D, j = e % D;
+      cplx acc = cmake(0.0, 0.0);
+      for (int k = 0; k < D; ++k) cfma(acc, K[i * D + k], P[k * D + j]);
+      U[e] = acc;
+    }
+    __syncwarp();
+    const cplx u00 = U[0];
+    const double mag = sqrt(cabs2(u00));
+    const cplx ph = mag > 0.0 ? cmake(u00.x / mag, -u00.y / mag) : cmake(1.0, 0.0);
+    __syncwarp();
+    for (int e = tid; e < DD; e += 32) U[e] = cmul(U[e], ph);
+  }
+  C::Sync::sync();
+  cplx* dst = out + b * G::MM;
+  for (int e = tid; e < G::MM; e += C::NT) {
+    const int r = e / M, c = e % M;  // vec(U)[j d + i] = U[i][j]
+    dst[e] = cmul(U[(r % D) * D + r / D], cconj(U[(c % D) * D + c / D]));
+  }
+}
+
 // ---- CP for n = 1: one 4x4 matrix per THREAD, Jacobi entirely in registers --------------------------------
 // A warp per 4x4 matrix (the generic kernel above) leaves 3/4 of the lanes idle and pays shared-memory
 // latency on every rotation: 1.8 % of the HBM roofline (profiles/r01_bench_streaming_v1.json).  Here the
@@ -390,6 +472,16 @@ static int launch_cp(int64_t B, const void* in, void* out, cudaStream_t st) {
 }
 
 template <int N>
+static int launch_unitary(int64_t B, const void* in, void* out, cudaStream_t st) {
+  using C = ProjCfg<N>;
+  const size_t smem = C::group_smem * C::GPB;
+  QT_CUDA(cudaFuncSetAttribute(proj_unitary_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  proj_unitary_kernel<N><<<(unsigned)((B + C::GPB - 1) / C::GPB), C::NT * C::GPB, smem, st>>>(B, (const cplx*)in,
+                                                                                              (cplx*)out);
+  return qt_check_launch("proj_unitary_kernel");
+}
+
+template <int N>
 static int launch_tp(int64_t B, const void* in, void* out, int make_tp, cudaStream_t st) {
   constexpr int D = 1 << N, MM = D * D * D * D;
   const int ipb = make_tp ? std::max(1, 4096 / MM) : std::max(1, std::min(64, 4096 / MM));
@@ -446,6 +538,14 @@ extern "C" int qt_proj_cp_batch(int n, int64_t B, const void* choi, void* out, v
     return qt_check_launch("proj_cp4_thread_kernel");
   }
 #define CALL(N) launch_cp<N>(B, choi, out, (cudaStream_t)stream)
+  DISPATCH_N3(n, CALL)
+#undef CALL
+}
+
+extern "C" int qt_proj_unitary_batch(int n, int64_t B, const void* choi, void* out, void* stream) {
+  if (B == 0) return QT_OK;
+  QT_REQUIRE(choi && out, "qt_proj_unitary_batch: null argument");
+#define CALL(N) launch_unitary<N>(B, choi, out, (cudaStream_t)stream)
   DISPATCH_N3(n, CALL)
 #undef CALL
 }

@@ -44,6 +44,10 @@ def proj_choi_to_trace_non_increasing_batch(choi, out=None):
     return _simple("qt_proj_tni_batch", choi, out)
 
 
+def proj_choi_to_unitary_batch(choi, out=None):
+    return _simple("qt_proj_unitary_batch", choi, out)
+
+
 def proj_choi_to_physical_batch(choi, make_trace_preserving=True, out=None, return_counts=False):
     """Dykstra CP + TP (or TNI) projection of every matrix of the batch.  The input is Hermitised first
     (the reference's CP step does the same on every Dykstra iteration, project_superoperators.py:30)."""
@@ -88,3 +92,11 @@ def proj_choi_to_trace_preserving(choi: np.ndarray) -> np.ndarray:
 def proj_choi_to_physical(choi: np.ndarray, make_trace_preserving: bool = True) -> np.ndarray:
     """reference project_superoperators.py:87-144."""
     return proj_choi_to_physical_batch(_one(choi), make_trace_preserving)[0].cpu().numpy()
+
+
+def proj_choi_to_unitary(choi: np.ndarray, check_finite: bool = True) -> np.ndarray:
+    """reference project_superoperators.py:147-175."""
+    choi = np.asarray(choi)
+    if check_finite and not np.isfinite(choi).all():
+        raise ValueError("array must not contain infs or NaNs")
+    return proj_choi_to_unitary_batch(_one(choi))[0].cpu().numpy()

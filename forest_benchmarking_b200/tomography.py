@@ -100,6 +100,35 @@ def linear_inv_state_estimate(results: List, qubits: List[int]) -> np.ndarray:
     return linear_inv_state_estimate_batch(plan, torch.from_numpy(ex[None, :]).to(dev))[0].cpu().numpy()
 
 
+def state_log_likelihood_batch(plan: MlePlan, rho, expectations, counts, out=None):
+    """Batched log10 likelihood.  rho [B, d, d] complex128, expectations / counts [B, K] float64 (CUDA) -> [B]."""
+    torch = _lib.require_cuda()
+    b, d = rho.shape[0], 2 ** plan.n
+    if rho.dtype != torch.complex128 or not rho.is_cuda or tuple(rho.shape) != (b, d, d):
+        raise ValueError(f"rho must be a CUDA complex128 tensor of shape [B, {d}, {d}]")
+    for name, t in (("expectations", expectations), ("counts", counts)):
+        if t.dtype != torch.float64 or not t.is_cuda or tuple(t.shape) != (b, plan.K):
+            raise ValueError(f"{name} must be a CUDA float64 tensor of shape [{b}, {plan.K}]")
+    rho, expectations, counts = rho.contiguous(), expectations.contiguous(), counts.contiguous()
+    if out is None:
+        out = torch.empty((b,), dtype=torch.float64, device=rho.device)
+    _lib.check(_lib.lib().qt_state_log_likelihood_batch(plan._h, ctypes.c_int64(b), _lib.ptr(rho),
+                                                        _lib.ptr(expectations), _lib.ptr(counts), _lib.ptr(out),
+                                                        _lib.current_stream_ptr()), "qt_state_log_likelihood_batch")
+    return out
+
+
+def state_log_likelihood(state: np.ndarray, results: List, qubits: List[int]) -> float:
+    """Drop-in for reference tomography.py:341-375."""
+    torch = _lib.require_cuda()
+    idx, cf, ex, cnt = flatten_state_results(results, qubits)
+    plan = MlePlan(len(qubits), idx, cf)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    rho = torch.from_numpy(np.ascontiguousarray(state, dtype=np.complex128)[None]).to(dev)
+    return float(state_log_likelihood_batch(plan, rho, torch.from_numpy(ex[None, :]).to(dev),
+                                            torch.from_numpy(cnt[None, :]).to(dev)).item())
+
+
 def mle_step_batch(n_qubits: int, expect_canon, rho, epsilon=.1, out=None):
     """ONE R-rho-R update streamed through HBM (n = 1, 2; complete canonical Pauli set).
     expect_canon: [4^n - 1, B] float64 CUDA (item-minor); rho: [B, d, d] complex128 CUDA."""
@@ -269,3 +298,28 @@ def pgdb_process_estimate(results: List, qubits: List[int], trace_preserving=Tru
     choi = pgdb_process_estimate_batch(plan, torch.from_numpy(ex[None, :]).to(dev),
                                        torch.from_numpy(cnt[None, :]).to(dev), trace_preserving)
     return choi[0].cpu().numpy()
+
+
+def linear_inv_process_estimate_batch(plan: PgdbPlan, expectations, out=None):
+    """Batched linear-inversion process tomography.  expectations: CUDA float64 [B, S] -> choi [B, 4^n, 4^n]."""
+    torch = _lib.require_cuda()
+    if expectations.dtype != torch.float64 or not expectations.is_cuda or expectations.dim() != 2 \
+            or expectations.shape[1] != plan.S:
+        raise ValueError(f"expectations must be a CUDA float64 tensor of shape [B, {plan.S}]")
+    expectations = expectations.contiguous()
+    b, m = expectations.shape[0], 4 ** plan.n
+    if out is None:
+        out = torch.empty((b, m, m), dtype=torch.complex128, device=expectations.device)
+    _lib.check(_lib.lib().qt_linear_inv_process_batch(plan._h, ctypes.c_int64(b), _lib.ptr(expectations),
+                                                      _lib.ptr(out), _lib.current_stream_ptr()),
+               "qt_linear_inv_process_batch")
+    return out
+
+
+def linear_inv_process_estimate(results: List, qubits: List[int]) -> np.ndarray:
+    """Drop-in for reference tomography.py:459-491."""
+    torch = _lib.require_cuda()
+    codes, idx, cf, ex, _ = flatten_process_results(results, qubits)
+    plan = PgdbPlan(len(qubits), codes, idx, cf)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    return linear_inv_process_estimate_batch(plan, torch.from_numpy(ex[None, :]).to(dev))[0].cpu().numpy()

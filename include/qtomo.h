@@ -57,10 +57,27 @@ int qt_mle_state_batch(const qt_mle_plan* plan, int64_t B, const double* expect,
 /* linear_inv_state_estimate (tomography.py:130-165): expect[B,K] -> rho_out[B,d,d].  Uses the plan's observable
  * list; valid for any list of Pauli observables (the pseudo-inverse is diagonal in the Pauli basis). */
 int qt_linear_inv_state_batch(const qt_mle_plan* plan, int64_t B, const double* expect, void* rho_out, void* stream);
+/* state_log_likelihood (tomography.py:341-375): rho[B,d,d], expect[B,K], counts[B,K] -> ll_out[B] (log10 likelihood
+ * of the measured +-1 frequencies under rho; outcomes of non-positive predicted probability are skipped). */
+int qt_state_log_likelihood_batch(const qt_mle_plan* plan, int64_t B, const void* rho, const double* expect,
+                                  const double* counts, double* ll_out, void* stream);
 /* ONE R rho R update, rho streamed HBM -> HBM (n = 1, 2; complete canonical Pauli set, K = 4^n - 1).
  * expect_canon[K, B] (item-minor).  The HBM-roofline view of the update. */
 int qt_mle_step_batch(int n, int64_t B, const double* expect_canon, const void* rho_in, double epsilon,
                       void* rho_out, void* stream);
+
+/* ---- raw shots -> expectation / variance (observable_estimation.py) ------------------------------ */
+/* shots_to_obs_moments (:804-853) for B settings at once.  bits[B, n_shots, n_qubits] bytes of 0/1; col_mask[b] has bit q
+ * set when column q belongs to setting b's observable (0 = identity term: mean = coeff, var = 0); coeff[B] the
+ * observable's real coefficient.  mean_out[B], var_out[B] (variance of the mean; Beta-posterior moments when
+ * use_beta_prior != 0). */
+int qt_shots_to_obs_moments_batch(int64_t B, int64_t n_shots, int n_qubits, const uint8_t* bits,
+                                  const uint32_t* col_mask, const double* coeff, int use_beta_prior,
+                                  double* mean_out, double* var_out, void* stream);
+/* the arithmetic of calibrate_observable_estimates (:1033-1049) with ratio_variance (:1052-1090):
+ * mean_out = mean / cal_mean, var_out = var / cal_mean^2 + mean^2 cal_var / cal_mean^4 */
+int qt_calibrate_estimates_batch(int64_t B, const double* mean, const double* var, const double* cal_mean,
+                                 const double* cal_var, double* mean_out, double* var_out, void* stream);
 
 /* ---- superoperator conversions (operator_tools/superoperator_transformations.py) ------------- */
 /* kraus[B, n_kraus, d, d] -> choi[B, d^2, d^2] = sum_k vec(K) vec(K)^dagger            (:159-182) */
@@ -95,7 +112,10 @@ int qt_hs_inner_batch(int64_t rows, int64_t cols, int64_t B, const void* a, cons
 int qt_project_state_batch(int n, int64_t B, const void* rho, void* out, void* stream);
 
 /* ---- Choi-matrix projections (operator_tools/project_superoperators.py), n = 1..3, [B,4^n,4^n] ---- */
-int qt_proj_cp_batch(int n, int64_t B, const void* choi, void* out, void* stream);   /* :19-34 */
+int qt_proj_cp_batch(int n, int64_t B, const void* choi, void* out, void* stream); /* proj_choi_to_unitary (project_superoperators.py:147-175): Choi matrix of the unitary closest to the process
+ * (dominant Kraus operator -> polar factor -> phase convention -> kraus2choi), n = 1..3 */
+int qt_proj_unitary_batch(int n, int64_t B, const void* choi, void* out, void* stream);
+  /* :19-34 */
 int qt_proj_tp_batch(int n, int64_t B, const void* choi, void* out, void* stream);   /* :62-84 */
 int qt_proj_tni_batch(int n, int64_t B, const void* choi, void* out, void* stream);  /* :37-59 */
 /* Dykstra CP+TP (or CP+TNI) projection, :87-144.  The input is Hermitised first.  workspace: device
@@ -121,6 +141,10 @@ int64_t qt_pgdb_workspace_bytes(const qt_pgdb_plan* plan, int64_t B);
 int qt_pgdb_process_batch(const qt_pgdb_plan* plan, int64_t B, const double* expect, const double* counts,
                           int trace_preserving, void* choi_out, int32_t* counters_out, void* workspace,
                           int64_t workspace_bytes, void* stream);
+/* linear_inv_process_estimate (tomography.py:459-491): expect[B,S] -> choi_out[B,m,m], minimum-norm least squares
+ * over the plan's settings list plus the identity term.  The per-observable pseudo-inverse weights are built from
+ * the plan on first use (the reference's dense pinv of the S x 16^n measurement matrix is never formed). */
+int qt_linear_inv_process_batch(qt_pgdb_plan* plan, int64_t B, const double* expect, void* choi_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -305,6 +305,17 @@ def proj_choi_to_physical(choi, make_trace_preserving=True, return_count=False):
 # --------------------------------------------------------------------------------------------
 # Distance measures  (distance_measures.py:64-114, calculational.py:77-91)
 # --------------------------------------------------------------------------------------------
+def proj_choi_to_unitary(choi):
+    """project_superoperators.py:147-175."""
+    choi = np.asarray(choi, dtype=complex)
+    d = int(round(np.sqrt(choi.shape[0])))
+    vals, vs = sla.eigh((choi + choi.conj().T) / 2)
+    kraus = unvec(vs[:, np.argmax(vals)].reshape(d * d, 1))
+    u, _, vh = sla.svd(kraus)
+    unitary = u @ vh
+    return kraus2choi(np.exp(-1j * np.angle(unitary[0, 0])) * unitary)
+
+
 def sqrtm_psd(m):
     """calculational.py:77-91."""
     w, v = sla.eigh(m)
@@ -372,6 +383,27 @@ def project_state_matrix_to_physical(rho):
     return (v * np.array(new)) @ v.conj().T
 
 
+def shots_to_obs_moments(bitarray, idxs, coeff=1.0, use_beta_dist_unbiased_prior=False):
+    """observable_estimation.py:804-853 with the observable given as (column indices, real coefficient)."""
+    bitarray = np.asarray(bitarray)
+    if len(idxs) == 0:
+        return coeff, 0
+    obs_vals = np.prod(1 - 2 * bitarray[:, list(idxs)].astype(np.int64), axis=1)
+    if use_beta_dist_unbiased_prior:
+        n_plus = int(np.sum(obs_vals == 1))
+        n_minus = len(obs_vals) - n_plus
+        a, b = n_plus + 1, n_minus + 1                      # scipy.stats.beta.mean / .var of beta(a, b)
+        bm, bv = a / (a + b), a * b / ((a + b) ** 2 * (a + b + 1))
+        return (2 * bm - 1) * coeff, 4 * bv * coeff ** 2   # utils.py:446-458
+    obs_vals = coeff * obs_vals
+    return np.mean(obs_vals).item(), np.var(obs_vals).item() / len(bitarray)
+
+
+def ratio_variance(a, var_a, b, var_b):
+    """observable_estimation.py:1052-1090."""
+    return var_a / b ** 2 + (a ** 2 * var_b) / b ** 4
+
+
 def resample_expectations_with_beta(expectations, counts, prior_counts=1):
     """tomography.py:378-409 on arrays: one np.random.beta draw per result, in order (global NumPy RNG)."""
     out = np.empty(len(expectations))
@@ -392,6 +424,20 @@ def linear_inv_state_estimate(pauli_idx, coeffs, expectations, n):
     m = np.vstack(rows)
     r = sla.pinv(m) @ np.asarray(expectations, dtype=float)
     return unvec(r) + np.eye(d) / d
+
+
+def state_log_likelihood(rho, pauli_idx, coeffs, expectations, counts, n):
+    """tomography.py:341-375 (log10 likelihood; outcomes of non-positive predicted probability are skipped)."""
+    ll = 0
+    for k, c, meas, cnt in zip(pauli_idx, coeffs, expectations, counts):
+        pred = np.real(np.trace(c * pauli_matrix(k, n) @ rho))
+        for sign in (1, -1):
+            f = cnt * (1 + sign * meas) / 2
+            pr = (1 + sign * pred) / 2
+            if pr <= 0:
+                continue
+            ll += f * np.log10(pr)
+    return ll
 
 
 def r_operator(rho, op_mats, expectations):

@@ -102,3 +102,49 @@ def test_dropin_signature(torch):
     got2 = tm.pgdb_process_estimate(res, qubits, trace_preserving=False)
     want2 = orc.pgdb_process_estimate(settings, np.ones(len(settings)), ex[0], cnt[0], 1, trace_preserving=False)
     assert relerr(got2, want2) < TOL
+
+
+@pytest.mark.parametrize("n,basis,batch", [(1, "pauli", 17), (1, "sic", 5), (2, "pauli", 9), (2, "sic", 4), (3, "sic", 2)])
+def test_linear_inv_process_estimate(torch, n, basis, batch):
+    """"next" row 3: linear inversion vs the oracle's dense pinv of the measurement matrix."""
+    from forest_benchmarking_b200 import tomography as tm, synthetic as sy
+    codes, pidx, ex, cnt, _ = sy.process_tomography_batch(500 + n, batch, n, in_basis=basis)
+    plan = tm.PgdbPlan(n, codes, pidx)
+    choi = tm.linear_inv_process_estimate_batch(plan, torch.from_numpy(np.ascontiguousarray(ex)).cuda()).cpu().numpy()
+    settings = [(tuple(int(c) for c in s), int(k)) for s, k in zip(codes, pidx)]
+    for b in range(0, batch, 1 if n < 3 else batch):
+        want = orc.linear_inv_process_estimate(settings, np.ones(len(settings)), ex[b], n)
+        assert relerr(choi[b], want) < 1e-11
+    # the same plan still serves PGDB
+    est, _ = tm.pgdb_process_estimate_batch(plan, torch.from_numpy(np.ascontiguousarray(ex[:1])).cuda(),
+                                            torch.from_numpy(np.ascontiguousarray(cnt[:1])).cuda(), return_counters=True)
+    assert relerr(est[0].cpu().numpy(), choi[0]) < 0.5
+
+
+def test_linear_inv_process_incomplete_and_weighted(torch):
+    """Half of the settings dropped (rank-deficient design: minimum-norm solution), shuffled, non-unit coefficients,
+    an identity observable; then the drop-in signature."""
+    from forest_benchmarking_b200 import tomography as tm
+    from forest_benchmarking_b200.observable_estimation import (ExperimentResult, ExperimentSetting, plusX, minusX,
+                                                               plusY, minusY, plusZ, minusZ)
+    from forest_benchmarking_b200.utils import all_traceless_pauli_terms
+    rng = np.random.default_rng(12)
+    _, settings, ex, cnt = orc.synth_process_tomography(31, 3, 2, in_basis="pauli")
+    keep = rng.permutation(len(settings))[: len(settings) // 2]
+    settings = [settings[i] for i in keep] + [((0, 4), 0)]
+    ex = np.concatenate([ex[:, keep], np.ones((3, 1))], axis=1)
+    coeffs = rng.choice([1.0, -1.0, 0.5, 2.0], len(settings))
+    codes = np.array([s for s, _ in settings], dtype=np.int32)
+    pidx = np.array([k for _, k in settings], dtype=np.int32)
+    plan = tm.PgdbPlan(2, codes, pidx, coeffs)
+    choi = tm.linear_inv_process_estimate_batch(plan, torch.from_numpy(np.ascontiguousarray(ex)).cuda()).cpu().numpy()
+    for b in range(3):
+        assert relerr(choi[b], orc.linear_inv_process_estimate(settings, coeffs, ex[b], 2)) < 1e-10
+    qubits = [3]
+    _, settings, ex, cnt = orc.synth_process_tomography(23, 1, 1, in_basis="pauli")
+    fac = [plusX, minusX, plusY, minusY, plusZ, minusZ]
+    terms = all_traceless_pauli_terms(qubits)
+    res = [ExperimentResult(ExperimentSetting(fac[c[0]](3), terms[k - 1]), e, int(n_))
+           for (c, k), e, n_ in zip(settings, ex[0], cnt[0])]
+    want = orc.linear_inv_process_estimate(settings, np.ones(len(settings)), ex[0], 1)
+    assert relerr(tm.linear_inv_process_estimate(res, qubits), want) < 1e-12

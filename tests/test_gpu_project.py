@@ -75,3 +75,28 @@ def test_known_answers_and_dropin(torch):
     assert np.allclose(ot.proj_choi_to_trace_non_increasing(bad), orc.proj_choi_to_trace_non_increasing(bad), atol=1e-13)
     with pytest.raises(ValueError):
         ot.proj_choi_to_completely_positive(np.full((4, 4), np.nan))
+
+
+@pytest.mark.parametrize("n,batch", [(1, 33), (2, 21), (3, 5)])
+def test_proj_choi_to_unitary(torch, n, batch):
+    """"next" row 3: closest unitary vs the oracle (eigh + SVD), noisy non-Hermitian inputs; a unitary
+    channel is a fixed point up to the phase convention."""
+    from forest_benchmarking_b200.operator_tools import project_superoperators as pj
+    rng = np.random.default_rng(60 + n)
+    d = 2 ** n
+    chois, us = [], []
+    for _ in range(batch):
+        u = orc.haar_unitary(rng, d)
+        g = rng.standard_normal((d * d, d * d)) + 1j * rng.standard_normal((d * d, d * d))
+        chois.append(.9 * orc.kraus2choi(u) + .1 * (g @ g.conj().T) / d ** 2 + .01 * g)
+        us.append(u)
+    chois = np.stack(chois)
+    got = pj.proj_choi_to_unitary_batch(torch.from_numpy(chois).cuda()).cpu().numpy()
+    for b in range(batch):
+        assert relerr(got[b], orc.proj_choi_to_unitary(chois[b])) < 1e-9
+        # the closest unitary is near the unitary the process was built around
+        assert relerr(got[b], orc.kraus2choi(us[b] * np.exp(-1j * np.angle(us[b][0, 0])))) < 0.6
+    exact = np.stack([orc.kraus2choi(u) for u in us])
+    fixed = pj.proj_choi_to_unitary_batch(torch.from_numpy(exact).cuda()).cpu().numpy()
+    assert max_relerr(fixed, exact) < 1e-10
+    assert relerr(pj.proj_choi_to_unitary(chois[0]), orc.proj_choi_to_unitary(chois[0])) < 1e-9

@@ -214,6 +214,42 @@ def test_linear_inv_state_estimate(torch):
     assert relerr(tm.linear_inv_state_estimate(res, qubits), orc.linear_inv_state_estimate(pidx, np.ones(3), ex[0], 1)) < 1e-12
 
 
+def test_state_log_likelihood(torch):
+    """"next" row 2: state_log_likelihood vs the oracle, incl. pure states (zero-probability outcomes
+    are skipped), duplicated / weighted observables, and the drop-in signature."""
+    from forest_benchmarking_b200 import tomography as tm
+    from forest_benchmarking_b200.observable_estimation import ExperimentResult, ExperimentSetting, zeros_state
+    from forest_benchmarking_b200.utils import all_traceless_pauli_terms
+    for n in (1, 2, 3, 4):
+        rho, pidx, ex, cnt = orc.synth_state_tomography(2001 + n, 9, n)
+        rho = np.array(rho)
+        rho[0] = 0.0
+        rho[0][0, 0] = 1.0  # |0..0><0..0|: P(-1) = 0 for every Z-type observable
+        plan = tm.MlePlan(n, pidx)
+        got = tm.state_log_likelihood_batch(plan, torch.from_numpy(rho).cuda(), torch.from_numpy(ex).cuda(),
+                                            torch.from_numpy(cnt.astype(np.float64)).cuda()).cpu().numpy()
+        want = np.array([orc.state_log_likelihood(rho[b], pidx, np.ones(len(pidx)), ex[b], cnt[b], n) for b in range(9)])
+        assert np.all(np.isfinite(got))
+        assert np.max(np.abs(got - want) / np.abs(want)) < 1e-11
+    rng = np.random.default_rng(6)
+    pidx = np.array([0, 7, 7, 12, 3, 1, 9, 9, 9], dtype=np.int32)
+    coeffs = np.array([1.0, -1.0, 0.5, 1.0, 1.0, 0.25, 1.0, 1.0, -0.3])
+    ex = rng.uniform(-.6, .6, size=(3, len(pidx)))
+    cnt = rng.integers(100, 1000, size=ex.shape).astype(np.float64)
+    rho = np.stack([orc.ginibre_state(rng, 4) for _ in range(3)])
+    got = tm.state_log_likelihood_batch(tm.MlePlan(2, pidx, coeffs), torch.from_numpy(rho).cuda(),
+                                        torch.from_numpy(ex).cuda(), torch.from_numpy(cnt).cuda()).cpu().numpy()
+    for b in range(3):
+        want = orc.state_log_likelihood(rho[b], pidx, coeffs, ex[b], cnt[b], 2)
+        assert abs(got[b] - want) < 1e-11 * abs(want)
+    qubits = [3, 5]
+    rho, pidx, ex, cnt = orc.synth_state_tomography(2002, 1, 2)
+    res = [ExperimentResult(ExperimentSetting(zeros_state(qubits), t), e, int(c))
+           for t, e, c in zip(all_traceless_pauli_terms(qubits), ex[0], cnt[0])]
+    want = orc.state_log_likelihood(rho[0], pidx, np.ones(len(pidx)), ex[0], cnt[0], 2)
+    assert abs(tm.state_log_likelihood(rho[0], res, qubits) - want) < 1e-11 * abs(want)
+
+
 def test_project_state_matrix_and_estimate_variance(torch):
     """"next" row 1: wizard projection vs the oracle, and the bootstrap estimate_variance as ONE batch
     vs a replica-by-replica NumPy restatement with the same seeded RNG stream (tomography.py:412-453)."""

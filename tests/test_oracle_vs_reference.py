@@ -121,6 +121,9 @@ def test_mle(ref, n, kw):
             assert relerr(gotb[0], want) < 1e-11
         assert relerr(orc.linear_inv_state_estimate(pidx, coeffs, ex[b], n),
                       ref.tomo.linear_inv_state_estimate(res, qubits)) < 1e-12
+        assert abs(orc.state_log_likelihood(want, pidx, coeffs, ex[b], cnt[b], n)
+                   - ref.tomo.state_log_likelihood(want, res, qubits)) < 1e-9 * abs(
+            ref.tomo.state_log_likelihood(want, res, qubits))
 
 
 def test_r_operator_with_coefficients_and_identity(ref):
@@ -205,3 +208,30 @@ def test_process_fidelities(ref):
         assert abs(orc.hilbert_schmidt_ip(p0, p1) - ref.dm.hilbert_schmidt_ip(p0, p1)) < 1e-12
         assert abs(orc.entanglement_fidelity(p0, p1) - ref.dm.entanglement_fidelity(p0, p1)) < 1e-13
         assert abs(orc.process_fidelity(p0, p1) - ref.dm.process_fidelity(p0, p1)) < 1e-13
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_proj_choi_to_unitary(ref, n):
+    from forest.benchmarking.operator_tools.project_superoperators import proj_choi_to_unitary
+    rng = np.random.default_rng(40 + n)
+    d = 2 ** n
+    u = orc.haar_unitary(rng, d)
+    g = rng.standard_normal((d * d, d * d)) + 1j * rng.standard_normal((d * d, d * d))
+    choi = .9 * orc.kraus2choi(u) + .1 * (g @ g.conj().T) / d ** 2 + .01 * g  # noisy, not Hermitian
+    assert relerr(orc.proj_choi_to_unitary(choi), proj_choi_to_unitary(choi)) < 1e-12
+
+
+def test_shots_to_obs_moments(ref):
+    from forest.benchmarking.observable_estimation import shots_to_obs_moments, ratio_variance
+    from pyquil.paulis import PauliTerm
+    rng = np.random.default_rng(9)
+    qubits = [4, 7, 9]
+    bits = (rng.random((257, 3)) < [.2, .5, .8]).astype(np.uint8)
+    for ops, idxs, c in [([("Z", 4)], [0], 1.0), ([("X", 7), ("Z", 9)], [1, 2], -0.5), ([("Y", 4), ("Y", 7), ("X", 9)], [0, 1, 2], 2.0),
+                         ([], [], 0.7)]:
+        term = PauliTerm.from_list(ops, coefficient=c) if ops else PauliTerm("I", 0, c)
+        for prior in (False, True):
+            want = shots_to_obs_moments(bits.astype(np.int64), qubits, term, prior)  # qc.run returns int64 bits
+            got = orc.shots_to_obs_moments(bits, idxs, c, prior)
+            assert np.allclose(got, want, rtol=1e-13, atol=1e-16)
+    assert np.isclose(orc.ratio_variance(.3, .01, .9, .002), ratio_variance(.3, .01, .9, .002), rtol=1e-15)
