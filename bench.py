@@ -437,7 +437,7 @@ def run_pgdb(args):
 
 
 def run_kernels(args):
-    """--workload streaming | convert | distances: per-kernel HBM-roofline tables (bench_kernels.py)."""
+    """--workload streaming | convert | distances | next: per-kernel HBM-roofline tables (bench_kernels.py)."""
     import torch
     import bench_kernels as bk
     rank, world, local = dist_info()
@@ -450,6 +450,10 @@ def run_kernels(args):
         rows = bk.streaming_rows(torch, peak)
         headline = next(r for r in rows if r["kernel"].startswith("mle_step_kernel<2>"))
         workload = "HBM-bound kernels of the path, one launch each over a 2 GiB working set (inputs > L2)"
+    elif args.workload == "next":
+        rows = bk.next_rows(torch, peak)
+        headline = next(r for r in rows if "n_qubits=2 shots=1000" in r["kernel"])
+        workload = "SURVEY 8(f) next rows: shots -> moments, log-likelihood, linear-inversion process estimate, closest unitary"
     elif args.workload == "convert":
         rows = bk.convert_rows(torch, peak)
         headline = next(r for r in rows if r["kernel"].startswith("superop2pauli_liouville n=3"))
@@ -476,7 +480,7 @@ def run_kernels(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="mle2q", choices=["mle2q", "pgdb3q", "pgdb2q", "pgdb1q", "streaming",
-                                                            "convert", "distances"])
+                                                            "convert", "distances", "next"])
     ap.add_argument("--in-basis", default="pauli", choices=["pauli", "sic"])
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -491,7 +495,7 @@ def main():
         run_reference_arm(args)
     elif args.workload.startswith("pgdb"):
         run_pgdb(args)
-    elif args.workload in ("streaming", "convert", "distances"):
+    elif args.workload in ("streaming", "convert", "distances", "next"):
         run_kernels(args)
     else:
         run_ours(args)

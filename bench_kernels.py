@@ -144,5 +144,45 @@ def distance_rows(torch, peak, pairs, n=4):
     return rows
 
 
+def next_rows(torch, peak, budget_bytes=4 << 30):
+    """SURVEY 8(f) "next" rows: raw shots -> moments (HBM-bound byte kernel), log-likelihood, linear-inversion process
+    estimate, closest unitary.  GB/s from the algorithmic bytes (inputs read once + outputs written once)."""
+    from forest_benchmarking_b200 import observable_estimation as oe, tomography as tm, synthetic as sy
+    from forest_benchmarking_b200.operator_tools import project_superoperators as pj
+    rows = []
+    g = torch.Generator(device="cuda").manual_seed(7)
+    for q, shots in ((1, 1000), (2, 1000), (2, 500), (4, 1000), (8, 1000), (3, 1000)):
+        b = budget_bytes // (shots * q)
+        bits = torch.randint(0, 2, (b, shots, q), device="cuda", generator=g, dtype=torch.uint8)
+        masks = torch.randint(1, 2 ** q, (b,), device="cuda", generator=g, dtype=torch.int32)
+        ms = _time(torch, lambda: oe.shots_to_obs_moments_batch(bits, masks))
+        kind = "SWAR" if q in (1, 2, 4, 8) else "bytes"
+        rows.append(_row(f"moments_{kind}_kernel n_qubits={q} shots={shots} (shots_to_obs_moments)", b,
+                         shots * q + 4 + 8 + 16, ms, peak))
+        del bits, masks
+    n = 2
+    b = 1 << 20
+    rho = _rand_states(torch, b, 2 ** n, 71)
+    k = 4 ** n - 1
+    plan = tm.MlePlan(n, np.arange(1, k + 1, dtype=np.int32))
+    ex = torch.rand((b, k), dtype=torch.float64, device="cuda", generator=g) * 1.2 - .6
+    cnt = torch.full((b, k), 1000.0, dtype=torch.float64, device="cuda")
+    ms = _time(torch, lambda: tm.state_log_likelihood_batch(plan, rho, ex, cnt))
+    rows.append(_row("log_likelihood_kernel<2> (state_log_likelihood)", b, 16 * 4 ** n + 16 * k + 8, ms, peak))
+    del rho, ex, cnt
+    for n, b in ((1, 1 << 20), (2, 1 << 16), (3, 1 << 10)):
+        pplan = tm.PgdbPlan.complete(n)
+        ex = torch.rand((b, pplan.S), dtype=torch.float64, device="cuda", generator=g) * 1.2 - .6
+        out = torch.empty((b, 4 ** n, 4 ** n), dtype=torch.complex128, device="cuda")
+        ms = _time(torch, lambda: tm.linear_inv_process_estimate_batch(pplan, ex, out=out))
+        rows.append(_row(f"linproc_kernel<{n}> (linear_inv_process_estimate, complete Pauli design)", b,
+                         8 * pplan.S + 16 * 16 ** n, ms, peak))
+        ms = _time(torch, lambda: pj.proj_choi_to_unitary_batch(out), reps=3, warmup=1)
+        rows.append(_row(f"proj_unitary_kernel<{n}> (proj_choi_to_unitary; eigensolver: FP64-bound)", b,
+                         32 * 16 ** n, ms, peak))
+        del ex, out
+    return rows
+
+
 def dumps(rows):
     return json.dumps(rows)

@@ -6,10 +6,10 @@
 // calibrate_observable_estimates' arithmetic (:1033-1049 + ratio_variance :1052-1090) is the elementwise kernel below.
 //
 // Integer / byte work, HBM-bound: one byte per shot and qubit is read once, two doubles per setting are written.
-// One warp per setting.  For n_qubits in {1, 2, 4, 8} the whole array is read as one flat stream of aligned 16-byte
-// words (a setting's byte range may start anywhere: the bytes of neighbouring settings in its first / last word are
-// masked off), and the per-shot parity is folded inside the 32-bit words (SWAR) before one popcount per word.
-// Other widths take the byte-per-lane kernel.
+// For n_qubits in {1, 2, 4, 8} the whole array is read as one flat stream of aligned 16-byte words by 8 / 16 / 32
+// lanes per setting (a setting's byte range may start anywhere: the bytes of neighbouring settings in its first /
+// last word are masked off), and the per-shot parity is folded inside the 32-bit words (SWAR) before one popcount
+// per word.  Other widths stage the setting through shared memory (warp per setting) and XOR the selected columns.
 #include "qt_common.cuh"
 #include "../../include/qtomo.h"
 
@@ -23,102 +23,175 @@ __device__ __forceinline__ unsigned col_pattern(unsigned colmask, int first_col,
   return pat;
 }
 
-// bytes of the u32 at flat byte address `a` that lie inside [lo, hi)
-__device__ __forceinline__ unsigned range_mask(long long a, long long lo, long long hi) {
-  unsigned m = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-    if (a + i >= lo && a + i < hi) m |= 0xffu << (8 * i);
-  return m;
-}
+// n_shots is common to the batch: its reciprocals come in as kernel arguments (MomInv), so the epilogue has no division
+struct MomInv {
+  double inv_n;        // 1 / S
+  double inv_ab;       // 1 / (S + 2)
+  double inv_ab2_ab1;  // 1 / ((S + 2)^2 (S + 3))
+};
 
 __device__ __forceinline__ void moments_epilogue(unsigned long long n_minus, long long S, bool identity, double coeff,
-                                                 int prior, double* mean, double* var) {
+                                                 int prior, MomInv iv, double* mean, double* var) {
   if (identity) {  // identity term (:826-827)
     *mean = coeff;
     *var = 0.0;
     return;
   }
-  const double nm = (double)n_minus, np_ = (double)(S - (long long)n_minus), n = (double)S;
+  const double nm = (double)n_minus, np_ = (double)(S - (long long)n_minus);
   if (prior) {  // Beta(n+ + 1, n- + 1) mean / variance, then bit -> Pauli moments (:838-847, utils.py:446-458)
-    const double a = np_ + 1.0, b = nm + 1.0, ab = a + b;
-    const double bm = a / ab, bv = a * b / (ab * ab * (ab + 1.0));
-    *mean = (2.0 * bm - 1.0) * coeff;
-    *var = 4.0 * bv * coeff * coeff;
+    const double a = np_ + 1.0, b = nm + 1.0;
+    *mean = (2.0 * (a * iv.inv_ab) - 1.0) * coeff;
+    *var = 4.0 * (a * b * iv.inv_ab2_ab1) * coeff * coeff;
   } else {  // np.mean / np.var of the +-coeff values, variance of the mean (:849-851)
-    const double m = coeff * (np_ - nm) / n;
+    const double m = coeff * (np_ - nm) * iv.inv_n;
     const double dp = coeff - m, dm = -coeff - m;
     *mean = m;
-    *var = (np_ * dp * dp + nm * dm * dm) / n / n;
+    *var = (np_ * dp * dp + nm * dm * dm) * iv.inv_n * iv.inv_n;
   }
 }
 
+// Number of shots with eigenvalue product -1 inside one aligned 16-byte word.  Every byte is 0 or 1, so the four
+// 32-bit words are first packed into bit planes 0..3 of one word (z = x0 + 2 x1 + 4 x2 + 8 x3, no carries), masked
+// with the column pattern replicated over the planes, and the per-shot XOR fold and the popcount run once.
 template <int Q>
+__device__ __forceinline__ unsigned swar_count(uint4 w, unsigned pat0, unsigned pat1) {
+  if (Q == 8) {  // a shot is two words with different column patterns
+    const unsigned y0 = (w.x & pat0) ^ (w.y & pat1), y1 = (w.z & pat0) ^ (w.w & pat1);
+    unsigned z = y0 + 2u * y1;
+    z ^= z >> 16;
+    z ^= z >> 8;
+    return __popc(z & 0x3u);
+  }
+  unsigned z = (w.x + 2u * w.y + 4u * w.z + 8u * w.w) & (pat0 * 15u);
+  if (Q == 1) return __popc(z);
+  if (Q == 2) {
+    z ^= z >> 8;
+    return __popc(z & 0x000f000fu);
+  }
+  z ^= z >> 16;
+  z ^= z >> 8;
+  return __popc(z & 0xfu);
+}
+
+// the bytes of the 16-byte word at flat address e that lie outside [lo, hi) are cleared
+__device__ __forceinline__ uint4 clip_word(uint4 w, long long e, long long lo, long long hi) {
+  const int b0 = (int)max(lo - e, 0LL), b1 = (int)min(hi - e, 16LL);       // valid bytes [b0, b1)
+  const unsigned en = ((1u << b1) - 1u) & ~((1u << b0) - 1u);             // 16 byte-enable bits
+  auto expand = [](unsigned nib) { return ((nib * 0x00204081u) & 0x01010101u) * 0xffu; };
+  w.x &= expand(en & 15u);
+  w.y &= expand((en >> 4) & 15u);
+  w.z &= expand((en >> 8) & 15u);
+  w.w &= expand((en >> 12) & 15u);
+  return w;
+}
+
+// G lanes per setting (8 / 16 / 32, chosen from the setting's size so that a lane has ~8 independent 16-byte loads in
+// flight).  Words that lie entirely inside the setting's byte range take the unmasked loop (4 loads issued before the
+// first use); the at most two edge words shared with the neighbouring settings are masked byte-wise.
+template <int Q, int G>
 __global__ void __launch_bounds__(256)
     moments_swar_kernel(int64_t B, int64_t S, const unsigned char* __restrict__ bits,
-                        const uint32_t* __restrict__ colmask, const double* __restrict__ coeff, int prior,
+                        const uint32_t* __restrict__ colmask, const double* __restrict__ coeff, int prior, MomInv iv,
                         double* __restrict__ mean, double* __restrict__ var) {
   static_assert(Q == 1 || Q == 2 || Q == 4 || Q == 8, "shots must tile a 32-bit word");
-  const int lane = threadIdx.x & 31;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int gl = threadIdx.x % G;
+  const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G, ngrp = ((int64_t)gridDim.x * blockDim.x) / G;
   const long long base = (long long)reinterpret_cast<uintptr_t>(bits);  // flat addresses: the alignment of `bits` is free
-  for (int64_t b = warp; b < B; b += nwarps) {
-    const unsigned cm = colmask[b] & ((Q >= 32) ? 0xffffffffu : ((1u << Q) - 1u));
-    const long long lo = base + b * S * Q, hi = lo + S * Q;
-    const unsigned pat0 = col_pattern(cm, 0, Q), pat1 = col_pattern(cm, 4, Q);
+  const int64_t rounds = (B + ngrp - 1) / ngrp;  // every lane of a warp runs the same number of rounds (shuffles below)
+  for (int64_t it = 0; it < rounds; ++it) {
+    const int64_t b = grp + it * ngrp;
+    const bool live = b < B;
+    const unsigned cm = live ? (colmask[b] & ((1u << Q) - 1u)) : 0u;
+    const long long lo = base + (live ? b : 0) * S * Q, hi = live ? lo + S * Q : lo;
+    const unsigned pat0 = col_pattern(cm, 0, Q), pat1 = (Q == 8) ? col_pattern(cm, 4, Q) : pat0;
     unsigned cnt = 0;
-    for (long long a = (lo & ~15LL) + 16LL * lane; a < hi; a += 16LL * 32) {
-      const uint4 w = *reinterpret_cast<const uint4*>(a);
-      unsigned x0 = w.x & pat0, x1 = w.y & ((Q == 8) ? pat1 : pat0), x2 = w.z & pat0, x3 = w.w & ((Q == 8) ? pat1 : pat0);
-      if (a < lo || a + 16 > hi) {  // first / last word of the setting: drop the neighbours' bytes
-        x0 &= range_mask(a, lo, hi);
-        x1 &= range_mask(a + 4, lo, hi);
-        x2 &= range_mask(a + 8, lo, hi);
-        x3 &= range_mask(a + 12, lo, hi);
-      }
-      if (Q == 1) {
-        cnt += __popc(x0) + __popc(x1) + __popc(x2) + __popc(x3);
-      } else if (Q == 2) {
-        x0 ^= x0 >> 8; x1 ^= x1 >> 8; x2 ^= x2 >> 8; x3 ^= x3 >> 8;
-        cnt += __popc(x0 & 0x00010001u) + __popc(x1 & 0x00010001u) + __popc(x2 & 0x00010001u) + __popc(x3 & 0x00010001u);
-      } else if (Q == 4) {
-        x0 ^= x0 >> 16; x1 ^= x1 >> 16; x2 ^= x2 >> 16; x3 ^= x3 >> 16;
-        x0 ^= x0 >> 8; x1 ^= x1 >> 8; x2 ^= x2 >> 8; x3 ^= x3 >> 8;
-        cnt += (x0 & 1u) + (x1 & 1u) + (x2 & 1u) + (x3 & 1u);
-      } else {
-        unsigned y0 = x0 ^ x1, y1 = x2 ^ x3;
-        y0 ^= y0 >> 16; y1 ^= y1 >> 16;
-        y0 ^= y0 >> 8; y1 ^= y1 >> 8;
-        cnt += (y0 & 1u) + (y1 & 1u);
-      }
+    const long long A0 = (lo + 15) & ~15LL, A1 = hi & ~15LL, stride = 16LL * G;
+    long long a = A0 + 16LL * gl;
+    for (; a + 3 * stride < A1; a += 4 * stride) {
+      const uint4 w0 = *reinterpret_cast<const uint4*>(a), w1 = *reinterpret_cast<const uint4*>(a + stride);
+      const uint4 w2 = *reinterpret_cast<const uint4*>(a + 2 * stride), w3 = *reinterpret_cast<const uint4*>(a + 3 * stride);
+      cnt += swar_count<Q>(w0, pat0, pat1) + swar_count<Q>(w1, pat0, pat1) + swar_count<Q>(w2, pat0, pat1) +
+             swar_count<Q>(w3, pat0, pat1);
+    }
+    for (; a < A1; a += stride) {
+      cnt += swar_count<Q>(*reinterpret_cast<const uint4*>(a), pat0, pat1);
+    }
+    // edge words
+    const long long E1 = lo & ~15LL, E2 = hi & ~15LL;
+    const bool need1 = live && (lo & 15), need2 = live && (hi & 15) && (E2 != E1 || !(lo & 15));
+    if ((need1 && gl == 0) || (need2 && gl == (G > 1 ? 1 : 0))) {
+      const long long e = (need1 && gl == 0) ? E1 : E2;
+      cnt += swar_count<Q>(clip_word(*reinterpret_cast<const uint4*>(e), e, lo, hi), pat0, pat1);
     }
     unsigned long long tot = cnt;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0) moments_epilogue(tot, S, cm == 0, coeff[b], prior, mean + b, var + b);
+    for (int o = G / 2; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (live && gl == 0) moments_epilogue(tot, S, cm == 0, coeff[b], prior, iv, mean + b, var + b);
   }
 }
 
-// any width up to 32 columns: one shot per lane, only the selected columns are read
+// Any width up to 32 columns.  One warp per setting: the setting's bytes are staged through shared memory in chunks of
+// whole shots with coalesced, aligned 16-byte loads (4 in flight per lane), then each lane takes the parity of the
+// selected columns of its shots out of shared memory (widths up to 8: word reads + funnel shift + popcount).
+constexpr int MOM_CHUNK = 2048;  // payload bytes per chunk (+ up to 30 bytes of alignment slack)
 __global__ void __launch_bounds__(256)
     moments_bytes_kernel(int64_t B, int64_t S, int Q, const unsigned char* __restrict__ bits,
-                         const uint32_t* __restrict__ colmask, const double* __restrict__ coeff, int prior,
+                         const uint32_t* __restrict__ colmask, const double* __restrict__ coeff, int prior, MomInv iv,
                          double* __restrict__ mean, double* __restrict__ var) {
+  __shared__ __align__(16) unsigned char stage_all[8][MOM_CHUNK + 32];
+  unsigned char* stage = stage_all[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const long long base = (long long)reinterpret_cast<uintptr_t>(bits);
+  const int64_t shots_per_chunk = MOM_CHUNK / Q;
   for (int64_t b = warp; b < B; b += nwarps) {
     const unsigned cm = colmask[b] & ((Q >= 32) ? 0xffffffffu : ((1u << Q) - 1u));
-    const unsigned char* src = bits + b * S * Q;
+    const long long lo = base + b * S * Q;
+    unsigned pat_lo = 0, pat_hi = 0;  // 0x01 in byte i when column i (lo) / column 4 + i (hi) is selected
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      pat_lo |= ((cm >> i) & 1u) << (8 * i);
+      pat_hi |= ((cm >> (4 + i)) & 1u) << (8 * i);
+    }
     unsigned cnt = 0;
-    for (int64_t s = lane; s < S; s += 32) {
-      unsigned par = 0;
-      for (unsigned m = cm; m; m &= m - 1) par ^= src[s * Q + (__ffs(m) - 1)];
-      cnt += par & 1u;
+    for (int64_t s0 = 0; s0 < S && cm; s0 += shots_per_chunk) {
+      const int64_t ns = min(shots_per_chunk, S - s0);
+      const long long c0 = lo + s0 * Q, c1 = c0 + ns * Q, a0 = c0 & ~15LL;
+      const int nwords = (int)((c1 - a0 + 15) >> 4);  // <= (MOM_CHUNK + 30) / 16
+      for (int w = lane; w < nwords; w += 128) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (w + 32 * u < nwords) v[u] = *reinterpret_cast<const uint4*>(a0 + 16LL * (w + 32 * u));
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (w + 32 * u < nwords) *reinterpret_cast<uint4*>(stage + 16 * (w + 32 * u)) = v[u];
+      }
+      __syncwarp();
+      const int off = (int)(c0 - a0);
+      if (Q <= 8) {
+        // a shot is at most 8 bytes: two / three aligned 32-bit reads, funnel-shifted to the shot's first byte
+        const unsigned* sw = reinterpret_cast<const unsigned*>(stage);
+        for (int s = lane; s < ns; s += 32) {
+          const int o = off + s * Q, i = o >> 2, sh = (o & 3) * 8;
+          const unsigned w0 = sw[i], w1 = sw[i + 1];
+          unsigned t = __funnelshift_r(w0, w1, sh) & pat_lo;
+          if (Q > 4) t ^= __funnelshift_r(w1, sw[i + 2], sh) & pat_hi;
+          cnt += __popc(t) & 1u;
+        }
+      } else {
+        for (int s = lane; s < ns; s += 32) {
+          unsigned par = 0;
+          for (unsigned m = cm; m; m &= m - 1) par ^= stage[off + s * Q + (__ffs(m) - 1)];
+          cnt += par & 1u;
+        }
+      }
+      __syncwarp();
     }
     unsigned long long tot = cnt;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-    if (lane == 0) moments_epilogue(tot, S, cm == 0, coeff[b], prior, mean + b, var + b);
+    if (lane == 0) moments_epilogue(tot, S, cm == 0, coeff[b], prior, iv, mean + b, var + b);
   }
 }
 
@@ -143,8 +216,26 @@ extern "C" int qt_shots_to_obs_moments_batch(int64_t B, int64_t n_shots, int n_q
   QT_REQUIRE(bits && col_mask && coeff && mean_out && var_out, "qt_shots_to_obs_moments_batch: null argument");
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned blocks = (unsigned)std::min<int64_t>((B + 7) / 8, (int64_t)QT_NUM_SMS * 8);
-#define SWAR(Q)                                                                                                    \
-  moments_swar_kernel<Q><<<blocks, 256, 0, st>>>(B, n_shots, bits, col_mask, coeff, use_beta_prior, mean_out, var_out)
+  const double sn = (double)n_shots;
+  const MomInv iv{1.0 / sn, 1.0 / (sn + 2.0), 1.0 / ((sn + 2.0) * (sn + 2.0) * (sn + 3.0))};
+// lanes per setting from the number of 16-byte words of one setting
+#define SWAR(Q)                                                                                                     \
+  do {                                                                                                              \
+    const int64_t words = (n_shots * Q + 15) / 16;                                                                  \
+    if (words >= 256) {                                                                                             \
+      const unsigned blocks = (unsigned)std::min<int64_t>((B + 7) / 8, (int64_t)QT_NUM_SMS * 8);                    \
+      moments_swar_kernel<Q, 32><<<blocks, 256, 0, st>>>(B, n_shots, bits, col_mask, coeff, use_beta_prior, iv,     \
+                                                         mean_out, var_out);                                        \
+    } else if (words >= 128) {                                                                                      \
+      const unsigned blocks = (unsigned)std::min<int64_t>((B + 15) / 16, (int64_t)QT_NUM_SMS * 8);                  \
+      moments_swar_kernel<Q, 16><<<blocks, 256, 0, st>>>(B, n_shots, bits, col_mask, coeff, use_beta_prior, iv,     \
+                                                         mean_out, var_out);                                        \
+    } else {                                                                                                        \
+      const unsigned blocks = (unsigned)std::min<int64_t>((B + 31) / 32, (int64_t)QT_NUM_SMS * 8);                  \
+      moments_swar_kernel<Q, 8><<<blocks, 256, 0, st>>>(B, n_shots, bits, col_mask, coeff, use_beta_prior, iv,      \
+                                                        mean_out, var_out);                                         \
+    }                                                                                                               \
+  } while (0)
   // the SWAR kernels need every shot aligned to its own width in flat addresses
   const int width = (reinterpret_cast<uintptr_t>(bits) % (uintptr_t)n_qubits == 0) ? n_qubits : 0;
   switch (width) {
@@ -153,7 +244,7 @@ extern "C" int qt_shots_to_obs_moments_batch(int64_t B, int64_t n_shots, int n_q
     case 4: SWAR(4); break;
     case 8: SWAR(8); break;
     default:
-      moments_bytes_kernel<<<blocks, 256, 0, st>>>(B, n_shots, n_qubits, bits, col_mask, coeff, use_beta_prior,
+      moments_bytes_kernel<<<blocks, 256, 0, st>>>(B, n_shots, n_qubits, bits, col_mask, coeff, use_beta_prior, iv,
                                                    mean_out, var_out);
   }
 #undef SWAR
