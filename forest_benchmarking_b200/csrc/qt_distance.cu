@@ -100,11 +100,14 @@ __global__ void fidelity_kernel(int64_t B, const cplx* __restrict__ rho, const c
   }
   // scipy.linalg.eigh reads the lower triangle only: build the Hermitian matrix it sees
   auto load_rho = [&]() {
-    for (int e = lane; e < DD; e += 32) {
+    for (int e = lane; e < DD; e += 32) {  // coalesced read; the lower triangle is mirrored into the upper one
       const int i = e / D, j = e % D;
-      cplx v = (i >= j) ? r[e] : cconj(r[j * D + i]);
+      cplx v = r[e];
       if (i == j) v.y = 0.0;
-      A[i * LD + j] = v;
+      if (i >= j) {
+        A[i * LD + j] = v;
+        if (i > j) A[j * LD + i] = cconj(v);
+      }
     }
     __syncwarp();
   };
@@ -144,11 +147,13 @@ __global__ void fidelity_kernel(int64_t B, const cplx* __restrict__ rho, const c
       __syncwarp();
     }
     if (ok) {
-      // W = sigma L  (L lower triangular in A)
+      // W = sigma L  (L lower triangular in A); sigma is staged in V first (coalesced): V is free until L^dagger W
+      for (int e = lane; e < DD; e += 32) V[(e / D) * LD + e % D] = s[e];
+      __syncwarp();
       for (int e = lane; e < DD; e += 32) {
         const int i = e / D, j = e % D;
         cplx acc = cmake(0.0, 0.0);
-        for (int k = j; k < D; ++k) cfma(acc, s[i * D + k], A[k * LD + j]);
+        for (int k = j; k < D; ++k) cfma(acc, V[i * LD + k], A[k * LD + j]);
         W[i * LD + j] = acc;
       }
       __syncwarp();

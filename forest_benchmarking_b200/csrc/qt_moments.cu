@@ -89,7 +89,8 @@ __device__ __forceinline__ uint4 clip_word(uint4 w, long long e, long long lo, l
 // flight).  Words that lie entirely inside the setting's byte range take the unmasked loop (4 loads issued before the
 // first use); the at most two edge words shared with the neighbouring settings are masked byte-wise.
 template <int Q, int G>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256)  // 43 registers, 5 blocks per SM; capping at 32 registers measured slower
+   
     moments_swar_kernel(int64_t B, int64_t S, const unsigned char* __restrict__ bits,
                         const uint32_t* __restrict__ colmask, const double* __restrict__ coeff, int prior, MomInv iv,
                         double* __restrict__ mean, double* __restrict__ var) {
