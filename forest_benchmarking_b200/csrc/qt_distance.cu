@@ -68,10 +68,115 @@ struct FidSmem {
       (sizeof(cplx) * MP * 3 + sizeof(double) * (D + JacobiScratch<D>::doubles) + 15) / 16 * 16;
 };
 
+// Fast path of the fidelity for a numerically positive-definite rho: rho = L L^dagger (Cholesky), and the eigenvalues of
+// L^dagger sigma L are those of sqrt(rho) sigma sqrt(rho) (similar matrices), so ONE values-only eigendecomposition
+// replaces eigh(rho) with vectors + sqrtm + the second eigh.  Two matrices of shared memory per warp instead of three
+// and no eigenvector registers: 1.5x the resident warps of fidelity_kernel.  A pivot that is not safely positive
+// (rank-deficient or non-PSD input, where the reference's clamping in sqrtm_psd matters) writes FID_FLAG and leaves the
+// item to fidelity_kernel, which runs the reference's own sequence on the flagged items.
+constexpr double FID_FLAG = -1.0;  // a fidelity is never negative
+template <int D>
+struct FidFastSmem {
+  static constexpr int LD = FidSmem<D>::LD, MP = FidSmem<D>::MP;
+  static constexpr size_t bytes = (sizeof(cplx) * MP * 2 + sizeof(double) * (D + JacobiScratch<D>::doubles) + 15) / 16 * 16;
+};
+
+template <int D>
+__global__ void __launch_bounds__(256, (D == 16) ? 3 : 1) fidelity_fast_kernel(int64_t B, const cplx* __restrict__ rho, const cplx* __restrict__ sigma,
+                                     double* __restrict__ out) {
+  constexpr int DD = D * D, LD = FidFastSmem<D>::LD, MP = FidFastSmem<D>::MP, PER = (DD + 31) / 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  cplx* A = reinterpret_cast<cplx*>(smem_raw + FidFastSmem<D>::bytes * wib);
+  cplx* W = A + MP;
+  double* ev = reinterpret_cast<double*>(W + MP);
+  const int64_t b = (int64_t)blockIdx.x * wpb + wib;
+  if (b >= B) return;
+  const cplx* r = rho + b * DD;
+  const cplx* s = sigma + b * DD;
+  // scipy.linalg.eigh reads the lower triangle only: factor the Hermitian matrix it sees
+  for (int e = lane; e < DD; e += 32) {
+    const int i = e / D, j = e % D;
+    cplx v = r[e];
+    if (i == j) v.y = 0.0;
+    if (i >= j) A[i * LD + j] = v;
+  }
+  __syncwarp();
+  double dmax = 0.0;
+  for (int k = 0; k < D; ++k) dmax = fmax(dmax, A[k * LD + k].x);
+  const double thr = 1e-10 * dmax;
+  bool ok = dmax > 0.0;
+  for (int j = 0; j < D && ok; ++j) {
+    const double piv = A[j * LD + j].x;
+    if (!(piv > thr)) {
+      ok = false;
+      break;
+    }
+    const double inv = rsqrt(piv);
+    __syncwarp();
+    for (int i = j + lane; i < D; i += 32) A[i * LD + j] = (i == j) ? cmake(piv * inv, 0.0) : cscale(A[i * LD + j], inv);
+    __syncwarp();
+    const int nt = D - j - 1;
+    for (int e = lane; e < nt * nt; e += 32) {
+      const int i = j + 1 + e / nt, k = j + 1 + e % nt;
+      if (k <= i) {
+        const cplx li = A[i * LD + j], lk = A[k * LD + j];
+        cplx v = A[i * LD + k];
+        v.x -= li.x * lk.x + li.y * lk.y;  // v -= li * conj(lk)
+        v.y -= li.y * lk.x - li.x * lk.y;
+        if (i == k) v.y = 0.0;
+        A[i * LD + k] = v;
+      }
+    }
+    __syncwarp();
+  }
+  if (!ok) {
+    if (lane == 0) out[b] = FID_FLAG;
+    return;
+  }
+  // W = sigma L  (L lower triangular in A)
+  for (int e = lane; e < DD; e += 32) {
+    const int i = e / D, j = e % D;
+    cplx acc = cmake(0.0, 0.0);
+    for (int k = j; k < D; ++k) cfma(acc, s[i * D + k], A[k * LD + j]);
+    W[i * LD + j] = acc;
+  }
+  __syncwarp();
+  // Y = L^dagger W: lower triangle (incl. diagonal) held in registers until every lane has finished reading L, then
+  // written over A together with its conjugate mirror -- the Hermitian matrix an eigensolver reading the lower
+  // triangle would see
+  cplx y[PER];
+#pragma unroll
+  for (int t = 0; t < PER; ++t) {
+    const int e = lane + 32 * t, i = e / D, j = e % D;
+    cplx acc = cmake(0.0, 0.0);
+    if (e < DD && i >= j)
+      for (int k = i; k < D; ++k) cfma(acc, cconj(A[k * LD + i]), W[k * LD + j]);
+    y[t] = acc;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int t = 0; t < PER; ++t) {
+    const int e = lane + 32 * t, i = e / D, j = e % D;
+    if (e < DD && i >= j) {
+      cplx v = y[t];
+      if (i == j) v.y = 0.0;
+      A[i * LD + j] = v;
+      if (i > j) A[j * LD + i] = cconj(v);
+    }
+  }
+  __syncwarp();
+  jacobi_eigh<D, 32, SyncWarp, false, LD>(A, nullptr, ev, ev + D, lane);
+  double acc = 0.0;
+  for (int k = lane; k < D; k += 32) acc += sqrt(fmax(ev[k], 0.0));
+  acc = warp_sum(acc);
+  if (lane == 0) out[b] = acc * acc;
+}
+
 // MODE 0: fidelity.  MODE 1: nuclear-norm trace distance.
 template <int D, int MODE>
 __global__ void fidelity_kernel(int64_t B, const cplx* __restrict__ rho, const cplx* __restrict__ sigma,
-                                double* __restrict__ out) {
+                                double* __restrict__ out, int only_flagged) {
   constexpr int DD = D * D, LD = FidSmem<D>::LD, MP = FidSmem<D>::MP;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -81,6 +186,7 @@ __global__ void fidelity_kernel(int64_t B, const cplx* __restrict__ rho, const c
   double* ev = reinterpret_cast<double*>(W + MP);
   const int64_t b = (int64_t)blockIdx.x * wpb + wib;
   if (b >= B) return;
+  if (only_flagged && out[b] != FID_FLAG) return;  // fidelity_fast_kernel already produced this item
   const cplx* r = rho + b * DD;
   const cplx* s = sigma + b * DD;
   if constexpr (MODE == 1) {
@@ -112,75 +218,6 @@ __global__ void fidelity_kernel(int64_t B, const cplx* __restrict__ rho, const c
     __syncwarp();
   };
   load_rho();
-  // Fast path for a numerically positive-definite rho: rho = L L^dagger (Cholesky), and the eigenvalues of
-  // L^dagger sigma L are those of sqrt(rho) sigma sqrt(rho) (similar matrices), so ONE values-only
-  // eigendecomposition replaces eigh(rho) with vectors + sqrtm + the second eigh.  A pivot that is not safely
-  // positive (rank-deficient or non-PSD input, where the reference's clamping in sqrtm_psd matters) falls back to
-  // the reference's own sequence below.
-  if constexpr (D >= 4) {
-    double dmax = 0.0;
-    for (int k = 0; k < D; ++k) dmax = fmax(dmax, A[k * LD + k].x);
-    const double thr = 1e-10 * dmax;
-    bool ok = dmax > 0.0;
-    for (int j = 0; j < D && ok; ++j) {
-      const double piv = A[j * LD + j].x;
-      if (!(piv > thr)) {
-        ok = false;
-        break;
-      }
-      const double inv = rsqrt(piv);
-      __syncwarp();
-      for (int i = j + lane; i < D; i += 32) A[i * LD + j] = (i == j) ? cmake(piv * inv, 0.0) : cscale(A[i * LD + j], inv);
-      __syncwarp();
-      const int nt = D - j - 1;
-      for (int e = lane; e < nt * nt; e += 32) {
-        const int i = j + 1 + e / nt, k = j + 1 + e % nt;
-        if (k <= i) {
-          const cplx li = A[i * LD + j], lk = A[k * LD + j];
-          cplx v = A[i * LD + k];
-          v.x -= li.x * lk.x + li.y * lk.y;  // v -= li * conj(lk)
-          v.y -= li.y * lk.x - li.x * lk.y;
-          if (i == k) v.y = 0.0;
-          A[i * LD + k] = v;
-        }
-      }
-      __syncwarp();
-    }
-    if (ok) {
-      // W = sigma L  (L lower triangular in A); sigma is staged in V first (coalesced): V is free until L^dagger W
-      for (int e = lane; e < DD; e += 32) V[(e / D) * LD + e % D] = s[e];
-      __syncwarp();
-      for (int e = lane; e < DD; e += 32) {
-        const int i = e / D, j = e % D;
-        cplx acc = cmake(0.0, 0.0);
-        for (int k = j; k < D; ++k) cfma(acc, V[i * LD + k], A[k * LD + j]);
-        W[i * LD + j] = acc;
-      }
-      __syncwarp();
-      // V = L^dagger W, then the Hermitian matrix an eigensolver reading the lower triangle would see
-      for (int e = lane; e < DD; e += 32) {
-        const int i = e / D, j = e % D;
-        cplx acc = cmake(0.0, 0.0);
-        for (int k = i; k < D; ++k) cfma(acc, cconj(A[k * LD + i]), W[k * LD + j]);
-        V[i * LD + j] = acc;
-      }
-      __syncwarp();
-      for (int e = lane; e < DD; e += 32) {
-        const int i = e / D, j = e % D;
-        cplx v = (i >= j) ? V[i * LD + j] : cconj(V[j * LD + i]);
-        if (i == j) v.y = 0.0;
-        W[i * LD + j] = v;
-      }
-      __syncwarp();
-      jacobi_eigh<D, 32, SyncWarp, false, LD>(W, nullptr, ev, ev + D, lane);
-      double acc = 0.0;
-      for (int k = lane; k < D; k += 32) acc += sqrt(fmax(ev[k], 0.0));
-      acc = warp_sum(acc);
-      if (lane == 0) out[b] = acc * acc;
-      return;
-    }
-    load_rho();  // the factorisation overwrote A
-  }
   jacobi_eigh<D, 32, SyncWarp, true, LD>(A, V, ev, ev + D, lane);
   // S = V sqrt(max(ev,0)) V^dagger  -> A
   for (int e = lane; e < DD; e += 32) {
@@ -357,9 +394,20 @@ static int launch_fid(int64_t B, const void* rho, const void* sigma, double* out
   const size_t per_warp = FidSmem<D>::bytes;
   int wpb = (int)max((size_t)1, min((size_t)8, (size_t)(112 * 1024) / per_warp));
   const size_t smem = per_warp * wpb;
+  int only_flagged = 0;
+  if constexpr (MODE == 0 && D >= 4) {
+    const size_t per_fast = FidFastSmem<D>::bytes;
+    const int wf = (int)max((size_t)1, min((size_t)8, (size_t)(74 * 1024) / per_fast));
+    QT_CUDA(cudaFuncSetAttribute(fidelity_fast_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_fast * wf)));
+    fidelity_fast_kernel<D><<<(unsigned)((B + wf - 1) / wf), 32 * wf, per_fast * wf, st>>>(B, (const cplx*)rho,
+                                                                                          (const cplx*)sigma, out);
+    int rc = qt_check_launch("fidelity_fast_kernel");
+    if (rc) return rc;
+    only_flagged = 1;
+  }
   QT_CUDA(cudaFuncSetAttribute(fidelity_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   fidelity_kernel<D, MODE><<<(unsigned)((B + wpb - 1) / wpb), 32 * wpb, smem, st>>>(B, (const cplx*)rho,
-                                                                                    (const cplx*)sigma, out);
+                                                                                    (const cplx*)sigma, out, only_flagged);
   return qt_check_launch("fidelity_kernel");
 }
 

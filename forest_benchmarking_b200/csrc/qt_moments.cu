@@ -73,6 +73,16 @@ __device__ __forceinline__ unsigned swar_count(uint4 w, unsigned pat0, unsigned 
   return __popc(z & 0xfu);
 }
 
+// 16-byte load that never touches memory outside the tensor [tlo, thi): a word that straddles either end is assembled
+// from byte loads (only the first word of the first setting and the last word of the last one can do so)
+__device__ __forceinline__ uint4 ld16_inside(long long a, long long tlo, long long thi) {
+  if (a >= tlo && a + 16 <= thi) return *reinterpret_cast<const uint4*>(a);
+  unsigned w[4] = {0u, 0u, 0u, 0u};
+  for (int i = 0; i < 16; ++i)
+    if (a + i >= tlo && a + i < thi) w[i >> 2] |= (unsigned)(*reinterpret_cast<const unsigned char*>(a + i)) << (8 * (i & 3));
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // the bytes of the 16-byte word at flat address e that lie outside [lo, hi) are cleared
 __device__ __forceinline__ uint4 clip_word(uint4 w, long long e, long long lo, long long hi) {
   const int b0 = (int)max(lo - e, 0LL), b1 = (int)min(hi - e, 16LL);       // valid bytes [b0, b1)
@@ -122,7 +132,7 @@ __global__ void __launch_bounds__(256)  // 43 registers, 5 blocks per SM; cappin
     const bool need1 = live && (lo & 15), need2 = live && (hi & 15) && (E2 != E1 || !(lo & 15));
     if ((need1 && gl == 0) || (need2 && gl == (G > 1 ? 1 : 0))) {
       const long long e = (need1 && gl == 0) ? E1 : E2;
-      cnt += swar_count<Q>(clip_word(*reinterpret_cast<const uint4*>(e), e, lo, hi), pat0, pat1);
+      cnt += swar_count<Q>(clip_word(ld16_inside(e, base, base + B * S * Q), e, lo, hi), pat0, pat1);
     }
     unsigned long long tot = cnt;
 #pragma unroll
@@ -163,7 +173,7 @@ __global__ void __launch_bounds__(256)
         uint4 v[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
-          if (w + 32 * u < nwords) v[u] = *reinterpret_cast<const uint4*>(a0 + 16LL * (w + 32 * u));
+          if (w + 32 * u < nwords) v[u] = ld16_inside(a0 + 16LL * (w + 32 * u), base, base + B * S * Q);
 #pragma unroll
         for (int u = 0; u < 4; ++u)
           if (w + 32 * u < nwords) *reinterpret_cast<uint4*>(stage + 16 * (w + 32 * u)) = v[u];

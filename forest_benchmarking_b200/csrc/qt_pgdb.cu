@@ -21,6 +21,7 @@
 #include <algorithm>
 #include <cmath>
 #include <map>
+#include <mutex>
 #include <type_traits>
 #include <utility>
 #include <vector>
@@ -37,6 +38,7 @@ struct qt_pgdb_plan {
   int* d_li_slot_ptr = nullptr;    // [4^n + 1]  CSR over the observable's canonical Pauli index
   int* d_li_member_col = nullptr;  // [S]        column of `expect` of each member
   double* d_li_member_w = nullptr; // [S, 4^n]   row of the slot's pseudo-inverse that multiplies that expectation
+  std::mutex li_mutex;
 };
 
 struct PgdbView {
@@ -619,9 +621,12 @@ static int launch_linproc(const qt_pgdb_plan* p, int64_t B, const double* expect
 extern "C" int qt_linear_inv_process_batch(qt_pgdb_plan* p, int64_t B, const double* expect, void* choi_out,
                                            void* stream) {
   QT_REQUIRE(p, "qt_linear_inv_process_batch: null plan");
-  if (!p->d_li_member_w) {
-    const int rc = build_linear_inversion(p);
-    if (rc != QT_OK) return rc;
+  {
+    std::lock_guard<std::mutex> guard(p->li_mutex);  // two host threads may share one plan
+    if (!p->d_li_member_w) {
+      const int rc = build_linear_inversion(p);
+      if (rc != QT_OK) return rc;
+    }
   }
   if (B == 0) return QT_OK;
   QT_REQUIRE(expect && choi_out, "qt_linear_inv_process_batch: null argument");
