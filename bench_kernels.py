@@ -121,6 +121,11 @@ def convert_rows(torch, peak, batch=16384, nk=2, budget_bytes=6 << 30):
             rows.append(_row(f"choi2kraus n={n} (eigensolver: FP64-bound, GB/s for reference only)", chunk,
                              16 * m * m + 16 * m * m + 8 * m, ms, peak, {"chunks_for_batch": reps,
                                                                           "batch_ms": round(ms * reps, 3)}))
+        if n == 4:
+            sub = a[:148].contiguous()
+            ms = _time(torch, lambda: st.choi2kraus_batch(sub), reps=1, warmup=1)
+            rows.append(_row("choi2kraus n=4 (one-sided Jacobi out of L2, one 256x256 matrix per SM, 148 matrices)", 148,
+                             16 * m * m + 16 * m * m + 8 * m, ms, peak, {"chunks_for_batch": 1, "batch_ms": round(ms, 3)}))
         del kraus, a, b_, ws
         torch.cuda.empty_cache()
     return rows

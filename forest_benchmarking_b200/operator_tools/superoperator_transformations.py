@@ -115,7 +115,7 @@ def pauli_liouville2choi_batch(pl):
 
 
 def choi2kraus_batch(choi, tol: float = 1e-9):
-    """choi [B, d^2, d^2] (n <= 3) -> (kraus [B, d^2, d, d], counts [B] int32, evals [B, d^2] ascending).
+    """choi [B, d^2, d^2] (n <= 5) -> (kraus [B, d^2, d, d], counts [B] int32, evals [B, d^2] ascending).
     kraus[b, :counts[b]] are the operators sqrt(lambda) unvec(v) with |lambda| > tol in ascending-eigenvalue
     order (reference :325-336); the remaining slots are zero."""
     torch = _lib.require_cuda()
@@ -126,6 +126,15 @@ def choi2kraus_batch(choi, tol: float = 1e-9):
     kraus = torch.empty((b, d2, d, d), dtype=torch.complex128, device=choi.device)
     evals = torch.empty((b, d2), dtype=torch.float64, device=choi.device)
     counts = torch.empty((b,), dtype=torch.int32, device=choi.device)
+    if n >= 4:  # the eigenproblem does not fit shared memory: one-sided Jacobi out of an L2-resident workspace
+        lib = _lib.lib()
+        nbytes = int(lib.qt_choi2kraus_large_workspace_bytes(ctypes.c_int(n), ctypes.c_int64(b)))
+        ws = torch.empty((nbytes // 16,), dtype=torch.complex128, device=choi.device)
+        _lib.check(lib.qt_choi2kraus_large_batch(ctypes.c_int(n), ctypes.c_int64(b), _lib.ptr(choi), ctypes.c_double(tol),
+                                                 _lib.ptr(evals), _lib.ptr(kraus), _lib.ptr(counts), _lib.ptr(ws),
+                                                 ctypes.c_int64(nbytes), ctypes.c_void_p(0), _lib.current_stream_ptr()),
+                   "qt_choi2kraus_large_batch")
+        return kraus, counts, evals
     _lib.check(_lib.lib().qt_choi2kraus_batch(ctypes.c_int(n), ctypes.c_int64(b), _lib.ptr(choi), ctypes.c_double(tol),
                                               _lib.ptr(evals), _lib.ptr(kraus), _lib.ptr(counts),
                                               _lib.current_stream_ptr()), "qt_choi2kraus_batch")

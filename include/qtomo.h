@@ -96,6 +96,13 @@ int qt_pl2superop_batch(int n, int64_t B, const void* pl, void* superop_out, voi
  * Eigenvector phases are a gauge: compare via kraus2choi(choi2kraus(C)) == C (the reference's own test). */
 int qt_choi2kraus_batch(int n, int64_t B, const void* choi, double tol, double* evals_out, void* kraus_out,
                         int32_t* count_out, void* stream);
+/* choi2kraus for n = 4, 5 (the 4^n x 4^n eigenproblem does not fit shared memory): one-sided Jacobi out of an L2-resident
+ * workspace of qt_choi2kraus_large_workspace_bytes(n, B) bytes; same outputs as qt_choi2kraus_batch;
+ * sweeps_out[B] (may be NULL) = Jacobi sweeps taken */
+int64_t qt_choi2kraus_large_workspace_bytes(int n, int64_t B);
+int qt_choi2kraus_large_batch(int n, int64_t B, const void* choi, double tol, double* evals_out, void* kraus_out,
+                              int32_t* count_out, void* workspace, int64_t workspace_bytes, int32_t* sweeps_out,
+                              void* stream);
 
 /* ---- distance measures (distance_measures.py) -------------------------------------------------- */
 /* rho, sigma: [B, 2^n, 2^n]; out[B] doubles */

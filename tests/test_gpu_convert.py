@@ -161,3 +161,35 @@ def test_chi_matrix_family(torch):
         assert relerr(st.pauli_liouville2chi(orc.choi2pauli_liouville(c0)), want[0]) < 1e-9
         ks = st.chi2kraus(want[0])
         assert relerr(st.kraus2choi(ks), c0) < 1e-9
+
+
+@pytest.mark.parametrize("n,batch", [(4, 3), (5, 1)])
+def test_choi2kraus_large(torch, n, batch):
+    """a17 at n = 4, 5 (one-sided Jacobi out of a global workspace): eigenvalues vs numpy's eigh of the lower triangle,
+    the reference's own round trip kraus2choi(choi2kraus(C)) == C, and the operator count for a low-rank channel."""
+    from forest_benchmarking_b200.operator_tools import superoperator_transformations as st
+    rng = np.random.default_rng(70 + n)
+    d, m = 2 ** n, 4 ** n
+    chois = []
+    for i in range(batch):
+        ks = [rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)) for _ in range(3)]
+        c = sum(orc.kraus2choi(k) for k in ks) / (3 * d)
+        if i == 0:
+            g = rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m))
+            c = c + 1e-3 * (g + g.conj().T)  # full rank, indefinite
+        chois.append(c)
+    chois = np.stack(chois)
+    kraus, counts, evals = st.choi2kraus_batch(torch.from_numpy(chois).cuda())
+    kraus, counts, evals = kraus.cpu().numpy(), counts.cpu().numpy(), evals.cpu().numpy()
+    for b in range(batch):
+        want = np.linalg.eigvalsh(chois[b])
+        assert np.abs(evals[b] - want).max() < 1e-11 * np.abs(want).max()
+        assert counts[b] == int((np.abs(want) > 1e-9).sum())
+        back = sum(orc.kraus2choi(k) for k in kraus[b, :counts[b]])
+        # negative eigenvalues come back as i sqrt|l| v, whose outer product is +|l| v v^dagger: compare the PSD part
+        vals, vecs = np.linalg.eigh(chois[b])
+        ref = (vecs * np.abs(np.where(np.abs(vals) > 1e-9, vals, 0.0))) @ vecs.conj().T
+        assert relerr(back, ref) < 1e-9
+        assert np.abs(kraus[b, counts[b]:]).max(initial=0.0) == 0.0
+    if batch > 1:
+        assert counts[1] == 3
