@@ -107,16 +107,16 @@ def _cpu_mle_item(args):
     pidx, ex, cnt, n, kw = args
     from oracle import ref_numpy as orc
     t0 = time.perf_counter()
-    _, it = orc.mle_state_estimate(pidx, np.ones(len(pidx)), ex, cnt, n, rebuild_paulis=True, **kw)
-    return time.perf_counter() - t0, it
+    rho, it = orc.mle_state_estimate(pidx, np.ones(len(pidx)), ex, cnt, n, rebuild_paulis=True, **kw)
+    return time.perf_counter() - t0, it, rho
 
 
-def cpu_mle_sample(n, items, procs, seed=2002):
+def cpu_mle_sample(n, items, procs, seed=2002, data=None, return_states=False):
     """Times the faithful scalar port of iterative_mle_state_estimate (re-krons the Pauli matrices every
     iteration like the reference's lifted_pauli call, tomography.py:327) on `items` experiments spread
     over `procs` processes.  Returns (items/s, per-item seconds, iterations)."""
     from forest_benchmarking_b200 import synthetic as sy
-    pidx, ex, cnt, _ = sy.state_tomography_batch(seed, items, n)
+    pidx, ex, cnt = data if data is not None else sy.state_tomography_batch(seed, items, n)[:3]
     jobs = [(pidx, ex[i], cnt[i], n, MLE_DEFAULTS) for i in range(items)]
     t0 = time.perf_counter()
     if procs > 1:
@@ -126,7 +126,33 @@ def cpu_mle_sample(n, items, procs, seed=2002):
     else:
         res = [_cpu_mle_item(j) for j in jobs]
     wall = time.perf_counter() - t0
+    if return_states:
+        return items / wall, [r[0] for r in res], [r[1] for r in res], np.stack([r[2] for r in res])
     return items / wall, [r[0] for r in res], [r[1] for r in res]
+
+
+def _cpu_pgdb_item(args):
+    settings, ex, cnt, n = args
+    from oracle import ref_numpy as orc
+    t0 = time.perf_counter()
+    choi, c = orc.pgdb_process_estimate(settings, np.ones(len(settings)), ex, cnt, n, return_counters=True)
+    return time.perf_counter() - t0, c, choi
+
+
+def cpu_pgdb_sample(n, codes, pidx, ex, cnt, procs):
+    """Times the oracle port of pgdb_process_estimate (dense design matrix, like the reference) on the given
+    experiments, one per process.  Returns (items/s, per-item seconds, counters, choi matrices)."""
+    settings = [(tuple(int(c) for c in s), int(k)) for s, k in zip(codes, pidx)]
+    jobs = [(settings, ex[i], cnt[i], n) for i in range(len(ex))]
+    t0 = time.perf_counter()
+    if procs > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_cpu_pgdb_item, jobs, chunksize=1)
+    else:
+        res = [_cpu_pgdb_item(j) for j in jobs]
+    wall = time.perf_counter() - t0
+    return len(jobs) / wall, [r[0] for r in res], [r[1] for r in res], np.stack([r[2] for r in res])
 
 
 def run_reference_arm(args):
@@ -313,12 +339,20 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             procs = min(cores, 8)
-            v, per_item, its = cpu_mle_sample(2, procs, procs)
+            # the first `procs` experiments of the batch the GPU just reconstructed: baseline timing AND parity
+            v, per_item, its, rho_cpu = cpu_mle_sample(2, procs, procs, data=(pidx, ex[:procs], cnt[:procs]),
+                                                       return_states=True)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
                                     "sec_per_item_one_core": float(np.mean(per_item)),
-                                    "sample": f"{procs} experiments of the same workload, one per process "
+                                    "sample": f"the first {procs} experiments of the GPU batch, one per process "
                                               f"(host has {cores} cores), oracle scalar port with per-iteration "
                                               f"Pauli re-kron like the reference; iterations {its}"}
+            rho_gpu, it_gpu = rho[:procs].cpu().numpy(), iters[:procs].cpu().numpy()
+            errs = [float(np.linalg.norm(rho_gpu[i] - rho_cpu[i]) / np.linalg.norm(rho_cpu[i])) for i in range(procs)]
+            line["parity"] = {"max_rel_frobenius_err": max(errs), "tolerance": 1e-6, "items": procs,
+                              "iteration_count_mismatches": int(sum(int(a) != int(b) for a, b in zip(it_gpu, its))),
+                              "against": "oracle port (pinned to the reference, tests/test_oracle_vs_reference.py) "
+                                         "on the same experiments"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -431,6 +465,22 @@ def run_pgdb(args):
                                       "frac": B * bytes_item / (ms_res * 1e-3) / 1e9 / hbm_peak,
                                       "note": "compulsory bytes only"}},
         }
+        want_cpu = (n <= 2 and not args.no_cpu_baseline) or args.cpu_baseline
+        if world == 1 and want_cpu:
+            os.environ.setdefault("OMP_NUM_THREADS", "1")
+            cores = os.cpu_count() or 1
+            items = min(cores, 8) if n <= 2 else 2
+            v, per_item, cs, choi_cpu = cpu_pgdb_sample(n, codes, pidx, ex[:items], cnt[:items], items)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": items, "kind": "port",
+                                    "sec_per_item_one_core": float(np.mean(per_item)),
+                                    "sample": f"the first {items} experiments of the GPU batch, one per process (host has "
+                                              f"{cores} cores), oracle port with the reference's dense design matrix"}
+            choi_gpu = out[:items].cpu().numpy()
+            errs = [float(np.linalg.norm(choi_gpu[i] - choi_cpu[i]) / np.linalg.norm(choi_cpu[i])) for i in range(items)]
+            line["parity"] = {"max_rel_frobenius_err": max(errs), "tolerance": 1e-6, "items": items,
+                              "outer_iteration_mismatches": int(sum(int(counters[i, 0]) != int(cs[i]["outer"])
+                                                                    for i in range(items))),
+                              "against": "oracle port (pinned to the reference) on the same experiments"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -488,6 +538,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-baseline", action="store_true", help="pgdb3q: also time 2 experiments on the host (minutes)")
     ap.add_argument("--eigh-tol", type=float, default=None, help="experiment: qt_set_eigh_tolerance value")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
