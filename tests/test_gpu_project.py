@@ -100,3 +100,24 @@ def test_proj_choi_to_unitary(torch, n, batch):
     fixed = pj.proj_choi_to_unitary_batch(torch.from_numpy(exact).cuda()).cpu().numpy()
     assert max_relerr(fixed, exact) < 1e-10
     assert relerr(pj.proj_choi_to_unitary(chois[0]), orc.proj_choi_to_unitary(chois[0])) < 1e-9
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_tni_in_place_and_out_of_place_agree(torch, n):
+    """The trace-non-increasing projection takes the two-pass path out of place (n >= 2) and the fused kernel in
+    place: both must give the oracle's answer, also for inputs whose partial trace has eigenvalues above AND below 1."""
+    from forest_benchmarking_b200.operator_tools import project_superoperators as ps
+    rng = np.random.default_rng(90 + n)
+    d, m = 2 ** n, 4 ** n
+    xs = []
+    for b in range(37):
+        g = rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m))
+        xs.append((g @ g.conj().T) * (rng.uniform(.3, 2.0) / m) + 0.05 * g)
+    xs = np.stack(xs)
+    want = np.stack([orc.proj_choi_to_trace_non_increasing(x) for x in xs])
+    xd = torch.from_numpy(xs).cuda()
+    oop = ps.proj_choi_to_trace_non_increasing_batch(xd).cpu().numpy()
+    inp = xd.clone()
+    ps.proj_choi_to_trace_non_increasing_batch(inp, out=inp)
+    assert max_relerr(oop, want) < 1e-12
+    assert max_relerr(inp.cpu().numpy(), want) < 1e-12
