@@ -119,6 +119,61 @@ def golden_distances(ref, name, seed, n, batch):
     print(f"{name}: done")
 
 
+def golden_next_rows(ref, name="next_rows"):
+    """linear-inversion process estimate, closest unitary, log-likelihood, shots -> moments,
+    ratio variance -- all outputs from the reference's own functions."""
+    from forest.benchmarking.operator_tools.project_superoperators import proj_choi_to_unitary
+    from forest.benchmarking.observable_estimation import shots_to_obs_moments, ratio_variance
+    from pyquil.paulis import PauliTerm
+    out = {}
+    # linear_inv_process_estimate: 1 qubit Pauli + SIC, 2 qubits SIC
+    for tag, seed, n, basis in (("lip_1q_pauli", 6001, 1, "pauli"), ("lip_1q_sic", 6002, 1, "sic"), ("lip_2q_sic", 6003, 2, "sic")):
+        _, settings, ex, cnt = orc.synth_process_tomography(seed, 3, n, in_basis=basis)
+        qubits = list(range(n))
+        coeffs = np.ones(len(settings))
+        out[tag + "_codes"] = np.array([s for s, _ in settings], dtype=np.int32)
+        out[tag + "_pidx"] = np.array([k for _, k in settings], dtype=np.int32)
+        out[tag + "_ex"] = ex
+        out[tag + "_choi"] = np.stack([ref.tomo.linear_inv_process_estimate(
+            rb.process_results(ref, settings, coeffs, ex[b], cnt[b], qubits), qubits) for b in range(3)])
+    # proj_choi_to_unitary
+    rng = np.random.default_rng(6004)
+    for n in (1, 2, 3):
+        d = 2 ** n
+        xs = []
+        for _ in range(4):
+            u = orc.haar_unitary(rng, d)
+            g = rng.standard_normal((d * d, d * d)) + 1j * rng.standard_normal((d * d, d * d))
+            xs.append(.9 * orc.kraus2choi(u) + .1 * (g @ g.conj().T) / d ** 2 + .01 * g)
+        xs = np.stack(xs)
+        out[f"unitary_n{n}_in"] = xs
+        out[f"unitary_n{n}_out"] = np.stack([proj_choi_to_unitary(x) for x in xs])
+    # state_log_likelihood
+    rho, pidx, ex, cnt = orc.synth_state_tomography(6005, 4, 2)
+    qubits = [0, 1]
+    out["ll_rho"], out["ll_pidx"], out["ll_ex"], out["ll_cnt"] = rho, pidx, ex, cnt
+    out["ll_value"] = np.array([ref.tomo.state_log_likelihood(
+        rho[b], rb.state_results(ref, pidx, np.ones(len(pidx)), ex[b], cnt[b], qubits), qubits) for b in range(4)])
+    # shots_to_obs_moments (qc.run returns int64 bits) and ratio_variance
+    rng = np.random.default_rng(6006)
+    qubits = [4, 7, 9]
+    bits = (rng.random((6, 300, 3)) < rng.uniform(.1, .9, size=(6, 1, 3))).astype(np.uint8)
+    masks = np.array([1, 2, 4, 3, 6, 7], dtype=np.int32)
+    coeffs = np.array([1.0, -1.0, 0.5, 2.0, 1.0, -0.25])
+    mom = np.empty((2, 6, 2))
+    for i in range(6):
+        ops = [("Z", q) for c, q in enumerate(qubits) if (masks[i] >> c) & 1]
+        term = PauliTerm.from_list(ops, coefficient=coeffs[i])
+        for prior in (0, 1):
+            mom[prior, i] = shots_to_obs_moments(bits[i].astype(np.int64), qubits, term, bool(prior))
+    out["mom_bits"], out["mom_masks"], out["mom_coeffs"], out["mom_out"] = bits, masks, coeffs, mom
+    a, va, b, vb = rng.uniform(-1, 1, 16), rng.uniform(1e-4, 1e-2, 16), rng.uniform(.7, 1, 16), rng.uniform(1e-5, 1e-3, 16)
+    out["rv_in"] = np.stack([a, va, b, vb])
+    out["rv_out"] = ratio_variance(a, va, b, vb)
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print(f"{name}: done")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-3q", action="store_true")
@@ -143,6 +198,7 @@ def main():
         "pgdb2": lambda: [golden_pgdb(ref, "pgdb_2q_pauli", 3003, 4, 2, "pauli"),
                           golden_pgdb(ref, "pgdb_2q_sic", 3006, 4, 2, "sic"),
                           golden_pgdb(ref, "pgdb_2q_sic_mixed", 3007, 2, 2, "sic", unitary=False)],
+        "next": lambda: golden_next_rows(ref),
         "pgdb3": lambda: [golden_pgdb(ref, "pgdb_3q_sic", 3008, 1, 3, "sic"),
                           golden_pgdb(ref, "pgdb_3q_pauli", 3003, 1, 3, "pauli")],
     }

@@ -81,3 +81,34 @@ def test_calibrate_estimates_batch(torch):
     assert np.allclose(cm.cpu().numpy(), a / b, rtol=1e-15)
     assert np.allclose(cv.cpu().numpy(), orc.ratio_variance(a, va, b, vb), rtol=1e-14)
     assert np.allclose(oe.ratio_variance(a, va, b, vb), orc.ratio_variance(a, va, b, vb), rtol=1e-15)
+
+
+def test_next_rows_golden(torch):
+    """Every SURVEY 8(f) entry point against outputs of the reference's own functions (tests/golden/next_rows.npz)."""
+    from util import golden, relerr
+    from forest_benchmarking_b200 import observable_estimation as oe, tomography as tm
+    from forest_benchmarking_b200.operator_tools import project_superoperators as pj
+    g = golden("next_rows")
+    for tag, n in (("lip_1q_pauli", 1), ("lip_1q_sic", 1), ("lip_2q_sic", 2)):
+        plan = tm.PgdbPlan(n, g[tag + "_codes"], g[tag + "_pidx"])
+        got = tm.linear_inv_process_estimate_batch(plan, torch.from_numpy(np.ascontiguousarray(g[tag + "_ex"])).cuda())
+        for b in range(3):
+            assert relerr(got[b].cpu().numpy(), g[tag + "_choi"][b]) < 1e-10
+    for n in (1, 2, 3):
+        got = pj.proj_choi_to_unitary_batch(torch.from_numpy(g[f"unitary_n{n}_in"]).cuda()).cpu().numpy()
+        for b in range(4):
+            assert relerr(got[b], g[f"unitary_n{n}_out"][b]) < 1e-9
+    plan = tm.MlePlan(2, g["ll_pidx"])
+    ll = tm.state_log_likelihood_batch(plan, torch.from_numpy(g["ll_rho"]).cuda(), torch.from_numpy(g["ll_ex"]).cuda(),
+                                       torch.from_numpy(g["ll_cnt"].astype(np.float64)).cuda()).cpu().numpy()
+    assert np.max(np.abs(ll - g["ll_value"]) / np.abs(g["ll_value"])) < 1e-11
+    for prior in (0, 1):
+        mean, var = oe.shots_to_obs_moments_batch(torch.from_numpy(g["mom_bits"]).cuda(),
+                                                  torch.from_numpy(g["mom_masks"]).cuda(),
+                                                  torch.from_numpy(g["mom_coeffs"]).cuda(), bool(prior))
+        assert np.allclose(mean.cpu().numpy(), g["mom_out"][prior, :, 0], rtol=1e-13, atol=1e-16)
+        assert np.allclose(var.cpu().numpy(), g["mom_out"][prior, :, 1], rtol=1e-12, atol=1e-18)
+    a, va, b, vb = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in g["rv_in"])
+    cm, cv = oe.calibrate_estimates_batch(a, va, b, vb)
+    assert np.allclose(cv.cpu().numpy(), g["rv_out"], rtol=1e-14)
+    assert np.allclose(cm.cpu().numpy(), g["rv_in"][0] / g["rv_in"][2], rtol=1e-15)

@@ -89,3 +89,26 @@ def test_pgdb(name):
                                              n, trace_preserving=bool(g["trace_preserving"]), return_counters=True)
         assert relerr(est, g["choi_ref"][b]) < 1e-9
         assert (cnt["eighs"], cnt["cost_evals"]) == tuple(g["counters_ref"][b])
+
+
+def test_next_rows():
+    """SURVEY 8(f) rows against outputs of the reference's own functions (oracle/make_golden.py --only next)."""
+    g = golden("next_rows")
+    for tag, n in (("lip_1q_pauli", 1), ("lip_1q_sic", 1), ("lip_2q_sic", 2)):
+        settings = [(tuple(int(c) for c in s), int(k)) for s, k in zip(g[tag + "_codes"], g[tag + "_pidx"])]
+        for b in range(3):
+            got = orc.linear_inv_process_estimate(settings, np.ones(len(settings)), g[tag + "_ex"][b], n)
+            assert relerr(got, g[tag + "_choi"][b]) < 1e-11
+    for n in (1, 2, 3):
+        for x, want in zip(g[f"unitary_n{n}_in"], g[f"unitary_n{n}_out"]):
+            assert relerr(orc.proj_choi_to_unitary(x), want) < 1e-11
+    for b in range(4):
+        got = orc.state_log_likelihood(g["ll_rho"][b], g["ll_pidx"], np.ones(len(g["ll_pidx"])), g["ll_ex"][b], g["ll_cnt"][b], 2)
+        assert abs(got - g["ll_value"][b]) < 1e-10 * abs(g["ll_value"][b])
+    for i in range(6):
+        idxs = [c for c in range(3) if (g["mom_masks"][i] >> c) & 1]
+        for prior in (0, 1):
+            got = orc.shots_to_obs_moments(g["mom_bits"][i], idxs, g["mom_coeffs"][i], bool(prior))
+            assert np.allclose(got, g["mom_out"][prior, i], rtol=1e-13, atol=1e-17)
+    a, va, b, vb = g["rv_in"]
+    assert np.allclose(orc.ratio_variance(a, va, b, vb), g["rv_out"], rtol=1e-15)
