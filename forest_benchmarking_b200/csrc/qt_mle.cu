@@ -269,13 +269,15 @@ __global__ void __launch_bounds__(32) mle_quad_kernel(int64_t B, int K, const in
     if (c == 0) iters_out[b] = it;
     done = true;
   }
-#pragma unroll 2
-  while (!__all_sync(0xffffffffu, done)) {
+  // One R-rho-R update Rin -> Rout (+ the squared Frobenius distance between them).  The convergence test of a trip is
+  // evaluated one trip LATER (`settle`), so its compare / shuffle / vote / branch chain never sits between two
+  // updates; the two state register sets alternate, which keeps the state a late test has to store intact.
+  auto update = [&](const Herm<D>& Rin, Herm<D>& Rout, double& diff_out) {
     // ---- th[j] = Tr(P_j R_c) / 2 for all 16 Paulis (static butterfly on the Hermitian-packed state) ----
     double th[S];
     {
-      const double s01 = R.h[0][0] + R.h[1][1], m01 = R.h[0][0] - R.h[1][1];
-      const double s23 = R.h[2][2] + R.h[3][3], m23 = R.h[2][2] - R.h[3][3];
+      const double s01 = Rin.h[0][0] + Rin.h[1][1], m01 = Rin.h[0][0] - Rin.h[1][1];
+      const double s23 = Rin.h[2][2] + Rin.h[3][3], m23 = Rin.h[2][2] - Rin.h[3][3];
       th[pauli_from_masks(0, 0, N)] = 0.5 * (s01 + s23);
       th[pauli_from_masks(0, 1, N)] = 0.5 * (m01 + m23);
       th[pauli_from_masks(0, 2, N)] = 0.5 * (s01 - s23);
@@ -294,7 +296,7 @@ __global__ void __launch_bounds__(32) mle_quad_kernel(int64_t B, int K, const in
           if (a < (a ^ x)) {
             // pair (a, a^x): even phase -> +-2 Re, odd phase -> -+2 Im of element (a, a^x)
             const bool neg = ((popc_c(z & a) & 1) != 0) != (odd ? (ph == 1) : (ph == 2));
-            const double v = odd ? R.im(a, a ^ x) : R.re(a, a ^ x);
+            const double v = odd ? Rin.im(a, a ^ x) : Rin.re(a, a ^ x);
             if (first) acc = neg ? -v : v;
             else acc = neg ? acc - v : acc + v;
             first = false;
@@ -367,7 +369,7 @@ __global__ void __launch_bounds__(32) mle_quad_kernel(int64_t B, int K, const in
       double ar = 0.0, ai = 0.0;
 #pragma unroll
       for (int k = 0; k < D; ++k) {
-        const double pr = R.re(r, k), pi = R.im(r, k), mr = M.re(k, 0), mi = M.im(k, 0);
+        const double pr = Rin.re(r, k), pi = Rin.im(r, k), mr = M.re(k, 0), mi = M.im(k, 0);
         ar = fma(pr, mr, ar);
         if (k != 0) ai = fma(pr, mi, ai);
         if (r != k) {
@@ -421,22 +423,40 @@ __global__ void __launch_bounds__(32) mle_quad_kernel(int64_t B, int K, const in
 #pragma unroll
       for (int k = 0; k < D; ++k) {
         const double v = nw.h[r][k] * inv;
-        const double dlt = v - R.h[r][k];
+        const double dlt = v - Rin.h[r][k];
         if (r == k) dd[r] = dlt * dlt;
         else dx[r ^ k] = fma(dlt, dlt, dx[r ^ k]);
-        R.h[r][k] = v;
+        Rout.h[r][k] = v;
       }
-    const double diff = ((dd[0] + dd[1]) + (dd[2] + dd[3])) + 2.0 * ((dx[1] + dx[2]) + dx[3]);
-    const int conv = __shfl_sync(0xffffffffu, (int)(diff < tol2), qbase);
+    diff_out = ((dd[0] + dd[1]) + (dd[2] + dd[3])) + 2.0 * ((dx[1] + dx[2]) + dx[3]);
+  };
+  // deferred bookkeeping of the PREVIOUS trip, whose result `Rnew` is the input of the trip that has just been issued
+  auto settle = [&](const Herm<D>& Rnew, double diff_prev) {
+    const int conv = __shfl_sync(0xffffffffu, (int)(diff_prev < tol2), qbase);
     if (!done && !conv) ++it;
     if (!done && (conv || it >= maxiter)) {
       cplx* out = rho_out + b * (D * D) + c * D;
-      out[c] = cmake(R.h[0][0], 0.0);
+      out[c] = cmake(Rnew.h[0][0], 0.0);
 #pragma unroll
-      for (int k = 1; k < D; ++k) out[k ^ c] = cmake(R.re(0, k), R.im(0, k));
+      for (int k = 1; k < D; ++k) out[k ^ c] = cmake(Rnew.re(0, k), Rnew.im(0, k));
       if (c == 0) iters_out[b] = it;
       done = true;
     }
+  };
+  // `it` starts one short and the first settle (nothing pending: distance = infinity) brings it to the
+  // reference's initial 1 without storing anything
+  Herm<D> R2;
+  double diff_pend = 1e300, diff_new;
+  if (!done) it = 0;
+  while (true) {
+    update(R, R2, diff_new);
+    settle(R, diff_pend);
+    diff_pend = diff_new;
+    if (__all_sync(0xffffffffu, done)) break;
+    update(R2, R, diff_new);
+    settle(R2, diff_pend);
+    diff_pend = diff_new;
+    if (__all_sync(0xffffffffu, done)) break;
   }
 }
 
