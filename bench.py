@@ -322,9 +322,9 @@ def run_ours(args):
                 "unit": "TFLOP/s", "frac": flops / (ms_kernel * 1e-3) / 1e12 / fp64_peak,
                 "peak_source": "measured live: qt_fp64_probe DFMA chains (MEASURED_PEAKS.json has no FP64 entry)",
                 "flop_model": "SURVEY.md 8(d): iters*(16d^3+10Kd+10K+6d^2) = 1870/iteration at n=2,K=15, actual iters",
-                "traffic": 520448,
+                "traffic": 524032,
                 "traffic_note": "dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full "
-                                "(profiles/r01_ncu_mle_quad_kernel_v1.md); the 1.5 MB of inputs/outputs stay in L2",
+                                "(profiles/r01_ncu_mle_quad_kernel_final.md); the 1.5 MB of inputs/outputs stay in L2",
                 "hbm_view": {"bound": "hbm", "achieved": B * bytes_item / (ms_kernel * 1e-3) / 1e9, "peak": hbm_peak,
                              "unit": "GB/s", "frac": B * bytes_item / (ms_kernel * 1e-3) / 1e9 / hbm_peak,
                              "note": "compulsory bytes only (380 B/item); the loop state never leaves registers, "
