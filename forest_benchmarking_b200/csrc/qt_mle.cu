@@ -746,6 +746,138 @@ __global__ void mle_step_kernel(int64_t B, int K, const double* __restrict__ exp
   for (int e = tid; e < nb * DD; e += 128) rho_out[b0 * DD + e] = tile[(e % DD) * 128 + (e / DD)];
 }
 
+// n = 2 with the Hermitian-packed arithmetic of mle_reg_kernel (rho is a state: its upper triangle is read): ~750
+// FP64 instructions per item instead of ~1160 with general complex products, and 16 state registers instead of 32.
+__global__ void __launch_bounds__(128) mle_step_herm_kernel(int64_t B, int K, const double* __restrict__ expect_canon,
+                                                            const cplx* __restrict__ rho_in, double eps,
+                                                            cplx* __restrict__ rho_out) {
+  constexpr int N = 2, D = 4, S = 16, DD = 16;
+  constexpr double TINY = 2.2250738585072014e-308;
+  __shared__ cplx tile[128 * DD];
+  const int tid = threadIdx.x;
+  const int64_t b0 = (int64_t)blockIdx.x * 128;
+  const int nb = (int)min((int64_t)128, B - b0);
+  for (int e = tid; e < nb * DD; e += 128) tile[(e % DD) * 128 + (e / DD)] = rho_in[b0 * DD + e];
+  __syncthreads();
+  if (tid < nb) {
+    Herm<D> rho;
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int c = r; c < D; ++c) {
+        const cplx e = tile[(r * D + c) * 128 + tid];
+        if (r == c) {
+          rho.h[r][r] = e.x;
+        } else {
+          rho.h[r][c] = e.x;
+          rho.h[c][r] = e.y;
+        }
+      }
+    double w[S];
+    double w0 = 0.0;
+    w[0] = 0.0;
+#pragma unroll
+    for (int j = 1; j < S; ++j) {
+      const int x = pauli_xmask(j, N), z = pauli_zmask(j, N);
+      const int ph = popc_c(x & z) & 3;
+      double t = 0.0;
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        const int r = c ^ x;  // Re( i^ph * rho[c, r] )
+        double v;
+        if (ph == 0) v = rho.re(c, r);
+        else if (ph == 1) v = -rho.im(c, r);
+        else if (ph == 2) v = -rho.re(c, r);
+        else v = rho.im(c, r);
+        t += ((popc_c(z & c) & 1) ? -1.0 : 1.0) * v;
+      }
+      const double e = expect_canon[(int64_t)(j - 1) * B + b0 + tid];
+      const double pp = 0.5 * (1.0 + t) + TINY, pm = 0.5 * (1.0 - t) + TINY;
+      const double ipm = fast_rcp(pp * pm);
+      const double ap = (0.5 * (1.0 + e)) * pm * ipm, am = (0.5 * (1.0 - e)) * pp * ipm;
+      w0 += 0.5 * (ap + am);
+      w[j] = 0.5 * (ap - am);
+    }
+    w[0] = w0;
+    const double sc = eps / (double)K;
+    Herm<D> M;
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int c = r; c < D; ++c) {
+        const int x = r ^ c;
+        double sre = 0.0, sim = 0.0;
+#pragma unroll
+        for (int z = 0; z < D; ++z) {
+          const int j = pauli_from_masks(x, z, N);
+          const int ph = popc_c(x & z) & 3;
+          const double sgn = (popc_c(z & c) & 1) ? -1.0 : 1.0;
+          if (ph == 0) sre += sgn * w[j];
+          else if (ph == 1) sim += sgn * w[j];
+          else if (ph == 2) sre -= sgn * w[j];
+          else sim -= sgn * w[j];
+        }
+        if (r == c) {
+          M.h[r][r] = (1.0 - eps) + sc * sre;
+        } else {
+          M.h[r][c] = sc * sre;
+          M.h[c][r] = sc * sim;
+        }
+      }
+    double Tr_[D][D], Ti_[D][D];
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        double ar = 0.0, ai = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const double mr = M.re(r, k), mi = M.im(r, k), pr = rho.re(k, c), pi = rho.im(k, c);
+          ar = fma(mr, pr, ar);
+          if (k != c) ai = fma(mr, pi, ai);
+          if (r != k) {
+            if (k != c) ar = fma(-mi, pi, ar);
+            ai = fma(mi, pr, ai);
+          }
+        }
+        Tr_[r][c] = ar;
+        Ti_[r][c] = ai;
+      }
+    Herm<D> nw;
+    double tr = 0.0;
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int c = r; c < D; ++c) {
+        double ar = 0.0, ai = 0.0;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          const double mr = M.re(k, c), mi = M.im(k, c);
+          ar = fma(Tr_[r][k], mr, ar);
+          if (k != c) ar = fma(-Ti_[r][k], mi, ar);
+          if (r != c) {
+            ai = fma(Ti_[r][k], mr, ai);
+            if (k != c) ai = fma(Tr_[r][k], mi, ai);
+          }
+        }
+        if (r == c) {
+          nw.h[r][r] = ar;
+          tr += ar;
+        } else {
+          nw.h[r][c] = ar;
+          nw.h[c][r] = ai;
+        }
+      }
+    const double inv = fast_rcp(tr);
+#pragma unroll
+    for (int r = 0; r < D; ++r)
+#pragma unroll
+      for (int c = 0; c < D; ++c) tile[(r * D + c) * 128 + tid] = cmake(nw.re(r, c) * inv, nw.im(r, c) * inv);
+  }
+  __syncthreads();
+  for (int e = tid; e < nb * DD; e += 128) rho_out[b0 * DD + e] = tile[(e % DD) * 128 + (e / DD)];
+}
+
 // =============================================================================================
 // Linear inversion (tomography.py:130-165): rho = unvec(pinv(M) e) + I/d with rows M_k = c_k vec(P_k)^dagger.
 // Distinct Paulis are orthogonal, so M^dagger M is diagonal in the Pauli basis and the pseudo-inverse is a
@@ -959,7 +1091,7 @@ extern "C" int qt_mle_step_batch(int n, int64_t B, const double* expect_canon, c
   if (n == 1)
     mle_step_kernel<1><<<blocks, 128, 0, st>>>(B, K, expect_canon, (const cplx*)rho_in, epsilon, (cplx*)rho_out);
   else
-    mle_step_kernel<2><<<blocks, 128, 0, st>>>(B, K, expect_canon, (const cplx*)rho_in, epsilon, (cplx*)rho_out);
+    mle_step_herm_kernel<<<blocks, 128, 0, st>>>(B, K, expect_canon, (const cplx*)rho_in, epsilon, (cplx*)rho_out);
   return qt_check_launch("mle_step_kernel");
 }
 

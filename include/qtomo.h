@@ -62,7 +62,8 @@ int qt_linear_inv_state_batch(const qt_mle_plan* plan, int64_t B, const double* 
 int qt_state_log_likelihood_batch(const qt_mle_plan* plan, int64_t B, const void* rho, const double* expect,
                                   const double* counts, double* ll_out, void* stream);
 /* ONE R rho R update, rho streamed HBM -> HBM (n = 1, 2; complete canonical Pauli set, K = 4^n - 1).
- * expect_canon[K, B] (item-minor).  The HBM-roofline view of the update. */
+ * expect_canon[K, B] (item-minor); rho_in must be Hermitian (a state: at n = 2 only its upper triangle is read).
+ * The HBM-roofline view of the update. */
 int qt_mle_step_batch(int n, int64_t B, const double* expect_canon, const void* rho_in, double epsilon,
                       void* rho_out, void* stream);
 
