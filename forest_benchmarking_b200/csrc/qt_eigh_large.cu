@@ -6,31 +6,34 @@
 //                   exactly when the eigenvalues are (a plain one-sided sweep on an indefinite matrix cannot separate
 //                   +lambda from -lambda);
 //   each step orthogonalises M/2 disjoint column pairs (round-robin order): a warp forms the 2 x 2 Gram matrix of its
-//   pair with coalesced loads + shuffles, and applies the rotation that diagonalises it to the two columns of U and of V.
+//   pair with coalesced loads + shuffles, and applies the rotation that diagonalises it to the two columns of U.
 //   Pairs of one step touch disjoint columns: one __syncthreads per step, nothing else.
-// Converged when no pair needed a rotation (|u_p . u_q|^2 <= 1e-29 |u_p|^2 |u_q|^2).  Then A v_k = (u_k - c v_k),
-// lambda_k = Re(v_k . u_k) - c, and the Kraus operators are written exactly like choi2kraus_kernel does for n <= 3.
-// Columns are stored as contiguous ROWS of the workspace arrays (Ut[k][r] = U[r][k]).
+// Converged when no pair needed a rotation (|u_p . u_q|^2 <= 1e-29 |u_p|^2 |u_q|^2).  The accumulated rotations V are
+// never formed: at convergence U = (A + c I) V has orthogonal columns, so V diagonalises (A + c I)^2 and
+// u_k = (lambda_k + c) v_k, i.e.  lambda_k = |u_k| - c  and  v_k = u_k / |u_k|  (c is taken 1/16 above ||A||_inf so
+// that |u_k| >= c / 16 > 0).  The Kraus operators are then written exactly like choi2kraus_kernel does for n <= 3.
+// Columns are stored as contiguous ROWS of the workspace array (Ut[k][r] = U[r][k]).
 #include "qt_eigh.cuh"
 #include "../../include/qtomo.h"
 
 #include <algorithm>
 
 template <int M>
-__global__ void __launch_bounds__(1024)
+__global__ void __launch_bounds__(M == 256 ? 512 : 1024)
     choi2kraus_large_kernel(int64_t B, const cplx* __restrict__ in, double tol, double* __restrict__ evals_out,
                             cplx* __restrict__ kraus_out, int* __restrict__ count_out, cplx* __restrict__ ws,
                             int* __restrict__ sweeps_out) {
-  constexpr int NT = 1024, NW = NT / 32, HP = M / 2, PER = M / 32;
+  constexpr int NT = (M == 256) ? 512 : 1024, NW = NT / 32, HP = M / 2, PER = M / 32;
   constexpr int D = (M == 256) ? 16 : 32;
-  constexpr bool HOLD = false;  // (holding the pair in registers between the Gram pass and the update spills at 64 registers per thread; the re-read hits L1)
-  __shared__ double ev[M];
+  // M = 256 (512 threads, 128 registers): the pair's two columns stay in registers between the Gram pass and the update;
+  // M = 1024 re-reads them
+  constexpr bool HOLD = (M == 256);
+  __shared__ double ev[M], sig[M];
   __shared__ int rank[M], pos[M];
   __shared__ double red[NW];
   __shared__ int rotated;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  cplx* U = ws + (size_t)blockIdx.x * 2 * M * M;
-  cplx* V = U + (size_t)M * M;
+  cplx* U = ws + (size_t)blockIdx.x * M * M;
   for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
     const cplx* src = in + b * (int64_t)M * M;
     // Hermitian matrix np.linalg.eigh sees (lower triangle), infinity norm, and the shifted start
@@ -50,13 +53,13 @@ __global__ void __launch_bounds__(1024)
     __syncthreads();
     double shift = 0.0;
     for (int w = 0; w < NW; ++w) shift = fmax(shift, red[w]);
+    shift = 1.0625 * shift + 1e-300;
     __syncthreads();
     for (int e = tid; e < M * M; e += NT) {
       const int k = e / M, r = e % M;  // column k, row r:  U[r][k] = conj(herm(k, r))
       cplx v = cconj(herm(k, r));
       if (k == r) v.x += shift;
       U[e] = v;
-      V[e] = cmake(k == r ? 1.0 : 0.0, 0.0);
     }
     __syncthreads();
     int sweep = 0;
@@ -99,14 +102,6 @@ __global__ void __launch_bounds__(1024)
             up[lane + 32 * t] = csub(cscale(x, c), cmul(cs, y));
             uq[lane + 32 * t] = cadd(cmul(s, x), cscale(y, c));
           }
-          cplx* vp = V + (size_t)p * M;
-          cplx* vq = V + (size_t)q * M;
-#pragma unroll
-          for (int t = 0; t < PER; ++t) {
-            const cplx x = vp[lane + 32 * t], y = vq[lane + 32 * t];
-            vp[lane + 32 * t] = csub(cscale(x, c), cmul(cs, y));
-            vq[lane + 32 * t] = cadd(cmul(s, x), cscale(y, c));
-          }
         }
         __syncthreads();
       }
@@ -114,15 +109,15 @@ __global__ void __launch_bounds__(1024)
       __syncthreads();
     }
     if (tid == 0 && sweeps_out) sweeps_out[b] = sweep;
-    // eigenvalues: Rayleigh quotients of the shifted matrix minus the shift
+    // eigenvalues: column norms of the shifted matrix minus the shift
     for (int k = wid; k < M; k += NW) {
       double acc = 0.0;
-      for (int r = lane; r < M; r += 32) {
-        const cplx v = V[(size_t)k * M + r], u = U[(size_t)k * M + r];
-        acc += v.x * u.x + v.y * u.y;
-      }
+      for (int r = lane; r < M; r += 32) acc += cabs2(U[(size_t)k * M + r]);
       acc = warp_sum(acc);
-      if (lane == 0) ev[k] = acc - shift;
+      if (lane == 0) {
+        sig[k] = sqrt(acc);
+        ev[k] = sig[k] - shift;
+      }
     }
     __syncthreads();
     for (int k = tid; k < M; k += NT) {
@@ -147,8 +142,8 @@ __global__ void __launch_bounds__(1024)
       const int k = e / M, r = e % M;  // eigenpair k, vec index r = j*D + i  ->  K[i][j]
       if (pos[k] < 0) continue;
       const double lam = ev[k];
-      const double sq = sqrt(fabs(lam));
-      const cplx v = V[e];
+      const double sq = sqrt(fabs(lam)) / sig[k];  // v_k = u_k / |u_k|
+      const cplx v = U[e];
       const cplx val = (lam >= 0.0) ? cscale(v, sq) : cmake(-sq * v.y, sq * v.x);
       dst[(size_t)pos[k] * M + (r % D) * D + (r / D)] = val;
     }
@@ -161,7 +156,7 @@ static int64_t large_grid(int64_t B) { return std::min<int64_t>(B, QT_NUM_SMS); 
 extern "C" int64_t qt_choi2kraus_large_workspace_bytes(int n, int64_t B) {
   if (n != 4 && n != 5) return -1;
   const int64_t M = 1LL << (2 * n);
-  return large_grid(B) * 2 * M * M * (int64_t)sizeof(cplx);
+  return large_grid(B) * M * M * (int64_t)sizeof(cplx);
 }
 
 extern "C" int qt_choi2kraus_large_batch(int n, int64_t B, const void* choi, double tol, double* evals_out,
@@ -176,7 +171,7 @@ extern "C" int qt_choi2kraus_large_batch(int n, int64_t B, const void* choi, dou
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)large_grid(B);
   if (n == 4)
-    choi2kraus_large_kernel<256><<<grid, 1024, 0, st>>>(B, (const cplx*)choi, tol, evals_out, (cplx*)kraus_out,
+    choi2kraus_large_kernel<256><<<grid, 512, 0, st>>>(B, (const cplx*)choi, tol, evals_out, (cplx*)kraus_out,
                                                          count_out, (cplx*)workspace, sweeps_out);
   else
     choi2kraus_large_kernel<1024><<<grid, 1024, 0, st>>>(B, (const cplx*)choi, tol, evals_out, (cplx*)kraus_out,
