@@ -514,8 +514,15 @@ def run_kernels(args):
         headline = rows[0]
         workload = f"BASELINE configs[4]: fidelity + trace_distance, 10^6 4-qubit pairs / {world} GPU(s)"
     clocks = sampler.stop()
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if args.workload == "convert":
+            cpu = bk.cpu_convert_baseline(torch)
+        elif args.workload == "distances":
+            cpu = bk.cpu_distance_baseline(torch)
     if rank == 0:
         print(json.dumps({
+            "cpu_baseline": cpu,
             "metric": "kernel roofline sweep", "value": headline["items_per_s"], "unit": "items/s (headline kernel)",
             "n_gpus": world, "steps": 5, "warmup": 3, "ms_per_step": headline["ms"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64 (complex128)", "data": "synthetic",

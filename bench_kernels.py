@@ -189,5 +189,68 @@ def next_rows(torch, peak, budget_bytes=4 << 30):
     return rows
 
 
+def cpu_convert_baseline(torch, per_n=None):
+    """Oracle port (single process) on a subsample of BASELINE configs[3]: seconds per matrix of every conversion, and
+    the GPU result's relative Frobenius error on the same matrices.  SURVEY 8(d): 64 matrices per n, 2 at n = 5."""
+    import time
+    from oracle import ref_numpy as orc
+    from forest_benchmarking_b200.operator_tools import superoperator_transformations as st
+    per_n = per_n or {1: 64, 2: 64, 3: 16, 4: 2, 5: 1}
+    out = {}
+    for n, cnt in per_n.items():
+        d = 2 ** n
+        rng = np.random.default_rng(4004 + n)
+        kraus = np.stack([[np.sqrt(.7) * orc.haar_unitary(rng, d), np.sqrt(.3) * orc.haar_unitary(rng, d)]
+                          for _ in range(cnt)])
+        kd = torch.from_numpy(kraus).cuda()
+        g_choi = st.kraus2choi_batch(kd)
+        g_sup = st.reshuffle_batch(g_choi)
+        g_pl = st.superop2pauli_liouville_batch(g_sup)
+        g_back = st.pauli_liouville2superop_batch(g_pl)
+        g_kraus, g_cnt, _ = st.choi2kraus_batch(g_choi)
+        gpu = {k: v.cpu().numpy() for k, v in dict(choi=g_choi, sup=g_sup, pl=g_pl, back=g_back, kraus=g_kraus).items()}
+        t = {k: 0.0 for k in ("kraus2choi", "choi2superop", "superop2pauli_liouville", "pauli_liouville2superop",
+                              "choi2kraus")}
+        err = 0.0
+
+        def rel(a, b):
+            return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300))
+        for i in range(cnt):
+            t0 = time.perf_counter(); choi = orc.kraus2choi(list(kraus[i])); t["kraus2choi"] += time.perf_counter() - t0
+            t0 = time.perf_counter(); sup = orc.choi2superop(choi); t["choi2superop"] += time.perf_counter() - t0
+            t0 = time.perf_counter(); pl = orc.superop2pauli_liouville(sup); t["superop2pauli_liouville"] += time.perf_counter() - t0
+            t0 = time.perf_counter(); back = orc.pauli_liouville2superop(pl); t["pauli_liouville2superop"] += time.perf_counter() - t0
+            t0 = time.perf_counter(); ks = orc.choi2kraus(choi); t["choi2kraus"] += time.perf_counter() - t0
+            err = max(err, rel(gpu["choi"][i], choi), rel(gpu["sup"][i], sup), rel(gpu["pl"][i], pl),
+                      rel(gpu["back"][i], back))
+            # Kraus operators carry an eigenvector phase: compare through kraus2choi (the reference's own test)
+            k_gpu = gpu["kraus"][i][: int(g_cnt[i].item())]
+            err = max(err, rel(sum(orc.kraus2choi(k) for k in k_gpu), sum(orc.kraus2choi(k) for k in ks)))
+        out[f"n={n}"] = {"matrices": cnt, "sec_per_matrix": {k: v / cnt for k, v in t.items()},
+                         "max_rel_frobenius_err_gpu_vs_port": err}
+    return out
+
+
+def cpu_distance_baseline(torch, pairs=2000, n=4):
+    """Oracle port on `pairs` pairs of BASELINE configs[4]: microseconds per pair and the GPU's absolute error."""
+    import time
+    from oracle import ref_numpy as orc
+    from forest_benchmarking_b200 import distance_measures as dm
+    d = 2 ** n
+    rho, sig = _rand_states(torch, pairs, d, 61), _rand_states(torch, pairs, d, 62)
+    fid = dm.fidelity_batch(rho, sig).cpu().numpy()
+    td = dm.trace_distance_batch(rho, sig).cpu().numpy()
+    r, s = rho.cpu().numpy(), sig.cpu().numpy()
+    t0 = time.perf_counter()
+    f_cpu = np.array([orc.fidelity(a, b) for a, b in zip(r, s)])
+    t1 = time.perf_counter()
+    t_cpu = np.array([orc.trace_distance(a, b) for a, b in zip(r, s)])
+    t2 = time.perf_counter()
+    return {"pairs": pairs, "fidelity_us_per_pair": (t1 - t0) / pairs * 1e6,
+            "trace_distance_us_per_pair": (t2 - t1) / pairs * 1e6,
+            "max_abs_err_fidelity": float(np.abs(fid - f_cpu).max()),
+            "max_abs_err_trace_distance": float(np.abs(td - t_cpu).max()), "cores": 1, "kind": "port"}
+
+
 def dumps(rows):
     return json.dumps(rows)
