@@ -4,6 +4,7 @@
 #include "../../include/qtomo.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <type_traits>
 
 template <int N>
@@ -607,7 +608,13 @@ static int launch_unitary(int64_t B, const void* in, void* out, cudaStream_t st)
 template <int N>
 static int launch_tp(int64_t B, const void* in, void* out, int make_tp, cudaStream_t st) {
   constexpr int D = 1 << N, MM = D * D * D * D;
-  const int ipb = make_tp ? std::max(1, 4096 / MM) : std::max(1, std::min(64, 4096 / MM));
+  // tile of items per block: QT_TP_TILE elements (16 KB) for the streaming TP pass -- several blocks per SM overlap their
+  // load / partial-trace / store phases; the fused TNI keeps the larger tile (its per-item eigensolver wants threads)
+  static const int tp_tile = []() {
+    const char* e = getenv("QT_TP_TILE");
+    return e ? atoi(e) : 1024;
+  }();
+  const int ipb = make_tp ? std::max(1, tp_tile / MM) : std::max(1, std::min(64, 4096 / MM));
   constexpr int PER = 3 * D * D * 2 + D + JacobiScratch<D>::doubles + (D % 2);
   const size_t smem = sizeof(cplx) * ((size_t)ipb * MM + (size_t)ipb * D * D) +
                       ((make_tp || D <= 4) ? 0 : sizeof(double) * (size_t)ipb * ((PER + 1) / 2 * 2));
