@@ -13,48 +13,57 @@
 
 #include <algorithm>
 
+// Small states (d = 2, 4: fewer than 32 elements) are packed IPW = 32 / d^2 pairs per warp, one element per lane, so
+// that every lane of every load is used; larger ones take one pair per warp with the element loop unrolled.
 template <int D>
 __global__ void trace_distance_kernel(int64_t B, const cplx* __restrict__ rho, const cplx* __restrict__ sigma,
                                       double* __restrict__ out) {
   constexpr int DD = D * D;
-  constexpr int G = (D >= 32) ? 1 : 32 / D;  // row groups held by one warp pass
-  const int lane = threadIdx.x & 31;
-  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (b >= B) return;
-  const cplx* r = rho + b * DD;
-  const cplx* s = sigma + b * DD;
-  double colsum = 0.0;  // lane owns column lane % D, rows lane / D + k*G
+  constexpr int IPW = (DD < 32) ? 32 / DD : 1;   // pairs per warp
+  constexpr int GL = (DD < 32) ? DD : 32;        // lanes per pair
+  const int lane = threadIdx.x & 31, gl = lane % GL;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t b = warp * IPW + lane / GL;
+  const bool live = b < B;
+  const cplx* r = rho + (live ? b : 0) * DD;
+  const cplx* s = sigma + (live ? b : 0) * DD;
+  double colsum = 0.0;  // lane owns column gl % D, rows gl / D + k * (GL / D)
   if (D <= 32) {
-    for (int e = lane; e < DD; e += 32) {
+#pragma unroll
+    for (int e = gl; e < DD; e += GL) {
       const cplx a = r[e], c = s[e];
       colsum += sqrt(cabs2(csub(a, c)));
     }
 #pragma unroll
-    for (int o = 16; o >= D; o >>= 1) colsum += __shfl_xor_sync(0xffffffffu, colsum, o);
+    for (int o = GL / 2; o >= D; o >>= 1) colsum += __shfl_xor_sync(0xffffffffu, colsum, o);
     double m = colsum;
 #pragma unroll
     for (int o = (D < 32 ? D : 32) / 2; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0) out[b] = 0.5 * m;
+    if (live && gl == 0) out[b] = 0.5 * m;
   }
-  (void)G;
 }
 
 template <int D>
 __global__ void purity_kernel(int64_t B, const cplx* __restrict__ rho, double* __restrict__ out) {
   constexpr int DD = D * D;
-  const int lane = threadIdx.x & 31;
-  const int64_t b = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (b >= B) return;
-  const cplx* r = rho + b * DD;
+  constexpr int IPW = (DD < 32) ? 32 / DD : 1;
+  constexpr int GL = (DD < 32) ? DD : 32;
+  const int lane = threadIdx.x & 31, gl = lane % GL;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t b = warp * IPW + lane / GL;
+  const bool live = b < B;
+  const cplx* r = rho + (live ? b : 0) * DD;
   // tr(rho rho) = sum_{ij} rho_ij rho_ji ; real part
   double acc = 0.0;
-  for (int e = lane; e < DD; e += 32) {
+#pragma unroll
+  for (int e = gl; e < DD; e += GL) {
     const int i = e / D, j = e % D;
     const cplx a = r[e], c = r[j * D + i];
     acc += a.x * c.x - a.y * c.y;
   }
-  acc = warp_sum(acc);
-  if (lane == 0) out[b] = acc;
+#pragma unroll
+  for (int o = GL / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (live && gl == 0) out[b] = acc;
 }
 
 // shared memory per warp: 3 matrices (leading dimension LD = D + 1 for D >= 8: the Jacobi block updates and the
@@ -347,6 +356,20 @@ __global__ void hs_inner_kernel(int64_t elems, int64_t B, const cplx* __restrict
                                 cplx* __restrict__ out, int block_per_pair) {
   __shared__ double red[2][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  if (block_per_pair == 2) {
+    // fewer than 32 elements per matrix (a power of two): 32 / elems pairs per warp, one element per lane
+    const int gl_n = (int)elems, ipw = 32 / gl_n, gl = lane % gl_n;
+    const int64_t p = ((int64_t)blockIdx.x * wpb + wib) * ipw + lane / gl_n;
+    const bool live = p < B;
+    cplx acc = cmake(0.0, 0.0);
+    if (live) cfma(acc, cconj(a[p * elems + gl]), b[p * elems + gl]);
+    for (int o = gl_n / 2; o > 0; o >>= 1) {
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    }
+    if (live && gl == 0) out[p] = acc;
+    return;
+  }
   if (!block_per_pair) {
     const int64_t p = (int64_t)blockIdx.x * wpb + wib;
     if (p >= B) return;
@@ -379,14 +402,18 @@ __global__ void hs_inner_kernel(int64_t elems, int64_t B, const cplx* __restrict
 template <int D>
 static int launch_td(int64_t B, const void* rho, const void* sigma, double* out, cudaStream_t st) {
   const int wpb = 8;
-  trace_distance_kernel<D><<<(unsigned)((B + wpb - 1) / wpb), 32 * wpb, 0, st>>>(B, (const cplx*)rho,
+  constexpr int IPW_TD = (D * D < 32) ? 32 / (D * D) : 1;
+  const int64_t warps_td = (B + IPW_TD - 1) / IPW_TD;
+  trace_distance_kernel<D><<<(unsigned)((warps_td + wpb - 1) / wpb), 32 * wpb, 0, st>>>(B, (const cplx*)rho,
                                                                                  (const cplx*)sigma, out);
   return qt_check_launch("trace_distance_kernel");
 }
 template <int D>
 static int launch_purity(int64_t B, const void* rho, double* out, cudaStream_t st) {
   const int wpb = 8;
-  purity_kernel<D><<<(unsigned)((B + wpb - 1) / wpb), 32 * wpb, 0, st>>>(B, (const cplx*)rho, out);
+  constexpr int IPW_P = (D * D < 32) ? 32 / (D * D) : 1;
+  const int64_t warps_p = (B + IPW_P - 1) / IPW_P;
+  purity_kernel<D><<<(unsigned)((warps_p + wpb - 1) / wpb), 32 * wpb, 0, st>>>(B, (const cplx*)rho, out);
   return qt_check_launch("purity_kernel");
 }
 template <int D, int MODE>
@@ -470,8 +497,10 @@ extern "C" int qt_hs_inner_batch(int64_t rows, int64_t cols, int64_t B, const vo
   QT_REQUIRE(rows > 0 && cols > 0 && a && b && out, "qt_hs_inner_batch: bad arguments");
   if (B == 0) return QT_OK;
   const int64_t elems = rows * cols;
-  const int block_per_pair = elems > 1024;
-  const int64_t blocks = block_per_pair ? std::min<int64_t>(B, (int64_t)QT_NUM_SMS * 8) : (B + 7) / 8;
+  const bool packed = elems < 32 && (elems & (elems - 1)) == 0;
+  const int block_per_pair = packed ? 2 : (elems > 1024 ? 1 : 0);
+  const int64_t blocks = packed ? (B + 8 * (32 / elems) - 1) / (8 * (32 / elems))
+                                : (block_per_pair ? std::min<int64_t>(B, (int64_t)QT_NUM_SMS * 8) : (B + 7) / 8);
   hs_inner_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(elems, B, (const cplx*)a, (const cplx*)b,
                                                                       (cplx*)out, block_per_pair);
   return qt_check_launch("hs_inner_kernel");
