@@ -349,7 +349,7 @@ __global__ void proj_tp_kernel(int64_t B, const cplx* __restrict__ in, cplx* __r
   }
 }
 
-// ---- TNI in two passes (n = 2, 3, out-of-place) --------------------------------------------------------
+// ---- TNI in two passes (out-of-place calls) -----------------------------------------------------------
 // The fused kernel above holds a tile of items in shared memory while ONE thread (n = 2) or warp (n = 3) per item
 // runs the d x d eigendecomposition: the other threads idle and the tile pins the occupancy (0.18 / 0.32 of the HBM
 // roof).  Here pass 1 reads only the elements the partial trace needs ((a b),(c b): a quarter (n = 3) to a half
@@ -357,10 +357,10 @@ __global__ void proj_tp_kernel(int64_t B, const cplx* __restrict__ in, cplx* __r
 // first d^2 elements of out[b]; pass 2 is a pure streaming kernel out = in - kron(E, I) that first lifts the E of
 // its items into shared memory (it is about to overwrite them).
 template <int N>
-__global__ void __launch_bounds__(N == 2 ? 128 : 256)
+__global__ void __launch_bounds__(N <= 2 ? 128 : 256)
     tni_correction_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out) {
   constexpr int D = 1 << N, M = D * D, MM = M * M;
-  if constexpr (N == 2) {
+  if constexpr (N <= 2) {
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const cplx* Cm = in + b * MM;
@@ -378,31 +378,35 @@ __global__ void __launch_bounds__(N == 2 ? 128 : 256)
     cplx o[4][4], v[4][4];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
-      dg[a] = pt[a][a].x;
+      dg[a] = (a < D) ? pt[a][a].x : 0.0;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         v[a][c] = cmake(a == c ? 1.0 : 0.0, 0.0);
         o[a][c] = cmake(0.0, 0.0);
-        if (a < c) o[a][c] = cmake(0.5 * (pt[a][c].x + pt[c][a].x), 0.5 * (pt[a][c].y - pt[c][a].y));
+        if (a < c && c < D) o[a][c] = cmake(0.5 * (pt[a][c].x + pt[c][a].x), 0.5 * (pt[a][c].y - pt[c][a].y));
       }
     }
-    for (int sweep = 0; sweep < 30; ++sweep) {
-      double off = 0.0, tot = 0.0;
+    if constexpr (D == 2) {
+      rot4<0, 1>(dg, o, v);  // a 2x2 Hermitian matrix is diagonalised by one rotation
+    } else {
+      for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, tot = 0.0;
 #pragma unroll
-      for (int a = 0; a < 4; ++a) {
-        tot = fma(dg[a], dg[a], tot);
+        for (int a = 0; a < 4; ++a) {
+          tot = fma(dg[a], dg[a], tot);
 #pragma unroll
-        for (int c = a + 1; c < 4; ++c) off += cabs2(o[a][c]);
+          for (int c = a + 1; c < 4; ++c) off += cabs2(o[a][c]);
+        }
+        off *= 2.0;
+        tot += off;
+        if (off <= 1e-26 * tot || tot == 0.0) break;
+        rot4<0, 1>(dg, o, v);
+        rot4<2, 3>(dg, o, v);
+        rot4<0, 2>(dg, o, v);
+        rot4<1, 3>(dg, o, v);
+        rot4<0, 3>(dg, o, v);
+        rot4<1, 2>(dg, o, v);
       }
-      off *= 2.0;
-      tot += off;
-      if (off <= 1e-26 * tot || tot == 0.0) break;
-      rot4<0, 1>(dg, o, v);
-      rot4<2, 3>(dg, o, v);
-      rot4<0, 2>(dg, o, v);
-      rot4<1, 3>(dg, o, v);
-      rot4<0, 3>(dg, o, v);
-      rot4<1, 2>(dg, o, v);
     }
     cplx* E = out + b * MM;
 #pragma unroll
@@ -619,15 +623,15 @@ static int launch_tp(int64_t B, const void* in, void* out, int make_tp, cudaStre
   const size_t smem = sizeof(cplx) * ((size_t)ipb * MM + (size_t)ipb * D * D) +
                       ((make_tp || D <= 4) ? 0 : sizeof(double) * (size_t)ipb * ((PER + 1) / 2 * 2));
   const unsigned blocks = (unsigned)((B + ipb - 1) / ipb);
-  if constexpr (N >= 2) {
+  {
     if (!make_tp && in != out) {  // two-pass TNI (the correction is parked in out[b], so not for in-place calls)
-      if (N == 2)
+      if (N <= 2)
         tni_correction_kernel<N><<<(unsigned)((B + 127) / 128), 128, 0, st>>>(B, (const cplx*)in, (cplx*)out);
       else
         tni_correction_kernel<N><<<(unsigned)((B + 7) / 8), 256, 0, st>>>(B, (const cplx*)in, (cplx*)out);
       int rc = qt_check_launch("tni_correction_kernel");
       if (rc) return rc;
-      const int ia = std::max(1, 8192 / MM);
+      const int ia = std::max(1, (N == 1 ? 1024 : 8192) / MM);
       tni_apply_kernel<N><<<(unsigned)((B + ia - 1) / ia), 256, sizeof(cplx) * ia * D * D, st>>>(B, (const cplx*)in,
                                                                                                   (cplx*)out, ia);
       return qt_check_launch("tni_apply_kernel");
