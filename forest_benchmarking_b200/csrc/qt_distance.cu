@@ -43,23 +43,40 @@ __global__ void trace_distance_kernel(int64_t B, const cplx* __restrict__ rho, c
   }
 }
 
+// tr(rho rho) = sum_ij rho_ij rho_ji (real part).  The transposed partner of an element is fetched without a second,
+// uncoalesced global read: by shuffle when a state fits one warp pass (d <= 4), from a padded shared-memory copy
+// of the state otherwise.
 template <int D>
 __global__ void purity_kernel(int64_t B, const cplx* __restrict__ rho, double* __restrict__ out) {
   constexpr int DD = D * D;
   constexpr int IPW = (DD < 32) ? 32 / DD : 1;
   constexpr int GL = (DD < 32) ? DD : 32;
-  const int lane = threadIdx.x & 31, gl = lane % GL;
-  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  constexpr int WPB = (D >= 32) ? 2 : 8, LD = D + 1;
+  const int lane = threadIdx.x & 31, gl = lane % GL, wib = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * WPB + wib;
   const int64_t b = warp * IPW + lane / GL;
   const bool live = b < B;
   const cplx* r = rho + (live ? b : 0) * DD;
-  // tr(rho rho) = sum_{ij} rho_ij rho_ji ; real part
   double acc = 0.0;
+  if constexpr (DD < 32) {
+    const int i = gl / D, j = gl % D;
+    const cplx a = r[gl];
+    cplx c;
+    c.x = __shfl_sync(0xffffffffu, a.x, (lane - gl) + j * D + i);
+    c.y = __shfl_sync(0xffffffffu, a.y, (lane - gl) + j * D + i);
+    acc = a.x * c.x - a.y * c.y;
+  } else {
+    __shared__ cplx tile[WPB][D * LD];
+    cplx* t = tile[wib];
 #pragma unroll
-  for (int e = gl; e < DD; e += GL) {
-    const int i = e / D, j = e % D;
-    const cplx a = r[e], c = r[j * D + i];
-    acc += a.x * c.x - a.y * c.y;
+    for (int e = lane; e < DD; e += 32) t[(e / D) * LD + e % D] = r[e];
+    __syncwarp();
+#pragma unroll
+    for (int e = lane; e < DD; e += 32) {
+      const int i = e / D, j = e % D;
+      const cplx a = t[i * LD + j], c = t[j * LD + i];
+      acc += a.x * c.x - a.y * c.y;
+    }
   }
 #pragma unroll
   for (int o = GL / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -412,8 +429,9 @@ template <int D>
 static int launch_purity(int64_t B, const void* rho, double* out, cudaStream_t st) {
   const int wpb = 8;
   constexpr int IPW_P = (D * D < 32) ? 32 / (D * D) : 1;
+  constexpr int WPB_P = (D >= 32) ? 2 : 8;  // must match purity_kernel
   const int64_t warps_p = (B + IPW_P - 1) / IPW_P;
-  purity_kernel<D><<<(unsigned)((warps_p + wpb - 1) / wpb), 32 * wpb, 0, st>>>(B, (const cplx*)rho, out);
+  purity_kernel<D><<<(unsigned)((warps_p + WPB_P - 1) / WPB_P), 32 * WPB_P, 0, st>>>(B, (const cplx*)rho, out);
   return qt_check_launch("purity_kernel");
 }
 template <int D, int MODE>

@@ -359,3 +359,16 @@ def test_fidelity_cholesky_fast_path_and_fallback(torch):
             assert abs(fid[b] - want) < 1e-6 * max(abs(want), 1e-3), (n, b, fid[b], want)
             if b % 4 == 3:
                 assert abs(fid[b] - want) < 1e-10
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5])
+def test_purity_all_sizes(torch, n):
+    """tr(rho rho) for Hermitian and for general complex matrices (the reference computes np.trace(rho @ rho))."""
+    from forest_benchmarking_b200 import distance_measures as dm
+    rng = np.random.default_rng(300 + n)
+    d = 2 ** n
+    x = rng.standard_normal((37, d, d)) + 1j * rng.standard_normal((37, d, d))
+    x[::2] = np.stack([orc.ginibre_state(rng, d) for _ in range(19)])
+    got = dm.purity_batch(torch.from_numpy(x).cuda()).cpu().numpy()
+    want = np.array([np.real(np.trace(m @ m)) for m in x])
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
