@@ -16,6 +16,14 @@
 #include "qt_pauli.cuh"
 #include "../../include/qtomo.h"
 
+// elements per block of the small-n tiles: 16 KB tiles keep 8 blocks resident per SM (cf. proj_tp_kernel)
+#ifndef QT_PL_TILE
+#define QT_PL_TILE 1024
+#endif
+#ifndef QT_RESHUFFLE_TILE
+#define QT_RESHUFFLE_TILE 1024
+#endif
+
 static constexpr int TILE_ELEMS = 4096;  // 64 KB of complex128 per block pass
 
 // ---------------------------------------------------------------------------------------------
@@ -178,7 +186,7 @@ extern "C" int qt_kraus2superop_batch(int d, int n_kraus, int64_t B, const void*
 template <int LOGD>
 struct ReshuffleCfg {
   static constexpr int D = 1 << LOGD;
-  static constexpr int TILE = 2048;                                   // elements per block (32 KB)
+  static constexpr int TILE = (LOGD <= 2) ? QT_RESHUFFLE_TILE : 2048;  // elements per block
   static constexpr int C2 = (TILE / (D * D) >= D) ? D : (TILE / (D * D) >= 1 ? TILE / (D * D) : 1);
   static constexpr int UNIT = D * C2 * D;                             // elements per unit
   static constexpr int UPB = (TILE / UNIT >= 1) ? TILE / UNIT : 1;    // units per block
@@ -269,7 +277,7 @@ struct PlCfg {
   static constexpr int RQN = (N <= 3) ? N : (N == 4 ? 2 : 1);     // row qubits handled by pass A
   static constexpr bool RADIX16 = (N == 2);                       // two butterfly stages per shared-memory pass
   static constexpr int TRA = 1 << (2 * RQN);                      // tile rows of pass A
-  static constexpr int IPB = (2048 / (TRA * L) >= 1) ? 2048 / (TRA * L) : 1;  // tiles per block (small n)
+  static constexpr int IPB = (QT_PL_TILE / (TRA * L) >= 1) ? QT_PL_TILE / (TRA * L) : 1;  // tiles per block (small n)
   static constexpr int LDA = L + 1;
   static constexpr size_t smem_a = sizeof(cplx) * IPB * TRA * LDA;
   static constexpr int NTA = (TRA * L * IPB >= 4096) ? 512 : 256;
