@@ -427,7 +427,6 @@ static int launch_td(int64_t B, const void* rho, const void* sigma, double* out,
 }
 template <int D>
 static int launch_purity(int64_t B, const void* rho, double* out, cudaStream_t st) {
-  const int wpb = 8;
   constexpr int IPW_P = (D * D < 32) ? 32 / (D * D) : 1;
   constexpr int WPB_P = (D >= 32) ? 2 : 8;  // must match purity_kernel
   const int64_t warps_p = (B + IPW_P - 1) / IPW_P;
