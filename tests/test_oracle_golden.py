@@ -112,3 +112,28 @@ def test_next_rows():
             assert np.allclose(got, g["mom_out"][prior, i], rtol=1e-13, atol=1e-17)
     a, va, b, vb = g["rv_in"]
     assert np.allclose(orc.ratio_variance(a, va, b, vb), g["rv_out"], rtol=1e-15)
+
+
+def test_more_known_answers():
+    """Hand-derivable values the reference's own tests pin, re-derived here."""
+    # column-stacking vec / unvec (superoperator_transformations.py:33-79)
+    a = np.array([[1, 2], [3, 4]])
+    assert np.array_equal(orc.vec(a).ravel(), [1, 3, 2, 4]) and np.array_equal(orc.unvec(orc.vec(a)), a)
+    # superoperator of the diagonal unitary I (x) Z is diag(conj(u) (x) u)
+    iz = np.diag([1.0, -1, 1, -1])
+    assert np.array_equal(np.diag(orc.kraus2superop([iz])).real, np.kron(np.diag(iz), np.diag(iz)))
+    # Smolin-Gambetta-Smith example: eigenvalues (3/5, 1/2, 7/20, 1/10, -11/20) -> (9/20, 7/20, 1/5, 0, 0)
+    rng = np.random.default_rng(1)
+    q, _ = np.linalg.qr(rng.standard_normal((5, 5)) + 1j * rng.standard_normal((5, 5)))
+    rho = (q * np.array([3 / 5, 1 / 2, 7 / 20, 1 / 10, -11 / 20])) @ q.conj().T
+    out = orc.project_state_matrix_to_physical(rho)
+    assert np.allclose(np.sort(np.linalg.eigvalsh(out))[::-1], [9 / 20, 7 / 20, 1 / 5, 0, 0], atol=1e-14)
+    assert np.allclose(out, (q * np.array([9 / 20, 7 / 20, 1 / 5, 0, 0])) @ q.conj().T, atol=1e-14)
+    # a CPTP map is a fixed point of the physical projection; the completely depolarising channel has purity 1/d
+    u = orc.haar_unitary(rng, 4)
+    choi = orc.kraus2choi([u])
+    assert np.allclose(orc.proj_choi_to_physical(choi), choi, atol=1e-12)
+    assert np.isclose(orc.purity(np.eye(4) / 4), 0.25)
+    # shots -> moments: 3 of 4 shots give +1 -> mean 1/2, variance of the mean (1 - 1/4) / 4
+    bits = np.array([[0, 0], [1, 1], [0, 0], [1, 0]])
+    assert orc.shots_to_obs_moments(bits, [0, 1]) == (0.5, 0.1875)
