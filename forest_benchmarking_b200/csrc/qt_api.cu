@@ -25,18 +25,33 @@ int qt_check_launch(const char* what) {
 
 extern "C" int qt_version(void) { return 100; }
 
-// Tuning knob: relative off-diagonal Frobenius norm at which the Jacobi eigensolver inside
-// qt_proj_physical_batch / qt_pgdb_process_batch stops.  Default 1e-8: Jacobi converges quadratically, so the
-// sweep that crosses 1e-8 typically lands near 1e-16.  Measured against the reference goldens
-// (profiles/r01_exp_eigh_tol_v2.txt): max relative Frobenius deviation of the PGDB estimate 1.6e-10 at 1e-8,
-// 4.4e-8 at 1e-7, 3.8e-7 at 1e-6 (parity budget 1e-6), with identical eigh / outer-iteration counts throughout.
-// 0 restores the tight 1e-15 * 4^n.
-static double g_eigh_rel2 = 1e-16;
-double qt_eigh_rel2() { return g_eigh_rel2; }
-extern "C" int qt_set_eigh_tolerance(double rel_off) {
-  QT_REQUIRE(rel_off >= 0.0 && rel_off < 1e-3, "qt_set_eigh_tolerance: tolerance %g out of range [0, 1e-3)", rel_off);
-  g_eigh_rel2 = rel_off * rel_off;
+// Relative off-diagonal Frobenius norm at which the Jacobi eigensolver inside qt_proj_physical_batch /
+// qt_pgdb_process_batch stops -- a per-call argument (the library keeps no mutable process state).  Default 1e-8:
+// Jacobi converges quadratically, so the sweep that crosses 1e-8 typically lands near 1e-16.  Measured against the
+// reference goldens (profiles/r01_exp_eigh_tol_v2.txt): max relative Frobenius deviation of the PGDB estimate
+// 1.6e-10 at 1e-8, 4.4e-8 at 1e-7, 3.8e-7 at 1e-6 (parity budget 1e-6), with identical eigh / outer-iteration
+// counts throughout.
+int qt_eigh_rel2_from_tol(double rel_tol, double* rel2_out, const char* who) {
+  if (rel_tol < 0.0) rel_tol = QT_EIGH_REL_TOL_DEFAULT;
+  if (!(rel_tol < 1e-3)) {
+    qt_set_error("%s: eigh_rel_tol %g out of range (< 0: default %g, 0: tight, else < 1e-3)", who, rel_tol,
+                 QT_EIGH_REL_TOL_DEFAULT);
+    return QT_ERR_ARG;
+  }
+  *rel2_out = rel_tol * rel_tol;  // 0 selects the solver's tight built-in threshold
   return QT_OK;
+}
+
+int qt_num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cached[dev] = v;
+  }
+  return cached[dev];
 }
 
 extern "C" int qt_last_error(char* buf, int len) {

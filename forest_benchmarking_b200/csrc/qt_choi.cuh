@@ -26,6 +26,11 @@
 #ifndef QT_N3_THREADS
 #define QT_N3_THREADS 512
 #endif
+// safety caps that the reference does not have (its loops are unbounded); hitting one is reported through the
+// per-item status word of the C ABI (QT_STATUS_* in include/qtomo.h)
+#define QT_DYKSTRA_MAX_ITER 10000
+#define QT_JACOBI_MAX_SWEEPS 30
+#define QT_PGDB_MAX_OUTER 100000
 
 template <int N, int NT, class Sync>
 struct ChoiGroup {
@@ -147,10 +152,10 @@ struct ChoiGroup {
         }
       }
       Sync::sync();
-      return jacobi_eigh<M, NT, Sync, true, LD>(X, V, ev, jscr, tid, /*init_v=*/false, 30, rel2);
+      return jacobi_eigh<M, NT, Sync, true, LD>(X, V, ev, jscr, tid, /*init_v=*/false, QT_JACOBI_MAX_SWEEPS, rel2);
     }
     v_valid = true;
-    return jacobi_eigh<M, NT, Sync, true, LD>(X, V, ev, jscr, tid, /*init_v=*/true, 30, rel2);
+    return jacobi_eigh<M, NT, Sync, true, LD>(X, V, ev, jscr, tid, /*init_v=*/true, QT_JACOBI_MAX_SWEEPS, rel2);
   }
 
   // Dykstra.  On entry S holds the (Hermitian) matrix to project; on exit S holds the projection.
@@ -158,9 +163,17 @@ struct ChoiGroup {
   // shared scratch of SMALL_DOUBLES doubles (16-byte aligned).  v_valid: V holds an eigenbasis to warm-start
   // from (kept up to date here).  Returns the number of CP projections (eigh calls); *sweeps_acc accumulates
   // the Jacobi sweeps they took.
+  // RAW (optional): the caller's original, NON-Hermitian input (dense M x M, global).  The reference feeds it to
+  // the loop as is (project_superoperators.py:108-111); its CP step Hermitises (:30), so the anti-Hermitian part
+  // A = (RAW - RAW^dagger)/2 never reaches the iterates, but it lives on in old_CP_change (= Q_H - A) and therefore
+  // enters the stopping rule: ||A||_F^2 in the first trip's ||dCP||^2, and -<A, CP_k - CP_{k-1}> (purely imaginary)
+  // inside the abs() of the old_CP_change inner product on every later trip.
+  // status (optional, one int per group): bit 0 set when the Dykstra loop hit max_iter, bit 1 when a Jacobi call
+  // used all its sweeps -- both caps are additions over the reference, so the caller must be able to see them.
   static __device__ int project_physical(cplx* S, cplx* Q, cplx* CPREV, cplx* X, cplx* V, cplx* T, double* small,
                                          bool make_tp, int tid, bool& v_valid, int* sweeps_acc = nullptr,
-                                         double rel2 = 0.0, int max_iter = 10000) {
+                                         double rel2 = 0.0, int max_iter = QT_DYKSTRA_MAX_ITER,
+                                         const cplx* RAW = nullptr, int* status = nullptr) {
     double* ev = small;
     double* jscr = ev + M;
     cplx* E = reinterpret_cast<cplx*>(jscr + JacobiScratch<M>::doubles);
@@ -186,6 +199,7 @@ struct ChoiGroup {
       Sync::sync();
       const int sw = eigh_warm(X, V, T, ev, jscr, v_valid, tid, rel2);
       if (sweeps_acc) *sweeps_acc += sw;
+      if (status && sw >= QT_JACOBI_MAX_SWEEPS) *status |= 2;
       ++n_eigh;
       recompose_psd(X, V, ev, [&](int r, int c) { return csub(S[r * M + c], Q[r * M + c]); }, tid);  // X = CP
       // criterion pieces + state update of Q, CPREV
@@ -196,6 +210,12 @@ struct ChoiGroup {
         const cplx d1 = csub(cp, s);
         n_dcp += cabs2(d1);
         cfma_conj(ip_q, csub(cp, cprev), q);  // conj(q) * (cp - cprev)
+        if (RAW) {
+          const cplx x = RAW[e], y = RAW[(e % M) * M + e / M];
+          const cplx a = cmake(0.5 * (x.x - y.x), 0.5 * (x.y + y.y));  // anti-Hermitian part of the input
+          if (n_eigh == 1) n_dcp += cabs2(a);
+          else cfma_conj(ip_q, csub(cprev, cp), a);  // - conj(a) * (cp - cprev)
+        }
         Q[e] = cadd(d1, q);                   // new_CP_change = CP - pre_CP = CP - S + Q
         CPREV[e] = cp;
       }
@@ -231,7 +251,11 @@ struct ChoiGroup {
       ip_t.y = group_sum<NT, Sync>(ip_t.y, red, tid);
       const double crit = n_dcp + D * n_dtp + 2.0 * sqrt(cabs2(ip_t)) + 2.0 * sqrt(cabs2(ip_q));
       Sync::sync();
-      if (crit < 1e-4 || n_eigh >= max_iter) break;
+      if (crit < 1e-4) break;
+      if (n_eigh >= max_iter) {
+        if (status) *status |= 1;
+        break;
+      }
       for (int e = tid; e < D * D; e += NT) E[e] = En[e];
       Sync::sync();
     }

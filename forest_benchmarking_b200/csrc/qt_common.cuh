@@ -17,7 +17,10 @@ typedef double2 cplx;  // .x = real, .y = imag
 #define QT_ERR_WORKSPACE (-4)
 
 void qt_set_error(const char* fmt, ...);
-double qt_eigh_rel2();  // squared relative off-diagonal tolerance of the Dykstra/PGDB eigensolver (0 = default)
+// eigh_rel_tol argument of the C ABI -> squared relative off-diagonal tolerance handed to the Jacobi solver
+// (< 0: the default 1e-8; 0: the tight 1e-15 * 4^n; otherwise the value, which must be < 1e-3)
+int qt_eigh_rel2_from_tol(double rel_tol, double* rel2_out, const char* who);
+int qt_num_sms();  // multiprocessor count of the current device (cached per device)
 int qt_check_launch(const char* what);
 
 #define QT_REQUIRE(cond, ...)                \
@@ -37,7 +40,7 @@ int qt_check_launch(const char* what);
     }                                                                        \
   } while (0)
 
-#define QT_NUM_SMS 148  // B200
+#define QT_NUM_SMS qt_num_sms()  // 148 on B200; queried, not assumed
 
 // ---------------------------------------------------------------------------------------------
 // complex arithmetic on double2

@@ -194,7 +194,7 @@ struct Pgdb {
 
   // One experiment.  EST = choi_out[b] (global).  ws: per-group workspace.  X, V, small: shared.
   static __device__ void run(const PgdbView& pv, const Data& dt, bool make_tp, cplx* EST, double* ws, cplx* X,
-                             cplx* V, cplx* T, double* small, int* counters, int tid, double rel2) {
+                             cplx* V, cplx* T, double* small, int* counters, int* status_out, int tid, double rel2) {
     cplx* Gr = reinterpret_cast<cplx*>(ws);
     cplx* U = Gr + MM;
     cplx* S = U + MM;
@@ -217,7 +217,7 @@ struct Pgdb {
     choi_to_pl_positions(X, tid);
     build_T(X, pv, Te, reinterpret_cast<double*>(T), tid);
     double old_cost = cost(pv, dt, Te, Tu, 0.0, red, tid);
-    int outer = 0, cost_evals = 1, eighs = 0, sweeps = 0;
+    int outer = 0, cost_evals = 1, eighs = 0, sweeps = 0, status = 0;
     bool v_valid = false;  // V keeps the last eigenbasis across Dykstra AND outer iterations (warm start)
     while (true) {
       ++outer;
@@ -242,7 +242,8 @@ struct Pgdb {
       }
       Sync::sync();
       // ---- projection ----
-      eighs += G::project_physical(S, Q, CPREV, X, V, T, small, make_tp, tid, v_valid, &sweeps, rel2);
+      eighs += G::project_physical(S, Q, CPREV, X, V, T, small, make_tp, tid, v_valid, &sweeps, rel2,
+                                   QT_DYKSTRA_MAX_ITER, nullptr, &status);
       // ---- update direction, its PTM image, <update, gradient> ----
       double ip = 0.0;
       for (int e = tid; e < MM; e += NT) {
@@ -279,7 +280,11 @@ struct Pgdb {
       for (int e = tid; e < pv.n_in * M; e += NT) Te[e] = fma(alpha, Tu[e], Te[e]);
       __threadfence_block();
       Sync::sync();
-      if (old_cost - new_cost < 1e-10 || outer >= 100000) break;
+      if (old_cost - new_cost < 1e-10) break;
+      if (outer >= QT_PGDB_MAX_OUTER) {
+        status |= QT_STATUS_PGDB_CAP;
+        break;
+      }
       old_cost = new_cost;
     }
     if (tid == 0 && counters) {
@@ -288,13 +293,15 @@ struct Pgdb {
       counters[2] = eighs;
       counters[3] = sweeps;
     }
+    if (tid == 0 && status_out) *status_out = status;
   }
 };
 
 template <int N>
 __global__ void __launch_bounds__(PgdbCfg<N>::NT * PgdbCfg<N>::GPB) pgdb_kernel(PgdbView pv, int64_t B, const double* __restrict__ expect,
                             const double* __restrict__ counts, int make_tp, cplx* __restrict__ choi_out,
-                            int* __restrict__ counters, double* __restrict__ workspace, double rel2) {
+                            int* __restrict__ counters, int* __restrict__ status_out, double* __restrict__ workspace,
+                            double rel2) {
   using C = PgdbCfg<N>;
   using G = typename C::G;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -326,7 +333,7 @@ __global__ void __launch_bounds__(PgdbCfg<N>::NT * PgdbCfg<N>::GPB) pgdb_kernel(
     dt.inv_total = 1.0 / tot;
     C::Sync::sync();
     Pgdb<N>::run(pv, dt, make_tp != 0, choi_out + b * G::MM, ws, X, V, T, small,
-                 counters ? counters + 4 * b : nullptr, tid, rel2);
+                 counters ? counters + 4 * b : nullptr, status_out ? status_out + b : nullptr, tid, rel2);
     C::Sync::sync();
   }
 }
@@ -438,19 +445,20 @@ extern "C" int64_t qt_pgdb_workspace_bytes(const qt_pgdb_plan* p, int64_t B) {
 
 template <int N>
 static int launch_pgdb(const qt_pgdb_plan* p, int64_t B, const double* expect, const double* counts, int make_tp,
-                       void* choi_out, int* counters, void* ws, cudaStream_t st) {
+                       double rel2, void* choi_out, int* counters, int* status, void* ws, cudaStream_t st) {
   using C = PgdbCfg<N>;
   PgdbView pv{p->S, p->n_in, p->canonical, p->d_state_id, p->d_pidx, p->d_coeff, p->d_svec};
   const size_t smem = C::group_smem * C::GPB;
   QT_CUDA(cudaMemsetAsync(ws, 0, 256, st));  // work-queue counter
   QT_CUDA(cudaFuncSetAttribute(pgdb_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pgdb_kernel<N><<<(unsigned)pgdb_grid<N>(B), C::NT * C::GPB, smem, st>>>(pv, B, expect, counts, make_tp,
-                                                                          (cplx*)choi_out, counters, (double*)ws, qt_eigh_rel2());
+                                                                          (cplx*)choi_out, counters, status, (double*)ws, rel2);
   return qt_check_launch("pgdb_kernel");
 }
 
 extern "C" int qt_pgdb_process_batch(const qt_pgdb_plan* p, int64_t B, const double* expect, const double* counts,
-                                     int trace_preserving, void* choi_out, int32_t* counters_out, void* workspace,
+                                     int trace_preserving, double eigh_rel_tol, void* choi_out,
+                                     int32_t* counters_out, int32_t* status_out, void* workspace,
                                      int64_t workspace_bytes, void* stream) {
   QT_REQUIRE(p, "qt_pgdb_process_batch: null plan");
   if (B == 0) return QT_OK;
@@ -460,12 +468,16 @@ extern "C" int qt_pgdb_process_batch(const qt_pgdb_plan* p, int64_t B, const dou
                  (long long)qt_pgdb_workspace_bytes(p, B));
     return QT_ERR_WORKSPACE;
   }
+  double rel2;
+  if (qt_eigh_rel2_from_tol(eigh_rel_tol, &rel2, "qt_pgdb_process_batch") != QT_OK) return QT_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
+#define QT_PGDB_ARGS p, B, expect, counts, trace_preserving, rel2, choi_out, counters_out, status_out, workspace, st
   switch (p->n) {
-    case 1: return launch_pgdb<1>(p, B, expect, counts, trace_preserving, choi_out, counters_out, workspace, st);
-    case 2: return launch_pgdb<2>(p, B, expect, counts, trace_preserving, choi_out, counters_out, workspace, st);
-    default: return launch_pgdb<3>(p, B, expect, counts, trace_preserving, choi_out, counters_out, workspace, st);
+    case 1: return launch_pgdb<1>(QT_PGDB_ARGS);
+    case 2: return launch_pgdb<2>(QT_PGDB_ARGS);
+    default: return launch_pgdb<3>(QT_PGDB_ARGS);
   }
+#undef QT_PGDB_ARGS
 }
 
 // =============================================================================================

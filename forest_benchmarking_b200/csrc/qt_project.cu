@@ -480,7 +480,8 @@ __global__ void __launch_bounds__(256)
 template <int N>
 __global__ void __launch_bounds__(ProjCfg<N>::NT * ProjCfg<N>::GPB)
     proj_physical_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out, int make_tp,
-                         cplx* __restrict__ workspace, int* __restrict__ eigh_calls, double rel2) {
+                         cplx* __restrict__ workspace, int* __restrict__ eigh_calls, int* __restrict__ status_out,
+                         double rel2) {
   using C = ProjCfg<N>;
   using G = typename C::G;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -489,6 +490,7 @@ __global__ void __launch_bounds__(ProjCfg<N>::NT * ProjCfg<N>::GPB)
   cplx* V = X + G::MP;
   cplx* T = V + G::MP;
   double* small = reinterpret_cast<double*>(T + G::MP);
+  double* red = small + G::SMALL_DOUBLES - 64;
   const int64_t group = (int64_t)blockIdx.x * C::GPB + gib;
   const int64_t n_groups = (int64_t)gridDim.x * C::GPB;
   cplx* Q = workspace + group * 2 * G::MM;
@@ -496,15 +498,23 @@ __global__ void __launch_bounds__(ProjCfg<N>::NT * ProjCfg<N>::GPB)
   for (int64_t b = group; b < B; b += n_groups) {
     const cplx* src = in + b * G::MM;
     cplx* S = out + b * G::MM;
+    // S = Hermitian part of the input (all the iterates ever see, project_superoperators.py:30); the
+    // anti-Hermitian part only enters the stopping rule (see ChoiGroup::project_physical)
+    double anti2 = 0.0;
     for (int e = tid; e < G::MM; e += C::NT) {
       const int r = e / G::M, c = e % G::M;
       const cplx x = src[e], y = src[c * G::M + r];
       S[e] = cmake(0.5 * (x.x + y.x), 0.5 * (x.y - y.y));
+      anti2 += 0.25 * ((x.x - y.x) * (x.x - y.x) + (x.y + y.y) * (x.y + y.y));
     }
+    anti2 = group_sum<C::NT, typename C::Sync>(anti2, red, tid);
     C::Sync::sync();
     bool v_valid = false;  // items are unrelated: the first decomposition of each starts cold
-    const int calls = G::project_physical(S, Q, CPREV, X, V, T, small, make_tp != 0, tid, v_valid, nullptr, rel2);
+    int st = 0;
+    const int calls = G::project_physical(S, Q, CPREV, X, V, T, small, make_tp != 0, tid, v_valid, nullptr, rel2,
+                                          QT_DYKSTRA_MAX_ITER, anti2 > 0.0 ? src : nullptr, &st);
     if (tid == 0 && eigh_calls) eigh_calls[b] = calls;
+    if (tid == 0 && status_out) status_out[b] = st;
     C::Sync::sync();
   }
 }
@@ -650,8 +660,8 @@ static int launch_tp(int64_t B, const void* in, void* out, int make_tp, cudaStre
 }
 
 template <int N>
-static int launch_physical(int64_t B, const void* in, void* out, int make_tp, void* ws, int64_t ws_bytes,
-                           int* eigh_calls, cudaStream_t st) {
+static int launch_physical(int64_t B, const void* in, void* out, int make_tp, double rel2, void* ws,
+                           int64_t ws_bytes, int* eigh_calls, int* status, cudaStream_t st) {
   using C = ProjCfg<N>;
   const int64_t blocks = physical_grid<N>(B);
   const int64_t need = blocks * C::GPB * 2 * C::G::MM * (int64_t)sizeof(cplx);
@@ -663,7 +673,7 @@ static int launch_physical(int64_t B, const void* in, void* out, int make_tp, vo
   const size_t smem = C::group_smem * C::GPB;
   QT_CUDA(cudaFuncSetAttribute(proj_physical_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   proj_physical_kernel<N><<<(unsigned)blocks, C::NT * C::GPB, smem, st>>>(B, (const cplx*)in, (cplx*)out, make_tp,
-                                                                          (cplx*)ws, eigh_calls, qt_eigh_rel2());
+                                                                          (cplx*)ws, eigh_calls, status, rel2);
   return qt_check_launch("proj_physical_kernel");
 }
 
@@ -724,12 +734,16 @@ extern "C" int64_t qt_proj_physical_workspace_bytes(int n, int64_t B) {
 }
 
 extern "C" int qt_proj_physical_batch(int n, int64_t B, const void* choi, void* out, int make_trace_preserving,
-                                      void* workspace, int64_t workspace_bytes, int32_t* eigh_calls_out,
-                                      void* stream) {
+                                      double eigh_rel_tol, void* workspace, int64_t workspace_bytes,
+                                      int32_t* eigh_calls_out, int32_t* status_out, void* stream) {
   if (B == 0) return QT_OK;
   QT_REQUIRE(choi && out && workspace, "qt_proj_physical_batch: null argument");
-#define CALL(N) \
-  launch_physical<N>(B, choi, out, make_trace_preserving, workspace, workspace_bytes, eigh_calls_out, (cudaStream_t)stream)
+  QT_REQUIRE(choi != out, "qt_proj_physical_batch: in-place call not supported (the input is re-read by the stopping rule)");
+  double rel2;
+  if (qt_eigh_rel2_from_tol(eigh_rel_tol, &rel2, "qt_proj_physical_batch") != QT_OK) return QT_ERR_ARG;
+#define CALL(N)                                                                                                  \
+  launch_physical<N>(B, choi, out, make_trace_preserving, rel2, workspace, workspace_bytes, eigh_calls_out, \
+                     status_out, (cudaStream_t)stream)
   DISPATCH_N3(n, CALL)
 #undef CALL
 }

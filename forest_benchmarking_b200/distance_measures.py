@@ -18,13 +18,20 @@ def _pair_call(fn_name, rho, sigma, out=None):
     torch = _lib.require_cuda()
     if rho.shape != sigma.shape or rho.dim() != 3 or rho.dtype != torch.complex128:
         raise ValueError("rho and sigma must be complex128 CUDA tensors of identical shape [B, d, d]")
+    if rho.shape[1] != rho.shape[2]:
+        raise ValueError("rho and sigma must be square matrices [B, d, d]")
     rho, sigma = rho.contiguous(), sigma.contiguous()
     b, d = rho.shape[0], rho.shape[1]
-    if out is None:
-        out = torch.empty((b,), dtype=torch.float64, device=rho.device)
-    fn = getattr(_lib.lib(), fn_name)
-    _lib.check(fn(ctypes.c_int(_n_qubits(d)), ctypes.c_int64(b), _lib.ptr(rho), _lib.ptr(sigma), _lib.ptr(out),
-                  _lib.current_stream_ptr()), fn_name)
+    n = _n_qubits(d)
+    dev = _lib.common_device(rho, sigma, out)
+    with _lib.on_device(dev):
+        if out is None:
+            out = torch.empty((b,), dtype=torch.float64, device=dev)
+        else:
+            _lib.check_tensor("out", out, torch.float64, (b,))
+        fn = getattr(_lib.lib(), fn_name)
+        _lib.check(fn(ctypes.c_int(n), ctypes.c_int64(b), _lib.ptr(rho), _lib.ptr(sigma), _lib.ptr(out),
+                      _lib.current_stream_ptr()), fn_name)
     return out
 
 
@@ -44,24 +51,46 @@ def trace_distance_nuclear_batch(rho, sigma, out=None):
 
 
 def purity_batch(rho, out=None):
+    """tr(rho rho) (un-renormalised, the reference's default) for [B, d, d] complex128 CUDA states -> [B]."""
     torch = _lib.require_cuda()
+    if rho.dim() != 3 or rho.shape[1] != rho.shape[2] or rho.dtype != torch.complex128 or not rho.is_cuda:
+        raise ValueError("rho must be a complex128 CUDA tensor of shape [B, d, d]")
     rho = rho.contiguous()
     b, d = rho.shape[0], rho.shape[1]
-    if out is None:
-        out = torch.empty((b,), dtype=torch.float64, device=rho.device)
-    _lib.check(_lib.lib().qt_purity_batch(ctypes.c_int(_n_qubits(d)), ctypes.c_int64(b), _lib.ptr(rho),
-                                          _lib.ptr(out), _lib.current_stream_ptr()), "qt_purity_batch")
+    n = _n_qubits(d)
+    dev = _lib.common_device(rho, out)
+    with _lib.on_device(dev):
+        if out is None:
+            out = torch.empty((b,), dtype=torch.float64, device=dev)
+        else:
+            _lib.check_tensor("out", out, torch.float64, (b,))
+        _lib.check(_lib.lib().qt_purity_batch(ctypes.c_int(n), ctypes.c_int64(b), _lib.ptr(rho),
+                                              _lib.ptr(out), _lib.current_stream_ptr()), "qt_purity_batch")
     return out
 
 
 def _one(x):
     torch = _lib.require_cuda()
-    return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.complex128))[None]).cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.complex128))[None]).to(dev)
+
+
+def _real_if_close_item(z, tol=1000):
+    """The reference's return idiom (distance_measures.py:37, 61, 84, 216, 303)."""
+    return np.ndarray.item(np.real_if_close(np.asarray(z), tol))
 
 
 def fidelity(rho: np.ndarray, sigma: np.ndarray, tol: float = 1000) -> float:
-    """Drop-in for reference distance_measures.py:64-84."""
-    return float(fidelity_batch(_one(rho), _one(sigma)).item())
+    """Drop-in for reference distance_measures.py:64-84: ``np.ndarray.item(np.real_if_close(fid, tol))``.
+
+    The reference's ``fid`` is ``trace(sqrtm_psd(M))**2``; sqrtm_psd (calculational.py:77-91) rebuilds the root from
+    the REAL eigenvalues of ``eigh``, so the trace is ``sum_i sqrt(max(w_i, 0))`` plus an imaginary part that is
+    pure rounding noise of the ``(v * w) @ v^dagger`` product (~1e-17).  The kernel returns that real sum squared, so
+    the value handed to ``real_if_close`` has an exactly-zero imaginary part and the result is a float for every
+    ``tol``; the reference can only return a complex number when ``tol`` is set below its own rounding noise
+    (tol << 1), in which case the two agree in the real part."""
+    fid = np.complex128(fidelity_batch(_one(rho), _one(sigma)).item())
+    return _real_if_close_item(fid, tol)
 
 
 def infidelity(rho: np.ndarray, sigma: np.ndarray, tol: float = 1000) -> float:
@@ -74,13 +103,22 @@ def trace_distance(rho: np.ndarray, sigma: np.ndarray) -> float:
     return float(trace_distance_batch(_one(rho), _one(sigma)).item())
 
 
-def purity(rho: np.ndarray, dim_renorm=True, tol: float = 1000) -> float:
-    """reference distance_measures.py:14-37."""
-    p = float(purity_batch(_one(rho)).item())
+def purity(rho: np.ndarray, dim_renorm=False, tol: float = 1000) -> float:
+    """reference distance_measures.py:14-37: tr(rho rho), optionally renormalised to [0, 1] (default: NOT)."""
+    p = np.complex128(hilbert_schmidt_ip_batch(_one(np.asarray(rho).conj().T), _one(rho)).item())
     if dim_renorm:
-        d = np.asarray(rho).shape[0]
-        p = (d / (d - 1.0)) * (p - 1.0 / d)
-    return p
+        dim = np.asarray(rho).shape[0]
+        p = (dim / (dim - 1.0)) * (p - 1.0 / dim)
+    return _real_if_close_item(p, tol)
+
+
+def impurity(rho: np.ndarray, dim_renorm=False, tol: float = 1000) -> float:
+    """reference distance_measures.py:40-61: 1 - tr(rho rho), optionally renormalised to [0, 1] (default: NOT)."""
+    imp = 1 - np.complex128(hilbert_schmidt_ip_batch(_one(np.asarray(rho).conj().T), _one(rho)).item())
+    if dim_renorm:
+        dim = np.asarray(rho).shape[0]
+        imp = (dim / (dim - 1.0)) * imp
+    return _real_if_close_item(imp, tol)
 
 
 def hilbert_schmidt_ip_batch(a, b, out=None):
@@ -89,16 +127,16 @@ def hilbert_schmidt_ip_batch(a, b, out=None):
     if a.shape != b.shape or a.dim() != 3 or a.dtype != torch.complex128 or b.dtype != torch.complex128:
         raise ValueError("a and b must be complex128 CUDA tensors of identical shape [B, r, c]")
     a, b = a.contiguous(), b.contiguous()
-    if out is None:
-        out = torch.empty((a.shape[0],), dtype=torch.complex128, device=a.device)
-    _lib.check(_lib.lib().qt_hs_inner_batch(ctypes.c_int64(a.shape[1]), ctypes.c_int64(a.shape[2]),
-                                            ctypes.c_int64(a.shape[0]), _lib.ptr(a), _lib.ptr(b), _lib.ptr(out),
-                                            _lib.current_stream_ptr()), "qt_hs_inner_batch")
+    dev = _lib.common_device(a, b, out)
+    with _lib.on_device(dev):
+        if out is None:
+            out = torch.empty((a.shape[0],), dtype=torch.complex128, device=dev)
+        else:
+            _lib.check_tensor("out", out, torch.complex128, (a.shape[0],))
+        _lib.check(_lib.lib().qt_hs_inner_batch(ctypes.c_int64(a.shape[1]), ctypes.c_int64(a.shape[2]),
+                                                ctypes.c_int64(a.shape[0]), _lib.ptr(a), _lib.ptr(b), _lib.ptr(out),
+                                                _lib.current_stream_ptr()), "qt_hs_inner_batch")
     return out
-
-
-def _real_if_close_item(z, tol=1000):
-    return np.ndarray.item(np.real_if_close(np.asarray(z), tol))
 
 
 def hilbert_schmidt_ip(A: np.ndarray, B: np.ndarray, tol: float = 1000) -> float:

@@ -111,12 +111,13 @@ def shots_to_obs_moments_batch(bitarrays, col_masks, coeffs=None, use_beta_dist_
     if coeffs.dtype != torch.float64 or not coeffs.is_cuda or tuple(coeffs.shape) != (b,):
         raise ValueError(f"coeffs must be a CUDA float64 tensor of shape [{b}]")
     bitarrays, col_masks, coeffs = bitarrays.contiguous(), col_masks.contiguous(), coeffs.contiguous()
-    mean = torch.empty((b,), dtype=torch.float64, device=bitarrays.device)
-    var = torch.empty_like(mean)
-    _lib.check(_lib.lib().qt_shots_to_obs_moments_batch(
-        ctypes.c_int64(b), ctypes.c_int64(s), ctypes.c_int(q), _lib.ptr(bitarrays), _lib.ptr(col_masks),
-        _lib.ptr(coeffs), ctypes.c_int(1 if use_beta_dist_unbiased_prior else 0), _lib.ptr(mean), _lib.ptr(var),
-        _lib.current_stream_ptr()), "qt_shots_to_obs_moments_batch")
+    with _lib.on_device(_lib.common_device(bitarrays, col_masks, coeffs)):
+        mean = torch.empty((b,), dtype=torch.float64, device=bitarrays.device)
+        var = torch.empty_like(mean)
+        _lib.check(_lib.lib().qt_shots_to_obs_moments_batch(
+            ctypes.c_int64(b), ctypes.c_int64(s), ctypes.c_int(q), _lib.ptr(bitarrays), _lib.ptr(col_masks),
+            _lib.ptr(coeffs), ctypes.c_int(1 if use_beta_dist_unbiased_prior else 0), _lib.ptr(mean), _lib.ptr(var),
+            _lib.current_stream_ptr()), "qt_shots_to_obs_moments_batch")
     return mean, var
 
 
@@ -165,8 +166,9 @@ def calibrate_estimates_batch(mean, var, cal_mean, cal_var):
     for t in ts:
         if t.dtype != torch.float64 or not t.is_cuda or tuple(t.shape) != (b,):
             raise ValueError(f"all arguments must be CUDA float64 tensors of shape [{b}]")
-    om, ov = torch.empty_like(ts[0]), torch.empty_like(ts[0])
-    _lib.check(_lib.lib().qt_calibrate_estimates_batch(ctypes.c_int64(b), *[_lib.ptr(t) for t in ts], _lib.ptr(om),
-                                                       _lib.ptr(ov), _lib.current_stream_ptr()),
-               "qt_calibrate_estimates_batch")
+    with _lib.on_device(_lib.common_device(*ts)):
+        om, ov = torch.empty_like(ts[0]), torch.empty_like(ts[0])
+        _lib.check(_lib.lib().qt_calibrate_estimates_batch(ctypes.c_int64(b), *[_lib.ptr(t) for t in ts], _lib.ptr(om),
+                                                           _lib.ptr(ov), _lib.current_stream_ptr()),
+                   "qt_calibrate_estimates_batch")
     return om, ov

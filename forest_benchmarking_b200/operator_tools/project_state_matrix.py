@@ -20,10 +20,14 @@ def project_state_matrix_to_physical_batch(rho, out=None):
     n = int(round(np.log2(d)))
     if 2 ** n != d or not 1 <= n <= 5:
         raise ValueError(f"dimension {d} is not 2^n with 1 <= n <= 5")
-    if out is None:
-        out = torch.empty_like(rho)
-    _lib.check(_lib.lib().qt_project_state_batch(ctypes.c_int(n), ctypes.c_int64(rho.shape[0]), _lib.ptr(rho),
-                                                 _lib.ptr(out), _lib.current_stream_ptr()), "qt_project_state_batch")
+    with _lib.on_device(_lib.common_device(rho, out)):
+        if out is None:
+            out = torch.empty_like(rho)
+        else:
+            _lib.check_tensor("out", out, torch.complex128, rho.shape)
+        _lib.check(_lib.lib().qt_project_state_batch(ctypes.c_int(n), ctypes.c_int64(rho.shape[0]), _lib.ptr(rho),
+                                                     _lib.ptr(out), _lib.current_stream_ptr()),
+                   "qt_project_state_batch")
     return out
 
 

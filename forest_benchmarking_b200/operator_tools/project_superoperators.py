@@ -25,10 +25,14 @@ def _prep(choi):
 
 def _simple(name, choi, out):
     torch, choi, n = _prep(choi)
-    if out is None:
-        out = torch.empty_like(choi)
-    _lib.check(getattr(_lib.lib(), name)(ctypes.c_int(n), ctypes.c_int64(choi.shape[0]), _lib.ptr(choi),
-                                         _lib.ptr(out), _lib.current_stream_ptr()), name)
+    dev = _lib.common_device(choi, out)
+    with _lib.on_device(dev):
+        if out is None:
+            out = torch.empty_like(choi)
+        else:
+            _lib.check_tensor("out", out, torch.complex128, choi.shape)
+        _lib.check(getattr(_lib.lib(), name)(ctypes.c_int(n), ctypes.c_int64(choi.shape[0]), _lib.ptr(choi),
+                                             _lib.ptr(out), _lib.current_stream_ptr()), name)
     return out
 
 
@@ -48,27 +52,48 @@ def proj_choi_to_unitary_batch(choi, out=None):
     return _simple("qt_proj_unitary_batch", choi, out)
 
 
-def proj_choi_to_physical_batch(choi, make_trace_preserving=True, out=None, return_counts=False):
-    """Dykstra CP + TP (or TNI) projection of every matrix of the batch.  The input is Hermitised first
-    (the reference's CP step does the same on every Dykstra iteration, project_superoperators.py:30)."""
+def proj_choi_to_physical_batch(choi, make_trace_preserving=True, out=None, return_counts=False,
+                                eigh_rel_tol=None, return_status=False):
+    """Dykstra CP + TP (or TNI) projection of every matrix of the batch (reference project_superoperators.py:87-144).
+
+    A non-Hermitian input is treated exactly like the reference treats it: its CP step Hermitises (:30), so the
+    iterates and the result only depend on the Hermitian part, while the anti-Hermitian part stays inside
+    ``old_CP_change`` and enters the stopping rule (:132-136) -- the kernel adds those terms, so the number of
+    Dykstra trips (``return_counts``) matches the reference for such inputs too.
+    ``eigh_rel_tol``: eigensolver stopping tolerance (None = library default 1e-8, 0 = tight), per call.
+    ``return_status``: also return the int32 [B] status words (non-zero where a safety cap was hit)."""
     torch, choi, n = _prep(choi)
     b = choi.shape[0]
-    if out is None:
-        out = torch.empty_like(choi)
     lib = _lib.lib()
-    nbytes = int(lib.qt_proj_physical_workspace_bytes(ctypes.c_int(n), ctypes.c_int64(b)))
-    ws = torch.empty((max(nbytes, 16) // 16,), dtype=torch.complex128, device=choi.device)
-    counts = torch.empty((b,), dtype=torch.int32, device=choi.device)
-    _lib.check(lib.qt_proj_physical_batch(ctypes.c_int(n), ctypes.c_int64(b), _lib.ptr(choi), _lib.ptr(out),
-                                          ctypes.c_int(1 if make_trace_preserving else 0), _lib.ptr(ws),
-                                          ctypes.c_int64(nbytes), _lib.ptr(counts), _lib.current_stream_ptr()),
-               "qt_proj_physical_batch")
-    return (out, counts) if return_counts else out
+    dev = _lib.common_device(choi, out)
+    with _lib.on_device(dev):
+        if out is None:
+            out = torch.empty_like(choi)
+        else:
+            _lib.check_tensor("out", out, torch.complex128, choi.shape)
+            if out.data_ptr() == choi.data_ptr():
+                raise ValueError("proj_choi_to_physical_batch cannot run in place")
+        nbytes = int(lib.qt_proj_physical_workspace_bytes(ctypes.c_int(n), ctypes.c_int64(b)))
+        ws = torch.empty((max(nbytes, 16) // 16,), dtype=torch.complex128, device=dev)
+        counts = torch.empty((b,), dtype=torch.int32, device=dev)
+        status = torch.zeros((b,), dtype=torch.int32, device=dev)
+        _lib.check(lib.qt_proj_physical_batch(ctypes.c_int(n), ctypes.c_int64(b), _lib.ptr(choi), _lib.ptr(out),
+                                              ctypes.c_int(1 if make_trace_preserving else 0),
+                                              ctypes.c_double(-1.0 if eigh_rel_tol is None else eigh_rel_tol),
+                                              _lib.ptr(ws), ctypes.c_int64(nbytes), _lib.ptr(counts), _lib.ptr(status),
+                                              _lib.current_stream_ptr()), "qt_proj_physical_batch")
+    res = (out,)
+    if return_counts:
+        res += (counts,)
+    if return_status:
+        res += (status,)
+    return res if len(res) > 1 else out
 
 
 def _one(x):
     torch = _lib.require_cuda()
-    return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.complex128))[None]).cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    return torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.complex128))[None]).to(dev)
 
 
 def proj_choi_to_completely_positive(choi: np.ndarray, check_finite: bool = True) -> np.ndarray:
@@ -91,7 +116,10 @@ def proj_choi_to_trace_preserving(choi: np.ndarray) -> np.ndarray:
 
 def proj_choi_to_physical(choi: np.ndarray, make_trace_preserving: bool = True) -> np.ndarray:
     """reference project_superoperators.py:87-144."""
-    return proj_choi_to_physical_batch(_one(choi), make_trace_preserving)[0].cpu().numpy()
+    from ..tomography import warn_on_status
+    out, status = proj_choi_to_physical_batch(_one(choi), make_trace_preserving, return_status=True)
+    warn_on_status(status.cpu().numpy(), "proj_choi_to_physical")
+    return out[0].cpu().numpy()
 
 
 def proj_choi_to_unitary(choi: np.ndarray, check_finite: bool = True) -> np.ndarray:

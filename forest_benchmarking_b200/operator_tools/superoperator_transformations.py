@@ -54,9 +54,10 @@ def _kraus_call(name, kraus):
     b, nk, d, d_ = kraus.shape
     if d != d_:
         raise ValueError("batched Kraus conversion needs square Kraus operators")
-    out = torch.empty((b, d * d, d * d), dtype=torch.complex128, device=kraus.device)
-    _lib.check(getattr(_lib.lib(), name)(ctypes.c_int(d), ctypes.c_int(nk), ctypes.c_int64(b), _lib.ptr(kraus),
-                                         _lib.ptr(out), _lib.current_stream_ptr()), name)
+    with _lib.on_device(kraus.device):
+        out = torch.empty((b, d * d, d * d), dtype=torch.complex128, device=kraus.device)
+        _lib.check(getattr(_lib.lib(), name)(ctypes.c_int(d), ctypes.c_int(nk), ctypes.c_int64(b), _lib.ptr(kraus),
+                                             _lib.ptr(out), _lib.current_stream_ptr()), name)
     return out
 
 
@@ -76,11 +77,16 @@ def reshuffle_batch(mat, out=None):
     mat = _check_c128(mat, 3)
     b, d2, _ = mat.shape
     d = 2 ** _nq(d2)
-    if out is None:
-        out = torch.empty_like(mat)
-    _lib.check(_lib.lib().qt_choi_superop_reshuffle_batch(ctypes.c_int(d), ctypes.c_int64(b), _lib.ptr(mat),
-                                                          _lib.ptr(out), _lib.current_stream_ptr()),
-               "qt_choi_superop_reshuffle_batch")
+    with _lib.on_device(_lib.common_device(mat, out)):
+        if out is None:
+            out = torch.empty_like(mat)
+        else:
+            _lib.check_tensor("out", out, torch.complex128, mat.shape)
+            if out.data_ptr() == mat.data_ptr():
+                raise ValueError("reshuffle_batch is out-of-place")
+        _lib.check(_lib.lib().qt_choi_superop_reshuffle_batch(ctypes.c_int(d), ctypes.c_int64(b), _lib.ptr(mat),
+                                                              _lib.ptr(out), _lib.current_stream_ptr()),
+                   "qt_choi_superop_reshuffle_batch")
     return out
 
 
@@ -89,12 +95,17 @@ def _pl_call(name, mat, out, workspace):
     mat = _check_c128(mat, 3)
     b, d2, _ = mat.shape
     n = _nq(d2)
-    if out is None:
-        out = torch.empty_like(mat)
-    if n >= 4 and workspace is None:
-        workspace = torch.empty_like(mat)
-    _lib.check(getattr(_lib.lib(), name)(ctypes.c_int(n), ctypes.c_int64(b), _lib.ptr(mat), _lib.ptr(out),
-                                         _lib.ptr(workspace), _lib.current_stream_ptr()), name)
+    with _lib.on_device(_lib.common_device(mat, out, workspace)):
+        if out is None:
+            out = torch.empty_like(mat)
+        else:
+            _lib.check_tensor("out", out, torch.complex128, mat.shape)
+        if n >= 4 and workspace is None:
+            workspace = torch.empty_like(mat)
+        if workspace is not None and workspace.numel() * workspace.element_size() < mat.numel() * 16:
+            raise ValueError("workspace is smaller than the batch")
+        _lib.check(getattr(_lib.lib(), name)(ctypes.c_int(n), ctypes.c_int64(b), _lib.ptr(mat), _lib.ptr(out),
+                                             _lib.ptr(workspace), _lib.current_stream_ptr()), name)
     return out
 
 
@@ -123,22 +134,23 @@ def choi2kraus_batch(choi, tol: float = 1e-9):
     b, d2, _ = choi.shape
     n = _nq(d2)
     d = 2 ** n
-    kraus = torch.empty((b, d2, d, d), dtype=torch.complex128, device=choi.device)
-    evals = torch.empty((b, d2), dtype=torch.float64, device=choi.device)
-    counts = torch.empty((b,), dtype=torch.int32, device=choi.device)
-    if n >= 4:  # the eigenproblem does not fit shared memory: one-sided Jacobi out of an L2-resident workspace
-        lib = _lib.lib()
-        nbytes = int(lib.qt_choi2kraus_large_workspace_bytes(ctypes.c_int(n), ctypes.c_int64(b)))
-        ws = torch.empty((nbytes // 16,), dtype=torch.complex128, device=choi.device)
-        _lib.check(lib.qt_choi2kraus_large_batch(ctypes.c_int(n), ctypes.c_int64(b), _lib.ptr(choi), ctypes.c_double(tol),
-                                                 _lib.ptr(evals), _lib.ptr(kraus), _lib.ptr(counts), _lib.ptr(ws),
-                                                 ctypes.c_int64(nbytes), ctypes.c_void_p(0), _lib.current_stream_ptr()),
-                   "qt_choi2kraus_large_batch")
+    with _lib.on_device(choi.device):
+        kraus = torch.empty((b, d2, d, d), dtype=torch.complex128, device=choi.device)
+        evals = torch.empty((b, d2), dtype=torch.float64, device=choi.device)
+        counts = torch.empty((b,), dtype=torch.int32, device=choi.device)
+        if n >= 4:  # the eigenproblem does not fit shared memory: one-sided Jacobi out of an L2-resident workspace
+            lib = _lib.lib()
+            nbytes = int(lib.qt_choi2kraus_large_workspace_bytes(ctypes.c_int(n), ctypes.c_int64(b)))
+            ws = torch.empty((nbytes // 16,), dtype=torch.complex128, device=choi.device)
+            _lib.check(lib.qt_choi2kraus_large_batch(ctypes.c_int(n), ctypes.c_int64(b), _lib.ptr(choi), ctypes.c_double(tol),
+                                                     _lib.ptr(evals), _lib.ptr(kraus), _lib.ptr(counts), _lib.ptr(ws),
+                                                     ctypes.c_int64(nbytes), ctypes.c_void_p(0), _lib.current_stream_ptr()),
+                       "qt_choi2kraus_large_batch")
+            return kraus, counts, evals
+        _lib.check(_lib.lib().qt_choi2kraus_batch(ctypes.c_int(n), ctypes.c_int64(b), _lib.ptr(choi), ctypes.c_double(tol),
+                                                  _lib.ptr(evals), _lib.ptr(kraus), _lib.ptr(counts),
+                                                  _lib.current_stream_ptr()), "qt_choi2kraus_batch")
         return kraus, counts, evals
-    _lib.check(_lib.lib().qt_choi2kraus_batch(ctypes.c_int(n), ctypes.c_int64(b), _lib.ptr(choi), ctypes.c_double(tol),
-                                              _lib.ptr(evals), _lib.ptr(kraus), _lib.ptr(counts),
-                                              _lib.current_stream_ptr()), "qt_choi2kraus_batch")
-    return kraus, counts, evals
 
 
 def kraus2chi_batch(kraus):

@@ -19,16 +19,20 @@ OPTIMAL = "optimal"
 FRO = "fro"
 
 KERNEL_AUTO, KERNEL_REGISTER, KERNEL_WARP, KERNEL_QUAD = 0, 1, 2, 3
+DEFAULT_MAXITER = 10_000  # iterative_mle_state_estimate's default (reference tomography.py:170)
 
 
 class MlePlan:
     """Device-side description of one list of observables (shared by every experiment of a batch)."""
 
     def __init__(self, n_qubits: int, pauli_idx, coeffs=None):
-        _lib.require_cuda()
+        torch = _lib.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device())  # the plan's tables live here
         self.n = int(n_qubits)
         idx = np.ascontiguousarray(pauli_idx, dtype=np.int32)
         cf = np.ones(len(idx)) if coeffs is None else np.ascontiguousarray(coeffs, dtype=np.float64)
+        if idx.ndim != 1 or cf.shape != idx.shape:
+            raise ValueError("pauli_idx and coeffs must be 1-D with one entry per result")
         self.K = len(idx)
         self.pauli_idx, self.coeffs = idx, cf
         self._h = ctypes.c_void_p()
@@ -46,7 +50,7 @@ class MlePlan:
 
 
 def iterative_mle_state_estimate_batch(plan: MlePlan, expectations, counts=None, epsilon=.1,
-                                       entropy_penalty=0.0, beta=0.0, tol=1e-9, maxiter=10_000,
+                                       entropy_penalty=0.0, beta=0.0, tol=1e-9, maxiter=DEFAULT_MAXITER,
                                        kernel=KERNEL_AUTO, out=None, iters_out=None):
     """Batched diluted MLE.  ``expectations`` / ``counts``: CUDA float64 tensors [B, K] (K = plan.K).
     Returns (rho [B, d, d] complex128 CUDA tensor, iterations [B] int32 CUDA tensor); iterations equals
@@ -60,19 +64,29 @@ def iterative_mle_state_estimate_batch(plan: MlePlan, expectations, counts=None,
     if expectations.shape[1] != plan.K:
         raise ValueError(f"expectations has {expectations.shape[1]} columns, plan has {plan.K}")
     expectations = expectations.contiguous()
-    if counts is not None:
-        counts = counts.to(torch.float64).contiguous()
     b = expectations.shape[0]
     d = 2 ** plan.n
-    if out is None:
-        out = torch.empty((b, d, d), dtype=torch.complex128, device=expectations.device)
-    if iters_out is None:
-        iters_out = torch.empty((b,), dtype=torch.int32, device=expectations.device)
-    _lib.check(_lib.lib().qt_mle_state_batch(
-        plan._h, ctypes.c_int64(b), _lib.ptr(expectations), _lib.ptr(counts), ctypes.c_double(epsilon),
-        ctypes.c_double(entropy_penalty), ctypes.c_double(beta), ctypes.c_double(tol), ctypes.c_int(maxiter),
-        ctypes.c_int(kernel), _lib.ptr(out), _lib.ptr(iters_out), _lib.current_stream_ptr()),
-        "qt_mle_state_batch")
+    if counts is not None:
+        if not counts.is_cuda or tuple(counts.shape) != (b, plan.K):
+            raise ValueError(f"counts must be a CUDA tensor of shape [{b}, {plan.K}]")
+        counts = counts.to(torch.float64).contiguous()
+    elif beta != 0.0:
+        raise ValueError("hedged MLE (beta != 0) needs the shot counts")
+    dev = _lib.common_device(expectations, counts, out, iters_out, plan=plan)
+    with _lib.on_device(dev):
+        if out is None:
+            out = torch.empty((b, d, d), dtype=torch.complex128, device=dev)
+        else:
+            _lib.check_tensor("out", out, torch.complex128, (b, d, d))
+        if iters_out is None:
+            iters_out = torch.empty((b,), dtype=torch.int32, device=dev)
+        else:
+            _lib.check_tensor("iters_out", iters_out, torch.int32, (b,))
+        _lib.check(_lib.lib().qt_mle_state_batch(
+            plan._h, ctypes.c_int64(b), _lib.ptr(expectations), _lib.ptr(counts), ctypes.c_double(epsilon),
+            ctypes.c_double(entropy_penalty), ctypes.c_double(beta), ctypes.c_double(tol), ctypes.c_int(maxiter),
+            ctypes.c_int(kernel), _lib.ptr(out), _lib.ptr(iters_out), _lib.current_stream_ptr()),
+            "qt_mle_state_batch")
     return out, iters_out
 
 
@@ -84,10 +98,15 @@ def linear_inv_state_estimate_batch(plan: MlePlan, expectations, out=None):
         raise ValueError(f"expectations must be a CUDA float64 tensor of shape [B, {plan.K}]")
     expectations = expectations.contiguous()
     b, d = expectations.shape[0], 2 ** plan.n
-    if out is None:
-        out = torch.empty((b, d, d), dtype=torch.complex128, device=expectations.device)
-    _lib.check(_lib.lib().qt_linear_inv_state_batch(plan._h, ctypes.c_int64(b), _lib.ptr(expectations), _lib.ptr(out),
-                                                    _lib.current_stream_ptr()), "qt_linear_inv_state_batch")
+    dev = _lib.common_device(expectations, out, plan=plan)
+    with _lib.on_device(dev):
+        if out is None:
+            out = torch.empty((b, d, d), dtype=torch.complex128, device=dev)
+        else:
+            _lib.check_tensor("out", out, torch.complex128, (b, d, d))
+        _lib.check(_lib.lib().qt_linear_inv_state_batch(plan._h, ctypes.c_int64(b), _lib.ptr(expectations),
+                                                        _lib.ptr(out), _lib.current_stream_ptr()),
+                   "qt_linear_inv_state_batch")
     return out
 
 
@@ -110,11 +129,16 @@ def state_log_likelihood_batch(plan: MlePlan, rho, expectations, counts, out=Non
         if t.dtype != torch.float64 or not t.is_cuda or tuple(t.shape) != (b, plan.K):
             raise ValueError(f"{name} must be a CUDA float64 tensor of shape [{b}, {plan.K}]")
     rho, expectations, counts = rho.contiguous(), expectations.contiguous(), counts.contiguous()
-    if out is None:
-        out = torch.empty((b,), dtype=torch.float64, device=rho.device)
-    _lib.check(_lib.lib().qt_state_log_likelihood_batch(plan._h, ctypes.c_int64(b), _lib.ptr(rho),
-                                                        _lib.ptr(expectations), _lib.ptr(counts), _lib.ptr(out),
-                                                        _lib.current_stream_ptr()), "qt_state_log_likelihood_batch")
+    dev = _lib.common_device(rho, expectations, counts, out, plan=plan)
+    with _lib.on_device(dev):
+        if out is None:
+            out = torch.empty((b,), dtype=torch.float64, device=dev)
+        else:
+            _lib.check_tensor("out", out, torch.float64, (b,))
+        _lib.check(_lib.lib().qt_state_log_likelihood_batch(plan._h, ctypes.c_int64(b), _lib.ptr(rho),
+                                                            _lib.ptr(expectations), _lib.ptr(counts), _lib.ptr(out),
+                                                            _lib.current_stream_ptr()),
+                   "qt_state_log_likelihood_batch")
     return out
 
 
@@ -133,17 +157,29 @@ def mle_step_batch(n_qubits: int, expect_canon, rho, epsilon=.1, out=None):
     """ONE R-rho-R update streamed through HBM (n = 1, 2; complete canonical Pauli set).
     expect_canon: [4^n - 1, B] float64 CUDA (item-minor); rho: [B, d, d] complex128 CUDA."""
     torch = _lib.require_cuda()
+    n = int(n_qubits)
+    if n not in (1, 2):
+        raise ValueError("mle_step_batch supports n_qubits = 1, 2")
+    d, k = 2 ** n, 4 ** n - 1
+    if rho.dim() != 3:
+        raise ValueError(f"rho must be a CUDA complex128 tensor of shape [B, {d}, {d}]")
     b = rho.shape[0]
-    if out is None:
-        out = torch.empty_like(rho)
-    _lib.check(_lib.lib().qt_mle_step_batch(ctypes.c_int(n_qubits), ctypes.c_int64(b), _lib.ptr(expect_canon),
-                                            _lib.ptr(rho), ctypes.c_double(epsilon), _lib.ptr(out),
-                                            _lib.current_stream_ptr()), "qt_mle_step_batch")
+    _lib.check_tensor("rho", rho, torch.complex128, (b, d, d))
+    _lib.check_tensor("expect_canon", expect_canon, torch.float64, (k, b))
+    dev = _lib.common_device(rho, expect_canon, out)
+    with _lib.on_device(dev):
+        if out is None:
+            out = torch.empty_like(rho)
+        else:
+            _lib.check_tensor("out", out, torch.complex128, (b, d, d))
+        _lib.check(_lib.lib().qt_mle_step_batch(ctypes.c_int(n), ctypes.c_int64(b), _lib.ptr(expect_canon),
+                                                _lib.ptr(rho), ctypes.c_double(epsilon), _lib.ptr(out),
+                                                _lib.current_stream_ptr()), "qt_mle_step_batch")
     return out
 
 
 def iterative_mle_state_estimate(results: List, qubits: List[int], epsilon=.1, entropy_penalty=0.0,
-                                 beta=0.0, tol=1e-9, maxiter=10_000) -> np.ndarray:
+                                 beta=0.0, tol=1e-9, maxiter=DEFAULT_MAXITER) -> np.ndarray:
     """Drop-in for reference tomography.py:168-270 (one experiment = a batch of one)."""
     torch = _lib.require_cuda()
     if (entropy_penalty != 0.0) and (beta != 0.0):
@@ -193,8 +229,9 @@ def estimate_variance(results: List, qubits: List[int], tomo_estimator, function
             rho = linear_inv_state_estimate_batch(plan, e)
         else:
             c = torch.from_numpy(np.tile(cnt, (n_resamples, 1))).to(dev)
-            rho, iters = iterative_mle_state_estimate_batch(plan, e, c)
-            if bool((iters >= 10_000).any().item()):
+            maxiter = DEFAULT_MAXITER  # the reference calls the estimator with its defaults (tomography.py:442)
+            rho, iters = iterative_mle_state_estimate_batch(plan, e, c, maxiter=maxiter)
+            if bool((iters >= maxiter).any().item()):
                 warnings.warn('Maximum number of iterations reached before convergence.')
     else:
         from .observable_estimation import ExperimentResult
@@ -229,7 +266,8 @@ class PgdbPlan:
     """Device-side description of one list of process-tomography settings (shared by the batch)."""
 
     def __init__(self, n_qubits: int, state_codes, pauli_idx, coeffs=None):
-        _lib.require_cuda()
+        torch = _lib.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device())  # the plan's tables live here
         self.n = int(n_qubits)
         codes = np.ascontiguousarray(state_codes, dtype=np.int32).reshape(-1, self.n)
         idx = np.ascontiguousarray(pauli_idx, dtype=np.int32)
@@ -264,29 +302,61 @@ class PgdbPlan:
                 pass
 
 
+STATUS_DYKSTRA_CAP, STATUS_JACOBI_CAP, STATUS_PGDB_CAP = 1, 2, 4  # QT_STATUS_* of include/qtomo.h
+
+
+def warn_on_status(status, what):
+    """The reference's loops are unbounded; the kernels carry safety caps (10000 Dykstra trips, 30 Jacobi sweeps,
+    100000 PGD steps).  A capped item is returned but NOT converged: say so instead of passing it off as valid."""
+    bits = int(np.bitwise_or.reduce(np.asarray(status, dtype=np.int64).ravel(), initial=0))
+    if bits & STATUS_PGDB_CAP:
+        warnings.warn(f"{what}: projected gradient descent stopped at its iteration cap before convergence.")
+    if bits & STATUS_DYKSTRA_CAP:
+        warnings.warn(f"{what}: a proj_choi_to_physical call stopped at its iteration cap before convergence.")
+    if bits & STATUS_JACOBI_CAP:
+        warnings.warn(f"{what}: an eigendecomposition used all its Jacobi sweeps; the result may be inaccurate.")
+    return bits
+
+
 def pgdb_process_estimate_batch(plan: PgdbPlan, expectations, counts, trace_preserving=True, out=None,
-                                return_counters=False, workspace=None):
+                                return_counters=False, workspace=None, eigh_rel_tol=None, return_status=False):
     """Batched PGDB.  expectations / counts: CUDA float64 [B, S].  Returns choi [B, 4^n, 4^n] complex128
-    (and, optionally, int32 [B, 4] counters: outer iterations, cost evaluations, eigh calls, Jacobi sweeps)."""
+    (and, optionally, int32 [B, 4] counters: outer iterations, cost evaluations, eigh calls, Jacobi sweeps; and
+    int32 [B] status words, non-zero where a safety cap was hit -- see ``warn_on_status``).
+    ``eigh_rel_tol``: stopping tolerance of the eigensolver behind the CP projection (None = library default 1e-8,
+    0 = tight); a per-call argument, nothing global."""
     torch = _lib.require_cuda()
     for t in (expectations, counts):
         if t.dtype != torch.float64 or not t.is_cuda or t.dim() != 2 or t.shape[1] != plan.S:
             raise ValueError(f"expectations and counts must be CUDA float64 tensors of shape [B, {plan.S}]")
+    if expectations.shape != counts.shape:
+        raise ValueError("expectations and counts must have the same shape")
     expectations, counts = expectations.contiguous(), counts.contiguous()
     b, m = expectations.shape[0], 4 ** plan.n
     lib = _lib.lib()
-    if out is None:
-        out = torch.empty((b, m, m), dtype=torch.complex128, device=expectations.device)
-    counters = torch.zeros((b, 4), dtype=torch.int32, device=expectations.device)
-    nbytes = int(lib.qt_pgdb_workspace_bytes(plan._h, ctypes.c_int64(b)))
-    if workspace is None or workspace.numel() * workspace.element_size() < nbytes:
-        workspace = torch.empty((max(nbytes, 8) // 8,), dtype=torch.float64, device=expectations.device)
-    _lib.check(lib.qt_pgdb_process_batch(plan._h, ctypes.c_int64(b), _lib.ptr(expectations), _lib.ptr(counts),
-                                         ctypes.c_int(1 if trace_preserving else 0), _lib.ptr(out),
-                                         _lib.ptr(counters), _lib.ptr(workspace),
-                                         ctypes.c_int64(workspace.numel() * workspace.element_size()),
-                                         _lib.current_stream_ptr()), "qt_pgdb_process_batch")
-    return (out, counters) if return_counters else out
+    dev = _lib.common_device(expectations, counts, out, workspace, plan=plan)
+    with _lib.on_device(dev):
+        if out is None:
+            out = torch.empty((b, m, m), dtype=torch.complex128, device=dev)
+        else:
+            _lib.check_tensor("out", out, torch.complex128, (b, m, m))
+        counters = torch.zeros((b, 4), dtype=torch.int32, device=dev)
+        status = torch.zeros((b,), dtype=torch.int32, device=dev)
+        nbytes = int(lib.qt_pgdb_workspace_bytes(plan._h, ctypes.c_int64(b)))
+        if workspace is None or workspace.numel() * workspace.element_size() < nbytes:
+            workspace = torch.empty((max(nbytes, 8) // 8,), dtype=torch.float64, device=dev)
+        _lib.check(lib.qt_pgdb_process_batch(plan._h, ctypes.c_int64(b), _lib.ptr(expectations), _lib.ptr(counts),
+                                             ctypes.c_int(1 if trace_preserving else 0),
+                                             ctypes.c_double(-1.0 if eigh_rel_tol is None else eigh_rel_tol),
+                                             _lib.ptr(out), _lib.ptr(counters), _lib.ptr(status), _lib.ptr(workspace),
+                                             ctypes.c_int64(workspace.numel() * workspace.element_size()),
+                                             _lib.current_stream_ptr()), "qt_pgdb_process_batch")
+    res = (out,)
+    if return_counters:
+        res += (counters,)
+    if return_status:
+        res += (status,)
+    return res if len(res) > 1 else out
 
 
 def pgdb_process_estimate(results: List, qubits: List[int], trace_preserving=True) -> np.ndarray:
@@ -295,8 +365,10 @@ def pgdb_process_estimate(results: List, qubits: List[int], trace_preserving=Tru
     codes, idx, cf, ex, cnt = flatten_process_results(results, qubits)
     plan = PgdbPlan(len(qubits), codes, idx, cf)
     dev = torch.device("cuda", torch.cuda.current_device())
-    choi = pgdb_process_estimate_batch(plan, torch.from_numpy(ex[None, :]).to(dev),
-                                       torch.from_numpy(cnt[None, :]).to(dev), trace_preserving)
+    choi, status = pgdb_process_estimate_batch(plan, torch.from_numpy(ex[None, :]).to(dev),
+                                               torch.from_numpy(cnt[None, :]).to(dev), trace_preserving,
+                                               return_status=True)
+    warn_on_status(status.cpu().numpy(), "pgdb_process_estimate")
     return choi[0].cpu().numpy()
 
 
@@ -308,11 +380,15 @@ def linear_inv_process_estimate_batch(plan: PgdbPlan, expectations, out=None):
         raise ValueError(f"expectations must be a CUDA float64 tensor of shape [B, {plan.S}]")
     expectations = expectations.contiguous()
     b, m = expectations.shape[0], 4 ** plan.n
-    if out is None:
-        out = torch.empty((b, m, m), dtype=torch.complex128, device=expectations.device)
-    _lib.check(_lib.lib().qt_linear_inv_process_batch(plan._h, ctypes.c_int64(b), _lib.ptr(expectations),
-                                                      _lib.ptr(out), _lib.current_stream_ptr()),
-               "qt_linear_inv_process_batch")
+    dev = _lib.common_device(expectations, out, plan=plan)
+    with _lib.on_device(dev):
+        if out is None:
+            out = torch.empty((b, m, m), dtype=torch.complex128, device=dev)
+        else:
+            _lib.check_tensor("out", out, torch.complex128, (b, m, m))
+        _lib.check(_lib.lib().qt_linear_inv_process_batch(plan._h, ctypes.c_int64(b), _lib.ptr(expectations),
+                                                          _lib.ptr(out), _lib.current_stream_ptr()),
+                   "qt_linear_inv_process_batch")
     return out
 
 

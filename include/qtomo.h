@@ -33,9 +33,14 @@ int qt_version(void);
 /* copies the last error message of this thread into buf (NUL-terminated, truncated to len) */
 int qt_last_error(char* buf, int len);
 
-/* Process-wide tuning knob: relative off-diagonal Frobenius norm at which the Jacobi eigensolver inside
- * qt_proj_physical_batch / qt_pgdb_process_batch declares convergence (default 1e-8; 0 = tight 1e-15 * 4^n). */
-int qt_set_eigh_tolerance(double rel_off);
+/* `eigh_rel_tol` argument of qt_proj_physical_batch / qt_pgdb_process_batch: relative off-diagonal Frobenius norm at
+ * which the Jacobi eigensolver behind proj_choi_to_completely_positive declares convergence.  Negative = the default
+ * below; 0 = tight (1e-15 * 4^n); otherwise < 1e-3.  A per-call argument: the library has no mutable global state. */
+#define QT_EIGH_REL_TOL_DEFAULT 1e-8
+/* per-item status bits (status_out arrays): the reference's loops are unbounded, ours carry safety caps */
+#define QT_STATUS_DYKSTRA_CAP 1 /* proj_choi_to_physical stopped at 10000 CP projections without meeting its rule */
+#define QT_STATUS_JACOBI_CAP 2  /* an eigendecomposition used all 30 sweeps */
+#define QT_STATUS_PGDB_CAP 4    /* pgdb_process_estimate stopped at 100000 outer iterations */
 
 /* FP64 FMA throughput probe (bench utility): blocks*threads*8*iters FMAs; scratch = 1 double on device */
 int qt_fp64_probe(int blocks, int threads, int iters, double* scratch, void* stream);
@@ -126,12 +131,15 @@ int qt_proj_unitary_batch(int n, int64_t B, const void* choi, void* out, void* s
   /* :19-34 */
 int qt_proj_tp_batch(int n, int64_t B, const void* choi, void* out, void* stream);   /* :62-84 */
 int qt_proj_tni_batch(int n, int64_t B, const void* choi, void* out, void* stream);  /* :37-59 */
-/* Dykstra CP+TP (or CP+TNI) projection, :87-144.  The input is Hermitised first.  workspace: device
- * buffer of qt_proj_physical_workspace_bytes(n, B) bytes; eigh_calls_out[B] (may be NULL) = number of CP
- * projections each item needed. */
+/* Dykstra CP+TP (or CP+TNI) projection, :87-144.  A non-Hermitian input is handled like the reference does: the
+ * iterates only see its Hermitian part, the anti-Hermitian part enters the stopping rule (so the trip count matches).
+ * out must not alias choi.  workspace: device buffer of qt_proj_physical_workspace_bytes(n, B) bytes;
+ * eigh_calls_out[B] (may be NULL) = number of CP projections each item needed; status_out[B] (may be NULL) =
+ * QT_STATUS_* bits. */
 int64_t qt_proj_physical_workspace_bytes(int n, int64_t B);
 int qt_proj_physical_batch(int n, int64_t B, const void* choi, void* out, int make_trace_preserving,
-                           void* workspace, int64_t workspace_bytes, int32_t* eigh_calls_out, void* stream);
+                           double eigh_rel_tol, void* workspace, int64_t workspace_bytes, int32_t* eigh_calls_out,
+                           int32_t* status_out, void* stream);
 
 /* ---- process tomography: pgdb_process_estimate (tomography.py:542-594) ------------------------- */
 typedef struct qt_pgdb_plan qt_pgdb_plan;
@@ -145,10 +153,11 @@ int qt_pgdb_plan_info(const qt_pgdb_plan* plan, int32_t* n_in_out, int32_t* cano
 int64_t qt_pgdb_workspace_bytes(const qt_pgdb_plan* plan, int64_t B);
 /* expect[B,S], counts[B,S] -> choi_out[B,4^n,4^n]; counters_out[B,4] (may be NULL) = outer iterations,
  * cost evaluations, eigh calls (the trip counts of tomography.py:570, :576/:582 and project_superoperators.py:115)
- * and the total number of Jacobi sweeps those eigh calls took (a cost figure; no reference counterpart) */
+ * and the total number of Jacobi sweeps those eigh calls took (a cost figure; no reference counterpart);
+ * status_out[B] (may be NULL) = QT_STATUS_* bits; eigh_rel_tol: see QT_EIGH_REL_TOL_DEFAULT */
 int qt_pgdb_process_batch(const qt_pgdb_plan* plan, int64_t B, const double* expect, const double* counts,
-                          int trace_preserving, void* choi_out, int32_t* counters_out, void* workspace,
-                          int64_t workspace_bytes, void* stream);
+                          int trace_preserving, double eigh_rel_tol, void* choi_out, int32_t* counters_out,
+                          int32_t* status_out, void* workspace, int64_t workspace_bytes, void* stream);
 /* linear_inv_process_estimate (tomography.py:459-491): expect[B,S] -> choi_out[B,m,m], minimum-norm least squares
  * over the plan's settings list plus the identity term.  The per-observable pseudo-inverse weights are built from
  * the plan on first use (the reference's dense pinv of the S x 16^n measurement matrix is never formed). */

@@ -105,6 +105,50 @@ def golden_algebra(ref, name, seed, n, batch):
     print(f"{name}: done")
 
 
+def golden_nonhermitian_physical(ref, name="proj_physical_nonherm"):
+    """proj_choi_to_physical on NON-Hermitian inputs (the reference does not Hermitise up front: the anti-Hermitian
+    part lives on in old_CP_change and enters the stopping rule, project_superoperators.py:112-136), with the
+    number of CP projections each call made; plus distance-measure defaults (purity / impurity without keywords)."""
+    import forest.benchmarking.operator_tools.project_superoperators as ps
+    out = {}
+    for n, seed, batch in ((1, 7001, 6), (2, 7002, 4), (3, 7003, 2)):
+        rng = np.random.default_rng(seed)
+        d = 2 ** n
+        xs, ys, ts, cnt, cnt_t = [], [], [], [], []
+        for b in range(batch):
+            u1, u2 = orc.haar_unitary(rng, d), orc.haar_unitary(rng, d)
+            choi = orc.kraus2choi([np.sqrt(.7) * u1, np.sqrt(.3) * u2])
+            g = rng.standard_normal((d * d, d * d)) + 1j * rng.standard_normal((d * d, d * d))
+            # growing anti-Hermitian share: from a small perturbation to one that changes the trip count
+            x = choi + (g + g.conj().T) / (4 * d * d) + (0.02 * 3 ** b) * (g - g.conj().T) / (4 * d * d)
+            xs.append(x)
+            with CallCounter(ps, "proj_choi_to_completely_positive") as c:
+                ys.append(ps.proj_choi_to_physical(x))
+            cnt.append(c.n)
+            with CallCounter(ps, "proj_choi_to_completely_positive") as c:
+                ts.append(ps.proj_choi_to_physical(x, False))
+            cnt_t.append(c.n)
+        out[f"n{n}_in"], out[f"n{n}_out"], out[f"n{n}_out_tni"] = np.stack(xs), np.stack(ys), np.stack(ts)
+        out[f"n{n}_calls"], out[f"n{n}_calls_tni"] = np.array(cnt, dtype=np.int32), np.array(cnt_t, dtype=np.int32)
+        # the same inputs Hermitised first: what a wrapper that symmetrises up front would count
+        herm = []
+        for x in xs:
+            with CallCounter(ps, "proj_choi_to_completely_positive") as c:
+                ps.proj_choi_to_physical((x + x.conj().T) / 2)
+            herm.append(c.n)
+        out[f"n{n}_calls_hermitised"] = np.array(herm, dtype=np.int32)
+        print(f"{name} n={n}: calls {cnt} (TNI {cnt_t}); Hermitised input would take {herm}")
+    rng = np.random.default_rng(7004)
+    rho = np.stack([orc.ginibre_state(rng, 4) for _ in range(4)])
+    out["rho"] = rho
+    out["purity_default"] = np.array([ref.dm.purity(r) for r in rho])
+    out["purity_renorm"] = np.array([ref.dm.purity(r, dim_renorm=True) for r in rho])
+    out["impurity_default"] = np.array([ref.dm.impurity(r) for r in rho])
+    out["impurity_renorm"] = np.array([ref.dm.impurity(r, dim_renorm=True) for r in rho])
+    out["fidelity_tol1e6"] = np.array([ref.dm.fidelity(rho[0], r, tol=1e6) for r in rho])
+    np.savez_compressed(os.path.join(OUT, name), **out)
+
+
 def golden_distances(ref, name, seed, n, batch):
     rng = np.random.default_rng(seed)
     d = 2 ** n
@@ -199,6 +243,8 @@ def main():
                           golden_pgdb(ref, "pgdb_2q_sic", 3006, 4, 2, "sic"),
                           golden_pgdb(ref, "pgdb_2q_sic_mixed", 3007, 2, 2, "sic", unitary=False)],
         "next": lambda: golden_next_rows(ref),
+        "nonherm": lambda: golden_nonhermitian_physical(ref),
+        "pgdb2_tni": lambda: golden_pgdb(ref, "pgdb_2q_pauli_tni", 3009, 2, 2, "pauli", tp=False),
         "pgdb3": lambda: [golden_pgdb(ref, "pgdb_3q_sic", 3008, 1, 3, "sic"),
                           golden_pgdb(ref, "pgdb_3q_pauli", 3003, 1, 3, "pauli")],
     }

@@ -361,6 +361,15 @@ def purity(rho, dim_renorm=False):
     return float(p)
 
 
+def impurity(rho, dim_renorm=False):
+    """distance_measures.py:40-61."""
+    imp = 1 - np.real(np.trace(rho @ rho))
+    if dim_renorm:
+        d = rho.shape[0]
+        imp = (d / (d - 1.0)) * imp
+    return float(imp)
+
+
 def project_state_matrix_to_physical(rho):
     """Smolin "wizard" projection onto trace-one PSD matrices, operator_tools/project_state_matrix.py:6-52:
     normalise the trace, eigh, and if any eigenvalue is negative zero the smallest ones while spreading their

@@ -54,15 +54,18 @@ def test_sweep_vs_oracle_and_roundtrip(torch, n, batch):
     # PTM of a CPTP map: real, first row (1,0,...,0)
     plh = pl.cpu().numpy()
     assert np.abs(plh.imag).max() < 1e-13 and np.allclose(plh[:, 0, 0], 1) and np.abs(plh[:, 0, 1:]).max() < 1e-13
-    # spot checks against the oracle (dense c2p @ S @ c2p^dagger is slow at n=5: one item)
+    # spot checks against the oracle (dense c2p @ S @ c2p^dagger with a 1024 x 1024 basis matrix at n = 5: one item)
     picks = range(batch) if n <= 3 else [0]
     ch = choi.cpu().numpy(); sh = sup.cpu().numpy(); ks = st.kraus2superop_batch(kd).cpu().numpy()
     for b in picks:
         assert relerr(ch[b], orc.kraus2choi(list(kraus[b]))) < 1e-14
         assert np.array_equal(sh[b], orc.choi2superop(ch[b]))
         assert relerr(ks[b], orc.kraus2superop(list(kraus[b]))) < 1e-14
-        if n <= 4:
-            assert relerr(plh[b], orc.superop2pauli_liouville(sh[b])) < 1e-13
+        want_pl = orc.superop2pauli_liouville(sh[b])
+        assert relerr(plh[b], want_pl) < 1e-13
+        # and the inverse direction from the ORACLE's PTM (not from our own forward result)
+        back = st.pauli_liouville2superop_batch(torch.from_numpy(np.ascontiguousarray(want_pl[None])).cuda())
+        assert relerr(back[0].cpu().numpy(), sh[b]) < 1e-13
 
 
 def test_pauli_basis_index_pin(torch):

@@ -19,15 +19,17 @@ def torch():
 def _run(torch, n, codes, pidx, ex, cnt, coeffs=None, tp=True):
     from forest_benchmarking_b200 import tomography as tm
     plan = tm.PgdbPlan(n, codes, pidx, coeffs)
-    choi, counters = tm.pgdb_process_estimate_batch(plan, torch.from_numpy(np.ascontiguousarray(ex)).cuda(),
-                                                    torch.from_numpy(np.ascontiguousarray(cnt)).cuda(), tp,
-                                                    return_counters=True)
+    choi, counters, status = tm.pgdb_process_estimate_batch(plan, torch.from_numpy(np.ascontiguousarray(ex)).cuda(),
+                                                            torch.from_numpy(np.ascontiguousarray(cnt)).cuda(), tp,
+                                                            return_counters=True, return_status=True)
     torch.cuda.synchronize()
+    assert not status.cpu().numpy().any(), "a safety cap was hit"
     return plan, choi.cpu().numpy(), counters.cpu().numpy()
 
 
 @pytest.mark.parametrize("name", ["pgdb_1q_pauli", "pgdb_1q_sic", "pgdb_1q_pauli_tni", "pgdb_1q_pauli_mixed",
-                                  "pgdb_2q_pauli", "pgdb_2q_sic", "pgdb_2q_sic_mixed", "pgdb_3q_sic", "pgdb_3q_pauli"])
+                                  "pgdb_2q_pauli", "pgdb_2q_sic", "pgdb_2q_sic_mixed", "pgdb_2q_pauli_tni", "pgdb_3q_sic",
+                                  "pgdb_3q_pauli"])
 def test_golden(torch, name):
     g = golden(name)
     n = int(g["n"])

@@ -121,3 +121,43 @@ def test_tni_in_place_and_out_of_place_agree(torch, n):
     ps.proj_choi_to_trace_non_increasing_batch(inp, out=inp)
     assert max_relerr(oop, want) < 1e-12
     assert max_relerr(inp.cpu().numpy(), want) < 1e-12
+
+
+@pytest.mark.parametrize("n", [1, 2, 3])
+def test_nonhermitian_input_matches_reference_trip_counts(torch, n):
+    """The reference does not Hermitise the input of proj_choi_to_physical: the anti-Hermitian part stays in
+    old_CP_change and changes the Birgin-Raydan stopping rule (project_superoperators.py:112-136).  Goldens from the
+    reference itself (oracle/make_golden.py --only nonherm): same projection AND same number of CP projections."""
+    from forest_benchmarking_b200.operator_tools import project_superoperators as ps
+    g = golden("proj_physical_nonherm")
+    x = torch.from_numpy(g[f"n{n}_in"]).cuda()
+    for tp, key in ((True, ""), (False, "_tni")):
+        out, calls, status = ps.proj_choi_to_physical_batch(x, tp, return_counts=True, return_status=True)
+        assert max_relerr(out.cpu().numpy(), g[f"n{n}_out{key}"]) < TOL
+        assert np.array_equal(calls.cpu().numpy(), g[f"n{n}_calls{key}"]), (calls.cpu().numpy(), g[f"n{n}_calls{key}"])
+        assert not status.cpu().numpy().any()
+    # Hermitian inputs of the same family: the counts the reference gives for the Hermitised matrices
+    xh = (x + x.conj().transpose(1, 2)) / 2
+    _, calls = ps.proj_choi_to_physical_batch(xh, True, return_counts=True)
+    assert np.array_equal(calls.cpu().numpy(), g[f"n{n}_calls_hermitised"])
+    # drop-in, single matrix
+    assert relerr(ps.proj_choi_to_physical(g[f"n{n}_in"][0]), g[f"n{n}_out"][0]) < TOL
+    with pytest.raises(ValueError):
+        ps.proj_choi_to_physical_batch(x, out=x)
+
+
+def test_eigh_tolerance_is_a_per_call_argument(torch):
+    """No process-global tuning state: two calls with different tolerances, then the default again -> the default
+    results are bit-identical, the tight result agrees to 1e-9."""
+    from forest_benchmarking_b200.operator_tools import project_superoperators as ps
+    g = golden("algebra_n2")
+    x = torch.from_numpy(g["noisy"]).cuda()
+    a = ps.proj_choi_to_physical_batch(x)
+    tight = ps.proj_choi_to_physical_batch(x, eigh_rel_tol=0.0)
+    loose = ps.proj_choi_to_physical_batch(x, eigh_rel_tol=1e-5)
+    b = ps.proj_choi_to_physical_batch(x)
+    assert torch.equal(a, b)
+    assert max_relerr(a.cpu().numpy(), tight.cpu().numpy()) < 1e-9
+    assert max_relerr(loose.cpu().numpy(), g["proj_physical"]) < 1e-3
+    with pytest.raises(Exception):
+        ps.proj_choi_to_physical_batch(x, eigh_rel_tol=0.5)

@@ -187,6 +187,75 @@ def test_distance_known_answers_and_dropin(torch):
     assert abs(dm.infidelity(z0, z0)) < 1e-14
 
 
+def test_distance_defaults_match_reference(torch):
+    """purity / impurity called WITHOUT keywords (reference default dim_renorm=False, distance_measures.py:14,40) and
+    the fidelity return idiom (a Python float through np.real_if_close(.., tol), :82-84); goldens from the reference
+    (oracle/make_golden.py --only nonherm)."""
+    from forest_benchmarking_b200 import distance_measures as dm
+    g = golden("proj_physical_nonherm")
+    assert abs(dm.purity(np.eye(2) / 2) - 0.5) < 1e-15 and abs(dm.impurity(np.eye(2) / 2) - 0.5) < 1e-15
+    assert abs(dm.purity(np.eye(2) / 2, dim_renorm=True)) < 1e-15
+    for b, rho in enumerate(g["rho"]):
+        assert abs(dm.purity(rho) - g["purity_default"][b]) < 1e-14
+        assert abs(dm.purity(rho, dim_renorm=True) - g["purity_renorm"][b]) < 1e-14
+        assert abs(dm.impurity(rho) - g["impurity_default"][b]) < 1e-14
+        assert abs(dm.impurity(rho, True) - g["impurity_renorm"][b]) < 1e-14
+        f = dm.fidelity(g["rho"][0], rho, tol=1e6)
+        assert type(f) is float and abs(f - g["fidelity_tol1e6"][b]) < 1e-12
+    assert type(dm.fidelity(g["rho"][0], g["rho"][1])) is float
+    assert type(dm.purity(g["rho"][0])) is float
+    # a non-Hermitian argument: tr(rho rho) is complex and the reference returns it as such
+    x = g["rho"][0] + 0.1j * np.triu(np.ones((4, 4)), 1)
+    want = np.trace(x @ x)
+    got = dm.purity(x)
+    assert isinstance(got, complex) and abs(got - want) < 1e-14
+
+
+def test_wrappers_reject_bad_tensors(torch):
+    """Every raw pointer handed to a kernel is checked first: dtype, device, exact shape, contiguity."""
+    from forest_benchmarking_b200 import tomography as tm
+    _, pidx, ex, cnt = orc.synth_state_tomography(77, 6, 2)
+    plan = tm.MlePlan(2, pidx)
+    e = torch.from_numpy(ex).cuda()
+    rho = torch.eye(4, dtype=torch.complex128, device="cuda").repeat(6, 1, 1) / 4
+    ec = torch.from_numpy(np.ascontiguousarray(ex.T)).cuda()
+    tm.mle_step_batch(2, ec, rho)
+    for bad in (lambda: tm.mle_step_batch(2, e, rho),                      # [B, K] instead of [K, B]
+                lambda: tm.mle_step_batch(2, ec.float(), rho),              # dtype
+                lambda: tm.mle_step_batch(2, ec, rho.to(torch.complex64)),
+                lambda: tm.mle_step_batch(1, ec, rho),                      # n_qubits vs rho
+                lambda: tm.mle_step_batch(2, ec, rho, out=rho[:3]),         # short out buffer
+                lambda: tm.mle_step_batch(2, ec.cpu(), rho),                # host tensor
+                lambda: tm.iterative_mle_state_estimate_batch(plan, e, out=torch.empty((5, 4, 4), dtype=torch.complex128, device="cuda")),
+                lambda: tm.iterative_mle_state_estimate_batch(plan, e, iters_out=torch.empty((6,), dtype=torch.int64, device="cuda")),
+                lambda: tm.iterative_mle_state_estimate_batch(plan, e, torch.from_numpy(cnt[:3]).cuda()),
+                lambda: tm.iterative_mle_state_estimate_batch(plan, e, None, beta=0.5),
+                lambda: tm.iterative_mle_state_estimate_batch(plan, e, out=torch.empty((6, 4, 8), dtype=torch.complex128, device="cuda")[:, :, ::2])):
+        with pytest.raises(ValueError):
+            bad()
+
+
+def test_tensor_on_another_device_than_current(torch):
+    """plans, streams and outputs must follow the operands' device, not whatever device is current."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from forest_benchmarking_b200 import tomography as tm, distance_measures as dm
+    _, pidx, ex, cnt = orc.synth_state_tomography(78, 16, 2)
+    with torch.cuda.device(1):
+        plan1 = tm.MlePlan(2, pidx)
+    e1 = torch.from_numpy(ex).to("cuda:1")
+    torch.cuda.set_device(0)
+    rho1, it1 = tm.iterative_mle_state_estimate_batch(plan1, e1, tol=1e-6, maxiter=2000)  # current device is 0
+    assert rho1.device == e1.device
+    plan0 = tm.MlePlan(2, pidx)
+    rho0, it0 = tm.iterative_mle_state_estimate_batch(plan0, e1.to("cuda:0"), tol=1e-6, maxiter=2000)
+    assert torch.equal(rho1.cpu(), rho0.cpu()) and torch.equal(it1.cpu(), it0.cpu())
+    with pytest.raises(ValueError):
+        tm.iterative_mle_state_estimate_batch(plan0, e1)  # plan on cuda:0, data on cuda:1
+    f = dm.fidelity_batch(rho1, rho1)
+    assert f.device == rho1.device and float((f - 1).abs().max()) < 1e-9
+
+
 def test_linear_inv_state_estimate(torch):
     """a4 / BASELINE configs[0]: linear inversion vs the oracle's pinv, complete and general observable lists."""
     from forest_benchmarking_b200 import tomography as tm

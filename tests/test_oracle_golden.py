@@ -137,3 +137,36 @@ def test_more_known_answers():
     # shots -> moments: 3 of 4 shots give +1 -> mean 1/2, variance of the mean (1 - 1/4) / 4
     bits = np.array([[0, 0], [1, 1], [0, 0], [1, 0]])
     assert orc.shots_to_obs_moments(bits, [0, 1]) == (0.5, 0.1875)
+
+
+def test_nonhermitian_physical_projection_and_distance_defaults():
+    """proj_choi_to_physical on NON-Hermitian inputs: result and number of CP projections as the reference produced
+    them (the anti-Hermitian part changes the trip count: see the *_calls_hermitised arrays); purity / impurity
+    called without keywords (dim_renorm defaults to False, distance_measures.py:14,40)."""
+    g = golden("proj_physical_nonherm")
+    changed = 0
+    for n in (1, 2, 3):
+        xs = g[f"n{n}_in"]
+        for b in range(len(xs)):
+            out, calls = orc.proj_choi_to_physical(xs[b], return_count=True)
+            assert relerr(out, g[f"n{n}_out"][b]) < 1e-12 and calls == g[f"n{n}_calls"][b]
+            out, calls = orc.proj_choi_to_physical(xs[b], False, return_count=True)
+            assert relerr(out, g[f"n{n}_out_tni"][b]) < 1e-12 and calls == g[f"n{n}_calls_tni"][b]
+        changed += int(np.sum(g[f"n{n}_calls"] != g[f"n{n}_calls_hermitised"]))
+    assert changed >= 4  # the fixture really exercises the difference
+    for b, rho in enumerate(g["rho"]):
+        assert abs(orc.purity(rho) - g["purity_default"][b]) < 1e-15
+        assert abs(orc.purity(rho, dim_renorm=True) - g["purity_renorm"][b]) < 1e-15
+        assert abs(orc.impurity(rho) - g["impurity_default"][b]) < 1e-15
+        assert abs(orc.impurity(rho, dim_renorm=True) - g["impurity_renorm"][b]) < 1e-15
+        assert abs(orc.fidelity(g["rho"][0], rho) - g["fidelity_tol1e6"][b]) < 1e-13
+
+
+def test_pgdb_2q_trace_non_increasing_golden():
+    g = golden("pgdb_2q_pauli_tni")
+    settings = [(tuple(int(c) for c in s), int(k)) for s, k in zip(g["state_codes"], g["pauli_idx"])]
+    assert not bool(g["trace_preserving"])
+    est, c = orc.pgdb_process_estimate(settings, np.ones(len(settings)), g["expectations"][0], g["counts"][0], 2,
+                                       trace_preserving=False, return_counters=True)
+    assert relerr(est, g["choi_ref"][0]) < 1e-10
+    assert (c["eighs"], c["cost_evals"]) == tuple(int(v) for v in g["counters_ref"][0])
