@@ -40,13 +40,22 @@ def test_golden(torch, name):
     print(name, "max rel err", err, "counters (outer, cost, eigh)", counters.tolist(), "ref (eigh, cost)",
           g["counters_ref"].tolist())
     assert err < TOL
-    # trip counts: same stopping rules; the decisions are threshold tests on rounded quantities, so allow a
-    # small slack and require most items to agree exactly
+    # Trip counts are part of the contract (same stopping rules).  Number of CP projections (eigh calls, the sum of
+    # all Dykstra trips over all outer steps): EXACT on every golden item (measured on B200, round 2: 0 mismatches on
+    # all 38 items of the 10 goldens, at the default eigensolver tolerance 1e-8 and at 0).
     ref_eigh, ref_cost = g["counters_ref"][:, 0], g["counters_ref"][:, 1]
-    assert np.all(np.abs(counters[:, 2] - ref_eigh) <= np.maximum(3, 0.02 * ref_eigh))
-    # cost evaluations include the final noise-level backtracking (alpha halved until < 1e-15 when no step can
-    # improve the cost any more), whose length depends on comparisons of numbers that agree to ~1e-16
+    assert np.array_equal(counters[:, 2], ref_eigh), (counters[:, 2], ref_eigh)
+    # Cost evaluations = outer steps + line-search halvings.  They agree exactly except for the LAST outer step of
+    # items whose line search ends in the noise: there `new_cost > old_cost + change` compares numbers that differ by
+    # ~1e-16 relative (the reference sums A @ vec(E) in BLAS order, the kernel sums its structured apply), and alpha is
+    # halved until it drops below 1e-15 (<= 50 halvings) or a rounding-level comparison succeeds.  Recorded mismatch
+    # set (round 2, B200): pgdb_1q_pauli items 0,2,5,6,7 (-9,-14,-2,+6,-5), pgdb_1q_sic items 0,1,2,3,4 (-9,+2,-1,..),
+    # pgdb_2q_pauli 0,2,3 (-5,-12,-5), pgdb_2q_sic 0,3 (-2,-5), pgdb_2q_sic_mixed 1 (+2), pgdb_2q_pauli_tni (+2,+3),
+    # pgdb_3q_pauli (-5); every other item exact.  Outer-step counts are compared exactly against the oracle in
+    # test_vs_oracle_batch and in bench.py's parity block.
     assert np.all(np.abs(counters[:, 1] - ref_cost) <= 15)
+    if name in ("pgdb_1q_pauli_tni", "pgdb_1q_pauli_mixed", "pgdb_3q_sic"):
+        assert np.array_equal(counters[:, 1], ref_cost)
 
 
 def test_noncanonical_settings_and_coefficients(torch):
@@ -77,7 +86,7 @@ def test_vs_oracle_batch(torch, n, basis, batch):
     for b in picks:
         want, cn = orc.pgdb_process_estimate(settings, np.ones(len(settings)), ex[b], cnt[b], n, return_counters=True)
         assert relerr(choi[b], want) < TOL
-        assert abs(counters[b, 0] - cn["outer"]) <= 1
+        assert counters[b, 0] == cn["outer"] and counters[b, 2] == cn["eighs"], (counters[b], cn)
     # properties: CPTP to the Dykstra tolerance, close to the true channel
     d = 2 ** n
     pt = np.einsum("zijkj->zik", choi.reshape(batch, d, d, d, d))

@@ -41,10 +41,9 @@ def test_mle_golden(torch, name, kernel):
         pytest.skip("quad kernel: n==2 vanilla only")
     rho, iters = _run_mle(torch, n, g["pauli_idx"], g["expectations"], g["counts"], kernel=kernel, **kw)
     assert max_relerr(rho, g["rho_ref"]) < TOL
-    # iteration counters: identical stopping rule; allow +-1 only where ||drho|| sits within rounding of tol
-    mism = np.nonzero(iters != g["iters_ref"])[0]
-    assert len(mism) <= max(1, len(iters) // 8), (iters, g["iters_ref"])
-    assert np.all(np.abs(iters - g["iters_ref"]) <= 2)
+    # iteration counters are part of the contract (identical stopping rule): exact on the goldens
+    print(name, "kernel", kernel, "iters", iters.tolist(), "ref", g["iters_ref"].tolist())
+    assert np.array_equal(iters, g["iters_ref"]), (iters, g["iters_ref"])
 
 
 @pytest.mark.parametrize("n,kernel", [(1, 1), (1, 2), (2, 1), (2, 2), (2, 3), (3, 2)])
@@ -54,7 +53,8 @@ def test_mle_vs_oracle_batch(torch, n, kernel):
     rho, iters = _run_mle(torch, n, pidx, ex, cnt, kernel=kernel, **kw)
     want, witers = orc.mle_state_estimate_batch(pidx, np.ones(len(pidx)), ex, n, **kw)
     assert max_relerr(rho, want) < TOL
-    assert np.all(np.abs(iters - witers) <= 2) and np.mean(iters != witers) < 0.1
+    print("mle_vs_oracle", n, kernel, "mismatches", np.nonzero(iters != witers)[0].tolist())
+    assert np.all(np.abs(iters - witers) <= 1) and np.mean(iters != witers) <= 0.05
     # size-independent properties: Hermitian, unit trace, positive
     assert np.allclose(rho, rho.conj().transpose(0, 2, 1), atol=1e-13)
     assert np.allclose(np.trace(rho, axis1=1, axis2=2), 1, atol=1e-12)
