@@ -532,7 +532,9 @@ def part_pgdb(ctx, n=3, global_batch=1024, in_basis="pauli"):
                                f"{plan.S} settings x 1000 shots, Haar-random unitary truth",
                    "global_batch": global_batch, "batch_per_gpu": B, "sharding": "contiguous B/N slices, no data-path "
                    "collective; ONE all_gather of the Choi matrices inside the timed region",
-                   "l2": "flushed between timed iterations", "eigh_rel_tol": tol if tol is not None else 1e-8,
+                   "l2": "flushed between timed iterations",
+                   "eigh_rel_tol": tol if tol is not None else ("library default: 1e-5 + first-order correction of the PSD "
+                                                                "projection" if n >= 3 else "library default: 1e-8"),
                    "outer_mean": float(counters[:, 0].mean()), "cost_evals_mean": float(counters[:, 1].mean()),
                    "eigh_calls_mean": float(counters[:, 2].mean()),
                    "jacobi_sweeps_per_eigh": float(counters[:, 3].sum() / max(1, counters[:, 2].sum()))},

@@ -31,11 +31,16 @@ extern "C" int qt_version(void) { return 100; }
 // reference goldens (profiles/r01_exp_eigh_tol_v2.txt): max relative Frobenius deviation of the PGDB estimate
 // 1.6e-10 at 1e-8, 4.4e-8 at 1e-7, 3.8e-7 at 1e-6 (parity budget 1e-6), with identical eigh / outer-iteration
 // counts throughout.
-int qt_eigh_rel2_from_tol(double rel_tol, double* rel2_out, const char* who) {
-  if (rel_tol < 0.0) rel_tol = QT_EIGH_REL_TOL_DEFAULT;
+//
+// n = 3 (64 x 64, the second-generation Dykstra loop of qt_choi.cuh) stops Jacobi EARLY, at 1e-5, and makes up for it
+// with the first-order (Loewner-matrix) correction of the PSD projection, whose residual is O(tol^2 / gap): measured
+// deviation from the reference goldens 2e-9 (CPU prototype scripts/proto/early_stop_cp.py) with identical trip counts,
+// at ~1 Jacobi sweep less per eigendecomposition.
+int qt_eigh_rel2_from_tol(double rel_tol, int n, double* rel2_out, const char* who) {
+  const double dflt = (n >= 3) ? QT_EIGH_REL_TOL_DEFAULT_CORRECTED : QT_EIGH_REL_TOL_DEFAULT;
+  if (rel_tol < 0.0) rel_tol = dflt;
   if (!(rel_tol < 1e-3)) {
-    qt_set_error("%s: eigh_rel_tol %g out of range (< 0: default %g, 0: tight, else < 1e-3)", who, rel_tol,
-                 QT_EIGH_REL_TOL_DEFAULT);
+    qt_set_error("%s: eigh_rel_tol %g out of range (< 0: default %g, 0: tight, else < 1e-3)", who, rel_tol, dflt);
     return QT_ERR_ARG;
   }
   *rel2_out = rel_tol * rel_tol;  // 0 selects the solver's tight built-in threshold

@@ -18,8 +18,8 @@ typedef double2 cplx;  // .x = real, .y = imag
 
 void qt_set_error(const char* fmt, ...);
 // eigh_rel_tol argument of the C ABI -> squared relative off-diagonal tolerance handed to the Jacobi solver
-// (< 0: the default 1e-8; 0: the tight 1e-15 * 4^n; otherwise the value, which must be < 1e-3)
-int qt_eigh_rel2_from_tol(double rel_tol, double* rel2_out, const char* who);
+// (< 0: the default for n qubits; 0: the tight 1e-15 * 4^n; otherwise the value, which must be < 1e-3)
+int qt_eigh_rel2_from_tol(double rel_tol, int n, double* rel2_out, const char* who);
 int qt_num_sms();  // multiprocessor count of the current device (cached per device)
 int qt_check_launch(const char* what);
 

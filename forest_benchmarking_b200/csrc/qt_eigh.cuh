@@ -90,7 +90,7 @@ struct JacobiScratch {
 // chain, 8: no barrier); 0 in every product instantiation.
 template <int M, int NT, int LD, bool WANT_V, int ABL = 0>
 __device__ int jacobi_eigh_ring(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v,
-                                int max_sweeps, double rel2);
+                                int max_sweeps, double rel2, bool clean_a = false);
 
 // A: M x M Hermitian in shared memory (row-major, leading dimension LD), overwritten (diagonal = eigenvalues).
 //    Both triangles are stored and kept exactly conjugate: only the blocks above the block diagonal are
@@ -100,11 +100,14 @@ __device__ int jacobi_eigh_ring(cplx* A, cplx* V, double* ev, double* scratch, i
 //    in that basis (warm start: A = V0^dagger A0 V0).
 // Stops when  off(A)^2 <= rel2 * ||A||_F^2  (rel2 <= 0: the default 1e-30 * M^2, i.e. a relative off-diagonal
 // Frobenius norm of 1e-15 * M).  Returns the number of sweeps performed.
+// clean_a (ring solver only): on exit A is the full Hermitian matrix V^dagger A0 V the iteration arrived at -- both
+// triangles exactly conjugate, eigenvalue estimates on the diagonal, the NOT yet annihilated remainder off it -- so
+// that a caller who stops early (large rel2) can use the remainder (first-order correction, next warm start).
 template <int M, int NT, class Sync, bool WANT_V, int LD = M>
 __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v = true,
-                           int max_sweeps = 30, double rel2 = 0.0) {
+                           int max_sweeps = 30, double rel2 = 0.0, bool clean_a = false) {
   if constexpr ((M == 64 && (NT == 512 || NT == 256) && WANT_V) || ((M == 16 || M == 8) && NT == 32)) {
-    return jacobi_eigh_ring<M, NT, LD, WANT_V>(A, V, ev, scratch, tid, init_v, max_sweeps, rel2);
+    return jacobi_eigh_ring<M, NT, LD, WANT_V>(A, V, ev, scratch, tid, init_v, max_sweeps, rel2, clean_a);
   }
   constexpr int HP = (M / 2 > 0) ? M / 2 : 1;
   constexpr int NOFF = HP * (HP - 1) / 2;                        // 2x2 blocks above the block diagonal
@@ -295,7 +298,7 @@ __device__ __forceinline__ void mbar_wait(double* slot, unsigned parity) {
 // ---------------------------------------------------------------------------------------------
 template <int M, int NT, int LD, bool WANT_V, int ABL>
 __device__ int jacobi_eigh_ring(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v,
-                                int max_sweeps, double rel2) {
+                                int max_sweeps, double rel2, bool clean_a) {
   constexpr int HP = M / 2, M1 = M - 1, NOFF = HP * (HP - 1) / 2;
   constexpr bool WARP = (NT == 32);               // one matrix per warp: __syncwarp instead of the mbarrier
   static_assert(HP <= 32 && (HP & (HP - 1)) == 0 && NT % HP == 0 && (WARP || HP == 32), "segment = shuffle group");
@@ -503,6 +506,35 @@ __device__ int jacobi_eigh_ring(cplx* A, cplx* V, double* ev, double* scratch, i
   }
   wait_pending();
   // a whole number of sweeps returns every column to its step-0 slot
+  if (clean_a) {
+    // Every unordered index pair is valid at exactly one position, owned by one thread (its 2x2 blocks, or the
+    // pair element of segment 0): re-read it as the norm pass does and write both triangles.  A thread only touches
+    // the two positions of pairs it owns, so no barrier is needed before the writes.
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      if (!has_block[k]) continue;
+      int pi, qi, pj, qj;
+      rr_pair(M, 0, bI[k], pi, qi);
+      rr_pair(M, 0, bJ[k], pj, qj);
+      cplx b00 = A[pi * LD + pj];
+      cplx b01 = near1[k] ? cconj(A[qj * LD + pi]) : A[pi * LD + qj];
+      const cplx b10 = A[qi * LD + pj];
+      cplx b11 = A[qi * LD + qj];
+      if (!fresh && near2[k]) b01 = cmake(0.0, 0.0);
+      if (!fresh && last2[k]) b00 = cmake(0.0, 0.0);
+      if (!fresh && first2[k]) b11 = cmake(0.0, 0.0);
+      A[pi * LD + pj] = b00; A[pj * LD + pi] = cconj(b00);
+      A[pi * LD + qj] = b01; A[qj * LD + pi] = cconj(b01);
+      A[qi * LD + pj] = b10; A[pj * LD + qi] = cconj(b10);
+      A[qi * LD + qj] = b11; A[qj * LD + qi] = cconj(b11);
+    }
+    if (seg == 0) {
+      const cplx v = A[col0q * LD + pr];
+      A[pr * LD + col0q] = cconj(v);
+      A[pr * LD + pr] = cmake(dp, 0.0);
+      A[col0q * LD + col0q] = cmake(dq, 0.0);
+    }
+  }
   if constexpr (WANT_V) {
 #pragma unroll
     for (int k = 0; k < RV; ++k) {
@@ -536,10 +568,10 @@ __device__ __forceinline__ int jacobi_eigh_warp(cplx* A, cplx* V, double* ev, in
 // Shared-memory M x M complex products with strided register tiles (TR x TC outputs per work item:
 // rows tr + i*M/TR, columns tc + j*M/TC -- so the lanes of a warp read consecutive columns and at most two
 // distinct rows: conflict-free with the padded leading dimension).
-//   MODE 0: C = A * B            MODE 1: C = A^dagger * B
+//   MODE 0: C = A * B            MODE 1: C = A^dagger * B            ACCUM: C += ...
 // C must not alias A or B.
 // ---------------------------------------------------------------------------------------------
-template <int M, int NT, int LD, int MODE>
+template <int M, int NT, int LD, int MODE, bool ACCUM = false>
 __device__ void smem_matmul(cplx* __restrict__ C, const cplx* __restrict__ A, const cplx* __restrict__ B, int tid) {
   // M = 64: 4x4 tiles on 256 work items -- 8 shared loads per 16 complex FMAs keeps the LDS pipe (4 cycles per
   // 16-byte warp load) level with the FP64 pipe; 2x4 tiles on 512 threads were LDS-bound
@@ -570,6 +602,9 @@ __device__ void smem_matmul(cplx* __restrict__ C, const cplx* __restrict__ A, co
 #pragma unroll
     for (int i = 0; i < TR; ++i)
 #pragma unroll
-      for (int j = 0; j < TC; ++j) C[(tr + i * NR) * LD + tc + j * NC] = acc[i][j];
+      for (int j = 0; j < TC; ++j) {
+        cplx* dst = &C[(tr + i * NR) * LD + tc + j * NC];
+        *dst = ACCUM ? cadd(*dst, acc[i][j]) : acc[i][j];
+      }
   }
 }

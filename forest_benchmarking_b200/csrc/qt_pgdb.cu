@@ -242,8 +242,13 @@ struct Pgdb {
       }
       Sync::sync();
       // ---- projection ----
-      eighs += G::project_physical(S, Q, CPREV, X, V, T, small, make_tp, tid, v_valid, &sweeps, rel2,
-                                   QT_DYKSTRA_MAX_ITER, nullptr, &status);
+      if constexpr (N >= 3) {
+        eighs += G::project_physical_v2(S, CPREV, X, V, T, small, make_tp, tid, v_valid, &sweeps, rel2,
+                                        QT_DYKSTRA_MAX_ITER, nullptr, &status);
+      } else {
+        eighs += G::project_physical(S, Q, CPREV, X, V, T, small, make_tp, tid, v_valid, &sweeps, rel2,
+                                     QT_DYKSTRA_MAX_ITER, nullptr, &status);
+      }
       // ---- update direction, its PTM image, <update, gradient> ----
       double ip = 0.0;
       for (int e = tid; e < MM; e += NT) {
@@ -469,7 +474,7 @@ extern "C" int qt_pgdb_process_batch(const qt_pgdb_plan* p, int64_t B, const dou
     return QT_ERR_WORKSPACE;
   }
   double rel2;
-  if (qt_eigh_rel2_from_tol(eigh_rel_tol, &rel2, "qt_pgdb_process_batch") != QT_OK) return QT_ERR_ARG;
+  if (qt_eigh_rel2_from_tol(eigh_rel_tol, p->n, &rel2, "qt_pgdb_process_batch") != QT_OK) return QT_ERR_ARG;
   cudaStream_t st = (cudaStream_t)stream;
 #define QT_PGDB_ARGS p, B, expect, counts, trace_preserving, rel2, choi_out, counters_out, status_out, workspace, st
   switch (p->n) {

@@ -511,8 +511,14 @@ __global__ void __launch_bounds__(ProjCfg<N>::NT * ProjCfg<N>::GPB)
     C::Sync::sync();
     bool v_valid = false;  // items are unrelated: the first decomposition of each starts cold
     int st = 0;
-    const int calls = G::project_physical(S, Q, CPREV, X, V, T, small, make_tp != 0, tid, v_valid, nullptr, rel2,
-                                          QT_DYKSTRA_MAX_ITER, anti2 > 0.0 ? src : nullptr, &st);
+    int calls;
+    if constexpr (N >= 3) {
+      calls = G::project_physical_v2(S, CPREV, X, V, T, small, make_tp != 0, tid, v_valid, nullptr, rel2,
+                                     QT_DYKSTRA_MAX_ITER, anti2 > 0.0 ? src : nullptr, &st);
+    } else {
+      calls = G::project_physical(S, Q, CPREV, X, V, T, small, make_tp != 0, tid, v_valid, nullptr, rel2,
+                                  QT_DYKSTRA_MAX_ITER, anti2 > 0.0 ? src : nullptr, &st);
+    }
     if (tid == 0 && eigh_calls) eigh_calls[b] = calls;
     if (tid == 0 && status_out) status_out[b] = st;
     C::Sync::sync();
@@ -740,7 +746,7 @@ extern "C" int qt_proj_physical_batch(int n, int64_t B, const void* choi, void* 
   QT_REQUIRE(choi && out && workspace, "qt_proj_physical_batch: null argument");
   QT_REQUIRE(choi != out, "qt_proj_physical_batch: in-place call not supported (the input is re-read by the stopping rule)");
   double rel2;
-  if (qt_eigh_rel2_from_tol(eigh_rel_tol, &rel2, "qt_proj_physical_batch") != QT_OK) return QT_ERR_ARG;
+  if (qt_eigh_rel2_from_tol(eigh_rel_tol, n, &rel2, "qt_proj_physical_batch") != QT_OK) return QT_ERR_ARG;
 #define CALL(N)                                                                                                  \
   launch_physical<N>(B, choi, out, make_trace_preserving, rel2, workspace, workspace_bytes, eigh_calls_out, \
                      status_out, (cudaStream_t)stream)

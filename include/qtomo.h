@@ -35,8 +35,11 @@ int qt_last_error(char* buf, int len);
 
 /* `eigh_rel_tol` argument of qt_proj_physical_batch / qt_pgdb_process_batch: relative off-diagonal Frobenius norm at
  * which the Jacobi eigensolver behind proj_choi_to_completely_positive declares convergence.  Negative = the default
- * below; 0 = tight (1e-15 * 4^n); otherwise < 1e-3.  A per-call argument: the library has no mutable global state. */
+ * below; 0 = tight (1e-15 * 4^n); otherwise < 1e-3.  A per-call argument: the library has no mutable global state.
+ * n <= 2: the remainder is dropped (error ~ tol).  n = 3: the remainder enters a first-order correction of the PSD
+ * projection (error ~ tol^2 / spectral gap), which is why its default can be 1e-5. */
 #define QT_EIGH_REL_TOL_DEFAULT 1e-8
+#define QT_EIGH_REL_TOL_DEFAULT_CORRECTED 1e-5
 /* per-item status bits (status_out arrays): the reference's loops are unbounded, ours carry safety caps */
 #define QT_STATUS_DYKSTRA_CAP 1 /* proj_choi_to_physical stopped at 10000 CP projections without meeting its rule */
 #define QT_STATUS_JACOBI_CAP 2  /* an eigendecomposition used all 30 sweeps */
