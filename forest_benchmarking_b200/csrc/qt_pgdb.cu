@@ -28,6 +28,8 @@
 
 struct qt_pgdb_plan {
   int n, S, n_in, canonical;
+  int nb = 0;            // > 0: the input states are the full product set of nb single-qubit states (see PgdbView)
+  double bvec[6][4];     // Pauli vectors (1, x, y, z) of those nb single-qubit states
   int* d_state_id;    // [S]
   int* d_pidx;        // [S]
   double* d_coeff;    // [S]
@@ -47,6 +49,11 @@ struct PgdbView {
   const int* pidx;
   const double* coeff;
   const double* svec;
+  // Kronecker structure of the input states (generate_process_tomography_experiment, tomography.py:71-97: itertools.product
+  // over one single-qubit set, first qubit most significant): state i = (s_0 .. s_{n-1}) in base nb and
+  // svec[i][j] = prod_q bvec[s_q][digit_q(j)].  nb == 0: no such structure, svec is used as a dense table.
+  int nb;
+  double bvec[6][4];
 };
 
 template <int N>
@@ -107,13 +114,81 @@ struct Pgdb {
       rt[e] = X[pauli_to_pos(k, N) * LD + pauli_to_pos(j, N)].x * scale;  // rt[j][k] = R[k][j] / d
     }
     Sync::sync();
-    for (int e = tid; e < pv.n_in * M; e += NT) {
-      const int i = e / M, k = e % M;
-      const double* sv = pv.svec + (int64_t)i * M;
-      double acc = 0.0;
+    if (pv.nb > 0) {
+      // svec = bvec (x) ... (x) bvec: contract the leading n-1 digits of j against the state prefix, then expand the
+      // last digit -- 4^n (n + 1) + 4 nb flops per (k, prefix) instead of 4^n nb per (k, prefix); no dense table read.
+      const int nb = pv.nb;
+      int npre = 1;
+      for (int q = 0; q < N - 1; ++q) npre *= nb;
+      for (int w = tid; w < npre * M; w += NT) {
+        const int k = w % M, pre = w / M;  // consecutive lanes = consecutive k: conflict-free rt reads, coalesced T stores
+        int sq[N > 1 ? N - 1 : 1];
+        {
+          int r = pre;
+          for (int q = N - 2; q >= 0; --q) {
+            sq[q] = r % nb;
+            r /= nb;
+          }
+        }
+        double u[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int jp = 0; jp < M / 4; ++jp) {  // jp = the leading n-1 base-4 digits of j
+          double wgt = 1.0;
+#pragma unroll
+          for (int q = 0; q < N - 1; ++q) wgt *= pv.bvec[sq[q]][(jp >> (2 * (N - 2 - q))) & 3];
+#pragma unroll
+          for (int jl = 0; jl < 4; ++jl) u[jl] = fma(rt[(jp * 4 + jl) * M + k], wgt, u[jl]);
+        }
+        for (int sl = 0; sl < nb; ++sl) {
+          const double* b = pv.bvec[sl];
+          T[(pre * nb + sl) * M + k] = fma(u[0], b[0], fma(u[1], b[1], fma(u[2], b[2], u[3] * b[3])));
+        }
+      }
+    } else {
+      for (int e = tid; e < pv.n_in * M; e += NT) {
+        const int i = e / M, k = e % M;
+        const double* sv = pv.svec + (int64_t)i * M;
+        double acc = 0.0;
 #pragma unroll 8
-      for (int j = 0; j < M; ++j) acc = fma(rt[j * M + k], sv[j], acc);
-      T[e] = acc;
+        for (int j = 0; j < M; ++j) acc = fma(rt[j * M + k], sv[j], acc);
+        T[e] = acc;
+      }
+    }
+    Sync::sync();
+  }
+
+  // Gp[k][j] = sum_i W[i][k] svec[i][j] into X at butterfly positions (the adjoint of build_T)
+  static __device__ void build_gp(const PgdbView& pv, const double* W, cplx* X, int tid) {
+    if (pv.nb > 0) {
+      const int nb = pv.nb;
+      int npre = 1;
+      for (int q = 0; q < N - 1; ++q) npre *= nb;
+      for (int w = tid; w < (M / 4) * M; w += NT) {
+        const int k = w % M, jp = w / M;  // jp = leading n-1 digits of j; this thread fills j = 4 jp + (0..3)
+        double y[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};  // y[s_last] = sum over state prefixes
+        for (int pre = 0; pre < npre; ++pre) {
+          double wgt = 1.0;
+          int r = pre;
+#pragma unroll
+          for (int q = N - 2; q >= 0; --q) {
+            wgt *= pv.bvec[r % nb][(jp >> (2 * (N - 2 - q))) & 3];
+            r /= nb;
+          }
+          for (int sl = 0; sl < nb; ++sl) y[sl] = fma(W[(pre * nb + sl) * M + k], wgt, y[sl]);
+        }
+#pragma unroll
+        for (int jl = 0; jl < 4; ++jl) {
+          double acc = 0.0;
+          for (int sl = 0; sl < nb; ++sl) acc = fma(y[sl], pv.bvec[sl][jl], acc);
+          X[pauli_to_pos(k, N) * LD + pauli_to_pos(jp * 4 + jl, N)] = cmake(acc, 0.0);
+        }
+      }
+    } else {
+      for (int e = tid; e < MM; e += NT) {
+        const int k = e / M, j = e % M;
+        double acc = 0.0;
+        for (int i = 0; i < pv.n_in; ++i) acc = fma(W[i * M + k], pv.svec[(int64_t)i * M + j], acc);
+        X[pauli_to_pos(k, N) * LD + pauli_to_pos(j, N)] = cmake(acc, 0.0);
+      }
     }
     Sync::sync();
   }
@@ -223,13 +298,7 @@ struct Pgdb {
       ++outer;
       // ---- gradient ----
       build_w(pv, dt, Te, W, tid);
-      for (int e = tid; e < MM; e += NT) {
-        const int k = e / M, j = e % M;
-        double acc = 0.0;
-        for (int i = 0; i < pv.n_in; ++i) acc = fma(W[i * M + k], pv.svec[(int64_t)i * M + j], acc);
-        X[pauli_to_pos(k, N) * LD + pauli_to_pos(j, N)] = cmake(acc, 0.0);
-      }
-      Sync::sync();
+      build_gp(pv, W, X, tid);
       pl_positions_to_choi(X, tid);
       // gradient = -(1/d^2) * (1/d) * X ; S = est - gradient / mu (Hermitian by construction up to rounding)
       const double gs = -1.0 / ((double)D * D * D);
@@ -390,11 +459,41 @@ extern "C" int qt_pgdb_plan_create(int n, int S, const int32_t* state_codes, con
       }
       svec[(size_t)i * M + j] = v;
     }
+  // Kronecker structure: state i = base-nb digits over one single-qubit set (last qubit fastest)
+  int nb = 0;
+  {
+    int cand = 1;
+    while (cand <= 6) {
+      long long pw = 1;
+      for (int q = 0; q < n; ++q) pw *= cand;
+      if (pw == n_in) break;
+      ++cand;
+    }
+    if (cand <= 6 && n_in >= cand) {
+      bool ok = true;
+      for (int i = 0; i < n_in && ok; ++i) {
+        int r = i;
+        for (int q = n - 1; q >= 0 && ok; --q) {
+          ok = states[i][q] == states[r % cand][n - 1];  // digit r % cand of the base set, read off the first nb states
+          r /= cand;
+        }
+      }
+      for (int a = 0; a < cand && ok; ++a)  // the base set itself must have distinct members with all leading codes equal
+        for (int q = 0; q + 1 < n && ok; ++q) ok = states[a][q] == states[0][n - 1];
+      if (ok) nb = cand;
+    }
+  }
   int canonical = (S == n_in * (M - 1));
   for (int s = 0; s < S && canonical; ++s)
     canonical = (sid[s] == s / (M - 1)) && (pauli_idx[s] == s % (M - 1) + 1) && (coeff[s] == 1.0);
   qt_pgdb_plan* p = new qt_pgdb_plan();
   p->n = n; p->S = S; p->n_in = n_in; p->canonical = canonical;
+  p->nb = nb;
+  for (int a = 0; a < 6; ++a) {
+    double b4[4] = {0.0, 0.0, 0.0, 0.0};
+    if (a < nb) bloch_of_state(states[a][n - 1], b4);
+    for (int c = 0; c < 4; ++c) p->bvec[a][c] = b4[c];
+  }
   p->d_state_id = nullptr; p->d_pidx = nullptr; p->d_coeff = nullptr; p->d_svec = nullptr;
   QT_CUDA(cudaMalloc(&p->d_state_id, sizeof(int) * S));
   QT_CUDA(cudaMalloc(&p->d_pidx, sizeof(int) * S));
@@ -452,7 +551,9 @@ template <int N>
 static int launch_pgdb(const qt_pgdb_plan* p, int64_t B, const double* expect, const double* counts, int make_tp,
                        double rel2, void* choi_out, int* counters, int* status, void* ws, cudaStream_t st) {
   using C = PgdbCfg<N>;
-  PgdbView pv{p->S, p->n_in, p->canonical, p->d_state_id, p->d_pidx, p->d_coeff, p->d_svec};
+  PgdbView pv{p->S, p->n_in, p->canonical, p->d_state_id, p->d_pidx, p->d_coeff, p->d_svec, p->nb, {}};
+  for (int a = 0; a < 6; ++a)
+    for (int c = 0; c < 4; ++c) pv.bvec[a][c] = p->bvec[a][c];
   const size_t smem = C::group_smem * C::GPB;
   QT_CUDA(cudaMemsetAsync(ws, 0, 256, st));  // work-queue counter
   QT_CUDA(cudaFuncSetAttribute(pgdb_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -90,11 +90,28 @@ def reshuffle_batch(mat, out=None):
     return out
 
 
-def _pl_call(name, mat, out, workspace):
+PL_VARIANTS = {"butterfly": 0, "dense_mma": 1}
+
+
+def _pl_call(name, mat, out, workspace, variant="butterfly"):
     torch = _lib.require_cuda()
     mat = _check_c128(mat, 3)
     b, d2, _ = mat.shape
     n = _nq(d2)
+    if variant != "butterfly":
+        # the reference's dense formulation on the FP64 tensor path (n = 2, 3): kept for the measured comparison
+        if variant not in PL_VARIANTS:
+            raise ValueError(f"unknown variant {variant!r}; choose from {sorted(PL_VARIANTS)}")
+        with _lib.on_device(_lib.common_device(mat, out)):
+            if out is None:
+                out = torch.empty_like(mat)
+            else:
+                _lib.check_tensor("out", out, torch.complex128, mat.shape)
+            _lib.check(_lib.lib().qt_superop_pl_batch_variant(
+                ctypes.c_int(n), ctypes.c_int64(b), _lib.ptr(mat), _lib.ptr(out), ctypes.c_void_p(0),
+                ctypes.c_int(1 if name == "qt_superop2pl_batch" else 0), ctypes.c_int(PL_VARIANTS[variant]),
+                _lib.current_stream_ptr()), "qt_superop_pl_batch_variant")
+        return out
     with _lib.on_device(_lib.common_device(mat, out, workspace)):
         if out is None:
             out = torch.empty_like(mat)
@@ -109,12 +126,12 @@ def _pl_call(name, mat, out, workspace):
     return out
 
 
-def superop2pauli_liouville_batch(superop, out=None, workspace=None):
-    return _pl_call("qt_superop2pl_batch", superop, out, workspace)
+def superop2pauli_liouville_batch(superop, out=None, workspace=None, variant="butterfly"):
+    return _pl_call("qt_superop2pl_batch", superop, out, workspace, variant)
 
 
-def pauli_liouville2superop_batch(pl, out=None, workspace=None):
-    return _pl_call("qt_pl2superop_batch", pl, out, workspace)
+def pauli_liouville2superop_batch(pl, out=None, workspace=None, variant="butterfly"):
+    return _pl_call("qt_pl2superop_batch", pl, out, workspace, variant)
 
 
 def choi2pauli_liouville_batch(choi):

@@ -99,6 +99,14 @@ int qt_choi_superop_reshuffle_batch(int d, int64_t B, const void* in, void* out,
  * workspace: NULL for n<=3; B*16^n*16 bytes of device memory for n = 4, 5 (two-pass path). */
 int qt_superop2pl_batch(int n, int64_t B, const void* superop, void* pl_out, void* workspace, void* stream);
 int qt_pl2superop_batch(int n, int64_t B, const void* pl, void* superop_out, void* workspace, void* stream);
+/* The same two conversions with the algorithm selectable (forward != 0: superop -> PL).  BUTTERFLY = the calls above
+ * (Kronecker-factored add-only stages, HBM-bound, the default everywhere).  DENSE_DMMA = the reference's formulation,
+ * two dense complex products with the 4^n x 4^n basis matrix (:253-264, :301-312) on the FP64 tensor path
+ * (mma.sync m8n8k4.f64); n = 2, 3 only; kept for the measured comparison (profiles/r02_ptm_dense_vs_butterfly.md). */
+#define QT_PL_VARIANT_BUTTERFLY 0
+#define QT_PL_VARIANT_DENSE_DMMA 1
+int qt_superop_pl_batch_variant(int n, int64_t B, const void* in, void* out, void* workspace, int forward, int variant,
+                                void* stream);
 /* choi2kraus (:325-336), n = 1..3: eigh of the lower triangle; evals_out[B,4^n] ascending (np.linalg.eigh order);
  * kraus_out[B,4^n,d,d]: sqrt(lambda_k) * unvec(v_k) for |lambda_k| > tol in ascending-eigenvalue order, compacted to
  * the front (count_out[b] operators, the rest zero); negative lambda -> i*sqrt(|lambda|) like np.lib.scimath.sqrt.

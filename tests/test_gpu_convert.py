@@ -196,3 +196,24 @@ def test_choi2kraus_large(torch, n, batch):
         assert np.abs(kraus[b, counts[b]:]).max(initial=0.0) == 0.0
     if batch > 1:
         assert counts[1] == 3
+
+
+@pytest.mark.parametrize("n,batch", [(2, 37), (3, 19)])
+def test_dense_fp64_mma_ptm_variant(torch, n, batch):
+    """The reference's dense formulation (two complex products with the 4^n x 4^n basis matrix,
+    superoperator_transformations.py:253-264, 301-312) on the FP64 tensor path vs the oracle and vs the default
+    butterfly kernels, both directions, ragged batch sizes."""
+    from forest_benchmarking_b200.operator_tools import superoperator_transformations as st
+    rng = np.random.default_rng(900 + n)
+    m = 4 ** n
+    x = rng.standard_normal((batch, m, m)) + 1j * rng.standard_normal((batch, m, m))  # generic (non-physical) matrices
+    xd = torch.from_numpy(x).cuda()
+    fwd = st.superop2pauli_liouville_batch(xd, variant="dense_mma").cpu().numpy()
+    inv = st.pauli_liouville2superop_batch(xd, variant="dense_mma").cpu().numpy()
+    for b in range(0, batch, 6):
+        assert relerr(fwd[b], orc.superop2pauli_liouville(x[b])) < 1e-13
+        assert relerr(inv[b], orc.pauli_liouville2superop(x[b])) < 1e-13
+    assert max_relerr(fwd, st.superop2pauli_liouville_batch(xd).cpu().numpy()) < 1e-13
+    assert max_relerr(inv, st.pauli_liouville2superop_batch(xd).cpu().numpy()) < 1e-13
+    with pytest.raises(Exception):
+        st.superop2pauli_liouville_batch(torch.zeros((2, 4, 4), dtype=torch.complex128, device="cuda"), variant="dense_mma")
