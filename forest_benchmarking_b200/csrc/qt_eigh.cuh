@@ -81,6 +81,7 @@ __device__ __forceinline__ double group_sum(double v, double* red, int tid) {
 }
 
 // Scratch layout (doubles, 16-byte aligned base): rs[2][M/2] (complex) | rc[2][M/2] | red[32]
+// (ring solvers: red[16] | .. | mbarrier at +32)
 template <int M>
 struct JacobiScratch {
   static constexpr int doubles = 3 * M + 32;
@@ -91,10 +92,6 @@ struct JacobiScratch {
 template <int M, int NT, int LD, bool WANT_V, int ABL = 0>
 __device__ int jacobi_eigh_ring(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v,
                                 int max_sweeps, double rel2, bool clean_a = false);
-
-template <int LD, int ABL = 0>
-__device__ int jacobi_eigh_ring_split64(cplx* A, cplx* V, double* ev, double* scratch, double* fifo, int tid,
-                                        bool init_v, int max_sweeps, double rel2, bool clean_a);
 
 // A: M x M Hermitian in shared memory (row-major, leading dimension LD), overwritten (diagonal = eigenvalues).
 //    Both triangles are stored and kept exactly conjugate: only the blocks above the block diagonal are
@@ -109,11 +106,7 @@ __device__ int jacobi_eigh_ring_split64(cplx* A, cplx* V, double* ev, double* sc
 // that a caller who stops early (large rel2) can use the remainder (first-order correction, next warm start).
 template <int M, int NT, class Sync, bool WANT_V, int LD = M>
 __device__ int jacobi_eigh(cplx* A, cplx* V, double* ev, double* scratch, int tid, bool init_v = true,
-                           int max_sweeps = 30, double rel2 = 0.0, bool clean_a = false, double* fifo = nullptr) {
-  if constexpr (M == 64 && NT == 512 && WANT_V) {
-    // role-split variant (A warps / V warps) when the caller lends a shared buffer for the rotation FIFO
-    if (fifo) return jacobi_eigh_ring_split64<LD>(A, V, ev, scratch, fifo, tid, init_v, max_sweeps, rel2, clean_a);
-  }
+                           int max_sweeps = 30, double rel2 = 0.0, bool clean_a = false) {
   if constexpr ((M == 64 && (NT == 512 || NT == 256) && WANT_V) || ((M == 16 || M == 8) && NT == 32)) {
     return jacobi_eigh_ring<M, NT, LD, WANT_V>(A, V, ev, scratch, tid, init_v, max_sweeps, rel2, clean_a);
   }
@@ -564,274 +557,6 @@ __device__ int jacobi_eigh_ring(cplx* A, cplx* V, double* ev, double* scratch, i
   (void)lane;
   return sweep;
 }
-
-// ---------------------------------------------------------------------------------------------
-// Ring eigensolver for M = 64 on 512 threads with the two halves of a step on DIFFERENT warps ("role split"):
-//   warps 0-7  (A warps): rotations + the 2x2-block update of A (two blocks per thread), one mbarrier per step
-//                         among these 256 threads only;
-//   warps 8-15 (V warps): V <- V J on registers (8 rows x one column pair per thread), nothing else.
-// In jacobi_eigh_ring every warp runs the same phase at the same time, so the shared-memory / shuffle bursts
-// (LDS 320 + SHFL 770 + STS 290 cycles per step) and the FP64 burst (~1200) take turns: 2430 cycles per step, the sum.
-// Here the V update is off the critical path: A warp 0 publishes the step's 32 rotations (c, s) in a FIFO in shared
-// memory (`fifo`, one slot per step of a sweep, one mbarrier per slot: 63 x (768 + 8) bytes -- the caller's idle
-// basis-change buffer), and the V warps consume them whenever the FP64 pipe and the shuffle unit have room; they may
-// lag by up to a sweep and are only met again at the sweep boundary.  The rotation parameters are computed by 8 warps
-// instead of 16.  Same ring bookkeeping, same results as jacobi_eigh_ring (validated against it by
-// scripts/ubench_jacobi.cu).
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void bar_a_group() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-__device__ __forceinline__ double a_group_sum(double v, double* red, int tid) {
-  v = warp_sum(v);
-  bar_a_group();
-  if ((tid & 31) == 0) red[tid >> 5] = v;
-  bar_a_group();
-  double tot = 0.0;
-#pragma unroll
-  for (int i = 0; i < 8; ++i) tot += red[i];
-  return tot;
-}
-
-// ABL (scripts/ubench_jacobi.cu only): 1 = the V warps skip their loop, 2 = the A warps skip the block update
-template <int LD, int ABL>
-__device__ int jacobi_eigh_ring_split64(cplx* A, cplx* V, double* ev, double* scratch, double* fifo, int tid,
-                                        bool init_v, int max_sweeps, double rel2, bool clean_a) {
-  constexpr int M = 64, HP = 32, M1 = 63, NOFF = HP * (HP - 1) / 2, NTA = 256, NB = 2, RV = 8;
-  const bool is_a = tid < NTA;
-  const int pr = tid & 31, seg = tid >> 5;       // A warps: seg 0..7; V warps: seg 8..15
-  const int vseg = seg - 8;                      // V warps: rows RV * vseg .. RV * vseg + 7
-  double* red = scratch;                         // 8 doubles (A-group reductions)
-  int* flag = reinterpret_cast<int*>(scratch + 16);  // [2]: "run another sweep", double-buffered over sweeps
-  double* mbar_a = scratch + 32;                 // step barrier of the A group
-  double* full = fifo + M1 * HP * 3;             // [M1] mbarriers, one per FIFO slot
-  if (init_v) {
-    for (int e = tid; e < M * M; e += 512) V[(e / M) * LD + e % M] = cmake((e / M == e % M) ? 1.0 : 0.0, 0.0);
-  }
-  if (tid == 0) mbar_init(mbar_a, NTA);
-  if (tid < M1) mbar_init(full + tid, 32);
-  __syncthreads();
-
-  // ---- A-warp state ----
-  bool has_block[NB], near1[NB], near2[NB], last2[NB], first2[NB];
-  int bI[NB], bJ[NB];
-#pragma unroll
-  for (int k = 0; k < NB; ++k) {
-    int w = tid + k * NTA, I = 0, J = 1;
-    has_block[k] = is_a && w < NOFF;
-    if (has_block[k]) {
-      while (w >= HP - 1 - I) {
-        w -= HP - 1 - I;
-        ++I;
-      }
-      J = I + 1 + w;
-    }
-    bI[k] = I;
-    bJ[k] = J;
-    near1[k] = (J == I + 1);
-    near2[k] = (J == I + 2);
-    last2[k] = (I == HP - 2);
-    first2[k] = (I == 0 && J == 1);
-  }
-  const int col0q = (pr == 0) ? M1 : M1 - pr;
-  double dp = 0.0, dq = 0.0;
-  if (is_a) {
-    dp = A[pr * LD + pr].x;
-    dq = A[col0q * LD + col0q].x;
-  }
-  bool fresh = true;
-  unsigned parity = 0;
-  bool pending = false;
-  auto wait_pending = [&]() {
-    if (pending) {
-      mbar_wait(mbar_a, parity);
-      parity ^= 1u;
-      pending = false;
-    }
-  };
-  // ---- V-warp state ----
-  cplx vp[RV], vq[RV];
-  if (!is_a) {
-#pragma unroll
-    for (int k = 0; k < RV; ++k) {
-      vp[k] = V[(RV * vseg + k) * LD + pr];
-      vq[k] = V[(RV * vseg + k) * LD + col0q];
-    }
-  }
-
-  int sweep = 0;
-  while (true) {
-    int p = pr, q = col0q;
-    int pi[NB], qi[NB], pj[NB], qj[NB];
-    if (is_a) {
-      wait_pending();
-      double off = 0.0;
-#pragma unroll
-      for (int k = 0; k < NB; ++k) {
-        rr_pair(M, 0, bI[k], pi[k], qi[k]);
-        rr_pair(M, 0, bJ[k], pj[k], qj[k]);
-        if (!has_block[k]) pi[k] = qi[k] = pj[k] = qj[k] = 0;
-        cplx b00 = A[pi[k] * LD + pj[k]];
-        cplx b01 = near1[k] ? A[qj[k] * LD + pi[k]] : A[pi[k] * LD + qj[k]];
-        const cplx b10 = A[qi[k] * LD + pj[k]];
-        cplx b11 = A[qi[k] * LD + qj[k]];
-        if (!fresh && near2[k]) b01 = cmake(0.0, 0.0);
-        if (!fresh && last2[k]) b00 = cmake(0.0, 0.0);
-        if (!fresh && first2[k]) b11 = cmake(0.0, 0.0);
-        if (has_block[k]) off += cabs2(b00) + cabs2(b01) + cabs2(b10) + cabs2(b11);
-      }
-      if (seg == 0) off += cabs2(A[q * LD + p]);
-      const double dg = (seg == 0) ? dp * dp + dq * dq : 0.0;
-      off = 2.0 * a_group_sum(off, red, tid);
-      const double tot = off + a_group_sum(dg, red, tid);
-      const bool done = (off <= (rel2 > 0.0 ? rel2 : 1e-30 * M * M) * tot) || tot == 0.0 || sweep >= max_sweeps;
-      if (tid == 0) flag[sweep & 1] = done ? 0 : 1;
-    }
-    __syncthreads();  // sweep boundary: the V warps have drained the FIFO of the previous sweep
-    if (!flag[sweep & 1]) break;
-    if (is_a) {
-#pragma unroll 1
-      for (int step = 0; step < M1; ++step) {
-        wait_pending();
-        const cplx beta = cconj(A[q * LD + p]);
-        cplx b00[NB], b01[NB], b10[NB], b11[NB];
-#pragma unroll
-        for (int k = 0; k < NB; ++k) {
-          b00[k] = A[pi[k] * LD + pj[k]];
-          b01[k] = A[near1[k] ? qj[k] * LD + pi[k] : pi[k] * LD + qj[k]];
-          b01[k].y = near1[k] ? -b01[k].y : b01[k].y;
-          b10[k] = A[qi[k] * LD + pj[k]];
-          b11[k] = A[qi[k] * LD + qj[k]];
-          b01[k] = (!fresh && near2[k]) ? cmake(0.0, 0.0) : b01[k];
-          b00[k] = (!fresh && last2[k]) ? cmake(0.0, 0.0) : b00[k];
-          b11[k] = (!fresh && first2[k]) ? cmake(0.0, 0.0) : b11[k];
-        }
-        double c, an, gn;
-        cplx s;
-        jacobi_rotation(dp, dq, beta, c, s, an, gn);
-        if (seg == 0) {  // publish the step's rotations for the V warps
-          double* slot = fifo + step * (3 * HP) + pr;  // c[32] | s.x[32] | s.y[32]: conflict-free 8-byte accesses
-          slot[0] = c;
-          slot[HP] = s.x;
-          slot[2 * HP] = s.y;
-          mbar_arrive(full + step);
-        }
-#pragma unroll
-        for (int k = 0; k < ((ABL & 2) ? 0 : NB); ++k) {
-          const double cI = __shfl_sync(0xffffffffu, c, bI[k]), cJ = __shfl_sync(0xffffffffu, c, bJ[k]);
-          cplx sI, sJ;
-          sI.x = __shfl_sync(0xffffffffu, s.x, bI[k]);
-          sI.y = __shfl_sync(0xffffffffu, s.y, bI[k]);
-          sJ.x = __shfl_sync(0xffffffffu, s.x, bJ[k]);
-          sJ.y = __shfl_sync(0xffffffffu, s.y, bJ[k]);
-          const cplx csJ = cconj(sJ), csI = cconj(sI);
-          const cplx x00 = csub(cscale(b00[k], cJ), cmul(csJ, b01[k]));
-          const cplx x01 = cadd(cmul(sJ, b00[k]), cscale(b01[k], cJ));
-          const cplx x10 = csub(cscale(b10[k], cJ), cmul(csJ, b11[k]));
-          const cplx x11 = cadd(cmul(sJ, b10[k]), cscale(b11[k], cJ));
-          const cplx y00 = csub(cscale(x00, cI), cmul(sI, x10));
-          const cplx y01 = csub(cscale(x01, cI), cmul(sI, x11));
-          const cplx y10 = cadd(cmul(csI, x00), cscale(x10, cI));
-          const cplx y11 = cadd(cmul(csI, x01), cscale(x11, cI));
-          if (has_block[k]) {
-            A[pi[k] * LD + pj[k]] = y00;
-            A[pi[k] * LD + qj[k]] = y01;
-            A[qi[k] * LD + pj[k]] = y10;
-            A[qi[k] * LD + qj[k]] = y11;
-          }
-        }
-        mbar_arrive(mbar_a);
-        pending = true;
-        {
-          const double upd = (pr == 0) ? an : gn;
-          const double rp = __shfl_down_sync(0xffffffffu, an, 1, HP), rq = __shfl_up_sync(0xffffffffu, upd, 1, HP);
-          dp = (pr == HP - 1) ? gn : rp;
-          dq = (pr == 0) ? gn : rq;
-        }
-        fresh = false;
-        const int nxt = (step + 1 == M1) ? 0 : step + 1;
-        rr_pair(M, nxt, pr, p, q);
-#pragma unroll
-        for (int k = 0; k < NB; ++k) {
-          rr_pair(M, nxt, bI[k], pi[k], qi[k]);
-          rr_pair(M, nxt, bJ[k], pj[k], qj[k]);
-          if (!has_block[k]) pi[k] = qi[k] = pj[k] = qj[k] = 0;
-        }
-      }
-    } else if (!(ABL & 1)) {
-      const unsigned par = (unsigned)(sweep & 1);
-#pragma unroll 1
-      for (int step = 0; step < M1; ++step) {
-        mbar_wait(full + step, par);
-        const double* slot = fifo + step * (3 * HP) + pr;
-        const double c_prev = slot[0];
-        const cplx s_prev = cmake(slot[HP], slot[2 * HP]);
-        const cplx cs = cconj(s_prev);
-#pragma unroll
-        for (int k = 0; k < RV; ++k) {
-          const cplx np = csub(cscale(vp[k], c_prev), cmul(cs, vq[k]));
-          const cplx nq = cadd(cmul(s_prev, vp[k]), cscale(vq[k], c_prev));
-          const cplx up = (pr == 0) ? np : nq;
-          cplx rp, rq;
-          rp.x = __shfl_down_sync(0xffffffffu, np.x, 1, HP);
-          rp.y = __shfl_down_sync(0xffffffffu, np.y, 1, HP);
-          rq.x = __shfl_up_sync(0xffffffffu, up.x, 1, HP);
-          rq.y = __shfl_up_sync(0xffffffffu, up.y, 1, HP);
-          vp[k] = (pr == HP - 1) ? nq : rp;
-          vq[k] = (pr == 0) ? nq : rq;
-        }
-      }
-    }
-    ++sweep;
-  }
-  if (is_a) {
-    wait_pending();
-    if (clean_a) {
-#pragma unroll
-      for (int k = 0; k < NB; ++k) {
-        if (!has_block[k]) continue;
-        int pi, qi, pj, qj;
-        rr_pair(M, 0, bI[k], pi, qi);
-        rr_pair(M, 0, bJ[k], pj, qj);
-        cplx b00 = A[pi * LD + pj];
-        cplx b01 = near1[k] ? cconj(A[qj * LD + pi]) : A[pi * LD + qj];
-        const cplx b10 = A[qi * LD + pj];
-        cplx b11 = A[qi * LD + qj];
-        if (!fresh && near2[k]) b01 = cmake(0.0, 0.0);
-        if (!fresh && last2[k]) b00 = cmake(0.0, 0.0);
-        if (!fresh && first2[k]) b11 = cmake(0.0, 0.0);
-        A[pi * LD + pj] = b00; A[pj * LD + pi] = cconj(b00);
-        A[pi * LD + qj] = b01; A[qj * LD + pi] = cconj(b01);
-        A[qi * LD + pj] = b10; A[pj * LD + qi] = cconj(b10);
-        A[qi * LD + qj] = b11; A[qj * LD + qi] = cconj(b11);
-      }
-      if (seg == 0) {
-        const cplx v = A[col0q * LD + pr];
-        A[pr * LD + col0q] = cconj(v);
-        A[pr * LD + pr] = cmake(dp, 0.0);
-        A[col0q * LD + col0q] = cmake(dq, 0.0);
-      }
-    }
-    if (seg == 0) {
-      ev[pr] = dp;
-      ev[col0q] = dq;
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < RV; ++k) {
-      V[(RV * vseg + k) * LD + pr] = vp[k];
-      V[(RV * vseg + k) * LD + col0q] = vq[k];
-    }
-  }
-  __syncthreads();
-  if (tid <= M1) {
-    const unsigned a = (unsigned)__cvta_generic_to_shared(tid == M1 ? mbar_a : full + tid);
-    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(a) : "memory");
-  }
-  __syncthreads();
-  return sweep;
-}
-// bytes of `fifo` the role-split solver needs (rotation slots + one mbarrier per slot)
-constexpr int QT_JACOBI_SPLIT_FIFO_BYTES = 63 * 32 * 3 * 8 + 63 * 8;
 
 // warp convenience wrapper used by the MLE variants and the distance kernels (scratch must hold
 // JacobiScratch<D>::doubles doubles, placed by the caller right after `ev`).
