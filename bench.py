@@ -544,14 +544,16 @@ def part_pgdb(ctx, n=3, global_batch=1024, in_basis="pauli"):
         "kernel_ms_per_rank": {"min": min(per_rank), "max": max(per_rank), "all": [round(x, 2) for x in per_rank]},
         "roofline": {"kernel": f"{kname} (fused PGD + Dykstra + Jacobi eigh, one experiment per "
                                f"{'block' if n == 3 else 'warp'})",
-                     "bound": "fp64", "achieved": flops / (ms_kernel * 1e-3) / 1e12, "peak": fp64_peak,
-                     "unit": "TFLOP/s", "frac": flops / (ms_kernel * 1e-3) / 1e12 / fp64_peak, "kernel_ms": ms_kernel,
+                     "bound": "fp64", "achieved": flops / (ms_kernel * 1e-3) / 1e12, "peak": fp64_peak * world,
+                     "peak_note": f"{world} GPU(s) x {fp64_peak:.2f} TFLOP/s",
+                     "unit": "TFLOP/s", "frac": flops / (ms_kernel * 1e-3) / 1e12 / (fp64_peak * world),
+                     "kernel_ms": ms_kernel,
                      "flop_model": "SURVEY.md 8(d): eigh*44m^3 + (cost_evals+2*outer)*F_A with the items' actual counters "
                                    "(all ranks' items / slowest rank's kernel time)",
                      "peak_source": fp64_src, "traffic": traffic, "traffic_source": traffic_src,
                      "hbm_view": {"bound": "hbm", "achieved": global_batch * bytes_item / (ms_kernel * 1e-3) / 1e9,
-                                  "peak": ctx.hbm_peak, "unit": "GB/s",
-                                  "frac": global_batch * bytes_item / (ms_kernel * 1e-3) / 1e9 / ctx.hbm_peak,
+                                  "peak": ctx.hbm_peak * world, "unit": "GB/s",
+                                  "frac": global_batch * bytes_item / (ms_kernel * 1e-3) / 1e9 / (ctx.hbm_peak * world),
                                   "note": "compulsory bytes only"}},
     }
     want_cpu = world == 1 and not args.no_cpu_baseline and (n <= 2 or not args.no_pgdb_cpu)

@@ -16,6 +16,8 @@
 #include "qt_pauli.cuh"
 #include "../../include/qtomo.h"
 
+#include <algorithm>
+
 // elements per block of the small-n tiles: 16 KB tiles keep 8 blocks resident per SM (cf. proj_tp_kernel)
 #ifndef QT_PL_TILE
 #define QT_PL_TILE 1024
@@ -25,6 +27,9 @@
 #endif
 
 static constexpr int TILE_ELEMS = 4096;  // 64 KB of complex128 per block pass
+#ifndef QT_PL3_REGISTER_KERNEL
+#define QT_PL3_REGISTER_KERNEL 1  // n = 3 superop <-> PTM: register-resident radix-16 kernel (0: shared-memory stages)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // kraus2choi / kraus2superop
@@ -427,10 +432,110 @@ __global__ void __launch_bounds__(PlCfg<N>::NTB) pl_pass_b_kernel(int64_t B, con
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// n = 3: register-resident radix-16 passes.
+// pl_pass_a_kernel<3> runs its six radix-4 stages in shared memory: 14 passes over a 64 KB tile per matrix, which made
+// it shared-memory-bandwidth bound at 0.53 of the HBM roof (profiles/r01_ncu_ptm3_kernel.md).  Here a 256-thread block
+// keeps the matrix in REGISTERS, 16 elements per thread, chosen so that two complete stages run without any exchange:
+//     pass 1  row stages q = 0, 1   (registers <-> bits 11..8 of the flat index e = row * 64 + col)
+//     pass 2  row stage  q = 2 and column stage q = 2   (bits 7, 6, 1, 0)
+//     pass 3  column stages q = 0, 1   (bits 5..2)
+// with ONE 64 KB shared buffer used twice as a transposition stage (4 passes over shared memory instead of 14).
+// Rows and columns are held in base-4 DIGIT order (digit q of an index at bits 5-2q, 4-2q = (j_q, i_q)), which after
+// the forward butterflies IS the canonical Pauli order; the computational ("position") order of the other side is
+// applied as a bit permutation on the global address, so both the loads and the stores are full 32-byte sectors.
+// The shared buffer is addressed through a linear (XOR) swizzle that makes both access patterns of each transposition
+// conflict-free: bank group = 3 parity bits, one of which toggles for every bit a quarter-warp varies.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int pl3_bits(int e, int b) { return (e >> b) & 1; }
+// transposition 1 (written in the pass-1 mapping, read in the pass-2 mapping)
+template <bool FWD>
+__device__ __forceinline__ int pl3_swz1(int e) {
+  const int e0 = pl3_bits(e, 0), e1 = pl3_bits(e, 1), e2 = pl3_bits(e, 2), e3 = pl3_bits(e, 3), e4 = pl3_bits(e, 4);
+  if (FWD)  // writers vary (e0, e2, e4), readers (e2, e3, e4)
+    return ((e >> 5) << 5) | (e1 << 4) | (e3 << 3) | (e4 << 2) | (e2 << 1) | (e0 ^ e3);
+  // !FWD: writers vary (e0, e1, e2), readers (e2, e3, e4)
+  return ((e >> 5) << 5) | (e4 << 4) | (e3 << 3) | (e2 << 2) | ((e1 ^ e4) << 1) | (e0 ^ e3);
+}
+// transposition 2 (written in the pass-2 mapping: (e2, e3, e4) vary; read in the pass-3 mapping: (e0, e1, e6) vary)
+__device__ __forceinline__ int pl3_swz2(int e) {
+  const int e0 = pl3_bits(e, 0), e1 = pl3_bits(e, 1), e2 = pl3_bits(e, 2), e3 = pl3_bits(e, 3), e4 = pl3_bits(e, 4);
+  const int e5 = pl3_bits(e, 5), e6 = pl3_bits(e, 6);
+  return ((e >> 7) << 7) | (e5 << 6) | (e6 << 5) | (e1 << 4) | (e0 << 3) | ((e4 ^ e6) << 2) | ((e3 ^ e1) << 1) | (e2 ^ e0);
+}
+// two stages on the 16 registers: the first on register bits (3, 2), the second on bits (1, 0)
+template <bool FWD, bool CONJ_HI, bool CONJ_LO>
+__device__ __forceinline__ void pl3_two_stages(cplx (&u)[16]) {
+#pragma unroll
+  for (int b = 0; b < 4; ++b) bfly4<FWD, CONJ_HI>(u[b], u[4 + b], u[8 + b], u[12 + b]);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) bfly4<FWD, CONJ_LO>(u[4 * a], u[4 * a + 1], u[4 * a + 2], u[4 * a + 3]);
+}
+
+template <bool FWD>
+__global__ void __launch_bounds__(256, 2) pl3_reg_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out) {
+  constexpr int N = 3, L = 64;
+  extern __shared__ __align__(16) cplx buf[];  // 4096 elements
+  const int tid = threadIdx.x;
+  // thread part of the flat index e in the three mappings (the register part is OR-ed / XOR-ed in per element)
+  const int col1 = tid & 63;                                     // pass 1: the global column this thread reads
+  const int t1 = (FWD ? pos_to_pauli(col1, N) : col1) | ((tid >> 6) << 6);
+  const int t2 = ((tid & 15) << 2) | ((tid >> 4) << 8);
+  const int t3 = (tid & 3) | ((tid >> 2) << 6);
+  const int s1w = pl3_swz1<FWD>(t1), s1r = pl3_swz1<FWD>(t2), s2w = pl3_swz2(t2), s2r = pl3_swz2(t3);
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    const cplx* src = in + b * (L * L);
+    cplx* dst = out + b * (L * L);
+    cplx u[16];
+    // ---- pass 1: registers <-> row digits 0, 1 (e bits 11..8); lanes <-> 32 consecutive global columns ----
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int tr = (r << 2) | (tid >> 6);
+      u[r] = src[(FWD ? pauli_to_pos(tr, N) : tr) * L + col1];
+    }
+    pl3_two_stages<FWD, false, false>(u);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) buf[s1w ^ pl3_swz1<FWD>(r << 8)] = u[r];
+    __syncthreads();
+    // ---- pass 2: registers <-> e bits (7, 6) = row digit 2 and (1, 0) = column digit 2 ----
+#pragma unroll
+    for (int r = 0; r < 16; ++r) u[r] = buf[s1r ^ pl3_swz1<FWD>(((r >> 2) << 6) | (r & 3))];
+    __syncthreads();
+    pl3_two_stages<FWD, false, true>(u);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) buf[s2w ^ pl3_swz2(((r >> 2) << 6) | (r & 3))] = u[r];
+    __syncthreads();
+    // ---- pass 3: registers <-> e bits 5..2 = column digits 0, 1; lanes <-> 4 consecutive columns x 8 rows ----
+#pragma unroll
+    for (int r = 0; r < 16; ++r) u[r] = buf[s2r ^ pl3_swz2(r << 2)];
+    __syncthreads();
+    pl3_two_stages<FWD, true, true>(u);
+    const int tr = tid >> 2;
+    const int64_t rowoff = (int64_t)(FWD ? tr : pauli_to_pos(tr, N)) * L;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int tc = (r << 2) | (tid & 3);
+      dst[rowoff + (FWD ? tc : pauli_to_pos(tc, N))] = cscale(u[r], 0.125);
+    }
+  }
+}
+
+template <bool FWD>
+static int launch_pl3_reg(int64_t B, const void* in, void* out, cudaStream_t st) {
+  const size_t smem = sizeof(cplx) * 4096;
+  QT_CUDA(cudaFuncSetAttribute(pl3_reg_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int64_t blocks = std::min<int64_t>(B, (int64_t)QT_NUM_SMS * 2 * 4);
+  pl3_reg_kernel<FWD><<<(unsigned)blocks, 256, smem, st>>>(B, (const cplx*)in, (cplx*)out);
+  return qt_check_launch("pl3_reg_kernel");
+}
+
 template <int N, bool FWD>
 static int launch_pl_n(int64_t B, const void* in, void* out, void* workspace, cudaStream_t st) {
   using C = PlCfg<N>;
   constexpr int REST = 1 << (2 * (N - C::RQN));
+#if QT_PL3_REGISTER_KERNEL
+  if constexpr (N == 3) return launch_pl3_reg<FWD>(B, in, out, st);
+#endif
   const int64_t n_tiles = B * REST;
   const int64_t blocks_a = (n_tiles + C::IPB - 1) / C::IPB;
   QT_CUDA(cudaFuncSetAttribute(pl_pass_a_kernel<N, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem_a));
