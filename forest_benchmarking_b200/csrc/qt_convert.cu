@@ -529,12 +529,160 @@ static int launch_pl3_reg(int64_t B, const void* in, void* out, cudaStream_t st)
   return qt_check_launch("pl3_reg_kernel");
 }
 
+// ---------------------------------------------------------------------------------------------
+// n = 4, 5: the same register-resident passes for the two HBM passes of the factored transform.
+//   pass A tile = 4^RQN rows x all 4^n columns = 4096 elements (n = 4: 16 x 256, n = 5: 4 x 1024): flat index
+//   e = (tile_row << 2n) | column_digits, six stages on the bit pairs (11,10) (9,8) | (7,6) (1,0) | (5,4) (3,2) exactly
+//   like pl3_reg_kernel (pairs at or above bit 2n are row stages, the others column stages), same swizzles.
+//   pass B, n = 4: 16 rows x 256 columns, two row stages: one register pass, no shared memory at all.
+//   pass B, n = 5: 256 rows x 16 columns, four row stages: two register passes around one transposition.
+// ---------------------------------------------------------------------------------------------
+template <int N, bool FWD>
+__global__ void __launch_bounds__(256, 2) pl_pass_a_reg_kernel(int64_t n_tiles, const cplx* __restrict__ in,
+                                                               cplx* __restrict__ out) {
+  using C = PlCfg<N>;
+  constexpr int L = C::L, RQN = C::RQN, CB = 2 * N;
+  constexpr int REST = 1 << (2 * (N - RQN));
+  static_assert(2 * RQN + CB == 12, "a pass-A tile is 4096 elements");
+  extern __shared__ __align__(16) cplx buf[];
+  const int tid = threadIdx.x;
+  const int t1 = FWD ? pos_to_pauli(tid, 4) : tid;  // e bits 7..0: the four trailing column digits
+  const int t2 = ((tid & 15) << 2) | ((tid >> 4) << 8);
+  const int t3 = (tid & 3) | ((tid >> 2) << 6);
+  const int s1w = pl3_swz1<FWD>(t1), s1r = pl3_swz1<FWD>(t2), s2w = pl3_swz2(t2), s2r = pl3_swz2(t3);
+  for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
+    const int64_t b = tile_id / REST;
+    const int fixed = (int)(tile_id % REST);
+    const cplx* src = in + b * (int64_t)L * L;
+    cplx* dst = out + b * (int64_t)L * L;
+    cplx u[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int e = t1 | (r << 8);
+      const int tc = e & (L - 1), idx = (e >> CB) * REST + fixed;
+      u[r] = src[(int64_t)(FWD ? pauli_to_pos(idx, N) : idx) * L + (FWD ? pauli_to_pos(tc, N) : tc)];
+    }
+    pl3_two_stages<FWD, (10 < CB), (8 < CB)>(u);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) buf[s1w ^ pl3_swz1<FWD>(r << 8)] = u[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) u[r] = buf[s1r ^ pl3_swz1<FWD>(((r >> 2) << 6) | (r & 3))];
+    __syncthreads();
+    pl3_two_stages<FWD, (6 < CB), true>(u);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) buf[s2w ^ pl3_swz2(((r >> 2) << 6) | (r & 3))] = u[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) u[r] = buf[s2r ^ pl3_swz2(r << 2)];
+    __syncthreads();
+    pl3_two_stages<FWD, true, true>(u);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int e = t3 | (r << 2);
+      const int tc = e & (L - 1), idx = (e >> CB) * REST + fixed;
+      // rows leave in position order (pass B expects them there); FWD columns are now canonical, !FWD columns positional
+      dst[(int64_t)pauli_to_pos(idx, N) * L + (FWD ? tc : pauli_to_pos(tc, N))] = u[r];
+    }
+  }
+}
+
+// n = 4 pass B: thread = column, registers = the 16 rows of the tile (row digits 2, 3)
+template <bool FWD>
+__global__ void __launch_bounds__(256) pl4_pass_b_reg_kernel(int64_t n_tiles, const cplx* __restrict__ in,
+                                                             cplx* __restrict__ out) {
+  constexpr int N = 4, L = 256;
+  const int c = threadIdx.x;
+  for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
+    const int64_t b = tile_id >> 4;
+    const int top = (int)(tile_id & 15);
+    const cplx* src = in + b * (int64_t)L * L;
+    cplx* dst = out + b * (int64_t)L * L;
+    cplx u[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) u[r] = src[(int64_t)pauli_to_pos(top * 16 + r, N) * L + c];
+    pl3_two_stages<FWD, false, false>(u);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int idx = top * 16 + r;
+      dst[(int64_t)(FWD ? idx : pauli_to_pos(idx, N)) * L + c] = cscale(u[r], 1.0 / 16.0);
+    }
+  }
+}
+
+// n = 5 pass B: tile = 256 rows (row digits 1..4) x 16 columns; e = (tile_row << 4) | column
+template <bool FWD>
+__global__ void __launch_bounds__(256, 2) pl5_pass_b_reg_kernel(int64_t n_tiles, const cplx* __restrict__ in,
+                                                                cplx* __restrict__ out) {
+  constexpr int N = 5, L = 1024, PANELS = L / 16;
+  extern __shared__ __align__(16) cplx buf[];
+  const int tid = threadIdx.x;
+  const int t2 = (tid & 15) | ((tid >> 4) << 8);  // pass 2: threads <-> e bits 3..0 and 11..8
+  for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
+    const int panel = (int)(tile_id % PANELS);
+    const int top = (int)((tile_id / PANELS) % 4);
+    const int64_t b = tile_id / (PANELS * 4);
+    const cplx* src = in + b * (int64_t)L * L + panel * 16;
+    cplx* dst = out + b * (int64_t)L * L + panel * 16;
+    cplx u[16];
+    // pass 1: registers <-> e bits 11..8 (row digits 1, 2); threads <-> e bits 7..0
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int e = tid | (r << 8);
+      u[r] = src[(int64_t)pauli_to_pos(top * 256 + (e >> 4), N) * L + (e & 15)];
+    }
+    pl3_two_stages<FWD, false, false>(u);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) buf[tid | (r << 8)] = u[r];
+    __syncthreads();
+    // pass 2: registers <-> e bits 7..4 (row digits 3, 4)
+#pragma unroll
+    for (int r = 0; r < 16; ++r) u[r] = buf[t2 | (r << 4)];
+    __syncthreads();
+    pl3_two_stages<FWD, false, false>(u);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const int e = t2 | (r << 4);
+      const int idx = top * 256 + (e >> 4);
+      dst[(int64_t)(FWD ? idx : pauli_to_pos(idx, N)) * L + (e & 15)] = cscale(u[r], 1.0 / 32.0);
+    }
+  }
+}
+
+template <int N, bool FWD>
+static int launch_pl_reg_two_pass(int64_t B, const void* in, void* out, void* workspace, cudaStream_t st) {
+  using C = PlCfg<N>;
+  constexpr int REST = 1 << (2 * (N - C::RQN));
+  QT_REQUIRE(workspace, "superop<->pauli_liouville with n >= 4 needs a workspace of B*16^n*16 bytes");
+  const size_t smem = sizeof(cplx) * 4096;
+  const int64_t cap = (int64_t)QT_NUM_SMS * 2 * 8;
+  const int64_t tiles_a = B * REST;
+  QT_CUDA(cudaFuncSetAttribute(pl_pass_a_reg_kernel<N, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pl_pass_a_reg_kernel<N, FWD><<<(unsigned)std::min(tiles_a, cap), 256, smem, st>>>(tiles_a, (const cplx*)in,
+                                                                                   (cplx*)workspace);
+  int rc = qt_check_launch("pl_pass_a_reg_kernel");
+  if (rc) return rc;
+  if constexpr (N == 4) {
+    const int64_t tiles_b = B * 16;
+    pl4_pass_b_reg_kernel<FWD><<<(unsigned)std::min(tiles_b, cap * 2), 256, 0, st>>>(tiles_b, (const cplx*)workspace,
+                                                                                  (cplx*)out);
+    return qt_check_launch("pl4_pass_b_reg_kernel");
+  } else {
+    const int64_t tiles_b = B * 4 * (C::L / 16);
+    QT_CUDA(cudaFuncSetAttribute(pl5_pass_b_reg_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pl5_pass_b_reg_kernel<FWD><<<(unsigned)std::min(tiles_b, cap), 256, smem, st>>>(tiles_b, (const cplx*)workspace,
+                                                                                  (cplx*)out);
+    return qt_check_launch("pl5_pass_b_reg_kernel");
+  }
+}
+
 template <int N, bool FWD>
 static int launch_pl_n(int64_t B, const void* in, void* out, void* workspace, cudaStream_t st) {
   using C = PlCfg<N>;
   constexpr int REST = 1 << (2 * (N - C::RQN));
 #if QT_PL3_REGISTER_KERNEL
   if constexpr (N == 3) return launch_pl3_reg<FWD>(B, in, out, st);
+  if constexpr (N >= 4) return launch_pl_reg_two_pass<N, FWD>(B, in, out, workspace, st);
 #endif
   const int64_t n_tiles = B * REST;
   const int64_t blocks_a = (n_tiles + C::IPB - 1) / C::IPB;
