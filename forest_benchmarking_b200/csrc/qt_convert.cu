@@ -30,6 +30,9 @@ static constexpr int TILE_ELEMS = 4096;  // 64 KB of complex128 per block pass
 #ifndef QT_PL3_REGISTER_KERNEL
 #define QT_PL3_REGISTER_KERNEL 1  // n = 3 superop <-> PTM: register-resident radix-16 kernel (0: shared-memory stages)
 #endif
+#ifndef QT_PL_FUSED_PASSES
+#define QT_PL_FUSED_PASSES 1  // n = 4, 5: both passes in one launch, intermediate in an L2-resident ring (0: two kernels)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // kraus2choi / kraus2superop
@@ -537,114 +540,191 @@ static int launch_pl3_reg(int64_t B, const void* in, void* out, cudaStream_t st)
 //   pass B, n = 4: 16 rows x 256 columns, two row stages: one register pass, no shared memory at all.
 //   pass B, n = 5: 256 rows x 16 columns, four row stages: two register passes around one transposition.
 // ---------------------------------------------------------------------------------------------
-template <int N, bool FWD>
-__global__ void __launch_bounds__(256, 2) pl_pass_a_reg_kernel(int64_t n_tiles, const cplx* __restrict__ in,
-                                                               cplx* __restrict__ out) {
+// global-memory access flavours: the two-kernel path uses plain accesses; the fused path streams the matrix in and
+// out (evict-first) and keeps the intermediate in L2 (written with .cg, read back with .cg: never through a stale L1 line)
+struct PlPlain {
+  static __device__ __forceinline__ cplx ld_in(const cplx* p) { return *p; }
+  static __device__ __forceinline__ void st_out(cplx* p, cplx v) { *p = v; }
+  static __device__ __forceinline__ cplx ld_ws(const cplx* p) { return *p; }
+  static __device__ __forceinline__ void st_ws(cplx* p, cplx v) { *p = v; }
+};
+struct PlFused {
+  static __device__ __forceinline__ cplx ld_in(const cplx* p) { return __ldcs(p); }
+  static __device__ __forceinline__ void st_out(cplx* p, cplx v) { __stcs(p, v); }
+  static __device__ __forceinline__ cplx ld_ws(const cplx* p) { return __ldcg(p); }
+  static __device__ __forceinline__ void st_ws(cplx* p, cplx v) { __stcg(p, v); }
+};
+
+// one pass-A tile: src = the input matrix, dst = the intermediate matrix (rows in position order)
+template <int N, bool FWD, class P>
+__device__ __forceinline__ void pl_tile_a(const cplx* __restrict__ src, cplx* __restrict__ dst, int fixed, cplx* buf,
+                                          int tid) {
   using C = PlCfg<N>;
   constexpr int L = C::L, RQN = C::RQN, CB = 2 * N;
   constexpr int REST = 1 << (2 * (N - RQN));
   static_assert(2 * RQN + CB == 12, "a pass-A tile is 4096 elements");
-  extern __shared__ __align__(16) cplx buf[];
-  const int tid = threadIdx.x;
   const int t1 = FWD ? pos_to_pauli(tid, 4) : tid;  // e bits 7..0: the four trailing column digits
   const int t2 = ((tid & 15) << 2) | ((tid >> 4) << 8);
   const int t3 = (tid & 3) | ((tid >> 2) << 6);
   const int s1w = pl3_swz1<FWD>(t1), s1r = pl3_swz1<FWD>(t2), s2w = pl3_swz2(t2), s2r = pl3_swz2(t3);
-  for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
-    const int64_t b = tile_id / REST;
-    const int fixed = (int)(tile_id % REST);
-    const cplx* src = in + b * (int64_t)L * L;
-    cplx* dst = out + b * (int64_t)L * L;
-    cplx u[16];
+  cplx u[16];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      const int e = t1 | (r << 8);
-      const int tc = e & (L - 1), idx = (e >> CB) * REST + fixed;
-      u[r] = src[(int64_t)(FWD ? pauli_to_pos(idx, N) : idx) * L + (FWD ? pauli_to_pos(tc, N) : tc)];
-    }
-    pl3_two_stages<FWD, (10 < CB), (8 < CB)>(u);
+  for (int r = 0; r < 16; ++r) {
+    const int e = t1 | (r << 8);
+    const int tc = e & (L - 1), idx = (e >> CB) * REST + fixed;
+    u[r] = P::ld_in(src + (int64_t)(FWD ? pauli_to_pos(idx, N) : idx) * L + (FWD ? pauli_to_pos(tc, N) : tc));
+  }
+  pl3_two_stages<FWD, (10 < CB), (8 < CB)>(u);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) buf[s1w ^ pl3_swz1<FWD>(r << 8)] = u[r];
-    __syncthreads();
+  for (int r = 0; r < 16; ++r) buf[s1w ^ pl3_swz1<FWD>(r << 8)] = u[r];
+  __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 16; ++r) u[r] = buf[s1r ^ pl3_swz1<FWD>(((r >> 2) << 6) | (r & 3))];
-    __syncthreads();
-    pl3_two_stages<FWD, (6 < CB), true>(u);
+  for (int r = 0; r < 16; ++r) u[r] = buf[s1r ^ pl3_swz1<FWD>(((r >> 2) << 6) | (r & 3))];
+  __syncthreads();
+  pl3_two_stages<FWD, (6 < CB), true>(u);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) buf[s2w ^ pl3_swz2(((r >> 2) << 6) | (r & 3))] = u[r];
-    __syncthreads();
+  for (int r = 0; r < 16; ++r) buf[s2w ^ pl3_swz2(((r >> 2) << 6) | (r & 3))] = u[r];
+  __syncthreads();
 #pragma unroll
-    for (int r = 0; r < 16; ++r) u[r] = buf[s2r ^ pl3_swz2(r << 2)];
-    __syncthreads();
-    pl3_two_stages<FWD, true, true>(u);
+  for (int r = 0; r < 16; ++r) u[r] = buf[s2r ^ pl3_swz2(r << 2)];
+  __syncthreads();
+  pl3_two_stages<FWD, true, true>(u);
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
-      const int e = t3 | (r << 2);
-      const int tc = e & (L - 1), idx = (e >> CB) * REST + fixed;
-      // rows leave in position order (pass B expects them there); FWD columns are now canonical, !FWD columns positional
-      dst[(int64_t)pauli_to_pos(idx, N) * L + (FWD ? tc : pauli_to_pos(tc, N))] = u[r];
-    }
+  for (int r = 0; r < 16; ++r) {
+    const int e = t3 | (r << 2);
+    const int tc = e & (L - 1), idx = (e >> CB) * REST + fixed;
+    // rows leave in position order (pass B expects them there); FWD columns are now canonical, !FWD columns positional
+    P::st_ws(dst + (int64_t)pauli_to_pos(idx, N) * L + (FWD ? tc : pauli_to_pos(tc, N)), u[r]);
   }
 }
 
-// n = 4 pass B: thread = column, registers = the 16 rows of the tile (row digits 2, 3)
-template <bool FWD>
-__global__ void __launch_bounds__(256) pl4_pass_b_reg_kernel(int64_t n_tiles, const cplx* __restrict__ in,
-                                                             cplx* __restrict__ out) {
-  constexpr int N = 4, L = 256;
-  const int c = threadIdx.x;
-  for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
-    const int64_t b = tile_id >> 4;
-    const int top = (int)(tile_id & 15);
-    const cplx* src = in + b * (int64_t)L * L;
-    cplx* dst = out + b * (int64_t)L * L;
-    cplx u[16];
+// one pass-B tile.  n = 4: tile = `top` (row digits 0, 1), thread = column, registers = the 16 rows (row digits 2, 3).
+// n = 5: tile = (top = row digit 0, panel of 16 columns), 256 rows; e = (tile_row << 4) | column.
+template <int N, bool FWD, class P>
+__device__ __forceinline__ void pl_tile_b(const cplx* __restrict__ src, cplx* __restrict__ dst, int tile, cplx* buf,
+                                          int tid) {
+  constexpr int L = 1 << (2 * N);
+  cplx u[16];
+  if constexpr (N == 4) {
+    const int top = tile, c = tid;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) u[r] = src[(int64_t)pauli_to_pos(top * 16 + r, N) * L + c];
+    for (int r = 0; r < 16; ++r) u[r] = P::ld_ws(src + (int64_t)pauli_to_pos(top * 16 + r, N) * L + c);
     pl3_two_stages<FWD, false, false>(u);
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
       const int idx = top * 16 + r;
-      dst[(int64_t)(FWD ? idx : pauli_to_pos(idx, N)) * L + c] = cscale(u[r], 1.0 / 16.0);
+      P::st_out(dst + (int64_t)(FWD ? idx : pauli_to_pos(idx, N)) * L + c, cscale(u[r], 1.0 / 16.0));
     }
-  }
-}
-
-// n = 5 pass B: tile = 256 rows (row digits 1..4) x 16 columns; e = (tile_row << 4) | column
-template <bool FWD>
-__global__ void __launch_bounds__(256, 2) pl5_pass_b_reg_kernel(int64_t n_tiles, const cplx* __restrict__ in,
-                                                                cplx* __restrict__ out) {
-  constexpr int N = 5, L = 1024, PANELS = L / 16;
-  extern __shared__ __align__(16) cplx buf[];
-  const int tid = threadIdx.x;
-  const int t2 = (tid & 15) | ((tid >> 4) << 8);  // pass 2: threads <-> e bits 3..0 and 11..8
-  for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
-    const int panel = (int)(tile_id % PANELS);
-    const int top = (int)((tile_id / PANELS) % 4);
-    const int64_t b = tile_id / (PANELS * 4);
-    const cplx* src = in + b * (int64_t)L * L + panel * 16;
-    cplx* dst = out + b * (int64_t)L * L + panel * 16;
-    cplx u[16];
-    // pass 1: registers <-> e bits 11..8 (row digits 1, 2); threads <-> e bits 7..0
+  } else {
+    constexpr int PANELS = L / 16;
+    const int panel = tile % PANELS, top = tile / PANELS;
+    const int t2 = (tid & 15) | ((tid >> 4) << 8);  // pass 2: threads <-> e bits 3..0 and 11..8
+    src += panel * 16;
+    dst += panel * 16;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) {
+    for (int r = 0; r < 16; ++r) {  // pass 1: registers <-> e bits 11..8 (row digits 1, 2); threads <-> e bits 7..0
       const int e = tid | (r << 8);
-      u[r] = src[(int64_t)pauli_to_pos(top * 256 + (e >> 4), N) * L + (e & 15)];
+      u[r] = P::ld_ws(src + (int64_t)pauli_to_pos(top * 256 + (e >> 4), N) * L + (e & 15));
     }
     pl3_two_stages<FWD, false, false>(u);
 #pragma unroll
     for (int r = 0; r < 16; ++r) buf[tid | (r << 8)] = u[r];
     __syncthreads();
-    // pass 2: registers <-> e bits 7..4 (row digits 3, 4)
 #pragma unroll
-    for (int r = 0; r < 16; ++r) u[r] = buf[t2 | (r << 4)];
+    for (int r = 0; r < 16; ++r) u[r] = buf[t2 | (r << 4)];  // pass 2: registers <-> e bits 7..4 (row digits 3, 4)
     __syncthreads();
     pl3_two_stages<FWD, false, false>(u);
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
       const int e = t2 | (r << 4);
       const int idx = top * 256 + (e >> 4);
-      dst[(int64_t)(FWD ? idx : pauli_to_pos(idx, N)) * L + (e & 15)] = cscale(u[r], 1.0 / 32.0);
+      P::st_out(dst + (int64_t)(FWD ? idx : pauli_to_pos(idx, N)) * L + (e & 15), cscale(u[r], 1.0 / 32.0));
+    }
+  }
+}
+
+template <int N>
+struct PlFuseCfg {
+  static constexpr int L = 1 << (2 * N);
+  static constexpr int TA = 1 << (2 * (N - PlCfg<N>::RQN));       // pass-A tiles per matrix
+  static constexpr int TB = (N == 4) ? 16 : 4 * (L / 16);         // pass-B tiles per matrix
+  static constexpr int LAG = (N == 4) ? 12 : 1;                   // matrices between a matrix's A tiles and its B tiles
+  static constexpr int RING = (N == 4) ? 24 : 3;                  // intermediate matrices kept (L2-resident ring)
+};
+
+template <int N, bool FWD>
+__global__ void __launch_bounds__(256, 2) pl_pass_a_reg_kernel(int64_t n_tiles, const cplx* __restrict__ in,
+                                                               cplx* __restrict__ out) {
+  constexpr int L = PlCfg<N>::L, REST = PlFuseCfg<N>::TA;
+  extern __shared__ __align__(16) cplx buf[];
+  for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
+    const int64_t b = tile_id / REST;
+    pl_tile_a<N, FWD, PlPlain>(in + b * (int64_t)L * L, out + b * (int64_t)L * L, (int)(tile_id % REST), buf, threadIdx.x);
+  }
+}
+
+template <int N, bool FWD>
+__global__ void __launch_bounds__(256, 2) pl_pass_b_reg_kernel(int64_t n_tiles, const cplx* __restrict__ in,
+                                                               cplx* __restrict__ out) {
+  constexpr int L = PlCfg<N>::L, TB = PlFuseCfg<N>::TB;
+  extern __shared__ __align__(16) cplx buf[];
+  for (int64_t tile_id = blockIdx.x; tile_id < n_tiles; tile_id += gridDim.x) {
+    const int64_t b = tile_id / TB;
+    pl_tile_b<N, FWD, PlPlain>(in + b * (int64_t)L * L, out + b * (int64_t)L * L, (int)(tile_id % TB), buf, threadIdx.x);
+  }
+}
+
+// Both passes in ONE launch with the intermediate in an L2-resident ring (n = 4: 24 x 1 MB, n = 5: 3 x 16.8 MB).
+// Persistent blocks pull work items from a global counter; the item order is, per matrix index m,
+//     [pass-A tiles of matrix m]  [pass-B tiles of matrix m - LAG],
+// so a B tile is normally dequeued long after the A tiles it depends on have finished.  Dependencies are enforced anyway:
+// a B tile waits until adone[m] == TA, an A tile that re-uses a ring slot waits until bdone[m - RING] == TB.  Every wait
+// is on items that were dequeued EARLIER, and the grid never exceeds the number of co-resident blocks, so there is no
+// deadlock.  Intermediate lines are written and read with .cg (L2 only), the matrix itself streams with evict-first hints:
+// the second HBM pass of the two-kernel path (profiles/r01_traffic_convert.md: 2.0x the algorithmic traffic) disappears.
+template <int N, bool FWD>
+__global__ void __launch_bounds__(256, 2) pl_fused_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out,
+                                                          cplx* __restrict__ ring, int ring_slots,
+                                                          unsigned long long* __restrict__ queue, int* __restrict__ adone,
+                                                          int* __restrict__ bdone) {
+  using F = PlFuseCfg<N>;
+  constexpr int L = F::L, TA = F::TA, TB = F::TB, LAG = F::LAG, PER = TA + TB;
+  extern __shared__ __align__(16) cplx buf[];
+  __shared__ long long item;
+  const int tid = threadIdx.x;
+  const long long n_items = (long long)(B + LAG) * PER;
+  auto wait_for = [&](int* counter, int want) {
+    if (tid == 0) {
+      while (atomicAdd(counter, 0) < want) __nanosleep(200);
+      __threadfence();
+    }
+    __syncthreads();
+  };
+  auto signal = [&](int* counter) {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) atomicAdd(counter, 1);
+  };
+  while (true) {
+    if (tid == 0) item = (long long)atomicAdd(queue, 1ULL);
+    __syncthreads();
+    const long long k = item;
+    __syncthreads();
+    if (k >= n_items) break;
+    const int64_t g = k / PER;
+    const int w = (int)(k % PER);
+    if (w < TA) {
+      const int64_t m = g;
+      if (m >= B) continue;
+      if (m >= ring_slots) wait_for(bdone + (m - ring_slots), TB);  // the slot's previous tenant has been consumed
+      pl_tile_a<N, FWD, PlFused>(in + m * (int64_t)L * L, ring + (m % ring_slots) * (int64_t)L * L, w, buf, tid);
+      signal(adone + m);
+    } else {
+      const int64_t m = g - LAG;
+      if (m < 0 || m >= B) continue;
+      wait_for(adone + m, TA);
+      pl_tile_b<N, FWD, PlFused>(ring + (m % ring_slots) * (int64_t)L * L, out + m * (int64_t)L * L, w - TA, buf, tid);
+      signal(bdone + m);
     }
   }
 }
@@ -652,28 +732,40 @@ __global__ void __launch_bounds__(256, 2) pl5_pass_b_reg_kernel(int64_t n_tiles,
 template <int N, bool FWD>
 static int launch_pl_reg_two_pass(int64_t B, const void* in, void* out, void* workspace, cudaStream_t st) {
   using C = PlCfg<N>;
-  constexpr int REST = 1 << (2 * (N - C::RQN));
+  using F = PlFuseCfg<N>;
   QT_REQUIRE(workspace, "superop<->pauli_liouville with n >= 4 needs a workspace of B*16^n*16 bytes");
   const size_t smem = sizeof(cplx) * 4096;
+  const int64_t mat_bytes = (int64_t)C::L * C::L * sizeof(cplx);
+#if QT_PL_FUSED_PASSES
+  // fused path: the caller's workspace (B matrices) holds the ring and, in its last matrix, the queue + the counters
+  if (B - 1 > F::LAG && 256 + 8 * B <= mat_bytes) {  // ring_slots > LAG: every wait is on an EARLIER item
+    const int ring_slots = (int)std::min<int64_t>(B - 1, F::RING);
+    unsigned char* tail = (unsigned char*)workspace + (B - 1) * mat_bytes;
+    unsigned long long* queue = (unsigned long long*)tail;
+    int* adone = (int*)(tail + 256);
+    int* bdone = adone + B;
+    QT_CUDA(cudaMemsetAsync(tail, 0, 256 + 8 * B, st));
+    QT_CUDA(cudaFuncSetAttribute(pl_fused_kernel<N, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    QT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pl_fused_kernel<N, FWD>, 256, smem));
+    QT_REQUIRE(per_sm >= 1, "pl_fused_kernel does not fit on this device");
+    const int64_t grid = std::min<int64_t>((int64_t)QT_NUM_SMS * per_sm, (B + F::LAG) * (F::TA + F::TB));
+    pl_fused_kernel<N, FWD><<<(unsigned)grid, 256, smem, st>>>(B, (const cplx*)in, (cplx*)out, (cplx*)workspace,
+                                                              ring_slots, queue, adone, bdone);
+    return qt_check_launch("pl_fused_kernel");
+  }
+#endif
   const int64_t cap = (int64_t)QT_NUM_SMS * 2 * 8;
-  const int64_t tiles_a = B * REST;
+  const int64_t tiles_a = B * F::TA, tiles_b = B * F::TB;
   QT_CUDA(cudaFuncSetAttribute(pl_pass_a_reg_kernel<N, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   pl_pass_a_reg_kernel<N, FWD><<<(unsigned)std::min(tiles_a, cap), 256, smem, st>>>(tiles_a, (const cplx*)in,
                                                                                    (cplx*)workspace);
   int rc = qt_check_launch("pl_pass_a_reg_kernel");
   if (rc) return rc;
-  if constexpr (N == 4) {
-    const int64_t tiles_b = B * 16;
-    pl4_pass_b_reg_kernel<FWD><<<(unsigned)std::min(tiles_b, cap * 2), 256, 0, st>>>(tiles_b, (const cplx*)workspace,
-                                                                                  (cplx*)out);
-    return qt_check_launch("pl4_pass_b_reg_kernel");
-  } else {
-    const int64_t tiles_b = B * 4 * (C::L / 16);
-    QT_CUDA(cudaFuncSetAttribute(pl5_pass_b_reg_kernel<FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pl5_pass_b_reg_kernel<FWD><<<(unsigned)std::min(tiles_b, cap), 256, smem, st>>>(tiles_b, (const cplx*)workspace,
-                                                                                  (cplx*)out);
-    return qt_check_launch("pl5_pass_b_reg_kernel");
-  }
+  QT_CUDA(cudaFuncSetAttribute(pl_pass_b_reg_kernel<N, FWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  pl_pass_b_reg_kernel<N, FWD><<<(unsigned)std::min(tiles_b, cap), 256, smem, st>>>(tiles_b, (const cplx*)workspace,
+                                                                                   (cplx*)out);
+  return qt_check_launch("pl_pass_b_reg_kernel");
 }
 
 template <int N, bool FWD>

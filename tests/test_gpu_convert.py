@@ -217,3 +217,22 @@ def test_dense_fp64_mma_ptm_variant(torch, n, batch):
     assert max_relerr(inv, st.pauli_liouville2superop_batch(xd).cpu().numpy()) < 1e-13
     with pytest.raises(Exception):
         st.superop2pauli_liouville_batch(torch.zeros((2, 4, 4), dtype=torch.complex128, device="cuda"), variant="dense_mma")
+
+
+@pytest.mark.parametrize("n,batch", [(4, 61), (5, 5)])
+def test_ptm_fused_two_pass_path(torch, n, batch):
+    """n = 4, 5 with enough matrices for the single-launch path (both passes through an L2-resident ring with
+    producer / consumer counters): every matrix against the two-kernel path taken by small batches (bit-identical: the
+    same arithmetic), spot checks against the oracle, ring re-use (batch > ring slots), both directions."""
+    from forest_benchmarking_b200.operator_tools import superoperator_transformations as st
+    rng = np.random.default_rng(1300 + n)
+    m = 4 ** n
+    x = torch.from_numpy(rng.standard_normal((batch, m, m)) + 1j * rng.standard_normal((batch, m, m))).cuda()
+    for fn, ref in ((st.superop2pauli_liouville_batch, orc.superop2pauli_liouville),
+                    (st.pauli_liouville2superop_batch, orc.pauli_liouville2superop)):
+        for rep in range(3):  # repeated launches re-use the workspace tail (queue + counters are reset per call)
+            got = fn(x)
+        small = torch.cat([fn(x[i:i + 2].contiguous()) for i in range(0, batch, 2)])[:batch]
+        assert torch.equal(got, small)
+        for b in ((0, batch // 2, batch - 1) if n == 4 else (batch - 1,)):
+            assert relerr(got[b].cpu().numpy(), ref(x[b].cpu().numpy())) < 1e-13
