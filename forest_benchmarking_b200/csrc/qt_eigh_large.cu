@@ -13,113 +13,140 @@
 // u_k = (lambda_k + c) v_k, i.e.  lambda_k = |u_k| - c  and  v_k = u_k / |u_k|  (c is taken 1/16 above ||A||_inf so
 // that |u_k| >= c / 16 > 0).  The Kraus operators are then written exactly like choi2kraus_kernel does for n <= 3.
 // Columns are stored as contiguous ROWS of the workspace array (Ut[k][r] = U[r][k]).
-#include "qt_eigh.cuh"
+#include "qt_choi.cuh"
 #include "../../include/qtomo.h"
 
 #include <algorithm>
+
+template <int M>
+struct LargeCfg {
+  static constexpr int NT = (M == 256) ? 512 : 1024, NW = NT / 32, HP = M / 2, PER = M / 32;
+  static constexpr int D = (M == 256) ? 16 : 32;
+  // M = 256 (512 threads, 128 registers): the pair's two columns stay in registers between the Gram pass and the update;
+  // M = 1024 re-reads them
+  static constexpr bool HOLD = (M == 256);
+};
+
+template <int M>
+struct LargeShared {
+  double ev[M], sig[M];
+  double red[LargeCfg<M>::NW];
+  int rotated;
+};
+
+// Eigendecomposition of the M x M Hermitian matrix herm(r, c) by the whole block.  U: M x M workspace (global / L2),
+// column k stored as the contiguous row U[k * M ..].  On exit sh.ev[k] are the eigenvalues (unordered), and
+// v_k = U[k, :] / sh.sig[k] the eigenvectors.  Returns the number of sweeps.
+template <int M, class HermFn>
+__device__ int large_eigh(HermFn herm, cplx* __restrict__ U, LargeShared<M>& sh) {
+  using C = LargeCfg<M>;
+  constexpr int NT = C::NT, NW = C::NW, HP = C::HP, PER = C::PER;
+  constexpr bool HOLD = C::HOLD;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  double rowmax = 0.0;
+  for (int r = wid; r < M; r += NW) {
+    double s = 0.0;
+    for (int c = lane; c < M; c += 32) s += sqrt(cabs2(herm(r, c)));
+    s = warp_sum(s);
+    rowmax = fmax(rowmax, s);
+  }
+  __syncthreads();
+  if (lane == 0) sh.red[wid] = rowmax;
+  __syncthreads();
+  double shift = 0.0;
+  for (int w = 0; w < NW; ++w) shift = fmax(shift, sh.red[w]);
+  shift = 1.0625 * shift + 1e-300;
+  __syncthreads();
+  for (int e = tid; e < M * M; e += NT) {
+    const int k = e / M, r = e % M;  // column k, row r:  U[r][k] = conj(herm(k, r))
+    cplx v = cconj(herm(k, r));
+    if (k == r) v.x += shift;
+    U[e] = v;
+  }
+  __syncthreads();
+  int sweep = 0;
+  for (; sweep < 60; ++sweep) {
+    if (tid == 0) sh.rotated = 0;
+    __syncthreads();
+    for (int step = 0; step < M - 1; ++step) {
+      for (int i = wid; i < HP; i += NW) {
+        int p, q;
+        rr_pair(M, step, i, p, q);
+        cplx* up = U + (size_t)p * M;
+        cplx* uq = U + (size_t)q * M;
+        cplx a[HOLD ? PER : 1], c2[HOLD ? PER : 1];
+        double alpha = 0.0, gamma = 0.0;
+        cplx beta = cmake(0.0, 0.0);
+#pragma unroll
+        for (int t = 0; t < PER; ++t) {
+          const cplx x = up[lane + 32 * t], y = uq[lane + 32 * t];
+          if (HOLD) {
+            a[t] = x;
+            c2[t] = y;
+          }
+          alpha += cabs2(x);
+          gamma += cabs2(y);
+          cfma(beta, cconj(x), y);  // beta = u_p^dagger u_q
+        }
+        alpha = warp_sum(alpha);
+        gamma = warp_sum(gamma);
+        beta.x = warp_sum(beta.x);
+        beta.y = warp_sum(beta.y);
+        if (cabs2(beta) <= 1e-29 * alpha * gamma) continue;  // warp-uniform
+        double c, an, gn;
+        cplx s;
+        jacobi_rotation(alpha, gamma, beta, c, s, an, gn);
+        const cplx cs = cconj(s);
+        if (lane == 0) sh.rotated = 1;
+#pragma unroll
+        for (int t = 0; t < PER; ++t) {
+          const cplx x = HOLD ? a[t] : up[lane + 32 * t], y = HOLD ? c2[t] : uq[lane + 32 * t];
+          up[lane + 32 * t] = csub(cscale(x, c), cmul(cs, y));
+          uq[lane + 32 * t] = cadd(cmul(s, x), cscale(y, c));
+        }
+      }
+      __syncthreads();
+    }
+    if (!sh.rotated) break;
+    __syncthreads();
+  }
+  // eigenvalues: column norms of the shifted matrix minus the shift
+  for (int k = wid; k < M; k += NW) {
+    double acc = 0.0;
+    for (int r = lane; r < M; r += 32) acc += cabs2(U[(size_t)k * M + r]);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      sh.sig[k] = sqrt(acc);
+      sh.ev[k] = sh.sig[k] - shift;
+    }
+  }
+  __syncthreads();
+  return sweep;
+}
 
 template <int M>
 __global__ void __launch_bounds__(M == 256 ? 512 : 1024)
     choi2kraus_large_kernel(int64_t B, const cplx* __restrict__ in, double tol, double* __restrict__ evals_out,
                             cplx* __restrict__ kraus_out, int* __restrict__ count_out, cplx* __restrict__ ws,
                             int* __restrict__ sweeps_out) {
-  constexpr int NT = (M == 256) ? 512 : 1024, NW = NT / 32, HP = M / 2, PER = M / 32;
-  constexpr int D = (M == 256) ? 16 : 32;
-  // M = 256 (512 threads, 128 registers): the pair's two columns stay in registers between the Gram pass and the update;
-  // M = 1024 re-reads them
-  constexpr bool HOLD = (M == 256);
-  __shared__ double ev[M], sig[M];
+  using C = LargeCfg<M>;
+  constexpr int NT = C::NT, D = C::D;
+  __shared__ LargeShared<M> sh;
   __shared__ int rank[M], pos[M];
-  __shared__ double red[NW];
-  __shared__ int rotated;
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  double* ev = sh.ev;
+  double* sig = sh.sig;
+  const int tid = threadIdx.x;
   cplx* U = ws + (size_t)blockIdx.x * M * M;
   for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
     const cplx* src = in + b * (int64_t)M * M;
-    // Hermitian matrix np.linalg.eigh sees (lower triangle), infinity norm, and the shifted start
+    // Hermitian matrix np.linalg.eigh sees (lower triangle)
     auto herm = [&](int r, int c) {
       cplx v = (r >= c) ? src[(size_t)r * M + c] : cconj(src[(size_t)c * M + r]);
       if (r == c) v.y = 0.0;
       return v;
     };
-    double rowmax = 0.0;
-    for (int r = wid; r < M; r += NW) {
-      double s = 0.0;
-      for (int c = lane; c < M; c += 32) s += sqrt(cabs2(herm(r, c)));
-      s = warp_sum(s);
-      rowmax = fmax(rowmax, s);
-    }
-    if (lane == 0) red[wid] = rowmax;
-    __syncthreads();
-    double shift = 0.0;
-    for (int w = 0; w < NW; ++w) shift = fmax(shift, red[w]);
-    shift = 1.0625 * shift + 1e-300;
-    __syncthreads();
-    for (int e = tid; e < M * M; e += NT) {
-      const int k = e / M, r = e % M;  // column k, row r:  U[r][k] = conj(herm(k, r))
-      cplx v = cconj(herm(k, r));
-      if (k == r) v.x += shift;
-      U[e] = v;
-    }
-    __syncthreads();
-    int sweep = 0;
-    for (; sweep < 60; ++sweep) {
-      if (tid == 0) rotated = 0;
-      __syncthreads();
-      for (int step = 0; step < M - 1; ++step) {
-        for (int i = wid; i < HP; i += NW) {
-          int p, q;
-          rr_pair(M, step, i, p, q);
-          cplx* up = U + (size_t)p * M;
-          cplx* uq = U + (size_t)q * M;
-          cplx a[HOLD ? PER : 1], c2[HOLD ? PER : 1];
-          double alpha = 0.0, gamma = 0.0;
-          cplx beta = cmake(0.0, 0.0);
-#pragma unroll
-          for (int t = 0; t < PER; ++t) {
-            const cplx x = up[lane + 32 * t], y = uq[lane + 32 * t];
-            if (HOLD) {
-              a[t] = x;
-              c2[t] = y;
-            }
-            alpha += cabs2(x);
-            gamma += cabs2(y);
-            cfma(beta, cconj(x), y);  // beta = u_p^dagger u_q
-          }
-          alpha = warp_sum(alpha);
-          gamma = warp_sum(gamma);
-          beta.x = warp_sum(beta.x);
-          beta.y = warp_sum(beta.y);
-          if (cabs2(beta) <= 1e-29 * alpha * gamma) continue;  // warp-uniform
-          double c, an, gn;
-          cplx s;
-          jacobi_rotation(alpha, gamma, beta, c, s, an, gn);
-          const cplx cs = cconj(s);
-          if (lane == 0) rotated = 1;
-#pragma unroll
-          for (int t = 0; t < PER; ++t) {
-            const cplx x = HOLD ? a[t] : up[lane + 32 * t], y = HOLD ? c2[t] : uq[lane + 32 * t];
-            up[lane + 32 * t] = csub(cscale(x, c), cmul(cs, y));
-            uq[lane + 32 * t] = cadd(cmul(s, x), cscale(y, c));
-          }
-        }
-        __syncthreads();
-      }
-      if (!rotated) break;
-      __syncthreads();
-    }
+    const int sweep = large_eigh<M>(herm, U, sh);
     if (tid == 0 && sweeps_out) sweeps_out[b] = sweep;
-    // eigenvalues: column norms of the shifted matrix minus the shift
-    for (int k = wid; k < M; k += NW) {
-      double acc = 0.0;
-      for (int r = lane; r < M; r += 32) acc += cabs2(U[(size_t)k * M + r]);
-      acc = warp_sum(acc);
-      if (lane == 0) {
-        sig[k] = sqrt(acc);
-        ev[k] = sig[k] - shift;
-      }
-    }
-    __syncthreads();
     for (int k = tid; k < M; k += NT) {
       int rk = 0;
       for (int j = 0; j < M; ++j) rk += (ev[j] < ev[k] || (ev[j] == ev[k] && j < k)) ? 1 : 0;
@@ -151,6 +178,188 @@ __global__ void __launch_bounds__(M == 256 ? 512 : 1024)
   }
 }
 
+// =============================================================================================
+// Choi-matrix projections for n = 4, 5 (operator_tools/project_superoperators.py:19-144).  The reference functions are
+// size-agnostic; the shared-memory kernels of qt_project.cu stop at 64 x 64.  Same algorithms here with every matrix in
+// global memory (L2-resident per block) and large_eigh as the eigensolver: correct, and bound by that solver
+// (~30 ms per 256 x 256 decomposition per SM) -- the reference's LAPACK call takes ~15 ms on one core at n = 4.
+// =============================================================================================
+// OUT = V max(ev, 0) V^dagger from the solver's output (v_k = U[k, :] / sig[k]); or X - V min(ev, 0) V^dagger when fewer
+// eigenvalues are negative.  x(r, c) returns the decomposed matrix.
+template <int M, class XFn>
+__device__ void large_recompose_psd(cplx* __restrict__ OUT, const cplx* __restrict__ U, const LargeShared<M>& sh, XFn x) {
+  constexpr int NT = LargeCfg<M>::NT;
+  const int tid = threadIdx.x;
+  int npos = 0;
+  for (int k = 0; k < M; ++k) npos += (sh.ev[k] > 0.0) ? 1 : 0;
+  const bool use_pos = npos <= M / 2;
+  // thread = (column c, group of 4 rows): U[k][c] is read once per k for 4 outputs; lanes walk c (coalesced)
+  for (int w = tid; w < (M / 4) * M; w += NT) {
+    const int c = w % M, r0 = (w / M) * 4;
+    cplx acc[4] = {cmake(0.0, 0.0), cmake(0.0, 0.0), cmake(0.0, 0.0), cmake(0.0, 0.0)};
+    for (int k = 0; k < M; ++k) {
+      const double lam = sh.ev[k];
+      const double wk = use_pos ? fmax(lam, 0.0) : fmax(-lam, 0.0);
+      if (wk == 0.0) continue;
+      const double wgt = wk / (sh.sig[k] * sh.sig[k]);
+      const cplx uc = U[(size_t)k * M + c];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) cfma_conj(acc[i], cscale(U[(size_t)k * M + r0 + i], wgt), uc);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) OUT[(size_t)(r0 + i) * M + c] = use_pos ? acc[i] : cadd(x(r0 + i, c), acc[i]);
+  }
+  __syncthreads();
+}
+
+template <int M>
+__global__ void __launch_bounds__(M == 256 ? 512 : 1024)
+    proj_cp_large_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out, cplx* __restrict__ ws) {
+  __shared__ LargeShared<M> sh;
+  cplx* U = ws + (size_t)blockIdx.x * M * M;
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    const cplx* src = in + b * (int64_t)M * M;
+    auto herm = [&](int r, int c) {  // (C + C^dagger) / 2, project_superoperators.py:30
+      const cplx x = src[(size_t)r * M + c], y = src[(size_t)c * M + r];
+      return cmake(0.5 * (x.x + y.x), 0.5 * (x.y - y.y));
+    };
+    large_eigh<M>(herm, U, sh);
+    large_recompose_psd<M>(out + b * (int64_t)M * M, U, sh, herm);
+  }
+}
+
+// TP / TNI correction matrix of one item (block per item): E = (Tr_out C - I)/d  or  (Tr_out C - clamp_le1)/d, parked in
+// the first d^2 elements of out[b] for tni_apply_kernel (qt_project.cu) -- the n <= 3 two-pass protocol.
+template <int N, bool MAKE_TP>
+__global__ void __launch_bounds__(256) tp_correction_large_kernel(int64_t B, const cplx* __restrict__ in,
+                                                                  cplx* __restrict__ out) {
+  using G = ChoiGroup<N, 256, SyncBlock>;
+  constexpr int D = G::D, M = G::M;
+  extern __shared__ __align__(16) unsigned char raw[];
+  cplx* pt = reinterpret_cast<cplx*>(raw);
+  cplx* E = pt + D * D;
+  cplx* P = E + D * D;
+  cplx* W = P + D * D;
+  double* pev = reinterpret_cast<double*>(W + D * D);
+  double* pscr = pev + D;
+  const int tid = threadIdx.x;
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    G::partial_trace_out(in + b * (int64_t)M * M, M, pt, tid);
+    G::tp_correction(pt, E, MAKE_TP, P, W, pev, pscr, tid);
+    cplx* dst = out + b * (int64_t)M * M;
+    for (int e = tid; e < D * D; e += 256) dst[e] = E[e];
+    __syncthreads();
+  }
+}
+
+// Dykstra (project_superoperators.py:87-144) with every matrix in global memory.  Per block: Q, CPREV, X (the CP
+// projection), U (solver workspace); S = out[b].  Same bookkeeping as ChoiGroup::project_physical.
+template <int N>
+__global__ void __launch_bounds__(N == 4 ? 512 : 1024)
+    proj_physical_large_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out, int make_tp,
+                               cplx* __restrict__ ws, int* __restrict__ eigh_calls, int* __restrict__ status_out) {
+  constexpr int M = 1 << (2 * N), D = 1 << N, NT = LargeCfg<M>::NT;
+  constexpr size_t MM = (size_t)M * M;
+  using G = ChoiGroup<N, NT, SyncBlock>;
+  __shared__ LargeShared<M> sh;
+  extern __shared__ __align__(16) unsigned char raw[];
+  cplx* E = reinterpret_cast<cplx*>(raw);
+  cplx* En = E + D * D;
+  cplx* ptS = En + D * D;
+  cplx* ptC = ptS + D * D;
+  cplx* P = ptC + D * D;
+  cplx* W = P + D * D;
+  double* pev = reinterpret_cast<double*>(W + D * D);
+  double* pscr = pev + D;
+  double* red = pscr + JacobiScratch<D>::doubles;
+  const int tid = threadIdx.x;
+  cplx* Q = ws + (size_t)blockIdx.x * 4 * MM;
+  cplx* CPREV = Q + MM;
+  cplx* X = CPREV + MM;
+  cplx* U = X + MM;
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    const cplx* src = in + b * MM;
+    cplx* S = out + b * MM;
+    double anti2 = 0.0;
+    for (size_t e = tid; e < MM; e += NT) {
+      const size_t r = e / M, c = e % M;
+      const cplx x = src[e], y = src[c * M + r];
+      S[e] = cmake(0.5 * (x.x + y.x), 0.5 * (x.y - y.y));
+      anti2 += 0.25 * ((x.x - y.x) * (x.x - y.x) + (x.y + y.y) * (x.y + y.y));
+      Q[e] = cmake(0.0, 0.0);
+      CPREV[e] = cmake(0.0, 0.0);
+    }
+    anti2 = group_sum<NT, SyncBlock>(anti2, red, tid);
+    const bool raw_in = anti2 > 0.0;
+    for (int e = tid; e < D * D; e += NT) E[e] = cmake(0.0, 0.0);
+    __threadfence_block();
+    __syncthreads();
+    int n_eigh = 0, st = 0;
+    while (true) {
+      auto pre_cp = [&](int r, int c) { return csub(S[(size_t)r * M + c], Q[(size_t)r * M + c]); };  // Hermitian
+      const int sw = large_eigh<M>(pre_cp, U, sh);
+      if (sw >= 60) st |= 2;
+      ++n_eigh;
+      large_recompose_psd<M>(X, U, sh, pre_cp);
+      __threadfence_block();
+      __syncthreads();
+      double n_dcp = 0.0;
+      cplx ip_q = cmake(0.0, 0.0);
+      for (size_t e = tid; e < MM; e += NT) {
+        const cplx cp = X[e], s = S[e], q = Q[e], cprev = CPREV[e];
+        const cplx d1 = csub(cp, s);
+        n_dcp += cabs2(d1);
+        cfma_conj(ip_q, csub(cp, cprev), q);
+        if (raw_in) {
+          const cplx x = src[e], y = src[(e % M) * M + e / M];
+          const cplx a = cmake(0.5 * (x.x - y.x), 0.5 * (x.y + y.y));
+          if (n_eigh == 1) n_dcp += cabs2(a);
+          else cfma_conj(ip_q, csub(cprev, cp), a);
+        }
+        Q[e] = cadd(d1, q);
+        CPREV[e] = cp;
+      }
+      G::partial_trace_out(S, M, ptS, tid);
+      G::partial_trace_out(X, M, ptC, tid);
+      for (int e = tid; e < D * D; e += NT) ptC[e] = cadd(ptC[e], cscale(E[e], (double)D));
+      __syncthreads();
+      G::tp_correction(ptC, En, make_tp != 0, P, W, pev, pscr, tid);
+      for (size_t e = tid; e < MM; e += NT) {
+        const int r = (int)(e / M), c = (int)(e % M);
+        cplx v = X[e];
+        if ((r % D) == (c % D)) v = cadd(v, csub(E[(r / D) * D + c / D], En[(r / D) * D + c / D]));
+        S[e] = v;
+      }
+      double n_dtp = 0.0;
+      cplx ip_t = cmake(0.0, 0.0);
+      for (int e = tid; e < D * D; e += NT) {
+        n_dtp += cabs2(csub(En[e], E[e]));
+        const cplx dpt = csub(csub(ptC[e], cscale(En[e], (double)D)), ptS[e]);
+        cfma_conj(ip_t, dpt, E[e]);
+      }
+      n_dcp = group_sum<NT, SyncBlock>(n_dcp, red, tid);
+      n_dtp = group_sum<NT, SyncBlock>(n_dtp, red, tid);
+      ip_q.x = group_sum<NT, SyncBlock>(ip_q.x, red, tid);
+      ip_q.y = group_sum<NT, SyncBlock>(ip_q.y, red, tid);
+      ip_t.x = group_sum<NT, SyncBlock>(ip_t.x, red, tid);
+      ip_t.y = group_sum<NT, SyncBlock>(ip_t.y, red, tid);
+      const double crit = n_dcp + D * n_dtp + 2.0 * sqrt(cabs2(ip_t)) + 2.0 * sqrt(cabs2(ip_q));
+      __threadfence_block();
+      __syncthreads();
+      if (crit < 1e-4) break;
+      if (n_eigh >= QT_DYKSTRA_MAX_ITER) {
+        st |= 1;
+        break;
+      }
+      for (int e = tid; e < D * D; e += NT) E[e] = En[e];
+      __syncthreads();
+    }
+    if (tid == 0 && eigh_calls) eigh_calls[b] = n_eigh;
+    if (tid == 0 && status_out) status_out[b] = st;
+    __syncthreads();
+  }
+}
+
 static int64_t large_grid(int64_t B) { return std::min<int64_t>(B, QT_NUM_SMS); }
 
 extern "C" int64_t qt_choi2kraus_large_workspace_bytes(int n, int64_t B) {
@@ -177,4 +386,63 @@ extern "C" int qt_choi2kraus_large_batch(int n, int64_t B, const void* choi, dou
     choi2kraus_large_kernel<1024><<<grid, 1024, 0, st>>>(B, (const cplx*)choi, tol, evals_out, (cplx*)kraus_out,
                                                           count_out, (cplx*)workspace, sweeps_out);
   return qt_check_launch("choi2kraus_large_kernel");
+}
+
+// ---- n = 4, 5 projections: host side -------------------------------------------------------------------------
+extern "C" int64_t qt_proj_cp_workspace_bytes(int n, int64_t B) {
+  if (n >= 1 && n <= 3) return 0;
+  if (n != 4 && n != 5) return -1;
+  const int64_t M = 1LL << (2 * n);
+  return large_grid(B) * M * M * (int64_t)sizeof(cplx);
+}
+
+int qt_large_proj_cp(int n, int64_t B, const void* in, void* out, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  QT_REQUIRE(ws && ws_bytes >= qt_proj_cp_workspace_bytes(n, B),
+             "qt_proj_cp_batch: n = %d needs a workspace of qt_proj_cp_workspace_bytes(n, B) = %lld bytes", n,
+             (long long)qt_proj_cp_workspace_bytes(n, B));
+  QT_REQUIRE(in != out, "qt_proj_cp_batch: n >= 4 is out-of-place");
+  const unsigned grid = (unsigned)large_grid(B);
+  if (n == 4) proj_cp_large_kernel<256><<<grid, 512, 0, st>>>(B, (const cplx*)in, (cplx*)out, (cplx*)ws);
+  else proj_cp_large_kernel<1024><<<grid, 1024, 0, st>>>(B, (const cplx*)in, (cplx*)out, (cplx*)ws);
+  return qt_check_launch("proj_cp_large_kernel");
+}
+
+template <int N, bool MAKE_TP>
+static int launch_tp_corr_large(int64_t B, const void* in, void* out, cudaStream_t st) {
+  constexpr int D = 1 << N;
+  const size_t smem = sizeof(cplx) * 4 * D * D + sizeof(double) * (D + JacobiScratch<D>::doubles);
+  QT_CUDA(cudaFuncSetAttribute(tp_correction_large_kernel<N, MAKE_TP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  tp_correction_large_kernel<N, MAKE_TP><<<(unsigned)std::min<int64_t>(B, (int64_t)QT_NUM_SMS * 4), 256, smem, st>>>(
+      B, (const cplx*)in, (cplx*)out);
+  return qt_check_launch("tp_correction_large_kernel");
+}
+
+// first pass of the TP / TNI projection at n = 4, 5 (the second pass is tni_apply_kernel in qt_project.cu)
+int qt_large_tp_correction(int n, int64_t B, const void* in, void* out, int make_tp, cudaStream_t st) {
+  if (n == 4) return make_tp ? launch_tp_corr_large<4, true>(B, in, out, st) : launch_tp_corr_large<4, false>(B, in, out, st);
+  return make_tp ? launch_tp_corr_large<5, true>(B, in, out, st) : launch_tp_corr_large<5, false>(B, in, out, st);
+}
+
+int64_t qt_large_physical_workspace_bytes(int n, int64_t B) {
+  const int64_t M = 1LL << (2 * n);
+  return large_grid(B) * 4 * M * M * (int64_t)sizeof(cplx);
+}
+
+template <int N>
+static int launch_physical_large(int64_t B, const void* in, void* out, int make_tp, void* ws, int* calls, int* status,
+                                 cudaStream_t st) {
+  constexpr int D = 1 << N;
+  const size_t smem = sizeof(cplx) * 6 * D * D + sizeof(double) * (D + JacobiScratch<D>::doubles + 64);
+  QT_CUDA(cudaFuncSetAttribute(proj_physical_large_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  proj_physical_large_kernel<N><<<(unsigned)large_grid(B), N == 4 ? 512 : 1024, smem, st>>>(
+      B, (const cplx*)in, (cplx*)out, make_tp, (cplx*)ws, calls, status);
+  return qt_check_launch("proj_physical_large_kernel");
+}
+
+int qt_large_proj_physical(int n, int64_t B, const void* in, void* out, int make_tp, void* ws, int64_t ws_bytes,
+                           int* calls, int* status, cudaStream_t st) {
+  QT_REQUIRE(ws_bytes >= qt_large_physical_workspace_bytes(n, B), "qt_proj_physical_batch: workspace too small (%lld < %lld bytes)",
+             (long long)ws_bytes, (long long)qt_large_physical_workspace_bytes(n, B));
+  if (n == 4) return launch_physical_large<4>(B, in, out, make_tp, ws, calls, status, st);
+  return launch_physical_large<5>(B, in, out, make_tp, ws, calls, status, st);
 }

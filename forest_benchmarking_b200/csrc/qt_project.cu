@@ -7,6 +7,13 @@
 #include <cstdlib>
 #include <type_traits>
 
+// n = 4, 5 (matrices that do not fit shared memory): qt_eigh_large.cu
+int qt_large_proj_cp(int n, int64_t B, const void* in, void* out, void* ws, int64_t ws_bytes, cudaStream_t st);
+int qt_large_tp_correction(int n, int64_t B, const void* in, void* out, int make_tp, cudaStream_t st);
+int64_t qt_large_physical_workspace_bytes(int n, int64_t B);
+int qt_large_proj_physical(int n, int64_t B, const void* in, void* out, int make_tp, void* ws, int64_t ws_bytes,
+                           int* calls, int* status, cudaStream_t st);
+
 template <int N>
 struct ProjCfg {
   static constexpr int NT = (N >= 3) ? QT_N3_THREADS : 32;           // threads per group
@@ -665,6 +672,17 @@ static int launch_tp(int64_t B, const void* in, void* out, int make_tp, cudaStre
   return qt_check_launch("proj_tp_kernel");
 }
 
+// n = 4, 5: correction matrix by one block per item (qt_eigh_large.cu), then the streaming out = in - kron(E, I)
+template <int N>
+static int launch_tp_large(int64_t B, const void* in, void* out, int make_tp, cudaStream_t st) {
+  constexpr int D = 1 << N;
+  QT_REQUIRE(in != out, "TP / TNI projection at n >= 4 is out-of-place");
+  int rc = qt_large_tp_correction(N, B, in, out, make_tp, st);
+  if (rc) return rc;
+  tni_apply_kernel<N><<<(unsigned)B, 256, sizeof(cplx) * D * D, st>>>(B, (const cplx*)in, (cplx*)out, 1);
+  return qt_check_launch("tni_apply_kernel");
+}
+
 template <int N>
 static int launch_physical(int64_t B, const void* in, void* out, int make_tp, double rel2, void* ws,
                            int64_t ws_bytes, int* eigh_calls, int* status, cudaStream_t st) {
@@ -689,13 +707,27 @@ static int launch_physical(int64_t B, const void* in, void* out, int make_tp, do
     case 2: return CALL(2);                                               \
     case 3: return CALL(3);                                               \
     default:                                                              \
-      qt_set_error("Choi projections support n = 1..3 qubits (got %d)", n); \
+      qt_set_error("this Choi operation supports n = 1..3 qubits (got %d)", n); \
       return QT_ERR_UNSUPPORTED;                                          \
   }
+
+extern "C" int qt_proj_cp_ws_batch(int n, int64_t B, const void* choi, void* out, void* workspace,
+                                   int64_t workspace_bytes, void* stream) {
+  if (n == 4 || n == 5) {
+    if (B == 0) return QT_OK;
+    QT_REQUIRE(choi && out, "qt_proj_cp_ws_batch: null argument");
+    return qt_large_proj_cp(n, B, choi, out, workspace, workspace_bytes, (cudaStream_t)stream);
+  }
+  return qt_proj_cp_batch(n, B, choi, out, stream);
+}
 
 extern "C" int qt_proj_cp_batch(int n, int64_t B, const void* choi, void* out, void* stream) {
   if (B == 0) return QT_OK;
   QT_REQUIRE(choi && out, "qt_proj_cp_batch: null argument");
+  if (n == 4 || n == 5) {
+    qt_set_error("qt_proj_cp_batch: n = %d needs a workspace: call qt_proj_cp_ws_batch", n);
+    return QT_ERR_WORKSPACE;
+  }
   if (n == 1) {
     proj_cp4_thread_kernel<<<(unsigned)((B + 127) / 128), 128, 0, (cudaStream_t)stream>>>(B, (const cplx*)choi,
                                                                                           (cplx*)out);
@@ -717,6 +749,8 @@ extern "C" int qt_proj_unitary_batch(int n, int64_t B, const void* choi, void* o
 extern "C" int qt_proj_tp_batch(int n, int64_t B, const void* choi, void* out, void* stream) {
   if (B == 0) return QT_OK;
   QT_REQUIRE(choi && out, "qt_proj_tp_batch: null argument");
+  if (n == 4) return launch_tp_large<4>(B, choi, out, 1, (cudaStream_t)stream);
+  if (n == 5) return launch_tp_large<5>(B, choi, out, 1, (cudaStream_t)stream);
 #define CALL(N) launch_tp<N>(B, choi, out, 1, (cudaStream_t)stream)
   DISPATCH_N3(n, CALL)
 #undef CALL
@@ -725,6 +759,8 @@ extern "C" int qt_proj_tp_batch(int n, int64_t B, const void* choi, void* out, v
 extern "C" int qt_proj_tni_batch(int n, int64_t B, const void* choi, void* out, void* stream) {
   if (B == 0) return QT_OK;
   QT_REQUIRE(choi && out, "qt_proj_tni_batch: null argument");
+  if (n == 4) return launch_tp_large<4>(B, choi, out, 0, (cudaStream_t)stream);
+  if (n == 5) return launch_tp_large<5>(B, choi, out, 0, (cudaStream_t)stream);
 #define CALL(N) launch_tp<N>(B, choi, out, 0, (cudaStream_t)stream)
   DISPATCH_N3(n, CALL)
 #undef CALL
@@ -735,6 +771,8 @@ extern "C" int64_t qt_proj_physical_workspace_bytes(int n, int64_t B) {
     case 1: return physical_grid<1>(B) * ProjCfg<1>::GPB * 2 * ProjCfg<1>::G::MM * (int64_t)sizeof(cplx);
     case 2: return physical_grid<2>(B) * ProjCfg<2>::GPB * 2 * ProjCfg<2>::G::MM * (int64_t)sizeof(cplx);
     case 3: return physical_grid<3>(B) * ProjCfg<3>::GPB * 2 * ProjCfg<3>::G::MM * (int64_t)sizeof(cplx);
+    case 4:
+    case 5: return qt_large_physical_workspace_bytes(n, B);
     default: return -1;
   }
 }
@@ -747,6 +785,9 @@ extern "C" int qt_proj_physical_batch(int n, int64_t B, const void* choi, void* 
   QT_REQUIRE(choi != out, "qt_proj_physical_batch: in-place call not supported (the input is re-read by the stopping rule)");
   double rel2;
   if (qt_eigh_rel2_from_tol(eigh_rel_tol, n, &rel2, "qt_proj_physical_batch") != QT_OK) return QT_ERR_ARG;
+  if (n == 4 || n == 5)  // one-sided Jacobi out of global memory: runs to its own (tight) convergence test
+    return qt_large_proj_physical(n, B, choi, out, make_trace_preserving, workspace, workspace_bytes, eigh_calls_out,
+                                  status_out, (cudaStream_t)stream);
 #define CALL(N)                                                                                                  \
   launch_physical<N>(B, choi, out, make_trace_preserving, rel2, workspace, workspace_bytes, eigh_calls_out, \
                      status_out, (cudaStream_t)stream)

@@ -13,31 +13,52 @@ __all__ = ["proj_choi_to_completely_positive", "proj_choi_to_trace_preserving",
            "proj_choi_to_trace_non_increasing_batch", "proj_choi_to_physical_batch"]
 
 
-def _prep(choi):
+def _prep(choi, max_n=5):
     torch = _lib.require_cuda()
     if not choi.is_cuda or choi.dtype != torch.complex128 or choi.dim() != 3 or choi.shape[1] != choi.shape[2]:
         raise ValueError("expected a complex128 CUDA tensor [B, 4^n, 4^n]")
     n = int(round(np.log2(choi.shape[1]) / 2))
-    if 4 ** n != choi.shape[1] or not 1 <= n <= 3:
-        raise ValueError("Choi projections support n = 1..3 qubits")
+    if 4 ** n != choi.shape[1] or not 1 <= n <= max_n:
+        raise ValueError(f"this Choi operation supports n = 1..{max_n} qubits")
     return torch, choi.contiguous(), n
 
 
-def _simple(name, choi, out):
-    torch, choi, n = _prep(choi)
+def _simple(name, choi, out, max_n=5):
+    torch, choi, n = _prep(choi, max_n)
     dev = _lib.common_device(choi, out)
     with _lib.on_device(dev):
         if out is None:
             out = torch.empty_like(choi)
         else:
             _lib.check_tensor("out", out, torch.complex128, choi.shape)
+        if n >= 4 and out.data_ptr() == choi.data_ptr():
+            raise ValueError("projections of 4- and 5-qubit Choi matrices are out-of-place")
         _lib.check(getattr(_lib.lib(), name)(ctypes.c_int(n), ctypes.c_int64(choi.shape[0]), _lib.ptr(choi),
                                              _lib.ptr(out), _lib.current_stream_ptr()), name)
     return out
 
 
 def proj_choi_to_completely_positive_batch(choi, out=None):
-    return _simple("qt_proj_cp_batch", choi, out)
+    """(C + C^dagger)/2 -> eigh -> clamp -> V L V^dagger for every matrix of the batch, n = 1..5 (n >= 4: the eigenproblem
+    runs out of an L2-resident workspace, one matrix per SM)."""
+    torch, choi, n = _prep(choi)
+    if n <= 3:
+        return _simple("qt_proj_cp_batch", choi, out)
+    lib = _lib.lib()
+    dev = _lib.common_device(choi, out)
+    with _lib.on_device(dev):
+        if out is None:
+            out = torch.empty_like(choi)
+        else:
+            _lib.check_tensor("out", out, torch.complex128, choi.shape)
+            if out.data_ptr() == choi.data_ptr():
+                raise ValueError("projections of 4- and 5-qubit Choi matrices are out-of-place")
+        nbytes = int(lib.qt_proj_cp_workspace_bytes(ctypes.c_int(n), ctypes.c_int64(choi.shape[0])))
+        ws = torch.empty((max(nbytes, 16) // 16,), dtype=torch.complex128, device=dev)
+        _lib.check(lib.qt_proj_cp_ws_batch(ctypes.c_int(n), ctypes.c_int64(choi.shape[0]), _lib.ptr(choi), _lib.ptr(out),
+                                           _lib.ptr(ws), ctypes.c_int64(nbytes), _lib.current_stream_ptr()),
+                   "qt_proj_cp_ws_batch")
+    return out
 
 
 def proj_choi_to_trace_preserving_batch(choi, out=None):
@@ -49,7 +70,7 @@ def proj_choi_to_trace_non_increasing_batch(choi, out=None):
 
 
 def proj_choi_to_unitary_batch(choi, out=None):
-    return _simple("qt_proj_unitary_batch", choi, out)
+    return _simple("qt_proj_unitary_batch", choi, out, max_n=3)
 
 
 def proj_choi_to_physical_batch(choi, make_trace_preserving=True, out=None, return_counts=False,

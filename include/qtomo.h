@@ -135,8 +135,16 @@ int qt_hs_inner_batch(int64_t rows, int64_t cols, int64_t B, const void* a, cons
 /* project_state_matrix_to_physical (operator_tools/project_state_matrix.py:6-52): closest trace-one PSD matrix */
 int qt_project_state_batch(int n, int64_t B, const void* rho, void* out, void* stream);
 
-/* ---- Choi-matrix projections (operator_tools/project_superoperators.py), n = 1..3, [B,4^n,4^n] ---- */
-int qt_proj_cp_batch(int n, int64_t B, const void* choi, void* out, void* stream); /* proj_choi_to_unitary (project_superoperators.py:147-175): Choi matrix of the unitary closest to the process
+/* ---- Choi-matrix projections (operator_tools/project_superoperators.py), [B,4^n,4^n] ----
+ * n = 1..3: shared-memory kernels.  n = 4, 5 (1 MB / 16.8 MB per matrix): the same algorithms out of global memory with
+ * the one-sided Jacobi solver of qt_choi2kraus_large_batch; CP needs a workspace (qt_proj_cp_ws_batch), TP / TNI / physical
+ * are out-of-place; proj_choi_to_unitary stays n <= 3. */
+int qt_proj_cp_batch(int n, int64_t B, const void* choi, void* out, void* stream); /* n = 1..3 */
+/* proj_choi_to_completely_positive for n = 1..5: workspace of qt_proj_cp_workspace_bytes(n, B) bytes (0 for n <= 3) */
+int64_t qt_proj_cp_workspace_bytes(int n, int64_t B);
+int qt_proj_cp_ws_batch(int n, int64_t B, const void* choi, void* out, void* workspace, int64_t workspace_bytes,
+                        void* stream);
+/* proj_choi_to_unitary (project_superoperators.py:147-175): Choi matrix of the unitary closest to the process
  * (dominant Kraus operator -> polar factor -> phase convention -> kraus2choi), n = 1..3 */
 int qt_proj_unitary_batch(int n, int64_t B, const void* choi, void* out, void* stream);
   /* :19-34 */

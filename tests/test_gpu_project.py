@@ -161,3 +161,42 @@ def test_eigh_tolerance_is_a_per_call_argument(torch):
     assert max_relerr(loose.cpu().numpy(), g["proj_physical"]) < 1e-3
     with pytest.raises(Exception):
         ps.proj_choi_to_physical_batch(x, eigh_rel_tol=0.5)
+
+
+@pytest.mark.parametrize("n,batch", [(4, 3), (5, 1)])
+def test_large_choi_projections(torch, n, batch):
+    """n = 4, 5 (256 x 256 / 1024 x 1024 Choi matrices: the reference functions are size-agnostic,
+    project_superoperators.py:19-144): CP / TP / TNI vs the oracle; Dykstra physical projection with trip counts at
+    n = 4 (Hermitian and non-Hermitian input)."""
+    from forest_benchmarking_b200.operator_tools import project_superoperators as ps
+    rng = np.random.default_rng(400 + n)
+    d, m = 2 ** n, 4 ** n
+    xs = []
+    for b in range(batch):
+        ks = [np.sqrt(.6) * orc.haar_unitary(rng, d), np.sqrt(.4) * orc.haar_unitary(rng, d)]
+        noise = rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m))
+        xs.append(orc.kraus2choi(ks) + (noise + noise.conj().T) * (0.2 / m) + (0.01 / m if b == 1 else 0.0) * noise)
+    xs = np.stack(xs)
+    xd = torch.from_numpy(xs).cuda()
+    cp = ps.proj_choi_to_completely_positive_batch(xd).cpu().numpy()
+    tp = ps.proj_choi_to_trace_preserving_batch(xd).cpu().numpy()
+    tni = ps.proj_choi_to_trace_non_increasing_batch(xd).cpu().numpy()
+    for b in range(batch):
+        assert relerr(cp[b], orc.proj_choi_to_completely_positive(xs[b])) < 1e-11
+        assert relerr(tp[b], orc.proj_choi_to_trace_preserving(xs[b])) < 1e-13
+        assert relerr(tni[b], orc.proj_choi_to_trace_non_increasing(xs[b])) < 1e-11
+    assert np.linalg.eigvalsh((cp[0] + cp[0].conj().T) / 2).min() > -1e-11
+    with pytest.raises(ValueError):
+        ps.proj_choi_to_trace_preserving_batch(xd, out=xd)
+    if n == 4:
+        phys, calls, status = ps.proj_choi_to_physical_batch(xd, return_counts=True, return_status=True)
+        phys, calls = phys.cpu().numpy(), calls.cpu().numpy()
+        assert not status.cpu().numpy().any()
+        for b in range(batch):
+            want, ne = orc.proj_choi_to_physical(xs[b], return_count=True)
+            assert relerr(phys[b], want) < TOL and int(calls[b]) == ne, (calls[b], ne)
+        pt = np.einsum("zijkj->zik", phys.reshape(batch, d, d, d, d))
+        assert np.abs(pt - np.eye(d)).max() < 1e-9
+        t, ct = ps.proj_choi_to_physical_batch(xd[:1], False, return_counts=True)
+        want, ne = orc.proj_choi_to_physical(xs[0], False, return_count=True)
+        assert relerr(t[0].cpu().numpy(), want) < TOL and int(ct[0]) == ne
