@@ -45,3 +45,50 @@ def all_gather_states(local, total: int, group=None):
             parts.append(recv[r * per: r * per + (b - a)])
         recv = torch.cat(parts, dim=0)
     return torch.view_as_complex(recv) if is_c else recv
+
+
+class SingleProcessComm:
+    """One host process driving several GPUs (no torch.distributed): NCCL communicators created through the C ABI
+    (``qt_comm_init_all``), and the path's single collective, an all-gather of per-device result slices
+    (``qt_allgather_bytes``).  ``devices``: CUDA device indices, one rank each, in rank order."""
+
+    def __init__(self, devices):
+        import ctypes
+        from . import _lib
+        self._lib, self._ct = _lib, ctypes
+        self.devices = [int(d) for d in devices]
+        arr = (ctypes.c_int32 * len(self.devices))(*self.devices)
+        self._h = ctypes.c_void_p()
+        _lib.check(_lib.lib().qt_comm_init_all(len(self.devices), arr, ctypes.byref(self._h)), "qt_comm_init_all")
+
+    def all_gather(self, slices):
+        """slices[r]: contiguous tensor on cuda:devices[r], identical shape / dtype on every rank.  Returns one tensor per
+        rank holding all slices concatenated along the first axis in rank order."""
+        import torch
+        ct = self._ct
+        n = len(self.devices)
+        if len(slices) != n:
+            raise ValueError(f"expected {n} slices, one per device")
+        shape, dtype = tuple(slices[0].shape), slices[0].dtype
+        for r, t in enumerate(slices):
+            if tuple(t.shape) != shape or t.dtype != dtype or not t.is_contiguous() or t.device.index != self.devices[r]:
+                raise ValueError(f"slice {r} must be a contiguous {dtype} tensor of shape {list(shape)} on cuda:{self.devices[r]}")
+        outs = [torch.empty((n * shape[0],) + shape[1:], dtype=dtype, device=t.device) for t in slices]
+        nbytes = slices[0].numel() * slices[0].element_size()
+        send = (ct.c_void_p * n)(*[t.data_ptr() for t in slices])
+        recv = (ct.c_void_p * n)(*[t.data_ptr() for t in outs])
+        streams = (ct.c_void_p * n)(*[torch.cuda.current_stream(t.device).cuda_stream for t in slices])
+        self._lib.check(self._lib.lib().qt_allgather_bytes(self._h, send, recv, ct.c_int64(nbytes), streams),
+                        "qt_allgather_bytes")
+        return outs
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            self._lib.lib().qt_comm_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -182,6 +182,16 @@ int qt_pgdb_process_batch(const qt_pgdb_plan* plan, int64_t B, const double* exp
  * the plan on first use (the reference's dense pinv of the S x 16^n measurement matrix is never formed). */
 int qt_linear_inv_process_batch(qt_pgdb_plan* plan, int64_t B, const double* expect, void* choi_out, void* stream);
 
+/* ---- multi-GPU: the one collective of the path for hosts without torch.distributed ----------------
+ * Single process, one communicator per device (ncclCommInitAll; NCCL is bound at run time with dlopen).
+ * qt_allgather_bytes: device r contributes sendbufs[r][0 .. nbytes_per_rank) and receives all slices in rank order in
+ * recvbufs[r][0 .. ndev * nbytes_per_rank); streams[r] (or NULL: default streams) orders the collective on device r. */
+typedef struct qt_comm qt_comm;
+int qt_comm_init_all(int ndev, const int32_t* devices, qt_comm** comm_out);
+int qt_allgather_bytes(qt_comm* comm, const void* const* sendbufs, void* const* recvbufs, int64_t nbytes_per_rank,
+                       void* const* streams);
+int qt_comm_destroy(qt_comm* comm);
+
 #ifdef __cplusplus
 }
 #endif

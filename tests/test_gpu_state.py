@@ -441,3 +441,27 @@ def test_purity_all_sizes(torch, n):
     got = dm.purity_batch(torch.from_numpy(x).cuda()).cpu().numpy()
     want = np.array([np.real(np.trace(m @ m)) for m in x])
     assert np.allclose(got, want, rtol=1e-12, atol=1e-12)
+
+
+def test_c_abi_single_process_allgather(torch):
+    """qt_comm_init_all / qt_allgather_bytes: the path's one collective for hosts without torch.distributed."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from forest_benchmarking_b200 import tomography as tm
+    from forest_benchmarking_b200.sharding import SingleProcessComm, shard_range
+    _, pidx, ex, cnt = orc.synth_state_tomography(79, 32, 2)
+    comm = SingleProcessComm([0, 1])
+    parts = []
+    for r in range(2):
+        lo, hi = shard_range(32, 2, r)
+        with torch.cuda.device(r):
+            plan = tm.MlePlan(2, pidx)
+            rho, _ = tm.iterative_mle_state_estimate_batch(plan, torch.from_numpy(ex[lo:hi]).to(f"cuda:{r}"), tol=1e-6,
+                                                           maxiter=2000)
+        parts.append(rho)
+    full = comm.all_gather(parts)
+    for r in range(2):
+        torch.cuda.synchronize(r)
+    want = torch.cat([p.cpu() for p in parts])
+    assert torch.equal(full[0].cpu(), want) and torch.equal(full[1].cpu(), want)
+    comm.close()
