@@ -469,7 +469,7 @@ struct MleWarpSmem {
   static constexpr int D = 1 << N, S = 1 << (2 * N);
   // rho, M, T (+ V for the eigen-decomposition used by the variants)
   __host__ __device__ static constexpr size_t bytes(bool variants) {
-    return (sizeof(cplx) * D * D * (variants ? 4 : 3) + sizeof(double) * S * 2 +
+    return (sizeof(cplx) * D * D * (variants ? 4 : 3) + sizeof(double) * S * 4 +
             sizeof(double) * (D + JacobiScratch<D>::doubles) + 15) / 16 * 16;
   }
 };
@@ -479,7 +479,8 @@ __global__ void mle_warp_kernel(int64_t B, int K, const int* __restrict__ slot_p
                                 const int* __restrict__ member_col, const double* __restrict__ member_coeff,
                                 const int* __restrict__ mask2idx, const double* __restrict__ expect,
                                 const double* __restrict__ counts, double eps, double entropy_penalty, double beta,
-                                double tol, int maxiter, cplx* __restrict__ rho_out, int* __restrict__ iters_out) {
+                                double tol, int maxiter, int unit_coeff, cplx* __restrict__ rho_out,
+                                int* __restrict__ iters_out) {
   constexpr int D = 1 << N, S = 1 << (2 * N), DD = D * D;
   constexpr double TINY = 2.2250738585072014e-308;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -493,10 +494,24 @@ __global__ void mle_warp_kernel(int64_t B, int K, const int* __restrict__ slot_p
   cplx* V = T + DD;                       // only when variants
   double* tv = reinterpret_cast<double*>(rho + (variants ? 4 : 3) * DD);
   double* wv = tv + S;
-  double* ev = wv + S;                    // [D] eigenvalues, followed by the Jacobi scratch
+  double* fpv = wv + S;                   // unit coefficients: sum over the slot's members of (1 + m_k)/2 ...
+  double* fmv = fpv + S;                  // ... and of (1 - m_k)/2: the loop then needs no global load and one reciprocal
+  double* ev = fmv + S;                   // [D] eigenvalues, followed by the Jacobi scratch
   const int64_t b = (int64_t)blockIdx.x * wpb + wib;
   if (b >= B) return;
   const double* ex = expect + b * K;
+  if (unit_coeff) {
+    for (int j = lane; j < S; j += 32) {
+      double ap = 0.0, am = 0.0;
+      for (int m = slot_ptr[j]; m < slot_ptr[j + 1]; ++m) {
+        const double e = ex[member_col[m]];
+        ap += 0.5 * (1.0 + e);
+        am += 0.5 * (1.0 - e);
+      }
+      fpv[j] = ap;
+      fmv[j] = am;
+    }
+  }
 
   double num_meas = 0.0;
   if (beta > 0.0) {
@@ -522,6 +537,15 @@ __global__ void mle_warp_kernel(int64_t B, int K, const int* __restrict__ slot_p
       }
       const double t = cmul_ipow(acc, ph).x;
       double wj = 0.0;
+      if (unit_coeff) {
+        // sum_m f_m / (pr + tiny) = (sum_m f_m) / (pr + tiny): one MUFU-seeded reciprocal for both outcomes (an IEEE
+        // division costs ~133 issue cycles per warp, profiles/r01_ubench_fp64.txt); same formulation as mle_reg_kernel
+        const double pp = 0.5 * (1.0 + t) + TINY, pm = 0.5 * (1.0 - t) + TINY;
+        const double ipm = fast_rcp(pp * pm);
+        const double ap = fpv[j] * pm * ipm, am = fmv[j] * pp * ipm;
+        w0 += 0.5 * (ap + am);
+        wj = 0.5 * (ap - am);
+      } else
       for (int m = slot_ptr[j]; m < slot_ptr[j + 1]; ++m) {
         const double e = ex[member_col[m]], cf = member_coeff[m];
         const double pred = cf * t;
@@ -542,7 +566,7 @@ __global__ void mle_warp_kernel(int64_t B, int K, const int* __restrict__ slot_p
       const int r = e / D, c = e % D, x = r ^ c;
       cplx acc = cmake(0.0, 0.0);
       for (int z = 0; z < D; ++z) {
-        const double wj = wv[mask2idx[x * D + z]];
+        const double wj = wv[pauli_from_masks(x, z, N)];  // == mask2idx[x * D + z], computed instead of loaded
         cplx term = cmul_ipow(cmake(wj, 0.0), __popc(x & z) & 3);
         if (__popc(z & c) & 1) acc = csub(acc, term); else acc = cadd(acc, term);
       }
@@ -625,7 +649,7 @@ __global__ void mle_warp_kernel(int64_t B, int K, const int* __restrict__ slot_p
     }
     // the reference divides by the complex trace; its imaginary part is rounding noise (~1e-17)
     tr = warp_sum(tr);
-    const double inv = 1.0 / tr;
+    const double inv = fast_rcp(tr);
     double diff = 0.0;
 #pragma unroll
     for (int i = 0; i < (DD + 31) / 32; ++i) {
@@ -1030,8 +1054,8 @@ static int launch_warp(const qt_mle_plan* p, int64_t B, const double* expect, co
   const int64_t blocks = (B + wpb - 1) / wpb;
   mle_warp_kernel<N><<<(unsigned)blocks, 32 * wpb, smem, st>>>(B, p->K, p->d_slot_ptr, p->d_member_col,
                                                                p->d_member_coeff, p->d_mask2idx, expect, counts, eps,
-                                                               entropy_penalty, beta, tol, maxiter, rho_out,
-                                                               iters_out);
+                                                               entropy_penalty, beta, tol, maxiter, p->unit_coeff,
+                                                               rho_out, iters_out);
   return qt_check_launch("mle_warp_kernel");
 }
 
