@@ -128,7 +128,7 @@ template <int M>
 __global__ void __launch_bounds__(M == 256 ? 512 : 1024)
     choi2kraus_large_kernel(int64_t B, const cplx* __restrict__ in, double tol, double* __restrict__ evals_out,
                             cplx* __restrict__ kraus_out, int* __restrict__ count_out, cplx* __restrict__ ws,
-                            int* __restrict__ sweeps_out) {
+                            int* __restrict__ sweeps_out, int skip_done) {
   using C = LargeCfg<M>;
   constexpr int NT = C::NT, D = C::D;
   __shared__ LargeShared<M> sh;
@@ -138,6 +138,7 @@ __global__ void __launch_bounds__(M == 256 ? 512 : 1024)
   const int tid = threadIdx.x;
   cplx* U = ws + (size_t)blockIdx.x * M * M;
   for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    if (skip_done && count_out[b] >= 0) continue;  // finished by choi2kraus_lowrank_kernel (block-uniform)
     const cplx* src = in + b * (int64_t)M * M;
     // Hermitian matrix np.linalg.eigh sees (lower triangle)
     auto herm = [&](int r, int c) {
@@ -173,6 +174,188 @@ __global__ void __launch_bounds__(M == 256 ? 512 : 1024)
       const cplx v = U[e];
       const cplx val = (lam >= 0.0) ? cscale(v, sq) : cmake(-sq * v.y, sq * v.x);
       dst[(size_t)pos[k] * M + (r % D) * D + (r / D)] = val;
+    }
+    __syncthreads();
+  }
+}
+
+// =============================================================================================
+// choi2kraus, n = 4, 5: certified low-rank fast path.
+// The Choi matrix of a channel with a handful of Kraus operators has that many non-zero eigenvalues, and choi2kraus only
+// returns eigenpairs with |lambda| > tol (superoperator_transformations.py:334-336).  One block per matrix, one thread
+// per row, three passes over the matrix (np.linalg.eigh's view of it: the lower triangle):
+//   1. Y = A Omega           (Omega: M x 8 pseudo-random probe; rows of Y stay in registers, ||A||_F on the way)
+//      Q = orth(Y)           (modified Gram-Schmidt, twice, block reductions)
+//   2. Z = A Q,  B = Q^dagger Z  (8 x 8),  B = W diag(mu) W^dagger  (warp Jacobi)
+//   3. residual = || A - Q B Q^dagger ||_F, element by element (no cancellation).
+// If residual <= 0.01 tol, Weyl's inequality bounds every eigenvalue outside the captured ones by 0.01 tol -- they are
+// below choi2kraus's threshold -- and the captured ones are exact to the same margin: the Kraus operators are
+// sqrt(mu_k) unvec(Q w_k), written exactly like the general kernel does (ascending order, i sqrt(|mu|) for mu < 0; the
+// eigenvalues reported for the discarded directions are 0).  Otherwise count_out[b] = -1 and the general one-sided
+// Jacobi kernel below handles the matrix: full-rank inputs cost one wasted scan (~1 % of the solver's time).
+// =============================================================================================
+__device__ __forceinline__ double lr_rand(unsigned a, unsigned b) {  // deterministic hash -> (-1, 1)
+  unsigned long long z = ((unsigned long long)a << 32 | b) + 0x9E3779B97F4A7C15ULL;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+  z ^= z >> 31;
+  return (double)(long long)(z >> 11) * (1.0 / 4503599627370496.0) - 1.0;  // 53 bits -> [0, 2) - 1
+}
+
+template <int M>
+__global__ void __launch_bounds__(M == 256 ? 256 : 1024)
+    choi2kraus_lowrank_kernel(int64_t B, const cplx* __restrict__ in, double tol, double* __restrict__ evals_out,
+                              cplx* __restrict__ kraus_out, int* __restrict__ count_out) {
+  constexpr int KC = 8, NT = M, NW = NT / 32, D = (M == 256) ? 16 : 32;
+  extern __shared__ __align__(16) unsigned char raw[];
+  cplx* Wm = reinterpret_cast<cplx*>(raw);            // [M][KC]: Omega, then Q
+  cplx* Bs = Wm + (size_t)M * KC;                     // [KC][KC]
+  cplx* Ws = Bs + KC * KC;                            // [KC][KC] eigenvectors of B
+  double* mu = reinterpret_cast<double*>(Ws + KC * KC);  // [KC] + Jacobi scratch
+  double* red = mu + KC + JacobiScratch<KC>::doubles;    // [NW][2]
+  __shared__ int order[KC], posk[KC], kept_s, ok_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, r = tid;
+  auto block_sum2 = [&](double a, double b, double& oa, double& ob) {
+    a = warp_sum(a);
+    b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) {
+      red[2 * wid] = a;
+      red[2 * wid + 1] = b;
+    }
+    __syncthreads();
+    double sa = 0.0, sb = 0.0;
+    for (int w = 0; w < NW; ++w) {
+      sa += red[2 * w];
+      sb += red[2 * w + 1];
+    }
+    oa = sa;
+    ob = sb;
+  };
+  for (int64_t b = blockIdx.x; b < B; b += gridDim.x) {
+    const cplx* A = in + b * (int64_t)M * M;
+    auto a_of = [&](int c) {  // row r of the Hermitian matrix np.linalg.eigh sees
+      cplx v = (c <= r) ? A[(size_t)r * M + c] : cconj(A[(size_t)c * M + r]);
+      if (c == r) v.y = 0.0;
+      return v;
+    };
+    auto apply = [&](cplx (&acc)[KC], double* norm2) {  // acc = (A W)[r, :]
+#pragma unroll
+      for (int j = 0; j < KC; ++j) acc[j] = cmake(0.0, 0.0);
+      double n2 = 0.0;
+      for (int c = 0; c < M; ++c) {
+        const cplx a = a_of(c);
+        n2 += cabs2(a);
+#pragma unroll
+        for (int j = 0; j < KC; ++j) cfma(acc[j], a, Wm[c * KC + j]);
+      }
+      if (norm2) *norm2 = n2;
+    };
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < KC; ++j) Wm[r * KC + j] = cmake(lr_rand(r, 2 * j), lr_rand(r, 2 * j + 1));
+    __syncthreads();
+    cplx y[KC];
+    double n2row;
+    apply(y, &n2row);
+    double normA2, dummy;
+    block_sum2(n2row, 0.0, normA2, dummy);
+    // Q = orth(Y): modified Gram-Schmidt, two rounds (rows in registers, columns reduced over the block)
+    for (int round = 0; round < 2; ++round) {
+#pragma unroll
+      for (int j = 0; j < KC; ++j) {
+#pragma unroll
+        for (int i = 0; i < j; ++i) {
+          double dr, di;  // <q_i, y_j>
+          block_sum2(y[i].x * y[j].x + y[i].y * y[j].y, y[i].x * y[j].y - y[i].y * y[j].x, dr, di);
+          y[j] = csub(y[j], cmul(cmake(dr, di), y[i]));
+        }
+        double nn, d2;
+        block_sum2(cabs2(y[j]), 0.0, nn, d2);
+        const double inv = nn > 0.0 ? rsqrt(nn) : 0.0;
+        y[j] = cscale(y[j], inv);
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < KC; ++j) Wm[r * KC + j] = y[j];  // Q
+    __syncthreads();
+    cplx z[KC];
+    apply(z, nullptr);
+    // B = Q^dagger Z (Hermitian part)
+    for (int i = 0; i < KC; ++i)
+      for (int j = i; j < KC; ++j) {
+        double br, bi;
+        block_sum2(y[i].x * z[j].x + y[i].y * z[j].y, y[i].x * z[j].y - y[i].y * z[j].x, br, bi);
+        if (tid == 0) {
+          Bs[i * KC + j] = cmake(br, i == j ? 0.0 : bi);
+          Bs[j * KC + i] = cmake(br, i == j ? 0.0 : -bi);
+        }
+      }
+    __syncthreads();
+    // residual || A - Q B Q^dagger ||_F^2 :  (Q B)[r, :] in registers
+    cplx qb[KC];
+#pragma unroll
+    for (int j = 0; j < KC; ++j) {
+      cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+      for (int i = 0; i < KC; ++i) cfma(acc, y[i], Bs[i * KC + j]);
+      qb[j] = acc;
+    }
+    double res2 = 0.0;
+    for (int c = 0; c < M; ++c) {
+      cplx pred = cmake(0.0, 0.0);
+#pragma unroll
+      for (int j = 0; j < KC; ++j) cfma_conj(pred, qb[j], Wm[c * KC + j]);
+      res2 += cabs2(csub(a_of(c), pred));
+    }
+    double resid2, d3;
+    block_sum2(res2, 0.0, resid2, d3);
+    const bool certified = resid2 <= (0.01 * tol) * (0.01 * tol);
+    if (!certified) {
+      if (tid == 0) count_out[b] = -1;  // the general kernel takes this matrix
+      continue;
+    }
+    // eigen-decomposition of the captured 8 x 8 block (warp 0), ascending order
+    if (tid < 32) {
+      jacobi_eigh<KC, 32, SyncWarp, true>(Bs, Ws, mu, mu + KC, lane);
+      if (lane < KC) {
+        int rk = 0;
+        for (int j = 0; j < KC; ++j) rk += (mu[j] < mu[lane] || (mu[j] == mu[lane] && j < lane)) ? 1 : 0;
+        order[rk] = lane;
+      }
+      __syncwarp();
+      if (lane == 0) {
+        int kept = 0;
+        for (int q = 0; q < KC; ++q) {
+          const int k = order[q];
+          posk[k] = (fabs(mu[k]) > tol) ? kept++ : -1;
+        }
+        kept_s = kept;
+      }
+    }
+    __syncthreads();
+    const int kept = kept_s;
+    // all M eigenvalues, ascending: negative captured ones, the M - KC discarded directions (reported as 0), the rest
+    {
+      int nneg = 0;
+      for (int q = 0; q < KC; ++q) nneg += (mu[order[q]] < 0.0) ? 1 : 0;
+      double v = 0.0;
+      if (r < nneg) v = mu[order[r]];
+      else if (r >= M - (KC - nneg)) v = mu[order[r - (M - KC)]];
+      evals_out[b * M + r] = v;
+    }
+    if (tid == 0) count_out[b] = kept;
+    cplx* dst = kraus_out + b * (int64_t)M * M;
+    for (size_t e = (size_t)kept * M + tid; e < (size_t)M * M; e += NT) dst[e] = cmake(0.0, 0.0);
+    for (int k = 0; k < KC; ++k) {
+      if (posk[k] < 0) continue;
+      cplx v = cmake(0.0, 0.0);  // (Q w_k)[r]
+#pragma unroll
+      for (int j = 0; j < KC; ++j) cfma(v, y[j], Ws[j * KC + k]);
+      const double lam = mu[k], sq = sqrt(fabs(lam));
+      const cplx val = (lam >= 0.0) ? cscale(v, sq) : cmake(-sq * v.y, sq * v.x);
+      dst[(size_t)posk[k] * M + (r % D) * D + (r / D)] = val;  // vec index r = j*D + i  ->  K[i][j]
     }
     __syncthreads();
   }
@@ -379,12 +562,28 @@ extern "C" int qt_choi2kraus_large_batch(int n, int64_t B, const void* choi, dou
              (long long)qt_choi2kraus_large_workspace_bytes(n, B));
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)large_grid(B);
+  if (sweeps_out) QT_CUDA(cudaMemsetAsync(sweeps_out, 0, sizeof(int32_t) * B, st));
+  // certified low-rank fast path first (count_out[b] = -1 where it does not apply), then the general solver
+  const int64_t M = 1LL << (2 * n);
+  const size_t smem = sizeof(cplx) * (M * 8 + 2 * 64) + sizeof(double) * (8 + JacobiScratch<8>::doubles + 2 * 32 + 8);
+  const unsigned fast_grid = (unsigned)std::min<int64_t>(B, (int64_t)QT_NUM_SMS * (n == 4 ? 4 : 1));
+  if (n == 4) {
+    QT_CUDA(cudaFuncSetAttribute(choi2kraus_lowrank_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    choi2kraus_lowrank_kernel<256><<<fast_grid, 256, smem, st>>>(B, (const cplx*)choi, tol, evals_out, (cplx*)kraus_out,
+                                                               count_out);
+  } else {
+    QT_CUDA(cudaFuncSetAttribute(choi2kraus_lowrank_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    choi2kraus_lowrank_kernel<1024><<<fast_grid, 1024, smem, st>>>(B, (const cplx*)choi, tol, evals_out, (cplx*)kraus_out,
+                                                                 count_out);
+  }
+  int rc = qt_check_launch("choi2kraus_lowrank_kernel");
+  if (rc) return rc;
   if (n == 4)
     choi2kraus_large_kernel<256><<<grid, 512, 0, st>>>(B, (const cplx*)choi, tol, evals_out, (cplx*)kraus_out,
-                                                         count_out, (cplx*)workspace, sweeps_out);
+                                                         count_out, (cplx*)workspace, sweeps_out, 1);
   else
     choi2kraus_large_kernel<1024><<<grid, 1024, 0, st>>>(B, (const cplx*)choi, tol, evals_out, (cplx*)kraus_out,
-                                                          count_out, (cplx*)workspace, sweeps_out);
+                                                          count_out, (cplx*)workspace, sweeps_out, 1);
   return qt_check_launch("choi2kraus_large_kernel");
 }
 

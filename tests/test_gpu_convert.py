@@ -166,16 +166,17 @@ def test_chi_matrix_family(torch):
         assert relerr(st.kraus2choi(ks), c0) < 1e-9
 
 
-@pytest.mark.parametrize("n,batch", [(4, 3), (5, 1)])
+@pytest.mark.parametrize("n,batch", [(4, 4), (5, 2)])
 def test_choi2kraus_large(torch, n, batch):
-    """a17 at n = 4, 5 (one-sided Jacobi out of a global workspace): eigenvalues vs numpy's eigh of the lower triangle,
-    the reference's own round trip kraus2choi(choi2kraus(C)) == C, and the operator count for a low-rank channel."""
+    """a17 at n = 4, 5: eigenvalues vs numpy's eigh of the lower triangle, the reference's own round trip
+    kraus2choi(choi2kraus(C)) == C, and the operator count.  Item 0 is full rank and item 3 has rank 10 (general one-sided
+    Jacobi solver out of a global workspace); items 1, 2 have rank 3 (certified low-rank fast path, 8 probe columns)."""
     from forest_benchmarking_b200.operator_tools import superoperator_transformations as st
     rng = np.random.default_rng(70 + n)
     d, m = 2 ** n, 4 ** n
     chois = []
     for i in range(batch):
-        ks = [rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)) for _ in range(3)]
+        ks = [rng.standard_normal((d, d)) + 1j * rng.standard_normal((d, d)) for _ in range(10 if i == 3 else 3)]
         c = sum(orc.kraus2choi(k) for k in ks) / (3 * d)
         if i == 0:
             g = rng.standard_normal((m, m)) + 1j * rng.standard_normal((m, m))
@@ -196,6 +197,8 @@ def test_choi2kraus_large(torch, n, batch):
         assert np.abs(kraus[b, counts[b]:]).max(initial=0.0) == 0.0
     if batch > 1:
         assert counts[1] == 3
+    if batch > 3:
+        assert counts[3] == 10
 
 
 @pytest.mark.parametrize("n,batch", [(2, 37), (3, 19)])
