@@ -173,15 +173,15 @@ static int launch_kraus_outer(int mode, int d, int nk, int64_t B, const void* kr
 }
 
 extern "C" int qt_kraus2choi_batch(int d, int n_kraus, int64_t B, const void* kraus, void* choi_out, void* stream) {
+  if (B == 0) return QT_OK;  // empty batch: nothing to check, nothing to do
   QT_REQUIRE(d >= 1 && d <= 32 && n_kraus >= 1 && kraus && choi_out, "qt_kraus2choi_batch: bad arguments");
-  if (B == 0) return QT_OK;
   return launch_kraus_outer(0, d, n_kraus, B, kraus, choi_out, (cudaStream_t)stream);
 }
 
 extern "C" int qt_kraus2superop_batch(int d, int n_kraus, int64_t B, const void* kraus, void* superop_out,
                                       void* stream) {
+  if (B == 0) return QT_OK;  // empty batch: nothing to check, nothing to do
   QT_REQUIRE(d >= 1 && d <= 32 && n_kraus >= 1 && kraus && superop_out, "qt_kraus2superop_batch: bad arguments");
-  if (B == 0) return QT_OK;
   return launch_kraus_outer(1, d, n_kraus, B, kraus, superop_out, (cudaStream_t)stream);
 }
 
@@ -252,9 +252,9 @@ static int launch_reshuffle(int64_t B, const void* in, void* out, cudaStream_t s
 }
 
 extern "C" int qt_choi_superop_reshuffle_batch(int d, int64_t B, const void* in, void* out, void* stream) {
+  if (B == 0) return QT_OK;  // empty batch: nothing to check, nothing to do
   QT_REQUIRE(d >= 2 && d <= 32 && (d & (d - 1)) == 0 && in && out && in != out,
              "qt_choi_superop_reshuffle_batch: bad arguments (d = 2, 4, 8, 16 or 32, out-of-place)");
-  if (B == 0) return QT_OK;
   cudaStream_t st = (cudaStream_t)stream;
   switch (d) {
     case 2: return launch_reshuffle<1>(B, in, out, st);
@@ -806,14 +806,14 @@ static int launch_pl(int n, int64_t B, const void* in, void* out, void* workspac
 
 extern "C" int qt_superop2pl_batch(int n, int64_t B, const void* superop, void* pl_out, void* workspace,
                                    void* stream) {
+  if (B == 0) return QT_OK;  // empty batch: nothing to check, nothing to do
   QT_REQUIRE(n >= 1 && n <= 5 && superop && pl_out, "qt_superop2pl_batch: bad arguments");
-  if (B == 0) return QT_OK;
   return launch_pl<true>(n, B, superop, pl_out, workspace, (cudaStream_t)stream);
 }
 
 extern "C" int qt_pl2superop_batch(int n, int64_t B, const void* pl, void* superop_out, void* workspace,
                                    void* stream) {
+  if (B == 0) return QT_OK;  // empty batch: nothing to check, nothing to do
   QT_REQUIRE(n >= 1 && n <= 5 && pl && superop_out, "qt_pl2superop_batch: bad arguments");
-  if (B == 0) return QT_OK;
   return launch_pl<false>(n, B, pl, superop_out, workspace, (cudaStream_t)stream);
 }

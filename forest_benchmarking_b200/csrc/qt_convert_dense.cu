@@ -183,6 +183,7 @@ extern "C" int qt_superop_pl_batch_variant(int n, int64_t B, const void* in, voi
     return forward ? qt_superop2pl_batch(n, B, in, out, workspace, stream)
                    : qt_pl2superop_batch(n, B, in, out, workspace, stream);
   QT_REQUIRE(variant == QT_PL_VARIANT_DENSE_DMMA, "qt_superop_pl_batch_variant: unknown variant %d", variant);
+  if (B == 0) return QT_OK;
   QT_REQUIRE(in && out && in != out, "qt_superop_pl_batch_variant: bad arguments (out-of-place)");
   if (n != 2 && n != 3) {
     qt_set_error("the dense FP64-MMA PTM variant exists for n = 2, 3 only (got %d)", n);

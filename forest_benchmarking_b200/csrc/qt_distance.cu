@@ -469,8 +469,8 @@ static int launch_fid(int64_t B, const void* rho, const void* sigma, double* out
 
 extern "C" int qt_trace_distance_batch(int n, int64_t B, const void* rho, const void* sigma, double* out,
                                        void* stream) {
+  if (B == 0) return QT_OK;  // empty batch: nothing to check, nothing to do
   QT_REQUIRE(rho && sigma && out, "qt_trace_distance_batch: null argument");
-  if (B == 0) return QT_OK;
 #define CALL(D) launch_td<D>(B, rho, sigma, out, (cudaStream_t)stream)
   DISPATCH_D(n, CALL)
 #undef CALL
@@ -478,32 +478,32 @@ extern "C" int qt_trace_distance_batch(int n, int64_t B, const void* rho, const 
 
 extern "C" int qt_trace_distance_nuclear_batch(int n, int64_t B, const void* rho, const void* sigma, double* out,
                                                void* stream) {
+  if (B == 0) return QT_OK;  // empty batch: nothing to check, nothing to do
   QT_REQUIRE(rho && sigma && out, "qt_trace_distance_nuclear_batch: null argument");
-  if (B == 0) return QT_OK;
 #define CALL(D) launch_fid<D, 1>(B, rho, sigma, out, (cudaStream_t)stream)
   DISPATCH_D(n, CALL)
 #undef CALL
 }
 
 extern "C" int qt_fidelity_batch(int n, int64_t B, const void* rho, const void* sigma, double* out, void* stream) {
+  if (B == 0) return QT_OK;  // empty batch: nothing to check, nothing to do
   QT_REQUIRE(rho && sigma && out, "qt_fidelity_batch: null argument");
-  if (B == 0) return QT_OK;
 #define CALL(D) launch_fid<D, 0>(B, rho, sigma, out, (cudaStream_t)stream)
   DISPATCH_D(n, CALL)
 #undef CALL
 }
 
 extern "C" int qt_purity_batch(int n, int64_t B, const void* rho, double* out, void* stream) {
+  if (B == 0) return QT_OK;  // empty batch: nothing to check, nothing to do
   QT_REQUIRE(rho && out, "qt_purity_batch: null argument");
-  if (B == 0) return QT_OK;
 #define CALL(D) launch_purity<D>(B, rho, out, (cudaStream_t)stream)
   DISPATCH_D(n, CALL)
 #undef CALL
 }
 
 extern "C" int qt_project_state_batch(int n, int64_t B, const void* rho, void* out, void* stream) {
+  if (B == 0) return QT_OK;  // empty batch: nothing to check, nothing to do
   QT_REQUIRE(rho && out, "qt_project_state_batch: null argument");
-  if (B == 0) return QT_OK;
 #define CALL(D) launch_project_state<D>(B, rho, out, (cudaStream_t)stream)
   DISPATCH_D(n, CALL)
 #undef CALL
@@ -511,8 +511,8 @@ extern "C" int qt_project_state_batch(int n, int64_t B, const void* rho, void* o
 
 extern "C" int qt_hs_inner_batch(int64_t rows, int64_t cols, int64_t B, const void* a, const void* b, void* out,
                                  void* stream) {
+  if (B == 0) return QT_OK;  // empty batch: nothing to check, nothing to do
   QT_REQUIRE(rows > 0 && cols > 0 && a && b && out, "qt_hs_inner_batch: bad arguments");
-  if (B == 0) return QT_OK;
   const int64_t elems = rows * cols;
   const bool packed = elems < 32 && (elems & (elems - 1)) == 0;
   const int block_per_pair = packed ? 2 : (elems > 1024 ? 1 : 0);

@@ -239,3 +239,31 @@ def test_ptm_fused_two_pass_path(torch, n, batch):
         assert torch.equal(got, small)
         for b in ((0, batch // 2, batch - 1) if n == 4 else (batch - 1,)):
             assert relerr(got[b].cpu().numpy(), ref(x[b].cpu().numpy())) < 1e-13
+
+
+def test_empty_batches_everywhere(torch):
+    """B = 0 through every batched entry point (the reference's list-based API degenerates to empty lists): no launch, an
+    empty result of the right shape."""
+    from forest_benchmarking_b200 import tomography as tm, distance_measures as dm
+    from forest_benchmarking_b200.operator_tools import superoperator_transformations as st, project_superoperators as ps
+    from forest_benchmarking_b200.operator_tools.project_state_matrix import project_state_matrix_to_physical_batch
+    z = lambda *shape: torch.empty(shape, dtype=torch.complex128, device="cuda")
+    for n in (1, 3, 4):
+        m, d = 4 ** n, 2 ** n
+        assert st.kraus2choi_batch(z(0, 2, d, d)).shape == (0, m, m)
+        assert st.reshuffle_batch(z(0, m, m)).shape == (0, m, m)
+        assert st.superop2pauli_liouville_batch(z(0, m, m)).shape == (0, m, m)
+        assert st.pauli_liouville2superop_batch(z(0, m, m)).shape == (0, m, m)
+        k, c, e = st.choi2kraus_batch(z(0, m, m))
+        assert k.shape == (0, m, d, d) and c.shape == (0,) and e.shape == (0, m)
+        assert ps.proj_choi_to_completely_positive_batch(z(0, m, m)).shape == (0, m, m)
+        assert ps.proj_choi_to_trace_preserving_batch(z(0, m, m)).shape == (0, m, m)
+        assert ps.proj_choi_to_physical_batch(z(0, m, m)).shape == (0, m, m)
+        assert dm.fidelity_batch(z(0, d, d), z(0, d, d)).shape == (0,)
+        assert dm.trace_distance_batch(z(0, d, d), z(0, d, d)).shape == (0,)
+        assert project_state_matrix_to_physical_batch(z(0, d, d)).shape == (0, d, d)
+    plan = tm.PgdbPlan.complete(1)
+    e0 = torch.empty((0, plan.S), dtype=torch.float64, device="cuda")
+    assert tm.pgdb_process_estimate_batch(plan, e0, e0).shape == (0, 4, 4)
+    assert tm.linear_inv_process_estimate_batch(plan, e0).shape == (0, 4, 4)
+    torch.cuda.synchronize()
