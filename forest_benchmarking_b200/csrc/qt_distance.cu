@@ -199,6 +199,206 @@ __global__ void __launch_bounds__(256, (D == 16) ? 3 : 1) fidelity_fast_kernel(i
   if (lane == 0) out[b] = acc * acc;
 }
 
+// ---------------------------------------------------------------------------------------------
+// fidelity, d = 4, 8, 16: D lanes per pair (lane = one row / column held in registers), 32 / D pairs in flight per
+// warp, 32 pairs per warp in all.  Per pair: Cholesky rho = L L^dagger (rows in registers, the finished column
+// broadcast through shared memory), W = sigma L and Y = L^dagger W (columns in registers), Householder reduction
+// of Y to a real symmetric tridiagonal matrix (rows in registers; only the diagonal d and the SQUARED off-diagonal
+// e^2 = |x|^2 are kept -- the phases of the complex off-diagonal do not change the spectrum).  After 32 pairs the
+// warp switches layout: lane j runs the square-root-free QL iteration (Pal-Walker-Kahan, the algorithm behind
+// LAPACK's dsterf) on pair j's (d, e^2), kept in a lane-interleaved shared-memory slab, and writes
+// (sum_k sqrt(max(ev_k, 0)))^2.  ~3.6 k warp instructions per pair against ~29 k for the warp-per-pair Jacobi
+// kernel above.  Pairs whose rho fails the pivot test, or whose QL does not converge, get FID_FLAG and are redone by
+// fidelity_kernel with the reference's own sequence.
+// ---------------------------------------------------------------------------------------------
+template <int D>
+struct FidTriSmem {
+  static constexpr int G = 32 / D, LD = D + 1, MP = D * LD;
+  // per warp: G Cholesky factors, G x 2 Householder vectors, the (d, e^2) slab of 32 pairs
+  static constexpr size_t bytes = sizeof(cplx) * (G * MP + 2 * 32) + sizeof(double) * 2 * D * 32;
+};
+constexpr int FID_TRI_WPB = 4;
+
+template <int D>
+__device__ __forceinline__ double group_sum(double v) {
+#pragma unroll
+  for (int o = D / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+template <int D>
+__device__ __forceinline__ double group_max(double v) {
+#pragma unroll
+  for (int o = D / 2; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// eigenvalues of the symmetric tridiagonal (d, e2) of one lane's pair, in place in d; false if not converged.
+// d[k] and e2[k] live at stride 32 doubles (lane-interleaved: no bank conflicts whatever k each lane is at).
+template <int D>
+__device__ __forceinline__ bool pwk_ql(double* __restrict__ d, double* __restrict__ e2) {
+  constexpr double EPS2 = 1.232595164407831e-32;  // (2^-53)^2
+  for (int l = 0; l < D; ++l) {
+    int it = 0;
+    while (true) {
+      int m = l;
+      while (m < D - 1 && !(e2[m * 32] <= EPS2 * fabs(d[m * 32] * d[(m + 1) * 32]))) ++m;
+      if (m == l) break;
+      if (++it > 40) return false;
+      double p = d[l * 32];
+      const double rte = sqrt(e2[l * 32]);
+      const double sg = (d[(l + 1) * 32] - p) / (2.0 * rte);
+      const double rr = fabs(sg) > 1e100 ? fabs(sg) : sqrt(fma(sg, sg, 1.0));
+      const double shift = p - rte / (sg + copysign(rr, sg));
+      double c = 1.0, s = 0.0, gamma = d[m * 32] - shift;
+      p = gamma * gamma;
+      for (int i = m - 1; i >= l; --i) {
+        const double bb = e2[i * 32], r = p + bb;
+        if (i != m - 1) e2[(i + 1) * 32] = s * r;
+        const double oldc = c, ir = fast_rcp(r);
+        c = p * ir;
+        s = bb * ir;
+        const double oldgam = gamma, al = d[i * 32];
+        gamma = c * (al - shift) - s * oldgam;
+        d[(i + 1) * 32] = oldgam + (al - gamma);
+        p = (c != 0.0) ? gamma * gamma * fast_rcp(c) : oldc * bb;
+      }
+      e2[l * 32] = s * p;
+      d[l * 32] = shift + gamma;
+    }
+  }
+  return true;
+}
+
+template <int D>
+__global__ void __launch_bounds__(32 * FID_TRI_WPB, (D == 16) ? 3 : 4)
+    fidelity_tri_kernel(int64_t B, const cplx* __restrict__ rho, const cplx* __restrict__ sigma, double* __restrict__ out) {
+  constexpr int DD = D * D, G = FidTriSmem<D>::G, LD = FidTriSmem<D>::LD, MP = FidTriSmem<D>::MP, ROUNDS = 32 / G;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int r = lane % D, g = lane / D, glane0 = g * D;
+  cplx* Lg = reinterpret_cast<cplx*>(smem_raw + FidTriSmem<D>::bytes * wib) + g * MP;
+  cplx* Ug = reinterpret_cast<cplx*>(smem_raw + FidTriSmem<D>::bytes * wib) + G * MP + g * D;
+  cplx* Wg = Ug + 32;
+  double* td = reinterpret_cast<double*>(reinterpret_cast<cplx*>(smem_raw + FidTriSmem<D>::bytes * wib) + G * MP + 64);
+  double* te = td + D * 32;
+  const int64_t b0 = ((int64_t)blockIdx.x * FID_TRI_WPB + wib) * 32;
+  if (b0 >= B) return;
+
+#pragma unroll 1
+  for (int t = 0; t < ROUNDS; ++t) {
+    if (b0 + t * G >= B) break;  // warp-uniform
+    const int slot = t * G + g;
+    const int64_t b = min(b0 + slot, B - 1);  // a group past the end recomputes the last pair; its slot is never read
+    const cplx* rp = rho + b * DD;
+    const cplx* sp = sigma + b * DD;
+    // ---- Cholesky, lane r owns row r (scipy's eigh reads the lower triangle only: so does this) ----
+    cplx a[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) a[c] = rp[r * D + c];
+    const double dmax = group_max<D>(rp[r * D + r].x);
+    const double thr = 1e-10 * dmax;
+    bool ok = dmax > 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      const double piv = __shfl_sync(0xffffffffu, a[j].x, glane0 + j);
+      ok = ok && (piv > thr);
+      const double inv = ok ? fast_rsqrt(piv) : 0.0;
+      cplx l = (r == j) ? cmake(piv * inv, 0.0) : cscale(a[j], inv);
+      if (r < j) l = cmake(0.0, 0.0);
+      a[j] = l;
+      Lg[r * LD + j] = l;
+      __syncwarp();
+#pragma unroll
+      for (int k = j + 1; k < D; ++k) {
+        const cplx lk = Lg[k * LD + j];
+        a[k].x = fma(-l.y, lk.y, fma(-l.x, lk.x, a[k].x));  // a[k] -= l * conj(lk)
+        a[k].y = fma(l.x, lk.y, fma(-l.y, lk.x, a[k].y));
+      }
+    }
+    // ---- W = sigma L, Y = L^dagger W: lane r owns COLUMN r ----
+    cplx y[D];
+    {
+      cplx lc[D], w[D];
+#pragma unroll
+      for (int m = 0; m < D; ++m) lc[m] = Lg[m * LD + r];
+#pragma unroll
+      for (int k = 0; k < D; ++k) {
+        cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+        for (int m = 0; m < D; ++m) cfma(acc, sp[k * D + m], lc[m]);
+        w[k] = acc;
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) {
+        cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+        for (int k = i; k < D; ++k) cfma(acc, cconj(Lg[k * LD + i]), w[k]);
+        y[i] = acc;
+      }
+    }
+    // row r of the Hermitian matrix an eigensolver reading the lower triangle would see: A[r][c] = conj(Y[c][r])
+#pragma unroll
+    for (int c = 0; c < D; ++c) a[c] = (c == r) ? cmake(y[c].x, 0.0) : cconj(y[c]);
+    // ---- Householder tridiagonalisation, lane r owns row r ----
+#pragma unroll
+    for (int k = 0; k < D - 2; ++k) {
+      const cplx x = (r > k) ? a[k] : cmake(0.0, 0.0);
+      Ug[r] = x;
+      const double n2 = group_sum<D>(cabs2(x));
+      __syncwarp();
+      const cplx alpha = Ug[k + 1];
+      if (r == 0) te[k * 32 + slot] = n2;
+      const double aa = cabs2(alpha);
+      // MUFU seeds + Newton steps (normal, positive arguments only): a column that is zero to 1e-290 is left alone
+      const bool live = n2 > 1e-290, has_a = aa > 1e-290;
+      const double rn = live ? fast_rsqrt(n2) : 0.0, ra = has_a ? fast_rsqrt(aa) : 0.0;
+      const double xn = n2 * rn, an = aa * ra;
+      const cplx ph = has_a ? cscale(alpha, ra) : cmake(1.0, 0.0);
+      const cplx u1 = cscale(ph, an + xn);  // u = x - gamma e1, gamma = -ph |x|: H x = gamma e1, H = I - beta u u^dagger
+      const double beta = live ? rn * fast_rcp(xn + an) : 0.0;
+      const cplx u = (r == k + 1) ? u1 : ((r > k + 1) ? x : cmake(0.0, 0.0));
+      cplx p = cmake(0.0, 0.0);
+      cfma(p, a[k + 1], u1);
+#pragma unroll
+      for (int c = k + 2; c < D; ++c) cfma(p, a[c], Ug[c]);
+      p = cscale(p, beta);
+      const double kk = 0.5 * beta * group_sum<D>(u.x * p.x + u.y * p.y);
+      const cplx w2 = cmake(p.x - kk * u.x, p.y - kk * u.y);
+      Wg[r] = w2;
+      __syncwarp();
+#pragma unroll
+      for (int c = k + 1; c < D; ++c) {  // A -= u w^dagger + w u^dagger
+        const cplx uc = (c == k + 1) ? u1 : Ug[c];
+        const cplx wc = Wg[c];
+        a[c].x = fma(-w2.y, uc.y, fma(-w2.x, uc.x, fma(-u.y, wc.y, fma(-u.x, wc.x, a[c].x))));
+        a[c].y = fma(w2.x, uc.y, fma(-w2.y, uc.x, fma(u.x, wc.y, fma(-u.y, wc.x, a[c].y))));
+      }
+      __syncwarp();
+    }
+    double dr = 0.0;
+#pragma unroll
+    for (int c = 0; c < D; ++c)
+      if (c == r) dr = a[c].x;
+    const double elast = __shfl_sync(0xffffffffu, cabs2(a[D - 2]), glane0 + D - 1);
+    td[r * 32 + slot] = (r == 0 && !ok) ? __longlong_as_double(0x7ff8000000000000LL) : dr;
+    if (r == 0) te[(D - 2) * 32 + slot] = elast;
+    __syncwarp();
+  }
+  // ---- lane j: eigenvalues of pair b0 + j ----
+  const int64_t b = b0 + lane;
+  if (b < B) {
+    double* d = td + lane;
+    double res = FID_FLAG;
+    if (d[0] == d[0] && pwk_ql<D>(d, te + lane)) {
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < D; ++k) acc += sqrt(fmax(d[k * 32], 0.0));
+      res = acc * acc;
+    }
+    out[b] = res;
+  }
+}
+
 // MODE 0: fidelity.  MODE 1: nuclear-norm trace distance.
 template <int D, int MODE>
 __global__ void fidelity_kernel(int64_t B, const cplx* __restrict__ rho, const cplx* __restrict__ sigma,
@@ -440,6 +640,19 @@ static int launch_fid(int64_t B, const void* rho, const void* sigma, double* out
   const size_t smem = per_warp * wpb;
   int only_flagged = 0;
   if constexpr (MODE == 0 && D >= 4) {
+    if constexpr (D <= 16) {
+      const size_t smem_tri = FidTriSmem<D>::bytes * FID_TRI_WPB;
+      QT_CUDA(cudaFuncSetAttribute(fidelity_tri_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_tri));
+      const int64_t per_block = 32 * FID_TRI_WPB;
+      fidelity_tri_kernel<D><<<(unsigned)((B + per_block - 1) / per_block), 32 * FID_TRI_WPB, smem_tri, st>>>(
+          B, (const cplx*)rho, (const cplx*)sigma, out);
+      int rc = qt_check_launch("fidelity_tri_kernel");
+      if (rc) return rc;
+      QT_CUDA(cudaFuncSetAttribute(fidelity_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      fidelity_kernel<D, MODE><<<(unsigned)((B + wpb - 1) / wpb), 32 * wpb, smem, st>>>(B, (const cplx*)rho,
+                                                                                        (const cplx*)sigma, out, 1);
+      return qt_check_launch("fidelity_kernel");
+    }
     const size_t per_fast = FidFastSmem<D>::bytes;
     const int wf = (int)max((size_t)1, min((size_t)8, (size_t)(74 * 1024) / per_fast));
     QT_CUDA(cudaFuncSetAttribute(fidelity_fast_kernel<D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_fast * wf)));

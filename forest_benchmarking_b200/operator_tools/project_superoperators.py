@@ -31,7 +31,7 @@ def _simple(name, choi, out, max_n=5):
             out = torch.empty_like(choi)
         else:
             _lib.check_tensor("out", out, torch.complex128, choi.shape)
-        if n >= 4 and out.data_ptr() == choi.data_ptr():
+        if n >= 4 and choi.numel() and out.data_ptr() == choi.data_ptr():
             raise ValueError("projections of 4- and 5-qubit Choi matrices are out-of-place")
         _lib.check(getattr(_lib.lib(), name)(ctypes.c_int(n), ctypes.c_int64(choi.shape[0]), _lib.ptr(choi),
                                              _lib.ptr(out), _lib.current_stream_ptr()), name)
@@ -51,7 +51,7 @@ def proj_choi_to_completely_positive_batch(choi, out=None):
             out = torch.empty_like(choi)
         else:
             _lib.check_tensor("out", out, torch.complex128, choi.shape)
-            if out.data_ptr() == choi.data_ptr():
+            if choi.numel() and out.data_ptr() == choi.data_ptr():
                 raise ValueError("projections of 4- and 5-qubit Choi matrices are out-of-place")
         nbytes = int(lib.qt_proj_cp_workspace_bytes(ctypes.c_int(n), ctypes.c_int64(choi.shape[0])))
         ws = torch.empty((max(nbytes, 16) // 16,), dtype=torch.complex128, device=dev)
@@ -92,7 +92,7 @@ def proj_choi_to_physical_batch(choi, make_trace_preserving=True, out=None, retu
             out = torch.empty_like(choi)
         else:
             _lib.check_tensor("out", out, torch.complex128, choi.shape)
-            if out.data_ptr() == choi.data_ptr():
+            if choi.numel() and out.data_ptr() == choi.data_ptr():
                 raise ValueError("proj_choi_to_physical_batch cannot run in place")
         nbytes = int(lib.qt_proj_physical_workspace_bytes(ctypes.c_int(n), ctypes.c_int64(b)))
         ws = torch.empty((max(nbytes, 16) // 16,), dtype=torch.complex128, device=dev)

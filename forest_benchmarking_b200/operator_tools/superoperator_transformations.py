@@ -82,7 +82,7 @@ def reshuffle_batch(mat, out=None):
             out = torch.empty_like(mat)
         else:
             _lib.check_tensor("out", out, torch.complex128, mat.shape)
-            if out.data_ptr() == mat.data_ptr():
+            if mat.numel() and out.data_ptr() == mat.data_ptr():
                 raise ValueError("reshuffle_batch is out-of-place")
         _lib.check(_lib.lib().qt_choi_superop_reshuffle_batch(ctypes.c_int(d), ctypes.c_int64(b), _lib.ptr(mat),
                                                               _lib.ptr(out), _lib.current_stream_ptr()),
