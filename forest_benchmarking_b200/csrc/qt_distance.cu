@@ -211,13 +211,37 @@ __global__ void __launch_bounds__(256, (D == 16) ? 3 : 1) fidelity_fast_kernel(i
 // kernel above.  Pairs whose rho fails the pivot test, or whose QL does not converge, get FID_FLAG and are redone by
 // fidelity_kernel with the reference's own sequence.
 // ---------------------------------------------------------------------------------------------
+// Register budget of the d = 16 instance: 4 blocks of 4 warps per SM need <= 128 registers.  Asking ptxas for exactly
+// that (__launch_bounds__(128, 4)) makes it spill 1.5 KB per thread; asking for (224, 2) -- a cap of 144 -- makes it
+// settle on 128 registers with ~140 bytes of spills, and a 128-thread launch is legal under a 224-thread bound.
+#ifndef FID_TRI_LB_T
+#define FID_TRI_LB_T 224
+#endif
+#ifndef FID_TRI_LB_B
+#define FID_TRI_LB_B 2
+#endif
+#ifndef FID_TRI_WPB_N
+#define FID_TRI_WPB_N 4
+#endif
+#ifndef FID_TRI_SYNC
+#define FID_TRI_SYNC 0
+#endif
+#ifndef FID_TRI_STAGE
+#define FID_TRI_STAGE 0
+#endif
+#if FID_TRI_SYNC
+#define FID_TRI_BAR() __syncthreads()
+#else
+#define FID_TRI_BAR() __syncwarp()
+#endif
+constexpr int FID_TRI_WPB = FID_TRI_WPB_N;
 template <int D>
 struct FidTriSmem {
-  static constexpr int G = 32 / D, LD = D + 1, MP = D * LD;
+  static constexpr int G = 32 / D, MP = D * (D + 1) / 2;  // L packed by rows: L[k][i] at k (k + 1) / 2 + i, i <= k
   // per warp: G Cholesky factors, G x 2 Householder vectors, the (d, e^2) slab of 32 pairs
-  static constexpr size_t bytes = sizeof(cplx) * (G * MP + 2 * 32) + sizeof(double) * 2 * D * 32;
+  static constexpr size_t base = sizeof(cplx) * (G * MP + 2 * 32) + sizeof(double) * 2 * D * 32;
+  static constexpr size_t bytes = base + (FID_TRI_STAGE ? sizeof(cplx) * G * D * D : 0);  // + sigma, staged by cp.async
 };
-constexpr int FID_TRI_WPB = 4;
 
 template <int D>
 __device__ __forceinline__ double group_sum(double v) {
@@ -270,9 +294,10 @@ __device__ __forceinline__ bool pwk_ql(double* __restrict__ d, double* __restric
 }
 
 template <int D>
-__global__ void __launch_bounds__(32 * FID_TRI_WPB, (D == 16) ? 3 : 4)
+__global__ void __launch_bounds__((D == 16) ? FID_TRI_LB_T : 32 * FID_TRI_WPB, (D == 16) ? FID_TRI_LB_B : 4)
     fidelity_tri_kernel(int64_t B, const cplx* __restrict__ rho, const cplx* __restrict__ sigma, double* __restrict__ out) {
-  constexpr int DD = D * D, G = FidTriSmem<D>::G, LD = FidTriSmem<D>::LD, MP = FidTriSmem<D>::MP, ROUNDS = 32 / G;
+  constexpr int DD = D * D, G = FidTriSmem<D>::G, MP = FidTriSmem<D>::MP, ROUNDS = 32 / G;
+  auto lidx = [](int k, int i) { return k * (k + 1) / 2 + i; };
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int r = lane % D, g = lane / D, glane0 = g * D;
@@ -281,16 +306,42 @@ __global__ void __launch_bounds__(32 * FID_TRI_WPB, (D == 16) ? 3 : 4)
   cplx* Wg = Ug + 32;
   double* td = reinterpret_cast<double*>(reinterpret_cast<cplx*>(smem_raw + FidTriSmem<D>::bytes * wib) + G * MP + 64);
   double* te = td + D * 32;
+#if FID_TRI_STAGE
+  cplx* Sg = reinterpret_cast<cplx*>(smem_raw + FidTriSmem<D>::bytes * wib + FidTriSmem<D>::base) + g * DD;
+#endif
   const int64_t b0 = ((int64_t)blockIdx.x * FID_TRI_WPB + wib) * 32;
+#if !FID_TRI_SYNC
   if (b0 >= B) return;
+#endif
 
 #pragma unroll 1
   for (int t = 0; t < ROUNDS; ++t) {
+#if !FID_TRI_SYNC
     if (b0 + t * G >= B) break;  // warp-uniform
+#endif
     const int slot = t * G + g;
     const int64_t b = min(b0 + slot, B - 1);  // a group past the end recomputes the last pair; its slot is never read
     const cplx* rp = rho + b * DD;
     const cplx* sp = sigma + b * DD;
+    {  // next round's rows on their way into L2 while this round computes (row r = D * 16 bytes)
+      const int64_t bn = min(b + G, B - 1);
+      const char* pr = reinterpret_cast<const char*>(rho + bn * DD + r * D);
+      const char* ps = reinterpret_cast<const char*>(sigma + bn * DD + r * D);
+#pragma unroll
+      for (int o = 0; o < D * 16; o += 128) {
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + o));
+      }
+    }
+#if FID_TRI_STAGE
+    // sigma on its way into shared memory while the Cholesky factorisation runs (16-byte cp.async, coalesced per row)
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(Sg + i * D + r);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(sp + i * D + r) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+#endif
     // ---- Cholesky, lane r owns row r (scipy's eigh reads the lower triangle only: so does this) ----
     cplx a[D];
 #pragma unroll
@@ -304,13 +355,12 @@ __global__ void __launch_bounds__(32 * FID_TRI_WPB, (D == 16) ? 3 : 4)
       ok = ok && (piv > thr);
       const double inv = ok ? fast_rsqrt(piv) : 0.0;
       cplx l = (r == j) ? cmake(piv * inv, 0.0) : cscale(a[j], inv);
-      if (r < j) l = cmake(0.0, 0.0);
       a[j] = l;
-      Lg[r * LD + j] = l;
-      __syncwarp();
+      if (r >= j) Lg[lidx(r, j)] = l;  // triangular numbers: distinct banks within each quarter warp
+      if (j % 4 == 3) FID_TRI_BAR(); else __syncwarp();
 #pragma unroll
       for (int k = j + 1; k < D; ++k) {
-        const cplx lk = Lg[k * LD + j];
+        const cplx lk = Lg[lidx(k, j)];
         a[k].x = fma(-l.y, lk.y, fma(-l.x, lk.x, a[k].x));  // a[k] -= l * conj(lk)
         a[k].y = fma(l.x, lk.y, fma(-l.y, lk.x, a[k].y));
       }
@@ -319,21 +369,30 @@ __global__ void __launch_bounds__(32 * FID_TRI_WPB, (D == 16) ? 3 : 4)
     cplx y[D];
     {
       cplx lc[D], w[D];
+#if FID_TRI_STAGE
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncwarp();
+      const cplx* sv = Sg;
+#else
+      const cplx* sv = sp;
+#endif
 #pragma unroll
-      for (int m = 0; m < D; ++m) lc[m] = Lg[m * LD + r];
+      for (int m = 0; m < D; ++m) lc[m] = (m >= r) ? Lg[lidx(m, r)] : cmake(0.0, 0.0);
 #pragma unroll
       for (int k = 0; k < D; ++k) {
         cplx acc = cmake(0.0, 0.0);
 #pragma unroll
-        for (int m = 0; m < D; ++m) cfma(acc, sp[k * D + m], lc[m]);
+        for (int m = 0; m < D; ++m) cfma(acc, sv[k * D + m], lc[m]);
         w[k] = acc;
+        if (FID_TRI_SYNC && k % 4 == 3) FID_TRI_BAR();
       }
 #pragma unroll
       for (int i = 0; i < D; ++i) {
         cplx acc = cmake(0.0, 0.0);
 #pragma unroll
-        for (int k = i; k < D; ++k) cfma(acc, cconj(Lg[k * LD + i]), w[k]);
+        for (int k = i; k < D; ++k) cfma(acc, cconj(Lg[lidx(k, i)]), w[k]);
         y[i] = acc;
+        if (FID_TRI_SYNC && i % 8 == 7) FID_TRI_BAR();
       }
     }
     // row r of the Hermitian matrix an eigensolver reading the lower triangle would see: A[r][c] = conj(Y[c][r])
@@ -373,7 +432,7 @@ __global__ void __launch_bounds__(32 * FID_TRI_WPB, (D == 16) ? 3 : 4)
         a[c].x = fma(-w2.y, uc.y, fma(-w2.x, uc.x, fma(-u.y, wc.y, fma(-u.x, wc.x, a[c].x))));
         a[c].y = fma(w2.x, uc.y, fma(-w2.y, uc.x, fma(u.x, wc.y, fma(-u.y, wc.x, a[c].y))));
       }
-      __syncwarp();
+      FID_TRI_BAR();
     }
     double dr = 0.0;
 #pragma unroll
