@@ -211,36 +211,25 @@ __global__ void __launch_bounds__(256, (D == 16) ? 3 : 1) fidelity_fast_kernel(i
 // kernel above.  Pairs whose rho fails the pivot test, or whose QL does not converge, get FID_FLAG and are redone by
 // fidelity_kernel with the reference's own sequence.
 // ---------------------------------------------------------------------------------------------
-// Register budget of the d = 16 instance: 4 blocks of 4 warps per SM need <= 128 registers.  Asking ptxas for exactly
-// that (__launch_bounds__(128, 4)) makes it spill 1.5 KB per thread; asking for (224, 2) -- a cap of 144 -- makes it
-// settle on 128 registers with ~140 bytes of spills, and a 128-thread launch is legal under a 224-thread bound.
+// Block shape of the d = 16 instance: 3 blocks of 4 warps per SM at 168 registers.  Measured alternatives (2^18 pairs,
+// profiles/r02_ubench_fidelity_tri.txt): 16 warps/SM at 128 registers 3.38 ms vs 3.28 ms; block-wide barriers that keep
+// the warps of an SM on the same code (instruction-cache misses 48.7 M -> 0.4 M) 3.5-3.6 ms; sigma staged by cp.async
+// 3.5 ms; all loops rolled over a shared-memory matrix (20 KB of code instead of 108 KB) 4.9 ms.
 #ifndef FID_TRI_LB_T
-#define FID_TRI_LB_T 224
+#define FID_TRI_LB_T 128
 #endif
 #ifndef FID_TRI_LB_B
-#define FID_TRI_LB_B 2
+#define FID_TRI_LB_B 3
 #endif
 #ifndef FID_TRI_WPB_N
 #define FID_TRI_WPB_N 4
-#endif
-#ifndef FID_TRI_SYNC
-#define FID_TRI_SYNC 0
-#endif
-#ifndef FID_TRI_STAGE
-#define FID_TRI_STAGE 0
-#endif
-#if FID_TRI_SYNC
-#define FID_TRI_BAR() __syncthreads()
-#else
-#define FID_TRI_BAR() __syncwarp()
 #endif
 constexpr int FID_TRI_WPB = FID_TRI_WPB_N;
 template <int D>
 struct FidTriSmem {
   static constexpr int G = 32 / D, MP = D * (D + 1) / 2;  // L packed by rows: L[k][i] at k (k + 1) / 2 + i, i <= k
   // per warp: G Cholesky factors, G x 2 Householder vectors, the (d, e^2) slab of 32 pairs
-  static constexpr size_t base = sizeof(cplx) * (G * MP + 2 * 32) + sizeof(double) * 2 * D * 32;
-  static constexpr size_t bytes = base + (FID_TRI_STAGE ? sizeof(cplx) * G * D * D : 0);  // + sigma, staged by cp.async
+  static constexpr size_t bytes = sizeof(cplx) * (G * MP + 2 * 32) + sizeof(double) * 2 * D * 32;
 };
 
 template <int D>
@@ -306,19 +295,12 @@ __global__ void __launch_bounds__((D == 16) ? FID_TRI_LB_T : 32 * FID_TRI_WPB, (
   cplx* Wg = Ug + 32;
   double* td = reinterpret_cast<double*>(reinterpret_cast<cplx*>(smem_raw + FidTriSmem<D>::bytes * wib) + G * MP + 64);
   double* te = td + D * 32;
-#if FID_TRI_STAGE
-  cplx* Sg = reinterpret_cast<cplx*>(smem_raw + FidTriSmem<D>::bytes * wib + FidTriSmem<D>::base) + g * DD;
-#endif
   const int64_t b0 = ((int64_t)blockIdx.x * FID_TRI_WPB + wib) * 32;
-#if !FID_TRI_SYNC
   if (b0 >= B) return;
-#endif
 
 #pragma unroll 1
   for (int t = 0; t < ROUNDS; ++t) {
-#if !FID_TRI_SYNC
     if (b0 + t * G >= B) break;  // warp-uniform
-#endif
     const int slot = t * G + g;
     const int64_t b = min(b0 + slot, B - 1);  // a group past the end recomputes the last pair; its slot is never read
     const cplx* rp = rho + b * DD;
@@ -333,15 +315,6 @@ __global__ void __launch_bounds__((D == 16) ? FID_TRI_LB_T : 32 * FID_TRI_WPB, (
         asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + o));
       }
     }
-#if FID_TRI_STAGE
-    // sigma on its way into shared memory while the Cholesky factorisation runs (16-byte cp.async, coalesced per row)
-#pragma unroll
-    for (int i = 0; i < D; ++i) {
-      const unsigned dst = (unsigned)__cvta_generic_to_shared(Sg + i * D + r);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(sp + i * D + r) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-#endif
     // ---- Cholesky, lane r owns row r (scipy's eigh reads the lower triangle only: so does this) ----
     cplx a[D];
 #pragma unroll
@@ -357,7 +330,7 @@ __global__ void __launch_bounds__((D == 16) ? FID_TRI_LB_T : 32 * FID_TRI_WPB, (
       cplx l = (r == j) ? cmake(piv * inv, 0.0) : cscale(a[j], inv);
       a[j] = l;
       if (r >= j) Lg[lidx(r, j)] = l;  // triangular numbers: distinct banks within each quarter warp
-      if (j % 4 == 3) FID_TRI_BAR(); else __syncwarp();
+      __syncwarp();
 #pragma unroll
       for (int k = j + 1; k < D; ++k) {
         const cplx lk = Lg[lidx(k, j)];
@@ -369,22 +342,14 @@ __global__ void __launch_bounds__((D == 16) ? FID_TRI_LB_T : 32 * FID_TRI_WPB, (
     cplx y[D];
     {
       cplx lc[D], w[D];
-#if FID_TRI_STAGE
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-      __syncwarp();
-      const cplx* sv = Sg;
-#else
-      const cplx* sv = sp;
-#endif
 #pragma unroll
       for (int m = 0; m < D; ++m) lc[m] = (m >= r) ? Lg[lidx(m, r)] : cmake(0.0, 0.0);
 #pragma unroll
       for (int k = 0; k < D; ++k) {
         cplx acc = cmake(0.0, 0.0);
 #pragma unroll
-        for (int m = 0; m < D; ++m) cfma(acc, sv[k * D + m], lc[m]);
+        for (int m = 0; m < D; ++m) cfma(acc, sp[k * D + m], lc[m]);
         w[k] = acc;
-        if (FID_TRI_SYNC && k % 4 == 3) FID_TRI_BAR();
       }
 #pragma unroll
       for (int i = 0; i < D; ++i) {
@@ -392,7 +357,6 @@ __global__ void __launch_bounds__((D == 16) ? FID_TRI_LB_T : 32 * FID_TRI_WPB, (
 #pragma unroll
         for (int k = i; k < D; ++k) cfma(acc, cconj(Lg[lidx(k, i)]), w[k]);
         y[i] = acc;
-        if (FID_TRI_SYNC && i % 8 == 7) FID_TRI_BAR();
       }
     }
     // row r of the Hermitian matrix an eigensolver reading the lower triangle would see: A[r][c] = conj(Y[c][r])
@@ -432,7 +396,7 @@ __global__ void __launch_bounds__((D == 16) ? FID_TRI_LB_T : 32 * FID_TRI_WPB, (
         a[c].x = fma(-w2.y, uc.y, fma(-w2.x, uc.x, fma(-u.y, wc.y, fma(-u.x, wc.x, a[c].x))));
         a[c].y = fma(w2.x, uc.y, fma(-w2.y, uc.x, fma(u.x, wc.y, fma(-u.y, wc.x, a[c].y))));
       }
-      FID_TRI_BAR();
+      __syncwarp();
     }
     double dr = 0.0;
 #pragma unroll
