@@ -635,11 +635,14 @@ def part_distances(ctx, pairs_total=1_000_000, n=4):
            "kernels": {k: {"ms": v, "pairs_per_s": ctx.world * B / (v * 1e-3),
                            "hbm_gbs": B * bytes_pair / (v * 1e-3) / 1e9,
                            "frac_of_hbm_peak": B * bytes_pair / (v * 1e-3) / 1e9 / ctx.hbm_peak} for k, v in ms_k.items()},
-           "roofline": {"kernel": "fidelity_fast_kernel<16> (Cholesky + values-only warp eigensolver per pair)",
+           "roofline": {"kernel": "fidelity_tri_kernel<16> (16 lanes per pair: Cholesky, L^dagger sigma L, Householder "
+                                   "tridiagonalisation; then one lane per pair: square-root-free QL)",
                         "bound": "hbm", "achieved": B * bytes_pair / (ms_k["fidelity"] * 1e-3) / 1e9, "peak": ctx.hbm_peak,
                         "unit": "GB/s", "frac": B * bytes_pair / (ms_k["fidelity"] * 1e-3) / 1e9 / ctx.hbm_peak,
-                        "peak_source": ctx.hbm_src, "traffic": kernel_traffic("fidelity_fast_kernel")[0],
-                        "note": "the fidelity kernel is FP64/MIO-bound (0.39 MFLOP per pair), the trace-distance "
+                        "peak_source": ctx.hbm_src, "traffic": kernel_traffic("fidelity_tri_kernel<16>")[0],
+                        "traffic_source": kernel_traffic("fidelity_tri_kernel<16>")[1],
+                        "note": "the fidelity kernel is instruction-issue / instruction-cache bound (~4.4 k warp "
+                                "instructions per pair, profiles/r02_ubench_fidelity_tri.txt), the trace-distance "
                                 "kernel is the HBM-bound one: see kernels.trace_distance"}}
     if ctx.world == 1 and not ctx.args.no_cpu_baseline:
         obj["cpu_baseline"] = bk.cpu_distance_baseline(torch)

@@ -22,6 +22,6 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:mle_
 python scripts/summarize_ncu.py full gpurun_out/${T}_prof_mle_quad.ncu-rep gpurun_out/${T}_ncu_mle_quad.md mle_quad
 timeout 900 ncu --set full --clock-control none -k regex:pgdb_kernel -s 1 -c 1 -o gpurun_out/${T}_prof_pgdb3 -f python bench.py --workload pgdb3q --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu_pgdb.log 2>&1
 python scripts/summarize_ncu.py full gpurun_out/${T}_prof_pgdb3.ncu-rep gpurun_out/${T}_ncu_pgdb3.md pgdb_kernel
-timeout 600 ncu --set full --clock-control none -k regex:"mle_step_herm_kernel|fidelity_fast_kernel" -c 2 -o gpurun_out/${T}_prof_misc -f python bench.py --workload distances --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu_misc.log 2>&1
-python scripts/make_traffic_json.py gpurun_out/${T}_traffic.json "mle_quad_kernel=gpurun_out/${T}_prof_mle_quad.ncu-rep:mle_quad" "pgdb_kernel<3>=gpurun_out/${T}_prof_pgdb3.ncu-rep:pgdb_kernel" "fidelity_fast_kernel=gpurun_out/${T}_prof_misc.ncu-rep:fidelity_fast" | head -30
+timeout 600 ncu --set full --clock-control none -k regex:"fidelity_tri_kernel" -s 3 -c 1 -o gpurun_out/${T}_prof_misc -f python bench.py --workload distances --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu_misc.log 2>&1
+python scripts/make_traffic_json.py gpurun_out/${T}_traffic.json "mle_quad_kernel=gpurun_out/${T}_prof_mle_quad.ncu-rep:mle_quad" "pgdb_kernel<3>=gpurun_out/${T}_prof_pgdb3.ncu-rep:pgdb_kernel" "fidelity_tri_kernel<16>=gpurun_out/${T}_prof_misc.ncu-rep:fidelity_tri" | head -30
 for w in streaming convert next; do timeout 900 python bench.py --workload $w > gpurun_out/${T}_bench_$w.json 2> gpurun_out/${T}_bench_$w.err; echo "$w rc=$?"; done

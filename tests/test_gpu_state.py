@@ -430,6 +430,48 @@ def test_fidelity_cholesky_fast_path_and_fallback(torch):
                 assert abs(fid[b] - want) < 1e-10
 
 
+@pytest.mark.parametrize("n", [2, 3, 4])
+def test_fidelity_tridiagonal_kernel_tails_and_structured_inputs(torch, n):
+    """The d = 4, 8, 16 fidelity kernel (Cholesky -> L^dagger sigma L -> Householder tridiagonalisation by d lanes per pair,
+    then one lane per pair runs the square-root-free QL): batch sizes that leave partial warps / partial rounds, and
+    inputs whose tridiagonal form has exact zeros (diagonal, identical, commuting, basis-state sigma), against the
+    oracle (distance_measures.py:64-84)."""
+    from forest_benchmarking_b200 import distance_measures as dm
+    rng = np.random.default_rng(100 + n)
+    d = 2 ** n
+    for B in (1, 31, 33, 391):
+        rho, sig, kind = [], [], []
+        for b in range(B):
+            k = b % 8
+            r = orc.ginibre_state(rng, d)
+            s = orc.ginibre_state(rng, d)
+            if k == 1:      # both diagonal: Y is diagonal, every e^2 is exactly zero
+                r, s = np.diag(np.diag(r).real).astype(complex), np.diag(np.diag(s).real).astype(complex)
+            elif k == 2:    # identical states: F = 1
+                s = r.copy()
+            elif k == 3:    # sigma a computational basis state (rank 1, exact zeros)
+                s = np.zeros((d, d), complex)
+                s[b % d, b % d] = 1.0
+            elif k == 4:    # maximally mixed rho
+                r = np.eye(d, dtype=complex) / d
+            elif k == 5:    # commuting pair (same eigenbasis)
+                w, v = np.linalg.eigh(r)
+                p = rng.dirichlet(np.ones(d))
+                s = (v * p) @ v.conj().T
+            elif k == 6:    # block-diagonal pair: the tridiagonal matrix splits
+                r[: d // 2, d // 2:] = r[d // 2:, : d // 2] = 0
+                s[: d // 2, d // 2:] = s[d // 2:, : d // 2] = 0
+                r, s = r / np.trace(r).real, s / np.trace(s).real
+            rho.append(r), sig.append(s), kind.append(k)
+        rho, sig = np.stack(rho), np.stack(sig)
+        fid = dm.fidelity_batch(torch.from_numpy(rho).cuda(), torch.from_numpy(sig).cuda()).cpu().numpy()
+        assert fid.shape == (B,) and np.all(np.isfinite(fid))
+        for b in range(0, B, 1 if B < 64 else 3):
+            want = np.real(orc.fidelity(rho[b], sig[b]))
+            tol = 1e-6 * max(abs(want), 1e-3) if kind[b] == 3 else 1e-10
+            assert abs(fid[b] - want) < tol, (n, B, b, kind[b], fid[b], want)
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 4, 5])
 def test_purity_all_sizes(torch, n):
     """tr(rho rho) for Hermitian and for general complex matrices (the reference computes np.trace(rho @ rho))."""
