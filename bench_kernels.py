@@ -162,12 +162,12 @@ def next_rows(torch, peak, budget_bytes=4 << 30):
     from forest_benchmarking_b200.operator_tools import project_superoperators as pj
     rows = []
     g = torch.Generator(device="cuda").manual_seed(7)
-    for q, shots in ((1, 1000), (2, 1000), (2, 500), (4, 1000), (8, 1000), (3, 1000)):
+    for q, shots in ((1, 1000), (2, 1000), (2, 500), (4, 1000), (8, 1000), (3, 1000), (5, 1000), (7, 1000), (11, 1000), (20, 1000)):
         b = budget_bytes // (shots * q)
         bits = torch.randint(0, 2, (b, shots, q), device="cuda", generator=g, dtype=torch.uint8)
         masks = torch.randint(1, 2 ** q, (b,), device="cuda", generator=g, dtype=torch.int32)
         ms = _time(torch, lambda: oe.shots_to_obs_moments_batch(bits, masks))
-        kind = "SWAR" if q in (1, 2, 4, 8) else "bytes"
+        kind = "SWAR" if q in (1, 2, 4, 8) else ("stream" if q <= 16 else "bytes")
         rows.append(_row(f"moments_{kind}_kernel n_qubits={q} shots={shots} (shots_to_obs_moments)", b,
                          shots * q + 4 + 8 + 16, ms, peak))
         del bits, masks

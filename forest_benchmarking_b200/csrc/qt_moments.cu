@@ -9,7 +9,9 @@
 // For n_qubits in {1, 2, 4, 8} the whole array is read as one flat stream of aligned 16-byte words by 8 / 16 / 32
 // lanes per setting (a setting's byte range may start anywhere: the bytes of neighbouring settings in its first /
 // last word are masked off), and the per-shot parity is folded inside the 32-bit words (SWAR) before one popcount
-// per word.  Other widths stage the setting through shared memory (warp per setting) and XOR the selected columns.
+// per word.  The other widths up to 16 (and misaligned 2 / 4 / 8-column arrays) read the same stream, compact every word
+// to one bit per byte and take the per-shot parities with a sliding XOR (moments_stream_kernel); settings of more than
+// 16 columns stage the setting through shared memory (warp per setting) and XOR the selected columns.
 #include "qt_common.cuh"
 #include "../../include/qtomo.h"
 
@@ -141,6 +143,106 @@ __global__ void __launch_bounds__(256)  // 43 registers, 5 blocks per SM; cappin
   }
 }
 
+// Widths that do not tile a 32-bit word (3, 5, 6, 7, 9 .. 16 columns; also 2 / 4 / 8 columns when `bits` is not
+// aligned to the shot width): the same flat stream of aligned 16-byte words, but a
+// shot may straddle two words and its position inside a word changes from word to word.  Each word is first COMPACTED
+// to one bit per byte (bytes are 0/1: (x * 0x01020408) >> 24 packs four of them), masked with the column pattern --
+// periodic in the stream with period Q, so one 32-bit constant per setting shifted by the word's phase (a - lo) mod Q --
+// and joined with the compacted previous word (the neighbouring lane's, by shuffle).  A sliding XOR over Q bits then
+// holds, at every shot-END position, the parity of that shot; the end positions are again a periodic mask.  About 35
+// integer instructions per 16 bytes, no shared memory, no alignment requirement on `bits`.
+template <int Q>
+__device__ __forceinline__ unsigned window_xor(unsigned x) {  // bit u of the result = x[u] ^ x[u-1] ^ .. ^ x[u-Q+1]
+  const unsigned w2 = x ^ (x << 1), w4 = w2 ^ (w2 << 2), w8 = w4 ^ (w4 << 4);  // windows of 2, 4, 8 bits
+  unsigned acc = 0;
+  int off = 0;
+  if (Q & 16) { acc ^= w8 ^ (w8 << 8); off += 16; }
+  if (Q & 8) { acc ^= w8 << off; off += 8; }
+  if (Q & 4) { acc ^= w4 << off; off += 4; }
+  if (Q & 2) { acc ^= w2 << off; off += 2; }
+  if (Q & 1) { acc ^= x << off; }
+  return acc;
+}
+__device__ __forceinline__ unsigned compact16(uint4 w) {  // bit t = low bit of byte t of the 16-byte word
+  const unsigned m = 0x01010101u, k = 0x01020408u;
+  const unsigned c0 = ((w.x & m) * k) >> 24, c1 = ((w.y & m) * k) >> 24, c2 = ((w.z & m) * k) >> 24, c3 = ((w.w & m) * k) >> 24;
+  return c0 | (c1 << 4) | (c2 << 8) | (c3 << 12);
+}
+template <int Q>
+struct StreamPat {
+  static constexpr unsigned rep() {
+    unsigned r = 0;
+    for (int k = 0; k * Q < 32; ++k) r |= 1u << (k * Q);
+    return r;
+  }
+  static constexpr unsigned REP = rep();            // 1 at the positions u = 0 (mod Q)
+  static constexpr unsigned END = rep() << (Q - 1); // 1 at the positions u = Q - 1 (mod Q): the last byte of a shot
+};
+
+template <int Q, int G>
+__global__ void __launch_bounds__(256)
+    moments_stream_kernel(int64_t B, int64_t S, const unsigned char* __restrict__ bits,
+                          const uint32_t* __restrict__ colmask, const double* __restrict__ coeff, int prior, MomInv iv,
+                          double* __restrict__ mean, double* __restrict__ var) {
+  static_assert(Q >= 2 && Q <= 16, "a shot reaches at most 15 bytes back into the previous 16-byte word");
+  const int gl = threadIdx.x % G;
+  const int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / G, ngrp = ((int64_t)gridDim.x * blockDim.x) / G;
+  const long long base = (long long)reinterpret_cast<uintptr_t>(bits);
+  const int64_t rounds = (B + ngrp - 1) / ngrp;
+  // the same trip count for every group of the warp (shuffles inside): the most words a setting can touch, in fours
+  const int max_words = (int)((S * Q + 15 + 15) >> 4);
+  const int trips = ((max_words + G - 1) / G + 3) / 4;
+  constexpr int INC = (16 * G) % Q;
+  for (int64_t it = 0; it < rounds; ++it) {
+    const int64_t b = grp + it * ngrp;
+    const bool live = b < B;
+    const unsigned cm = live ? (colmask[b] & ((1u << Q) - 1u)) : 0u;
+    const long long lo = base + (live ? b : 0) * S * Q, hi = live ? lo + S * Q : lo;
+    const unsigned cpat = cm * StreamPat<Q>::REP;  // column pattern along the stream (bits beyond 32 are never used)
+    const long long W0 = lo & ~15LL;
+    const int nwords = live ? (int)(((hi - 1 - W0) >> 4) + 1) : 0;
+    int ph = (int)((W0 + 16LL * gl - lo) % Q);     // phase of byte 0 of this lane's first word (may be before lo)
+    if (ph < 0) ph += Q;
+    unsigned cnt = 0, carry = 0;
+    for (int k4 = 0; k4 < trips; ++k4) {
+      uint4 v[4];
+      unsigned en[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int w = (4 * k4 + u) * G + gl;
+        const long long a = W0 + 16LL * w;
+        v[u] = make_uint4(0u, 0u, 0u, 0u);
+        en[u] = 0u;
+        if (w < nwords) {
+          if (a >= lo && a + 16 <= hi) {
+            v[u] = *reinterpret_cast<const uint4*>(a);
+            en[u] = 0xffffu;
+          } else {  // the first / last word of the setting: shared with its neighbours (or the end of the tensor)
+            v[u] = ld16_inside(a, base, base + B * S * Q);
+            const int b0 = (int)max(lo - a, 0LL), b1 = (int)min(hi - a, 16LL);
+            en[u] = ((1u << b1) - 1u) & ~((1u << b0) - 1u);
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned c = compact16(v[u]) & (cpat >> ph) & en[u];
+        unsigned prev = __shfl_up_sync(0xffffffffu, c, 1, G);
+        if (gl == 0) prev = carry;                      // the word before lane 0's is lane G-1's of the previous step
+        carry = __shfl_sync(0xffffffffu, c, G - 1, G);
+        const unsigned y = window_xor<Q>(prev | (c << 16));
+        cnt += __popc((y >> 16) & (StreamPat<Q>::END >> ph) & en[u]);
+        ph += INC;
+        if (ph >= Q) ph -= Q;
+      }
+    }
+    unsigned long long tot = cnt;
+#pragma unroll
+    for (int o = G / 2; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (live && gl == 0) moments_epilogue(tot, S, cm == 0, coeff[b], prior, iv, mean + b, var + b);
+  }
+}
+
 // Any width up to 32 columns.  One warp per setting: the setting's bytes are staged through shared memory in chunks of
 // whole shots with coalesced, aligned 16-byte loads (4 in flight per lane), then each lane takes the parity of the
 // selected columns of its shots out of shared memory (widths up to 8: word reads + funnel shift + popcount).
@@ -247,8 +349,47 @@ extern "C" int qt_shots_to_obs_moments_batch(int64_t B, int64_t n_shots, int n_q
                                                         mean_out, var_out);                                         \
     }                                                                                                               \
   } while (0)
-  // the SWAR kernels need every shot aligned to its own width in flat addresses
-  const int width = (reinterpret_cast<uintptr_t>(bits) % (uintptr_t)n_qubits == 0) ? n_qubits : 0;
+#define STREAM(Q)                                                                                                   \
+  do {                                                                                                              \
+    const int64_t words = (n_shots * Q + 15) / 16;                                                                  \
+    if (words >= 256) {                                                                                             \
+      const unsigned blocks = (unsigned)std::min<int64_t>((B + 7) / 8, (int64_t)QT_NUM_SMS * 8);                    \
+      moments_stream_kernel<Q, 32><<<blocks, 256, 0, st>>>(B, n_shots, bits, col_mask, coeff, use_beta_prior, iv,   \
+                                                           mean_out, var_out);                                      \
+    } else if (words >= 128) {                                                                                      \
+      const unsigned blocks = (unsigned)std::min<int64_t>((B + 15) / 16, (int64_t)QT_NUM_SMS * 8);                  \
+      moments_stream_kernel<Q, 16><<<blocks, 256, 0, st>>>(B, n_shots, bits, col_mask, coeff, use_beta_prior, iv,   \
+                                                           mean_out, var_out);                                      \
+    } else {                                                                                                        \
+      const unsigned blocks = (unsigned)std::min<int64_t>((B + 31) / 32, (int64_t)QT_NUM_SMS * 8);                  \
+      moments_stream_kernel<Q, 8><<<blocks, 256, 0, st>>>(B, n_shots, bits, col_mask, coeff, use_beta_prior, iv,    \
+                                                          mean_out, var_out);                                       \
+    }                                                                                                               \
+  } while (0)
+  // the SWAR kernels need every shot aligned to its own width in flat addresses; the stream kernel does not
+  const bool pow2 = n_qubits == 1 || n_qubits == 2 || n_qubits == 4 || n_qubits == 8;
+  const bool aligned = reinterpret_cast<uintptr_t>(bits) % (uintptr_t)n_qubits == 0;
+  if (n_qubits >= 2 && n_qubits <= 16 && !(pow2 && aligned)) {
+    switch (n_qubits) {
+      case 2: STREAM(2); break;
+      case 3: STREAM(3); break;
+      case 4: STREAM(4); break;
+      case 5: STREAM(5); break;
+      case 6: STREAM(6); break;
+      case 7: STREAM(7); break;
+      case 8: STREAM(8); break;
+      case 9: STREAM(9); break;
+      case 10: STREAM(10); break;
+      case 11: STREAM(11); break;
+      case 12: STREAM(12); break;
+      case 13: STREAM(13); break;
+      case 14: STREAM(14); break;
+      case 15: STREAM(15); break;
+      default: STREAM(16); break;
+    }
+    return qt_check_launch("moments_stream_kernel");
+  }
+  const int width = aligned ? n_qubits : 0;
   switch (width) {
     case 1: SWAR(1); break;
     case 2: SWAR(2); break;
@@ -259,6 +400,7 @@ extern "C" int qt_shots_to_obs_moments_batch(int64_t B, int64_t n_shots, int n_q
                                                    mean_out, var_out);
   }
 #undef SWAR
+#undef STREAM
   return qt_check_launch("moments_kernel");
 }
 

@@ -19,10 +19,10 @@ def _bits(rng, b, s, q):
     return (rng.random((b, s, q)) < p).astype(np.uint8)
 
 
-@pytest.mark.parametrize("q", [1, 2, 3, 4, 5, 8, 11])
+@pytest.mark.parametrize("q", [1, 2, 3, 4, 5, 6, 7, 8, 9, 11, 13, 16, 17])
 @pytest.mark.parametrize("s", [1, 37, 500, 1000])
 def test_shots_to_obs_moments_batch(torch, q, s):
-    """Every width (SWAR kernels for 1/2/4/8 columns, byte kernel otherwise), shot counts that leave the settings
+    """Every width (SWAR kernels for 1/2/4/8 columns, compacting stream kernel for the other widths up to 16, byte kernel beyond), shot counts that leave the settings
     unaligned to the 16-byte words, all column subsets incl. the identity term, both estimators."""
     from forest_benchmarking_b200 import observable_estimation as oe
     rng = np.random.default_rng(100 * q + s)
