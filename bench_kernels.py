@@ -179,7 +179,7 @@ def next_rows(torch, peak, budget_bytes=4 << 30):
     ex = torch.rand((b, k), dtype=torch.float64, device="cuda", generator=g) * 1.2 - .6
     cnt = torch.full((b, k), 1000.0, dtype=torch.float64, device="cuda")
     ms = _time(torch, lambda: tm.state_log_likelihood_batch(plan, rho, ex, cnt))
-    rows.append(_row("log_likelihood_kernel<2> (state_log_likelihood)", b, 16 * 4 ** n + 16 * k + 8, ms, peak))
+    rows.append(_row("log_likelihood_packed_kernel<2> (state_log_likelihood; 30 log10 per experiment: FP64-bound)", b, 16 * 4 ** n + 16 * k + 8, ms, peak))
     del rho, ex, cnt
     for n, b in ((1, 1 << 20), (2, 1 << 16), (3, 1 << 10)):
         pplan = tm.PgdbPlan.complete(n)
