@@ -17,7 +17,8 @@ __all__ = ["vec", "unvec", "kraus2choi", "kraus2superop", "kraus2pauli_liouville
            "chi2superop", "chi2kraus", "choi2chi", "superop2chi", "pauli_liouville2chi", "superop2kraus",
            "pauli_liouville2kraus", "kraus2chi_batch", "chi2choi_batch", "kraus2choi_batch", "kraus2superop_batch", "reshuffle_batch",
            "superop2pauli_liouville_batch", "pauli_liouville2superop_batch",
-           "choi2pauli_liouville_batch", "pauli_liouville2choi_batch"]
+           "choi2pauli_liouville_batch", "pauli_liouville2choi_batch", "pauli2computational_basis_matrix",
+           "computational2pauli_basis_matrix"]
 
 
 def vec(matrix: np.ndarray) -> np.ndarray:
@@ -32,6 +33,22 @@ def unvec(vector: np.ndarray, shape: Optional[Tuple[int, int]] = None) -> np.nda
         dim = int(np.sqrt(vector.size))
         shape = dim, dim
     return vector.reshape(*shape).T
+
+
+def pauli2computational_basis_matrix(dim) -> np.ndarray:
+    """sum_k |sigma_k>> <k|: column k is vec(sigma_k), unnormalised Paulis in canonical order (reference :374-408).
+    Host-side constant; the device kernels never materialise it (a Pauli is a pair of bit masks there)."""
+    from ..synthetic import pauli_stack
+    n = int(round(np.log2(dim)))
+    if 2 ** n != dim or n < 1:
+        raise ValueError("dim must be a power of two")
+    ops = pauli_stack(n)
+    return np.ascontiguousarray(ops.transpose(0, 2, 1).reshape(4 ** n, dim * dim).T.astype(complex))
+
+
+def computational2pauli_basis_matrix(dim) -> np.ndarray:
+    """(1/dim) sum_k |k> <<sigma_k|: the inverse of pauli2computational_basis_matrix (reference :411-438)."""
+    return pauli2computational_basis_matrix(dim).conj().T / dim
 
 
 def _check_c128(t, ndim):

@@ -78,3 +78,18 @@ def test_bootstrap_resampling_consumes_the_reference_rng_stream():
     np.random.seed(5)
     want = np.stack([orc.resample_expectations_with_beta(ex[0], cnt[0]) for _ in range(3)])
     assert np.array_equal(got, want)
+
+
+def test_basis_change_matrices_match_the_oracle():
+    """pauli2computational_basis_matrix / computational2pauli_basis_matrix (superoperator_transformations.py:374-438):
+    host-side constants, identical to the oracle's (which is pinned against the reference), mutually inverse."""
+    from oracle import ref_numpy as orc
+    from forest_benchmarking_b200.operator_tools import superoperator_transformations as st
+    for d in (2, 4, 8):
+        p2c = st.pauli2computational_basis_matrix(d)
+        assert p2c.dtype == np.complex128 and np.array_equal(p2c, orc.pauli2computational_basis_matrix(d))
+        c2p = st.computational2pauli_basis_matrix(d)
+        assert np.array_equal(c2p, orc.computational2pauli_basis_matrix(d))
+        assert np.allclose(c2p @ p2c, np.eye(d * d), atol=1e-15)
+    with pytest.raises(ValueError):
+        st.pauli2computational_basis_matrix(3)
