@@ -186,7 +186,8 @@ def next_rows(torch, peak, budget_bytes=4 << 30):
         ex = torch.rand((b, pplan.S), dtype=torch.float64, device="cuda", generator=g) * 1.2 - .6
         out = torch.empty((b, 4 ** n, 4 ** n), dtype=torch.complex128, device="cuda")
         ms = _time(torch, lambda: tm.linear_inv_process_estimate_batch(pplan, ex, out=out))
-        rows.append(_row(f"linproc_kernel<{n}> (linear_inv_process_estimate, complete Pauli design)", b,
+        name = f"linproc_kernel<{n}>" if n == 1 else f"linproc_accum_kernel<{n}> + linproc_kernel<{n}> (two launches)"
+        rows.append(_row(f"{name} (linear_inv_process_estimate, complete Pauli design)", b,
                          8 * pplan.S + 16 * 16 ** n, ms, peak))
         ms = _time(torch, lambda: pj.proj_choi_to_unitary_batch(out), reps=3, warmup=1)
         rows.append(_row(f"proj_unitary_kernel<{n}> (proj_choi_to_unitary; eigensolver: FP64-bound)", b,

@@ -599,7 +599,8 @@ extern "C" int qt_pgdb_process_batch(const qt_pgdb_plan* p, int64_t B, const dou
 // R[k, :] = sum_s w_s e_s, adds the identity term (R[0, 0] += 1, the eye(d^2)/d of the reference) and goes
 // PTM -> Choi in shared memory.  Checked against the oracle's dense pinv to 1e-14.
 // =============================================================================================
-template <int N>
+// FROM_X: the PTM (at butterfly positions, real parts) is already in choi_out, left there by linproc_accum_kernel
+template <int N, bool FROM_X>
 __global__ void __launch_bounds__(PgdbCfg<N>::NT * PgdbCfg<N>::GPB)
     linproc_kernel(int64_t B, int S, const int* __restrict__ slot_ptr, const int* __restrict__ member_col,
                    const double* __restrict__ member_w, const double* __restrict__ expect, cplx* __restrict__ choi_out) {
@@ -610,18 +611,78 @@ __global__ void __launch_bounds__(PgdbCfg<N>::NT * PgdbCfg<N>::GPB)
   const int gib = threadIdx.x / C::NT, tid = threadIdx.x % C::NT;
   cplx* X = reinterpret_cast<cplx*>(smem_raw) + (size_t)G::MP * gib;
   for (int64_t b = (int64_t)blockIdx.x * C::GPB + gib; b < B; b += (int64_t)gridDim.x * C::GPB) {
-    const double* ex = expect + b * S;
-    for (int e = tid; e < MM; e += C::NT) {
-      const int k = e / M, j = e % M;
-      double acc = (e == 0) ? 1.0 : 0.0;
-      for (int m = slot_ptr[k]; m < slot_ptr[k + 1]; ++m) acc = fma(member_w[(int64_t)m * M + j], ex[member_col[m]], acc);
-      X[pauli_to_pos(k, N) * LD + pauli_to_pos(j, N)] = cmake(acc, 0.0);
+    if constexpr (FROM_X) {
+      const cplx* src = choi_out + b * MM;
+      for (int e = tid; e < MM; e += C::NT) X[(e / M) * LD + e % M] = src[e];
+    } else {
+      const double* ex = expect + b * S;
+      for (int e = tid; e < MM; e += C::NT) {
+        const int k = e / M, j = e % M;
+        double acc = (e == 0) ? 1.0 : 0.0;
+        for (int m = slot_ptr[k]; m < slot_ptr[k + 1]; ++m) acc = fma(member_w[(int64_t)m * M + j], ex[member_col[m]], acc);
+        X[pauli_to_pos(k, N) * LD + pauli_to_pos(j, N)] = cmake(acc, 0.0);
+      }
     }
     C::Sync::sync();
     Pgdb<N>::pl_positions_to_choi(X, tid);
     cplx* dst = choi_out + b * MM;
     for (int e = tid; e < MM; e += C::NT) dst[e] = cscale(X[(e / M) * LD + e % M], 1.0 / D);
     C::Sync::sync();
+  }
+}
+
+// n = 2, 3: the accumulation R[k, :] = sum_s w_s e_s re-reads the whole weight table (n = 2: 69 KB, n = 3: 7 MB) for
+// every experiment when one block works on one experiment (0.07 / 0.02 of the HBM roof).  Here a block takes EB
+// experiments at once: thread (kg, j) walks the members of slot k = k0 + kg, loads w_s[j] ONCE and applies it to the EB
+// expectation values of that setting (staged through shared memory in chunks of CH members, read back as broadcasts).
+// The PTM goes to choi_out (butterfly positions, real); linproc_kernel<N, true> turns it into the Choi matrix in place.
+template <int N, int EB, int CH>
+__global__ void __launch_bounds__(256)
+    linproc_accum_kernel(int64_t B, int S, const int* __restrict__ slot_ptr, const int* __restrict__ member_col,
+                         const double* __restrict__ member_w, const double* __restrict__ expect, cplx* __restrict__ ptm_out) {
+  constexpr int M = 1 << (2 * N), MM = M * M, KG = 256 / M;  // KG slots per pass
+  static_assert(M <= 256 && EB % 2 == 0, "one thread per (slot of the pass, column)");
+  extern __shared__ __align__(16) double et[];  // [KG][CH][EB]
+  const int tid = threadIdx.x, j = tid % M, kg = tid / M;
+  const int64_t b0 = (int64_t)blockIdx.x * EB;
+  const int nb = (int)min((int64_t)EB, B - b0);
+  {
+    const int k0 = blockIdx.y * KG;  // one pass of KG slots per block: (B / EB) x (M / KG) blocks fill the machine at small B
+    const int k = k0 + kg, m_lo = slot_ptr[k], len = slot_ptr[k + 1] - m_lo;
+    int lenmax = 0;
+    for (int kk = 0; kk < KG; ++kk) lenmax = max(lenmax, slot_ptr[k0 + kk + 1] - slot_ptr[k0 + kk]);
+    double acc[EB];
+#pragma unroll
+    for (int bb = 0; bb < EB; ++bb) acc[bb] = 0.0;
+    for (int c0 = 0; c0 < lenmax; c0 += CH) {
+      __syncthreads();
+      const int clen = min(CH, lenmax - c0);  // members actually present in this chunk (the longest slot of the pass)
+      for (int idx = tid; idx < KG * clen * EB; idx += 256) {
+        const int bb = idx % EB, mm = (idx / EB) % clen, kk = idx / (EB * clen);
+        const int lo = slot_ptr[k0 + kk], ln = slot_ptr[k0 + kk + 1] - lo;
+        double v = 0.0;
+        if (c0 + mm < ln && bb < nb) v = expect[(b0 + bb) * S + member_col[lo + c0 + mm]];
+        et[(kk * CH + mm) * EB + bb] = v;
+      }
+      __syncthreads();
+      const int cnt = min(CH, len - c0);
+      const double* erow = et + (size_t)kg * CH * EB;
+#pragma unroll 8
+      for (int mm = 0; mm < cnt; ++mm) {  // unrolled: eight independent weight loads in flight (L2 latency)
+        const double wv = member_w[(int64_t)(m_lo + c0 + mm) * M + j];
+#pragma unroll
+        for (int bb = 0; bb < EB; bb += 2) {
+          const double2 e2 = *reinterpret_cast<const double2*>(erow + mm * EB + bb);
+          acc[bb] = fma(wv, e2.x, acc[bb]);
+          acc[bb + 1] = fma(wv, e2.y, acc[bb + 1]);
+        }
+      }
+    }
+    const int pos = pauli_to_pos(k, N) * M + pauli_to_pos(j, N);
+    const double idt = (k == 0 && j == 0) ? 1.0 : 0.0;  // the eye(d^2) / d term of the reference
+#pragma unroll
+    for (int bb = 0; bb < EB; ++bb)
+      if (bb < nb) ptm_out[(b0 + bb) * MM + pos] = cmake(acc[bb] + idt, 0.0);
   }
 }
 
@@ -730,10 +791,24 @@ static int launch_linproc(const qt_pgdb_plan* p, int64_t B, const double* expect
   const size_t smem = sizeof(cplx) * C::G::MP * C::GPB;
   const int per_sm = (N >= 3) ? 3 : 8;
   const int64_t grid = std::min<int64_t>((B + C::GPB - 1) / C::GPB, (int64_t)QT_NUM_SMS * per_sm);
-  QT_CUDA(cudaFuncSetAttribute(linproc_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  linproc_kernel<N><<<(unsigned)grid, C::NT * C::GPB, smem, st>>>(B, p->S, p->d_li_slot_ptr, p->d_li_member_col,
-                                                                  p->d_li_member_w, expect, (cplx*)choi_out);
-  return qt_check_launch("linproc_kernel");
+  if constexpr (N >= 2) {
+    constexpr int EB = 8, CH = 64, KG = 256 >> (2 * N);
+    const size_t smem_a = sizeof(double) * KG * CH * EB;
+    QT_CUDA(cudaFuncSetAttribute(linproc_accum_kernel<N, EB, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_a));
+    linproc_accum_kernel<N, EB, CH><<<dim3((unsigned)((B + EB - 1) / EB), (1u << (2 * N)) / KG), 256, smem_a, st>>>(
+        B, p->S, p->d_li_slot_ptr, p->d_li_member_col, p->d_li_member_w, expect, (cplx*)choi_out);
+    int rc = qt_check_launch("linproc_accum_kernel");
+    if (rc) return rc;
+    QT_CUDA(cudaFuncSetAttribute(linproc_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    linproc_kernel<N, true><<<(unsigned)grid, C::NT * C::GPB, smem, st>>>(B, p->S, p->d_li_slot_ptr, p->d_li_member_col,
+                                                                          p->d_li_member_w, expect, (cplx*)choi_out);
+    return qt_check_launch("linproc_kernel");
+  } else {
+    QT_CUDA(cudaFuncSetAttribute(linproc_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    linproc_kernel<N, false><<<(unsigned)grid, C::NT * C::GPB, smem, st>>>(B, p->S, p->d_li_slot_ptr, p->d_li_member_col,
+                                                                           p->d_li_member_w, expect, (cplx*)choi_out);
+    return qt_check_launch("linproc_kernel");
+  }
 }
 
 extern "C" int qt_linear_inv_process_batch(qt_pgdb_plan* p, int64_t B, const double* expect, void* choi_out,
