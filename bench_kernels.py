@@ -122,7 +122,7 @@ def convert_rows(torch, peak, batch=16384, nk=2, budget_bytes=6 << 30):
         # choi2kraus: n <= 3 shared-memory eigensolver (FP64-bound); n = 4, 5: certified low-rank fast path (three scans of the
         # matrix) for these 2-Kraus-operator channels, general one-sided Jacobi solver for anything it cannot certify
         ms = _time(torch, lambda: st.choi2kraus_batch(a), reps=3, warmup=1)
-        label = "eigensolver: FP64-bound, GB/s for reference only" if n <= 3 else "rank-2 inputs: certified low-rank path"
+        label = "eigensolver: FP64-bound, GB/s for reference only" if n <= 2 else "rank-2 inputs: certified low-rank path"
         rows.append(_row(f"choi2kraus n={n} ({label})", chunk, 16 * m * m + 16 * m * m + 8 * m, ms, peak,
                          {"chunks_for_batch": reps, "batch_ms": round(ms * reps, 3)}))
         if n == 4:

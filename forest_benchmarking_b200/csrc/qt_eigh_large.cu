@@ -203,10 +203,11 @@ __device__ __forceinline__ double lr_rand(unsigned a, unsigned b) {  // determin
 }
 
 template <int M>
-__global__ void __launch_bounds__(M == 256 ? 256 : 1024)
+__global__ void __launch_bounds__(M <= 256 ? M : 1024)
     choi2kraus_lowrank_kernel(int64_t B, const cplx* __restrict__ in, double tol, double* __restrict__ evals_out,
                               cplx* __restrict__ kraus_out, int* __restrict__ count_out) {
-  constexpr int KC = 8, NT = M, NW = NT / 32, D = (M == 256) ? 16 : 32;
+  constexpr int KC = 8, NT = M, NW = NT / 32, D = (M == 64) ? 8 : (M == 256) ? 16 : 32;
+  static_assert(M == 64 || M == 256 || M == 1024, "one thread per row, whole warps");
   extern __shared__ __align__(16) unsigned char raw[];
   cplx* Wm = reinterpret_cast<cplx*>(raw);            // [M][KC]: Omega, then Q
   cplx* Bs = Wm + (size_t)M * KC;                     // [KC][KC]
@@ -585,6 +586,16 @@ extern "C" int qt_choi2kraus_large_batch(int n, int64_t B, const void* choi, dou
     choi2kraus_large_kernel<1024><<<grid, 1024, 0, st>>>(B, (const cplx*)choi, tol, evals_out, (cplx*)kraus_out,
                                                           count_out, (cplx*)workspace, sweeps_out, 1);
   return qt_check_launch("choi2kraus_large_kernel");
+}
+
+// n = 3 (64 x 64): the same certified low-rank path in front of the shared-memory Jacobi kernel of qt_project.cu, which
+// then only visits the items left at count_out[b] = -1.  55 ms -> ~1 ms per 16384 two-Kraus-operator channels.
+int qt_choi2kraus_lowrank64(int64_t B, const void* choi, double tol, double* evals_out, void* kraus_out,
+                            int32_t* count_out, cudaStream_t st) {
+  const size_t smem = sizeof(cplx) * (64 * 8 + 2 * 64) + sizeof(double) * (8 + JacobiScratch<8>::doubles + 2 * 32 + 8);
+  const unsigned grid = (unsigned)std::min<int64_t>(B, (int64_t)QT_NUM_SMS * 16);
+  choi2kraus_lowrank_kernel<64><<<grid, 64, smem, st>>>(B, (const cplx*)choi, tol, evals_out, (cplx*)kraus_out, count_out);
+  return qt_check_launch("choi2kraus_lowrank_kernel");
 }
 
 // ---- n = 4, 5 projections: host side -------------------------------------------------------------------------

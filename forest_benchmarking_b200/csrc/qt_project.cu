@@ -9,6 +9,8 @@
 
 // n = 4, 5 (matrices that do not fit shared memory): qt_eigh_large.cu
 int qt_large_proj_cp(int n, int64_t B, const void* in, void* out, void* ws, int64_t ws_bytes, cudaStream_t st);
+int qt_choi2kraus_lowrank64(int64_t B, const void* choi, double tol, double* evals_out, void* kraus_out,
+                            int32_t* count_out, cudaStream_t st);
 int qt_large_tp_correction(int n, int64_t B, const void* in, void* out, int make_tp, cudaStream_t st);
 int64_t qt_large_physical_workspace_bytes(int n, int64_t B);
 int qt_large_proj_physical(int n, int64_t B, const void* in, void* out, int make_tp, void* ws, int64_t ws_bytes,
@@ -541,7 +543,7 @@ __global__ void __launch_bounds__(ProjCfg<N>::NT * ProjCfg<N>::GPB)
 template <int N>
 __global__ void __launch_bounds__(ProjCfg<N>::NT * ProjCfg<N>::GPB)
     choi2kraus_kernel(int64_t B, const cplx* __restrict__ in, double tol, double* __restrict__ evals_out,
-                      cplx* __restrict__ kraus_out, int* __restrict__ count_out) {
+                      cplx* __restrict__ kraus_out, int* __restrict__ count_out, int skip_done) {
   using C = ProjCfg<N>;
   using G = typename C::G;
   constexpr int M = G::M, D = G::D, LD = G::LD;
@@ -555,6 +557,7 @@ __global__ void __launch_bounds__(ProjCfg<N>::NT * ProjCfg<N>::GPB)
   int* rank = pos + M;                                                       // [M]
   const int64_t b = (int64_t)blockIdx.x * C::GPB + gib;
   if (b >= B) return;
+  if (skip_done && count_out[b] >= 0) return;  // finished by the certified low-rank path (uniform over the group)
   const cplx* src = in + b * G::MM;
   for (int e = tid; e < G::MM; e += C::NT) {
     const int r = e / M, c = e % M;
@@ -598,9 +601,15 @@ static int launch_choi2kraus(int64_t B, const void* in, double tol, double* eval
                              cudaStream_t st) {
   using C = ProjCfg<N>;
   const size_t smem = C::group_smem * C::GPB;
+  int skip_done = 0;
+  if constexpr (N == 3) {  // channels with <= 8 Kraus operators never reach the 64 x 64 Jacobi solver
+    const int rc = qt_choi2kraus_lowrank64(B, in, tol, evals, kraus, count, st);
+    if (rc) return rc;
+    skip_done = 1;
+  }
   QT_CUDA(cudaFuncSetAttribute(choi2kraus_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   choi2kraus_kernel<N><<<(unsigned)((B + C::GPB - 1) / C::GPB), C::NT * C::GPB, smem, st>>>(
-      B, (const cplx*)in, tol, evals, (cplx*)kraus, count);
+      B, (const cplx*)in, tol, evals, (cplx*)kraus, count, skip_done);
   return qt_check_launch("choi2kraus_kernel");
 }
 
