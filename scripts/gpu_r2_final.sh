@@ -23,5 +23,8 @@ python scripts/summarize_ncu.py full gpurun_out/${T}_prof_mle_quad.ncu-rep gpuru
 timeout 900 ncu --set full --clock-control none -k regex:pgdb_kernel -s 1 -c 1 -o gpurun_out/${T}_prof_pgdb3 -f python bench.py --workload pgdb3q --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu_pgdb.log 2>&1
 python scripts/summarize_ncu.py full gpurun_out/${T}_prof_pgdb3.ncu-rep gpurun_out/${T}_ncu_pgdb3.md pgdb_kernel
 timeout 600 ncu --set full --clock-control none -k regex:"fidelity_tri_kernel" -s 3 -c 1 -o gpurun_out/${T}_prof_misc -f python bench.py --workload distances --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu_misc.log 2>&1
-python scripts/make_traffic_json.py gpurun_out/${T}_traffic.json "mle_quad_kernel=gpurun_out/${T}_prof_mle_quad.ncu-rep:mle_quad" "pgdb_kernel<3>=gpurun_out/${T}_prof_pgdb3.ncu-rep:pgdb_kernel" "fidelity_tri_kernel<16>=gpurun_out/${T}_prof_misc.ncu-rep:fidelity_tri" | head -30
+timeout 600 ncu --set full --clock-control none -k regex:mle_warp_kernel -s 1 -c 1 -o gpurun_out/${T}_prof_mle3q -f python bench.py --workload mle3q --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/${T}_ncu_mle3q.log 2>&1
+python scripts/summarize_ncu.py full gpurun_out/${T}_prof_mle3q.ncu-rep gpurun_out/${T}_ncu_mle_warp3.md mle_warp
+python scripts/summarize_ncu.py full gpurun_out/${T}_prof_misc.ncu-rep gpurun_out/${T}_ncu_fidelity_tri.md fidelity_tri
+python scripts/make_traffic_json.py gpurun_out/${T}_traffic.json "mle_quad_kernel=gpurun_out/${T}_prof_mle_quad.ncu-rep:mle_quad" "pgdb_kernel<3>=gpurun_out/${T}_prof_pgdb3.ncu-rep:pgdb_kernel" "fidelity_tri_kernel<16>=gpurun_out/${T}_prof_misc.ncu-rep:fidelity_tri" "mle_warp_kernel<3>=gpurun_out/${T}_prof_mle3q.ncu-rep:mle_warp" | head -30
 for w in streaming convert next; do timeout 900 python bench.py --workload $w > gpurun_out/${T}_bench_$w.json 2> gpurun_out/${T}_bench_$w.err; echo "$w rc=$?"; done
