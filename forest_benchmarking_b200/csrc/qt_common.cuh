@@ -137,6 +137,11 @@ __host__ __device__ __forceinline__ constexpr int pauli_from_masks(int x, int z,
   return idx;
 }
 
+// Thread-per-item kernels stage 128 items through shared memory element-major: tile[element * QT_TS + item].  With a
+// stride of exactly 128 complex numbers the coalesced side of the transposition (consecutive lanes = consecutive
+// elements of one item) puts a whole quarter warp on the same banks (8-way conflict); 129 spreads it over all 32.
+constexpr int QT_TS = 129;
+
 // ---------------------------------------------------------------------------------------------
 // warp reductions
 // ---------------------------------------------------------------------------------------------

@@ -686,19 +686,19 @@ __global__ void mle_step_kernel(int64_t B, int K, const double* __restrict__ exp
   // expect_canon: [S-1, B] canonical-order expectations, item-minor (coalesced); K = S-1 results.
   constexpr int D = 1 << N, S = 1 << (2 * N), DD = D * D;
   constexpr double TINY = 2.2250738585072014e-308;
-  __shared__ cplx tile[128 * DD];
+  __shared__ cplx tile[QT_TS * DD];
   const int tid = threadIdx.x;
   const int64_t b0 = (int64_t)blockIdx.x * 128;
   const int nb = (int)min((int64_t)128, B - b0);
   // coalesced load of nb matrices (16 B per element, consecutive threads -> consecutive elements)
-  for (int e = tid; e < nb * DD; e += 128) tile[(e % DD) * 128 + (e / DD)] = rho_in[b0 * DD + e];
+  for (int e = tid; e < nb * DD; e += 128) tile[(e % DD) * QT_TS + (e / DD)] = rho_in[b0 * DD + e];
   __syncthreads();
   if (tid < nb) {
     cplx r[D][D];
 #pragma unroll
     for (int i = 0; i < D; ++i)
 #pragma unroll
-      for (int j = 0; j < D; ++j) r[i][j] = tile[(i * D + j) * 128 + tid];
+      for (int j = 0; j < D; ++j) r[i][j] = tile[(i * D + j) * QT_TS + tid];
     double w[S];
     double w0 = 0.0;
     w[0] = 0.0;
@@ -764,10 +764,10 @@ __global__ void mle_step_kernel(int64_t B, int K, const double* __restrict__ exp
 #pragma unroll
     for (int i = 0; i < D; ++i)
 #pragma unroll
-      for (int c = 0; c < D; ++c) tile[(i * D + c) * 128 + tid] = cscale(r[i][c], inv);
+      for (int c = 0; c < D; ++c) tile[(i * D + c) * QT_TS + tid] = cscale(r[i][c], inv);
   }
   __syncthreads();
-  for (int e = tid; e < nb * DD; e += 128) rho_out[b0 * DD + e] = tile[(e % DD) * 128 + (e / DD)];
+  for (int e = tid; e < nb * DD; e += 128) rho_out[b0 * DD + e] = tile[(e % DD) * QT_TS + (e / DD)];
 }
 
 // n = 2 with the Hermitian-packed arithmetic of mle_reg_kernel (rho is a state: its upper triangle is read): ~750
@@ -777,11 +777,11 @@ __global__ void __launch_bounds__(128) mle_step_herm_kernel(int64_t B, int K, co
                                                             cplx* __restrict__ rho_out) {
   constexpr int N = 2, D = 4, S = 16, DD = 16;
   constexpr double TINY = 2.2250738585072014e-308;
-  __shared__ cplx tile[128 * DD];
+  __shared__ cplx tile[QT_TS * DD];
   const int tid = threadIdx.x;
   const int64_t b0 = (int64_t)blockIdx.x * 128;
   const int nb = (int)min((int64_t)128, B - b0);
-  for (int e = tid; e < nb * DD; e += 128) tile[(e % DD) * 128 + (e / DD)] = rho_in[b0 * DD + e];
+  for (int e = tid; e < nb * DD; e += 128) tile[(e % DD) * QT_TS + (e / DD)] = rho_in[b0 * DD + e];
   __syncthreads();
   if (tid < nb) {
     Herm<D> rho;
@@ -789,7 +789,7 @@ __global__ void __launch_bounds__(128) mle_step_herm_kernel(int64_t B, int K, co
     for (int r = 0; r < D; ++r)
 #pragma unroll
       for (int c = r; c < D; ++c) {
-        const cplx e = tile[(r * D + c) * 128 + tid];
+        const cplx e = tile[(r * D + c) * QT_TS + tid];
         if (r == c) {
           rho.h[r][r] = e.x;
         } else {
@@ -896,10 +896,10 @@ __global__ void __launch_bounds__(128) mle_step_herm_kernel(int64_t B, int K, co
 #pragma unroll
     for (int r = 0; r < D; ++r)
 #pragma unroll
-      for (int c = 0; c < D; ++c) tile[(r * D + c) * 128 + tid] = cmake(nw.re(r, c) * inv, nw.im(r, c) * inv);
+      for (int c = 0; c < D; ++c) tile[(r * D + c) * QT_TS + tid] = cmake(nw.re(r, c) * inv, nw.im(r, c) * inv);
   }
   __syncthreads();
-  for (int e = tid; e < nb * DD; e += 128) rho_out[b0 * DD + e] = tile[(e % DD) * 128 + (e / DD)];
+  for (int e = tid; e < nb * DD; e += 128) rho_out[b0 * DD + e] = tile[(e % DD) * QT_TS + (e / DD)];
 }
 
 // =============================================================================================

@@ -179,23 +179,23 @@ __device__ __forceinline__ void rot4(double (&d)[4], cplx (&o)[4][4], cplx (&v)[
 
 __global__ void __launch_bounds__(128) proj_cp4_thread_kernel(int64_t B, const cplx* __restrict__ in,
                                                               cplx* __restrict__ out) {
-  __shared__ cplx tile[16 * 128];  // element-major: tile[e * 128 + item] -> conflict-free per-thread access
+  __shared__ cplx tile[16 * QT_TS];  // element-major: tile[e * QT_TS + item] -> conflict-free per-thread access, padded stride for the transposing side
   const int tid = threadIdx.x;
   const int64_t b0 = (int64_t)blockIdx.x * 128;
   const int nb = (int)min((int64_t)128, B - b0);
-  for (int e = tid; e < nb * 16; e += 128) tile[(e % 16) * 128 + e / 16] = in[b0 * 16 + e];
+  for (int e = tid; e < nb * 16; e += 128) tile[(e % 16) * QT_TS + e / 16] = in[b0 * 16 + e];
   __syncthreads();
   if (tid < nb) {
     double d[4];
     cplx o[4][4], v[4][4];
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
-      d[r] = tile[(r * 4 + r) * 128 + tid].x;
+      d[r] = tile[(r * 4 + r) * QT_TS + tid].x;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         v[r][c] = cmake(r == c ? 1.0 : 0.0, 0.0);
         if (r < c) {  // Hermitian part (C + C^dagger) / 2, project_superoperators.py:30
-          const cplx x = tile[(r * 4 + c) * 128 + tid], y = tile[(c * 4 + r) * 128 + tid];
+          const cplx x = tile[(r * 4 + c) * QT_TS + tid], y = tile[(c * 4 + r) * QT_TS + tid];
           o[r][c] = cmake(0.5 * (x.x + y.x), 0.5 * (x.y - y.y));
         }
       }
@@ -227,12 +227,12 @@ __global__ void __launch_bounds__(128) proj_cp4_thread_kernel(int64_t B, const c
 #pragma unroll
         for (int k = 0; k < 4; ++k) cfma_conj(acc, cscale(v[r][k], fmax(d[k], 0.0)), v[c][k]);
         if (r == c) acc.y = 0.0;
-        tile[(r * 4 + c) * 128 + tid] = acc;
-        if (r != c) tile[(c * 4 + r) * 128 + tid] = cconj(acc);
+        tile[(r * 4 + c) * QT_TS + tid] = acc;
+        if (r != c) tile[(c * 4 + r) * QT_TS + tid] = cconj(acc);
       }
   }
   __syncthreads();
-  for (int e = tid; e < nb * 16; e += 128) out[b0 * 16 + e] = tile[(e % 16) * 128 + e / 16];
+  for (int e = tid; e < nb * 16; e += 128) out[b0 * 16 + e] = tile[(e % 16) * QT_TS + e / 16];
 }
 
 // ---- TP / TNI: streaming kernel, several items per block for small n --------------------------------
