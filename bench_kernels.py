@@ -72,7 +72,8 @@ def streaming_rows(torch, peak, budget_bytes=2 << 30):
         ms = _time(torch, lambda: pj.proj_choi_to_trace_preserving_batch(c, out=out))
         rows.append(_row(f"proj_tp_kernel<{n}> (proj_choi_to_trace_preserving)", b, 32 * m * m, ms, peak))
         ms = _time(torch, lambda: pj.proj_choi_to_trace_non_increasing_batch(c, out=out))
-        rows.append(_row(f"proj_tp_kernel<{n}> TNI (proj_choi_to_trace_non_increasing)", b, 32 * m * m, ms, peak))
+        tni = "tni_fused1_kernel (one pass, thread per item)" if n == 1 else f"tni_correction_kernel<{n}> + tni_apply_kernel<{n}> (two passes)"
+        rows.append(_row(f"{tni} (proj_choi_to_trace_non_increasing)", b, 32 * m * m, ms, peak))
         if n == 1:
             ms = _time(torch, lambda: pj.proj_choi_to_completely_positive_batch(c, out=out))
             rows.append(_row("proj_cp_kernel<1> (proj_choi_to_completely_positive, 4x4)", b, 32 * m * m, ms, peak))

@@ -467,6 +467,59 @@ __global__ void __launch_bounds__(N <= 2 ? 128 : 256)
   }
 }
 
+// n = 1 in ONE pass: a 4 x 4 Choi matrix is 16 registers of one thread (128 items per block through the padded
+// transposition tile), its 2 x 2 partial trace is diagonalised by a single rotation, and the corrected matrix goes
+// straight back out: 512 bytes of traffic per item instead of the ~900 of the two-pass route (the correction parked in
+// out[b] cost a quarter of a read and of a write on top of the two full reads).
+__global__ void __launch_bounds__(128) tni_fused1_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out) {
+  constexpr int D = 2, M = 4;
+  __shared__ cplx tile[16 * QT_TS];
+  const int tid = threadIdx.x;
+  for (int64_t b0 = (int64_t)blockIdx.x * 128; b0 < B; b0 += (int64_t)gridDim.x * 128) {
+    const int nb = (int)min((int64_t)128, B - b0);
+    for (int e = tid; e < nb * 16; e += 128) tile[(e % 16) * QT_TS + e / 16] = in[b0 * 16 + e];
+    __syncthreads();
+    if (tid < nb) {
+      cplx pt[4][4];
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int c = 0; c < D; ++c)
+          pt[a][c] = cadd(tile[((a * D) * M + c * D) * QT_TS + tid], tile[((a * D + 1) * M + c * D + 1) * QT_TS + tid]);
+      double dg[4];
+      cplx o[4][4], v[4][4];
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        dg[a] = (a < D) ? pt[a][a].x : 0.0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          v[a][c] = cmake(a == c ? 1.0 : 0.0, 0.0);
+          o[a][c] = cmake(0.0, 0.0);
+          if (a < c && c < D) o[a][c] = cmake(0.5 * (pt[a][c].x + pt[c][a].x), 0.5 * (pt[a][c].y - pt[c][a].y));
+        }
+      }
+      rot4<0, 1>(dg, o, v);  // a 2x2 Hermitian matrix is diagonalised by one rotation
+#pragma unroll
+      for (int a = 0; a < D; ++a)
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          cplx acc = cmake(0.0, 0.0);
+#pragma unroll
+          for (int k = 0; k < D; ++k) cfma_conj(acc, cscale(v[a][k], fmin(dg[k], 1.0)), v[c][k]);
+          const cplx E = cscale(csub(pt[a][c], acc), 1.0 / D);
+#pragma unroll
+          for (int bb = 0; bb < D; ++bb) {  // out = in - kron(E, I): elements ((a bb), (c bb))
+            const int idx = ((a * D + bb) * M + c * D + bb) * QT_TS + tid;
+            tile[idx] = csub(tile[idx], E);
+          }
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < nb * 16; e += 128) out[b0 * 16 + e] = tile[(e % 16) * QT_TS + e / 16];
+    __syncthreads();
+  }
+}
+
 template <int N>
 __global__ void __launch_bounds__(256)
     tni_apply_kernel(int64_t B, const cplx* __restrict__ in, cplx* __restrict__ out, int items_per_block) {
@@ -656,6 +709,11 @@ static int launch_tp(int64_t B, const void* in, void* out, int make_tp, cudaStre
                       ((make_tp || D <= 4) ? 0 : sizeof(double) * (size_t)ipb * ((PER + 1) / 2 * 2));
   const unsigned blocks = (unsigned)((B + ipb - 1) / ipb);
   {
+    if (!make_tp && N == 1) {  // one pass, in place or not
+      const unsigned fb = (unsigned)std::min<int64_t>((B + 127) / 128, (int64_t)QT_NUM_SMS * 16);
+      tni_fused1_kernel<<<fb, 128, 0, st>>>(B, (const cplx*)in, (cplx*)out);
+      return qt_check_launch("tni_fused1_kernel");
+    }
     if (!make_tp && in != out) {  // two-pass TNI (the correction is parked in out[b], so not for in-place calls)
       if (N <= 2)
         tni_correction_kernel<N><<<(unsigned)((B + 127) / 128), 128, 0, st>>>(B, (const cplx*)in, (cplx*)out);
