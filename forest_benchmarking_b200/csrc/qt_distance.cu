@@ -207,8 +207,8 @@ __global__ void __launch_bounds__(256, (D == 16) ? 3 : 1) fidelity_fast_kernel(i
 // e^2 = |x|^2 are kept -- the phases of the complex off-diagonal do not change the spectrum).  After 32 pairs the
 // warp switches layout: lane j runs the square-root-free QL iteration (Pal-Walker-Kahan, the algorithm behind
 // LAPACK's dsterf) on pair j's (d, e^2), kept in a lane-interleaved shared-memory slab, and writes
-// (sum_k sqrt(max(ev_k, 0)))^2.  ~3.6 k warp instructions per pair against ~29 k for the warp-per-pair Jacobi
-// kernel above.  Pairs whose rho fails the pivot test, or whose QL does not converge, get FID_FLAG and are redone by
+// (sum_k sqrt(max(ev_k, 0)))^2.  4.4 k warp instructions per pair (22 % of them the QL phase) against ~29 k for the
+// warp-per-pair Jacobi kernel above (ncu: profiles/r02_ncu_fidelity_tri_final.md).  Pairs whose rho fails the pivot test, or whose QL does not converge, get FID_FLAG and are redone by
 // fidelity_kernel with the reference's own sequence.
 // ---------------------------------------------------------------------------------------------
 // Block shape of the d = 16 instance: 3 blocks of 4 warps per SM at 168 registers.  Measured alternatives (2^18 pairs,
