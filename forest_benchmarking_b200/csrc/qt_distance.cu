@@ -54,18 +54,37 @@ __global__ void purity_kernel(int64_t B, const cplx* __restrict__ rho, double* _
   constexpr int WPB = (D >= 32) ? 2 : 8, LD = D + 1;
   const int lane = threadIdx.x & 31, gl = lane % GL, wib = threadIdx.x >> 5;
   const int64_t warp = (int64_t)blockIdx.x * WPB + wib;
+  if constexpr (DD < 32) {
+    // a warp moves only 32 elements per step: persistent warps, four steps' loads in flight, so that the kernel is
+    // bound by HBM and not by how fast blocks can be issued (0.67 of the roof with one step per warp)
+    const int i = gl / D, j = gl % D, src = (lane - gl) + j * D + i;
+    const int64_t nwarps = (int64_t)gridDim.x * WPB, steps = (B + IPW - 1) / IPW;
+    for (int64_t s0 = warp * 4; s0 < steps; s0 += nwarps * 4) {
+      cplx a[4];
+      int64_t bb[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        bb[u] = (s0 + u) * IPW + lane / GL;
+        a[u] = (bb[u] < B) ? rho[bb[u] * DD + gl] : cmake(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        cplx c;
+        c.x = __shfl_sync(0xffffffffu, a[u].x, src);
+        c.y = __shfl_sync(0xffffffffu, a[u].y, src);
+        double acc = a[u].x * c.x - a[u].y * c.y;
+#pragma unroll
+        for (int o = GL / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (bb[u] < B && gl == 0) out[bb[u]] = acc;
+      }
+    }
+    return;
+  }
   const int64_t b = warp * IPW + lane / GL;
   const bool live = b < B;
   const cplx* r = rho + (live ? b : 0) * DD;
   double acc = 0.0;
-  if constexpr (DD < 32) {
-    const int i = gl / D, j = gl % D;
-    const cplx a = r[gl];
-    cplx c;
-    c.x = __shfl_sync(0xffffffffu, a.x, (lane - gl) + j * D + i);
-    c.y = __shfl_sync(0xffffffffu, a.y, (lane - gl) + j * D + i);
-    acc = a.x * c.x - a.y * c.y;
-  } else {
+  if constexpr (DD >= 32) {
     __shared__ cplx tile[WPB][D * LD];
     cplx* t = tile[wib];
 #pragma unroll
@@ -598,16 +617,30 @@ __global__ void hs_inner_kernel(int64_t elems, int64_t B, const cplx* __restrict
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   if (block_per_pair == 2) {
     // fewer than 32 elements per matrix (a power of two): 32 / elems pairs per warp, one element per lane
+    // persistent warps, four steps' loads in flight (see purity_kernel)
     const int gl_n = (int)elems, ipw = 32 / gl_n, gl = lane % gl_n;
-    const int64_t p = ((int64_t)blockIdx.x * wpb + wib) * ipw + lane / gl_n;
-    const bool live = p < B;
-    cplx acc = cmake(0.0, 0.0);
-    if (live) cfma(acc, cconj(a[p * elems + gl]), b[p * elems + gl]);
-    for (int o = gl_n / 2; o > 0; o >>= 1) {
-      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
-      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+    const int64_t nwarps = (int64_t)gridDim.x * wpb, steps = (B + ipw - 1) / ipw;
+    for (int64_t s0 = ((int64_t)blockIdx.x * wpb + wib) * 4; s0 < steps; s0 += nwarps * 4) {
+      cplx av[4], bv[4];
+      int64_t pp[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        pp[u] = (s0 + u) * ipw + lane / gl_n;
+        const bool live = pp[u] < B;
+        av[u] = live ? a[pp[u] * elems + gl] : cmake(0.0, 0.0);
+        bv[u] = live ? b[pp[u] * elems + gl] : cmake(0.0, 0.0);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        cplx acc = cmake(0.0, 0.0);
+        cfma(acc, cconj(av[u]), bv[u]);
+        for (int o = gl_n / 2; o > 0; o >>= 1) {
+          acc.x += __shfl_xor_sync(0xffffffffu, acc.x, o);
+          acc.y += __shfl_xor_sync(0xffffffffu, acc.y, o);
+        }
+        if (pp[u] < B && gl == 0) out[pp[u]] = acc;
+      }
     }
-    if (live && gl == 0) out[p] = acc;
     return;
   }
   if (!block_per_pair) {
@@ -653,7 +686,9 @@ static int launch_purity(int64_t B, const void* rho, double* out, cudaStream_t s
   constexpr int IPW_P = (D * D < 32) ? 32 / (D * D) : 1;
   constexpr int WPB_P = (D >= 32) ? 2 : 8;  // must match purity_kernel
   const int64_t warps_p = (B + IPW_P - 1) / IPW_P;
-  purity_kernel<D><<<(unsigned)((warps_p + WPB_P - 1) / WPB_P), 32 * WPB_P, 0, st>>>(B, (const cplx*)rho, out);
+  int64_t blocks_p = (warps_p + WPB_P - 1) / WPB_P;
+  if (D * D < 32) blocks_p = std::min<int64_t>((blocks_p + 3) / 4, (int64_t)QT_NUM_SMS * 32);  // persistent, 4 steps per trip
+  purity_kernel<D><<<(unsigned)blocks_p, 32 * WPB_P, 0, st>>>(B, (const cplx*)rho, out);
   return qt_check_launch("purity_kernel");
 }
 template <int D, int MODE>
@@ -752,7 +787,7 @@ extern "C" int qt_hs_inner_batch(int64_t rows, int64_t cols, int64_t B, const vo
   const int64_t elems = rows * cols;
   const bool packed = elems < 32 && (elems & (elems - 1)) == 0;
   const int block_per_pair = packed ? 2 : (elems > 1024 ? 1 : 0);
-  const int64_t blocks = packed ? (B + 8 * (32 / elems) - 1) / (8 * (32 / elems))
+  const int64_t blocks = packed ? std::min<int64_t>((B + 32 * (32 / elems) - 1) / (32 * (32 / elems)), (int64_t)QT_NUM_SMS * 32)
                                 : (block_per_pair ? std::min<int64_t>(B, (int64_t)QT_NUM_SMS * 8) : (B + 7) / 8);
   hs_inner_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(elems, B, (const cplx*)a, (const cplx*)b,
                                                                       (cplx*)out, block_per_pair);
