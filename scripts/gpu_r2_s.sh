@@ -1,5 +1,6 @@
 #!/bin/bash
-# round 2, call S: fidelity_tri_kernel variants (block size / barriers / rolled W-Y loop / prefetch), n = 4, 2^18 pairs
+# round 2, call S: fidelity_tri_kernel block-shape variants (scripts/ubench_fid_variants.txt; the barrier / staging / rolled
+# variants of profiles/r02_ubench_fidelity_tri.txt are in the git history of qt_distance.cu), n = 4, 2^18 pairs
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 SRC="scripts/ubench_fid.cu forest_benchmarking_b200/csrc/qt_distance.cu forest_benchmarking_b200/csrc/qt_api.cu"
