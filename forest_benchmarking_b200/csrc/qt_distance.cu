@@ -265,37 +265,37 @@ __device__ __forceinline__ double group_max(double v) {
 }
 
 // eigenvalues of the symmetric tridiagonal (d, e2) of one lane's pair, in place in d; false if not converged.
-// d[k] and e2[k] live at stride 32 doubles (lane-interleaved: no bank conflicts whatever k each lane is at).
-template <int D>
+// d[k] and e2[k] live at stride ST doubles (lane-interleaved: no bank conflicts whatever k each lane is at).
+template <int D, int ST = 32>
 __device__ __forceinline__ bool pwk_ql(double* __restrict__ d, double* __restrict__ e2) {
   constexpr double EPS2 = 1.232595164407831e-32;  // (2^-53)^2
   for (int l = 0; l < D; ++l) {
     int it = 0;
     while (true) {
       int m = l;
-      while (m < D - 1 && !(e2[m * 32] <= EPS2 * fabs(d[m * 32] * d[(m + 1) * 32]))) ++m;
+      while (m < D - 1 && !(e2[m * ST] <= EPS2 * fabs(d[m * ST] * d[(m + 1) * ST]))) ++m;
       if (m == l) break;
       if (++it > 40) return false;
-      double p = d[l * 32];
-      const double rte = sqrt(e2[l * 32]);
-      const double sg = (d[(l + 1) * 32] - p) / (2.0 * rte);
+      double p = d[l * ST];
+      const double rte = sqrt(e2[l * ST]);
+      const double sg = (d[(l + 1) * ST] - p) / (2.0 * rte);
       const double rr = fabs(sg) > 1e100 ? fabs(sg) : sqrt(fma(sg, sg, 1.0));
       const double shift = p - rte / (sg + copysign(rr, sg));
-      double c = 1.0, s = 0.0, gamma = d[m * 32] - shift;
+      double c = 1.0, s = 0.0, gamma = d[m * ST] - shift;
       p = gamma * gamma;
       for (int i = m - 1; i >= l; --i) {
-        const double bb = e2[i * 32], r = p + bb;
-        if (i != m - 1) e2[(i + 1) * 32] = s * r;
+        const double bb = e2[i * ST], r = p + bb;
+        if (i != m - 1) e2[(i + 1) * ST] = s * r;
         const double oldc = c, ir = fast_rcp(r);
         c = p * ir;
         s = bb * ir;
-        const double oldgam = gamma, al = d[i * 32];
+        const double oldgam = gamma, al = d[i * ST];
         gamma = c * (al - shift) - s * oldgam;
-        d[(i + 1) * 32] = oldgam + (al - gamma);
+        d[(i + 1) * ST] = oldgam + (al - gamma);
         p = (c != 0.0) ? gamma * gamma * fast_rcp(c) : oldc * bb;
       }
-      e2[l * 32] = s * p;
-      d[l * 32] = shift + gamma;
+      e2[l * ST] = s * p;
+      d[l * ST] = shift + gamma;
     }
   }
   return true;
@@ -438,6 +438,184 @@ __global__ void __launch_bounds__((D == 16) ? FID_TRI_LB_T : 32 * FID_TRI_WPB, (
       res = acc * acc;
     }
     out[b] = res;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fidelity, d = 32 (n = 5): the same Cholesky -> L^dagger sigma L -> tridiagonal -> QL sequence with ONE pair per warp
+// (lane r owns row / column r) and the matrix in shared memory: at this size the register-resident rows of
+// fidelity_tri_kernel would need 128 registers per matrix row and ~400 KB of unrolled code, so every loop over the
+// dimension is rolled here (the trade measured at d = 16 in profiles/r02_ubench_fidelity_tri.txt; against the
+// values-only Jacobi kernel, which needs ~10 sweeps at d = 32, it is still a large net gain).  The warp's 32 pairs are
+// processed in batches of SLOTS pairs followed by one QL phase on SLOTS lanes: a smaller (d, e^2) slab buys resident warps.
+// Measured on 32768 pairs (scripts/ubench_fid.cu 5 32768): 16 slots, one warp per block 4.54 ms; 2 / 4 warps per block
+// 4.77 / 4.75 ms; 8 slots 5.0-5.3 ms; 32 slots 7.07 ms; the Jacobi kernel it replaces 15.8 ms.
+// ---------------------------------------------------------------------------------------------
+template <int SLOTS>
+struct FidTri32Smem {
+  static constexpr int D = 32, LD = D + 1, MP = D * LD;
+  static constexpr size_t bytes = sizeof(cplx) * (MP + 2 * D) + sizeof(double) * 2 * D * SLOTS;
+};
+#ifndef FID_TRI32_WPB_N
+#define FID_TRI32_WPB_N 1
+#endif
+#ifndef FID_TRI32_SLOTS_N
+#define FID_TRI32_SLOTS_N 16
+#endif
+#ifndef FID_TRI32_MINB
+#define FID_TRI32_MINB 8
+#endif
+constexpr int FID_TRI32_WPB = FID_TRI32_WPB_N, FID_TRI32_SLOTS = FID_TRI32_SLOTS_N;
+
+// y[0..IM) += conj(L[k][0..IM)) * (sigma[k][.] . L[., r]) for k = k0..k1-1 (L[k][i] = 0 for i > k: IM >= k1 suffices)
+template <int IM>
+__device__ __forceinline__ void fid_tri32_wy(cplx (&y)[32], const cplx* __restrict__ sp, const cplx* __restrict__ Ag,
+                                             int r, int k0, int k1) {
+  constexpr int D = 32, LD = 33;
+#pragma unroll 1
+  for (int k = k0; k < k1; ++k) {
+    cplx w0 = cmake(0.0, 0.0), w1 = cmake(0.0, 0.0);  // two chains
+#pragma unroll 8
+    for (int m = 0; m < D; m += 2) {  // sigma[k][m]: every lane reads the same 16 bytes (broadcast); L[m][r]: lane-contiguous
+      cfma(w0, sp[k * D + m], Ag[m * LD + r]);
+      cfma(w1, sp[k * D + m + 1], Ag[(m + 1) * LD + r]);
+    }
+    const cplx wk = cadd(w0, w1);
+#pragma unroll
+    for (int i = 0; i < IM; ++i) cfma(y[i], cconj(Ag[k * LD + i]), wk);
+  }
+}
+
+template <int SLOTS>
+__global__ void __launch_bounds__(32 * FID_TRI32_WPB, FID_TRI32_MINB)
+    fidelity_tri32_kernel(int64_t B, const cplx* __restrict__ rho, const cplx* __restrict__ sigma, double* __restrict__ out) {
+  constexpr int D = 32, DD = D * D, LD = FidTri32Smem<SLOTS>::LD, MP = FidTri32Smem<SLOTS>::MP;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int r = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  cplx* Ag = reinterpret_cast<cplx*>(smem_raw + FidTri32Smem<SLOTS>::bytes * wib);
+  cplx* Ug = Ag + MP;
+  cplx* Wg = Ug + D;
+  double* td = reinterpret_cast<double*>(Wg + D);
+  double* te = td + D * SLOTS;
+  const int64_t b0 = ((int64_t)blockIdx.x * FID_TRI32_WPB + wib) * 32;
+  if (b0 >= B) return;
+#pragma unroll 1
+  for (int batch = 0; batch < 32 / SLOTS; ++batch) {
+    const int64_t bb0 = b0 + batch * SLOTS;
+    if (bb0 >= B) break;
+#pragma unroll 1
+    for (int slot = 0; slot < SLOTS; ++slot) {
+      if (bb0 + slot >= B) break;  // warp-uniform; the slots past the end are never read
+      const int64_t b = bb0 + slot;
+      const cplx* rp = rho + b * DD;
+      const cplx* sp = sigma + b * DD;
+      if (b + 1 < B) {  // the next pair's rows on their way into L2 (row r = 512 bytes)
+        const char* pr = reinterpret_cast<const char*>(rho + (b + 1) * DD + r * D);
+        const char* ps = reinterpret_cast<const char*>(sigma + (b + 1) * DD + r * D);
+#pragma unroll
+        for (int o = 0; o < D * 16; o += 128) {
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + o));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ps + o));
+        }
+      }
+      // ---- rho -> shared memory, coalesced (scipy's eigh reads the lower triangle only: so does everything below) ----
+#pragma unroll 8
+      for (int e = r; e < DD; e += 32) Ag[(e >> 5) * LD + (e & 31)] = rp[e];
+      __syncwarp();
+      const double dmax = warp_max(Ag[r * LD + r].x);
+      const double thr = 1e-10 * dmax;
+      bool ok = dmax > 0.0;
+      // ---- Cholesky in place; rows above the diagonal of a column are written as zeros ----
+#pragma unroll 1
+      for (int j = 0; j < D; ++j) {
+        const double piv = Ag[j * LD + j].x;
+        ok = ok && (piv > thr);
+        const double inv = ok ? fast_rsqrt(piv) : 0.0;
+        cplx l = cscale(Ag[r * LD + j], inv);
+        if (r == j) l = cmake(piv * inv, 0.0);
+        if (r < j) l = cmake(0.0, 0.0);
+        Ag[r * LD + j] = l;
+        __syncwarp();
+#pragma unroll 4
+        for (int k = D - 1; k > j; --k) {  // row r of the trailing block (rows r < k hold scratch that is zeroed later)
+          const cplx lk = Ag[k * LD + j];
+          cplx v = Ag[r * LD + k];
+          v.x = fma(-l.y, lk.y, fma(-l.x, lk.x, v.x));  // v -= l * conj(lk)
+          v.y = fma(l.x, lk.y, fma(-l.y, lk.x, v.y));
+          Ag[r * LD + k] = v;
+        }
+        __syncwarp();
+      }
+      // ---- Y = L^dagger sigma L, lane r accumulates COLUMN r ----
+      cplx y[D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) y[i] = cmake(0.0, 0.0);
+      fid_tri32_wy<D / 2>(y, sp, Ag, r, 0, D / 2);
+      fid_tri32_wy<D>(y, sp, Ag, r, D / 2, D);
+      __syncwarp();
+      // row r of the Hermitian matrix an eigensolver reading the lower triangle would see: A[r][c] = conj(Y[c][r])
+#pragma unroll
+      for (int c = 0; c < D; ++c) Ag[r * LD + c] = (c == r) ? cmake(y[c].x, 0.0) : cconj(y[c]);
+      __syncwarp();
+      // ---- Householder tridiagonalisation in place, lane r owns row r ----
+#pragma unroll 1
+      for (int k = 0; k < D - 2; ++k) {
+        const cplx x = (r > k) ? Ag[r * LD + k] : cmake(0.0, 0.0);
+        const double n2 = warp_sum(cabs2(x));
+        const cplx alpha = cmake(__shfl_sync(0xffffffffu, x.x, k + 1), __shfl_sync(0xffffffffu, x.y, k + 1));
+        if (r == 0) te[k * SLOTS + slot] = n2;
+        const double aa = cabs2(alpha);
+        const bool live = n2 > 1e-290, has_a = aa > 1e-290;
+        const double rn = live ? fast_rsqrt(n2) : 0.0, ra = has_a ? fast_rsqrt(aa) : 0.0;
+        const double xn = n2 * rn, an = aa * ra;
+        const cplx ph = has_a ? cscale(alpha, ra) : cmake(1.0, 0.0);
+        // u = x - gamma e1 with gamma = -ph |x|:  H = I - beta u u^dagger is unitary and H x = gamma e1
+        const cplx u = (r == k + 1) ? cscale(ph, an + xn) : x;
+        const double beta = live ? rn * fast_rcp(xn + an) : 0.0;
+        Ug[r] = u;
+        __syncwarp();
+        cplx p0 = cmake(0.0, 0.0), p1 = cmake(0.0, 0.0);
+        int c = D - 1;
+        for (; c > k + 1; c -= 2) {
+          cfma(p0, Ag[r * LD + c], Ug[c]);
+          cfma(p1, Ag[r * LD + c - 1], Ug[c - 1]);
+        }
+        if (c == k + 1) cfma(p0, Ag[r * LD + c], Ug[c]);
+        const cplx p = cscale(cadd(p0, p1), beta);
+        const double kk = 0.5 * beta * warp_sum(u.x * p.x + u.y * p.y);
+        const cplx w2 = cmake(fma(-kk, u.x, p.x), fma(-kk, u.y, p.y));
+        Wg[r] = w2;
+        __syncwarp();
+#pragma unroll 3
+        for (int c2 = D - 1; c2 > k; --c2) {  // A -= u w^dagger + w u^dagger
+          const cplx uc = Ug[c2], wc = Wg[c2];
+          cplx v = Ag[r * LD + c2];
+          v.x = fma(-w2.y, uc.y, fma(-w2.x, uc.x, fma(-u.y, wc.y, fma(-u.x, wc.x, v.x))));
+          v.y = fma(w2.x, uc.y, fma(-w2.y, uc.x, fma(u.x, wc.y, fma(-u.y, wc.x, v.y))));
+          Ag[r * LD + c2] = v;
+        }
+        __syncwarp();
+      }
+      const double dr = Ag[r * LD + r].x;
+      const double elast = cabs2(Ag[(D - 1) * LD + D - 2]);
+      td[r * SLOTS + slot] = (r == 0 && !ok) ? __longlong_as_double(0x7ff8000000000000LL) : dr;
+      if (r == 0) te[(D - 2) * SLOTS + slot] = elast;
+      __syncwarp();
+    }
+    // ---- lane j < SLOTS: eigenvalues of pair bb0 + j ----
+    const int64_t b = bb0 + r;
+    if (r < SLOTS && b < B) {
+      double* d = td + r;
+      double res = FID_FLAG;
+      if (d[0] == d[0] && pwk_ql<D, SLOTS>(d, te + r)) {
+        double acc = 0.0;
+#pragma unroll 4
+        for (int k = 0; k < D; ++k) acc += sqrt(fmax(d[k * SLOTS], 0.0));
+        res = acc * acc;
+      }
+      out[b] = res;
+    }
+    __syncwarp();
   }
 }
 
@@ -705,6 +883,20 @@ static int launch_fid(int64_t B, const void* rho, const void* sigma, double* out
       fidelity_tri_kernel<D><<<(unsigned)((B + per_block - 1) / per_block), 32 * FID_TRI_WPB, smem_tri, st>>>(
           B, (const cplx*)rho, (const cplx*)sigma, out);
       int rc = qt_check_launch("fidelity_tri_kernel");
+      if (rc) return rc;
+      QT_CUDA(cudaFuncSetAttribute(fidelity_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      fidelity_kernel<D, MODE><<<(unsigned)((B + wpb - 1) / wpb), 32 * wpb, smem, st>>>(B, (const cplx*)rho,
+                                                                                        (const cplx*)sigma, out, 1);
+      return qt_check_launch("fidelity_kernel");
+    }
+    if constexpr (D == 32) {
+      const size_t smem_tri = FidTri32Smem<FID_TRI32_SLOTS>::bytes * FID_TRI32_WPB;
+      QT_CUDA(cudaFuncSetAttribute(fidelity_tri32_kernel<FID_TRI32_SLOTS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem_tri));
+      const int64_t per_block = 32 * FID_TRI32_WPB;
+      fidelity_tri32_kernel<FID_TRI32_SLOTS><<<(unsigned)((B + per_block - 1) / per_block), 32 * FID_TRI32_WPB, smem_tri, st>>>(
+          B, (const cplx*)rho, (const cplx*)sigma, out);
+      int rc = qt_check_launch("fidelity_tri32_kernel");
       if (rc) return rc;
       QT_CUDA(cudaFuncSetAttribute(fidelity_kernel<D, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       fidelity_kernel<D, MODE><<<(unsigned)((B + wpb - 1) / wpb), 32 * wpb, smem, st>>>(B, (const cplx*)rho,

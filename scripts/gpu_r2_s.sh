@@ -12,6 +12,6 @@ done < scripts/ubench_fid_variants.txt
 wait
 i=0
 while read -r flags; do
-  echo "[$flags]"; timeout 120 /tmp/ubench_fid_$i.bin 4 262144
+  echo "[$flags]"; timeout 120 /tmp/ubench_fid_$i.bin ${UB_N:-4} ${UB_B:-262144}
   i=$((i+1))
 done < scripts/ubench_fid_variants.txt | tee gpurun_out/r2s_ubench_fid.txt

@@ -12,7 +12,7 @@ __global__ void make_states(long long B, int D, double2* out, unsigned seed) {
   long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   unsigned s = seed + (unsigned)b * 2654435761u;
-  double2 G[16 * 16];
+  double2 G[32 * 32];  // up to d = 32 (local memory: setup only)
   for (int e = 0; e < D * D; ++e) {
     s = s * 1664525u + 1013904223u; double x = (double)(s >> 8) / (1 << 24) - 0.5;
     s = s * 1664525u + 1013904223u; double y = (double)(s >> 8) / (1 << 24) - 0.5;

@@ -430,16 +430,16 @@ def test_fidelity_cholesky_fast_path_and_fallback(torch):
                 assert abs(fid[b] - want) < 1e-10
 
 
-@pytest.mark.parametrize("n", [2, 3, 4])
+@pytest.mark.parametrize("n", [2, 3, 4, 5])
 def test_fidelity_tridiagonal_kernel_tails_and_structured_inputs(torch, n):
-    """The d = 4, 8, 16 fidelity kernel (Cholesky -> L^dagger sigma L -> Householder tridiagonalisation by d lanes per pair,
-    then one lane per pair runs the square-root-free QL): batch sizes that leave partial warps / partial rounds, and
+    """The fidelity kernels for d = 4 .. 32 (Cholesky -> L^dagger sigma L -> Householder tridiagonalisation by d lanes per
+    pair, then one lane per pair runs the square-root-free QL; d = 32: one pair per warp, matrix in shared memory): batch sizes that leave partial warps / partial rounds, and
     inputs whose tridiagonal form has exact zeros (diagonal, identical, commuting, basis-state sigma), against the
     oracle (distance_measures.py:64-84)."""
     from forest_benchmarking_b200 import distance_measures as dm
     rng = np.random.default_rng(100 + n)
     d = 2 ** n
-    for B in (1, 31, 33, 391):
+    for B in ((1, 31, 33, 391) if n < 5 else (1, 17, 33, 100)):
         rho, sig, kind = [], [], []
         for b in range(B):
             k = b % 8
