@@ -474,6 +474,34 @@ struct MleWarpSmem {
   }
 };
 
+// Sign bookkeeping of the warp kernel without per-term popcounts, selects and phase switches.
+// walsh_parity<N>(m): bit v (v < 2^N) = parity(m & v), built by doubling (the upper half of every 2^(b+1)-block is the
+// lower half, complemented if bit b of m is set).  popc2_patterns<N>(m, p0, p1): bits 0 and 1 of popcount(m & v).
+template <int N>
+__device__ __forceinline__ unsigned walsh_parity(int m) {
+  unsigned p = 0;
+#pragma unroll
+  for (int b = 0; b < N; ++b) {
+    const unsigned half = (1u << (1 << b)) - 1u;
+    const unsigned lo = p & half;
+    p = lo | ((((m >> b) & 1) ? (~lo & half) : lo) << (1 << b));
+  }
+  return p;
+}
+template <int N>
+__device__ __forceinline__ void popc2_patterns(int m, unsigned& p0, unsigned& p1) {
+  p0 = 0;
+  p1 = 0;
+#pragma unroll
+  for (int b = 0; b < N; ++b) {
+    const unsigned half = (1u << (1 << b)) - 1u;
+    const unsigned l0 = p0 & half, l1 = p1 & half;
+    const bool add = (m >> b) & 1;  // count + 1 in the upper half: bit 0 flips, bit 1 takes the carry
+    p0 = l0 | ((add ? (~l0 & half) : l0) << (1 << b));
+    p1 = l1 | ((add ? ((l1 ^ l0) & half) : l1) << (1 << b));
+  }
+}
+
 template <int N>
 __global__ void mle_warp_kernel(int64_t B, int K, const int* __restrict__ slot_ptr,
                                 const int* __restrict__ member_col, const double* __restrict__ member_coeff,
@@ -531,9 +559,20 @@ __global__ void mle_warp_kernel(int64_t B, int K, const int* __restrict__ slot_p
       const int x = pauli_xmask(j, N), z = pauli_zmask(j, N);
       const int ph = __popc(x & z) & 3;
       cplx acc = cmake(0.0, 0.0);
-      for (int c = 0; c < D; ++c) {
-        cplx v = rho[c * D + (c ^ x)];
-        if (__popc(z & c) & 1) acc = csub(acc, v); else acc = cadd(acc, v);
+      if constexpr (N <= 4) {
+        const unsigned zpar = walsh_parity<N>(z);  // bit c = parity(z & c): the sign of rho[c][c ^ x] in the trace
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+          const cplx v = rho[c * D + (c ^ x)];
+          const int sw = (int)((zpar >> c) << 31);  // acc -= v  ==  acc += (-v), bit for bit
+          acc.x += flip_sign(v.x, sw);
+          acc.y += flip_sign(v.y, sw);
+        }
+      } else {  // d = 32: the unrolled form spills; keep the loop
+        for (int c = 0; c < D; ++c) {
+          cplx v = rho[c * D + (c ^ x)];
+          if (__popc(z & c) & 1) acc = csub(acc, v); else acc = cadd(acc, v);
+        }
       }
       const double t = cmul_ipow(acc, ph).x;
       double wj = 0.0;
@@ -564,11 +603,32 @@ __global__ void mle_warp_kernel(int64_t B, int K, const int* __restrict__ slot_p
     const double invK = 1.0 / (double)K;
     for (int e = lane; e < DD; e += 32) {
       const int r = e / D, c = e % D, x = r ^ c;
+      // term z is  w[(x, z)] i^{|x & z|} (-1)^{|z & c|}: real for an even phase, imaginary for an odd one, negative when
+      // bit 1 of the phase and the parity of z & c differ.  The canonical index of (x, z) is linear in the bits of z:
+      // digit b = x_b ? 1 + z_b : 3 z_b.  Same terms, same order as the phase switch + conditional add it replaces.
       cplx acc = cmake(0.0, 0.0);
-      for (int z = 0; z < D; ++z) {
-        const double wj = wv[pauli_from_masks(x, z, N)];  // == mask2idx[x * D + z], computed instead of loaded
-        cplx term = cmul_ipow(cmake(wj, 0.0), __popc(x & z) & 3);
-        if (__popc(z & c) & 1) acc = csub(acc, term); else acc = cadd(acc, term);
+      if constexpr (N <= 4) {
+        unsigned p0, p1;
+        popc2_patterns<N>(x, p0, p1);
+        const unsigned neg = p1 ^ walsh_parity<N>(c);
+        int idx[D];
+        idx[0] = pauli_from_masks(x, 0, N);
+#pragma unroll
+        for (int z = 1; z < D; ++z) {
+          const int b = 31 - __builtin_clz(z & -z);  // lowest set bit of z (compile time after unrolling)
+          idx[z] = idx[z & (z - 1)] + ((((x >> b) & 1) ? 1 : 3) << (2 * b));
+        }
+#pragma unroll
+        for (int z = 0; z < D; ++z) {
+          const double sv = flip_sign(wv[idx[z]], (int)((neg >> z) << 31));
+          if ((p0 >> z) & 1) acc.y += sv; else acc.x += sv;
+        }
+      } else {
+        for (int z = 0; z < D; ++z) {
+          const double wj = wv[pauli_from_masks(x, z, N)];  // == mask2idx[x * D + z], computed instead of loaded
+          cplx term = cmul_ipow(cmake(wj, 0.0), __popc(x & z) & 3);
+          if (__popc(z & c) & 1) acc = csub(acc, term); else acc = cadd(acc, term);
+        }
       }
       acc = cscale(acc, invK);
       if (r == c) acc.x -= 1.0;
